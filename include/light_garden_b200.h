@@ -1,0 +1,287 @@
+/*
+ * light_garden_b200 — C ABI of the B200-native trace + line-accumulation path.
+ *
+ * This is the drop-in boundary for sphereflow/light_garden's two hot paths.
+ * The reference has no FFI of its own (it is one Rust binary); the boundary is
+ * the two Rust call sites that a patched app redirects here:
+ *
+ *   B1  LightGarden::draw -> Tracer::trace_all() -> Vec<(P2, Color)>
+ *       (src/light_garden/mod.rs:691, src/light_garden/tracer.rs:276-358)
+ *   B2  Renderer::render -> SubRenderPass::update_vertex_buffer + render into
+ *       the Rgba16Float target (src/renderer.rs:431,164-188,
+ *       src/sub_render_pass.rs:188-212, src/texture_renderer.rs:5)
+ *
+ * Conventions
+ *   - every function returns int32_t: 0 = LG_OK, negative = error; nothing
+ *     unwinds across the boundary (the reference panics instead:
+ *     src/light_garden/tracer.rs:192, src/framework.rs:44,51,84).
+ *   - lg_last_error(ctx) returns a human readable message for the last failure.
+ *   - the caller owns every host buffer it passes in; the library copies.
+ *   - the library owns device buffers, its stream and its NCCL communicator.
+ *   - one lg_ctx drives ONE device; a context is thread-compatible, not
+ *     thread-safe (the reference mutates the Tracer only from the winit event
+ *     loop thread, src/framework.rs:180-258).
+ *   - calls are blocking (return after the stream drained) unless stated.
+ *   - all structs are plain C, naturally aligned, no padding surprises:
+ *     sizes are asserted in csrc/lg_capi.cu and in tests/test_abi.py.
+ *
+ * There is NO CPU fallback behind this ABI: without a CUDA device lg_create
+ * fails with LG_ERR_CUDA.
+ */
+#ifndef LIGHT_GARDEN_B200_H
+#define LIGHT_GARDEN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LG_ABI_VERSION 1
+
+/* ---- status codes ------------------------------------------------------- */
+enum {
+  LG_OK = 0,
+  LG_ERR_INVALID = -1,     /* bad argument / malformed scene                  */
+  LG_ERR_CUDA = -2,        /* CUDA runtime error or no device                 */
+  LG_ERR_NOMEM = -3,       /* device or host allocation failed                */
+  LG_ERR_UNSUPPORTED = -4, /* legal in the reference, not supported here      */
+  LG_ERR_OVERFLOW = -5,    /* segment buffer / split stack capacity exceeded  */
+  LG_ERR_NCCL = -6,        /* NCCL missing or failed                          */
+  LG_ERR_STATE = -7        /* call order violated (e.g. trace before scene)   */
+};
+
+/* ---- precision of the device trace ------------------------------------- */
+/* The reference computes geometry in f64 (collision2d Float = f64) and colour
+ * in f32 (src/light_garden/light.rs:7). LG_PRECISION_F32 is the throughput
+ * path named by BASELINE.json's north_star; LG_PRECISION_F64 is the
+ * reference-width path used for exact parity runs. */
+enum { LG_PRECISION_F32 = 0, LG_PRECISION_F64 = 1 };
+
+/* ---- geometry (collision2d `Geo`, exhaustively matched at
+ *      src/light_garden/drawer.rs:23-99) ----------------------------------- */
+enum {
+  LG_GEO_CIRCLE = 0,  /* Geo::GeoCircle       p = {ox, oy, radius}            */
+  LG_GEO_RECT = 1,    /* Geo::GeoRect         p = {ox, oy, width, height}, rot */
+  LG_GEO_SEGMENT = 2, /* Geo::GeoLineSegment  p = {ax, ay, bx, by}            */
+  LG_GEO_BEZIER = 3,  /* Geo::GeoCubicBezier  p = {x0,y0,x1,y1,x2,y2,x3,y3}   */
+  LG_GEO_LOGIC = 4    /* Geo::GeoLogic        p = {ox, oy}, rot, op, a, b     */
+};
+/* collision2d LogicOp (src/light_garden/mod.rs:368-372) */
+enum { LG_OP_AND = 0, LG_OP_OR = 1, LG_OP_ANDNOT = 2 };
+
+/* One node of a geometry tree. `rot` is a nalgebra Rotation2 exactly as serde
+ * writes it, column-major [m11, m21, m12, m22] = [cos, sin, -sin, cos]
+ * (default.ron:24-29). Children of a LOGIC node live in that node's local
+ * frame: world = origin + rot * local (src/light_garden/object.rs:393-410). */
+typedef struct LgGeoNode {
+  int32_t kind;    /* LG_GEO_*                                               */
+  int32_t op;      /* LG_OP_* (LOGIC only)                                   */
+  int32_t child_a; /* node index (LOGIC only), else -1                       */
+  int32_t child_b; /* node index (LOGIC only), else -1                       */
+  double p[8];
+  double rot[4];
+} LgGeoNode; /* 112 bytes */
+
+/* Object{object_enum, material_opt} (src/light_garden/object.rs:51-55).
+ * StraightMirror -> SEGMENT root without material, CurvedMirror -> BEZIER root
+ * without material, Lens -> LOGIC(And, circle, circle) with material. */
+typedef struct LgObject {
+  int32_t root;         /* index into the LgGeoNode array                    */
+  int32_t has_material; /* material_opt.is_some()                            */
+  double refractive_index;
+} LgObject; /* 16 bytes */
+
+/* Tracer{max_bounce, cutoff_color, canvas_bounds}
+ * (src/light_garden/tracer.rs:4-17, defaults 37-39). canvas is given the way
+ * the app builds it: Rect::from_tlbr(top, left, bottom, right)
+ * (src/sub_render_pass.rs:156). */
+typedef struct LgTraceParams {
+  uint32_t max_bounce;
+  float cutoff_color[4];
+  uint32_t _pad;
+  double canvas_tlbr[4];
+} LgTraceParams; /* 56 bytes */
+
+/* ---- lights (src/light_garden/light.rs:10-14) --------------------------- */
+enum { LG_LIGHT_POINT = 0, LG_LIGHT_DIRECTIONAL = 1, LG_LIGHT_SPOT = 2 };
+typedef struct LgLight {
+  int32_t kind;
+  int32_t _pad;
+  uint64_t num_rays;
+  float color[4];
+  double position[2];       /* Point/Spot position; Directional: start.a     */
+  double b[2];              /* Directional: start.b                          */
+  double spot_angle;        /* Spot only                                     */
+  double spot_direction[2]; /* Spot only                                     */
+} LgLight; /* 88 bytes */
+
+/* One primary ray as Tracer::trace receives it (tracer.rs:360-367). */
+typedef struct LgRay {
+  double origin[2];
+  double direction[2]; /* unit                                                */
+  float color[4];
+  double refractive_index; /* medium the ray starts in                        */
+} LgRay; /* 56 bytes */
+
+/* ---- segments ------------------------------------------------------------ */
+/* Compact device segment: what SubRenderPass::update_vertex_buffer would
+ * upload for one vertex pair of a traced ray (positions cast to f32, one colour
+ * for both ends; sub_render_pass.rs:189-196, tracer.rs:451-452,474-475). */
+typedef struct LgSegment {
+  float a[2];
+  float b[2];
+  float color[4];
+} LgSegment; /* 32 bytes */
+
+/* General vertex pair (P2, Color),(P2, Color) for host supplied lines: control
+ * polygons, grid, drawer overlays (tracer.rs:342-349, mod.rs:692). */
+typedef struct LgVertexPair {
+  double a[2];
+  double b[2];
+  float color_a[4];
+  float color_b[4];
+} LgVertexPair; /* 64 bytes */
+
+/* Order / provenance tag of a traced segment. The reference's output order is
+ * light -> ray -> generation -> queue order; the device emits
+ * unordered, and (ray, generation, path) is the sort key that restores it.
+ * `path` holds one bit per ancestor generation, most significant = first
+ * split: 0 = reflected child (pushed first, tracer.rs:456-458), 1 = refracted
+ * child (tracer.rs:460-472). */
+typedef struct LgSegmentTag {
+  uint64_t ray;        /* global primary-ray index (lights concatenated)      */
+  uint64_t path;
+  uint32_t generation; /* 0 = primary ray                                    */
+  int32_t hit_object;  /* object index, or -1 when the ray left via canvas   */
+} LgSegmentTag; /* 24 bytes */
+
+typedef struct LgSegmentF64 {
+  double a[2];
+  double b[2];
+} LgSegmentF64; /* 32 bytes: unrounded endpoints, F64 contexts with tags only */
+
+/* ---- string mod (src/light_garden/string_mod.rs:4-15) -------------------- */
+enum { LG_SM_ADD = 0, LG_SM_MUL = 1, LG_SM_POW = 2, LG_SM_BASE = 3 };
+enum { LG_CURVE_CIRCLE = 0 };
+typedef struct LgModRemColor {
+  uint64_t modulo;
+  uint64_t rem;
+  float color[4];
+} LgModRemColor; /* 32 bytes */
+typedef struct LgStringMod {
+  uint64_t modulo;
+  uint64_t num;
+  uint64_t turns;
+  int32_t mode;  /* LG_SM_*                                                  */
+  int32_t curve; /* LG_CURVE_*                                               */
+  float color[4];
+} LgStringMod; /* 48 bytes */
+
+/* ---- accumulation target -------------------------------------------------- */
+enum { LG_RGBA32F = 0, LG_RGBA16F = 1 };
+
+typedef struct LgTraceStats {
+  uint64_t primary_rays;    /* rays this context traced (its shard)          */
+  uint64_t ray_steps;       /* popped rays that passed the cutoff test       */
+  uint64_t object_tests;    /* ray_steps * n_objects (brute force)           */
+  uint64_t segments;        /* segments emitted                              */
+  uint64_t pixel_updates;   /* fragments blended by accumulate               */
+  float trace_ms;           /* CUDA-event time of the trace kernels          */
+  float accumulate_ms;      /* CUDA-event time of the accumulate kernels     */
+  uint32_t trace_launches;  /* kernels launched by the last trace/render     */
+  uint32_t accumulate_launches;
+} LgTraceStats; /* 56 bytes */
+
+typedef struct lg_ctx lg_ctx;
+
+/* ---- lifecycle ------------------------------------------------------------ */
+int32_t lg_abi_version(void);
+int32_t lg_device_count(int32_t *count);
+int32_t lg_create(int32_t device, int32_t precision, lg_ctx **out);
+int32_t lg_destroy(lg_ctx *ctx);
+const char *lg_last_error(const lg_ctx *ctx);
+
+/* ---- B1: scene + trace ---------------------------------------------------- */
+/* Replaces the state Tracer::trace_all reads: objects + params
+ * (tracer.rs:4-17). Lowers every Geo tree to world-space primitives. */
+int32_t lg_scene_set(lg_ctx *ctx, const LgObject *objects, uint32_t n_objects,
+                     const LgGeoNode *nodes, uint32_t n_nodes,
+                     const LgTraceParams *params);
+/* Replaces Tracer.lights; the per-light start medium of tracer.rs:280-287 is
+ * evaluated here. */
+int32_t lg_lights_set(lg_ctx *ctx, const LgLight *lights, uint32_t n_lights);
+/* Data-parallel shard of the primary rays: rank r of `world` takes the rays
+ * [r*n/world, (r+1)*n/world) of every light. Default 0 of 1. */
+int32_t lg_shard_set(lg_ctx *ctx, uint32_t rank, uint32_t world);
+/* Capacity of the device segment buffer in segments (default 64 Mi). */
+int32_t lg_segment_capacity_set(lg_ctx *ctx, uint64_t n_segments);
+/* Keep LgSegmentTag (and LgSegmentF64 on F64 contexts) per segment. */
+int32_t lg_tags_enable(lg_ctx *ctx, int32_t enable);
+
+/* Ray emission alone: Light::set_num_rays (light.rs:103-115,163-174,225-249)
+ * for rays [first, first+count) of light `light`. */
+int32_t lg_emit_rays(lg_ctx *ctx, uint32_t light, uint64_t first,
+                     uint64_t count, LgRay *dst);
+
+/* Tracer::trace_all (tracer.rs:276-330) for this context's shard: emits the
+ * rays on the device and traces them; segments stay on the device.
+ * LG_ERR_OVERFLOW if they do not fit the segment buffer (use lg_render). */
+int32_t lg_trace(lg_ctx *ctx, LgTraceStats *stats);
+/* Tracer::trace (tracer.rs:360-493) on caller supplied primary rays. */
+int32_t lg_trace_rays(lg_ctx *ctx, const LgRay *rays, uint64_t n_rays,
+                      LgTraceStats *stats);
+int32_t lg_segments_count(lg_ctx *ctx, uint64_t *n);
+/* Copies up to `cap` segments out, in device (unordered) order. tags/f64 may
+ * be NULL. */
+int32_t lg_segments_read(lg_ctx *ctx, LgSegment *dst, LgSegmentTag *tags,
+                         LgSegmentF64 *f64, uint64_t cap, uint64_t *n);
+
+/* ---- B2: accumulation ----------------------------------------------------- */
+/* Rgba16Float render target of width x height (texture_renderer.rs:69-80);
+ * the working image is RGBA fp32. */
+int32_t lg_image_configure(lg_ctx *ctx, uint32_t width, uint32_t height);
+/* LoadOp::Clear(BLACK) (renderer.rs:174-177): rgb = 0, alpha =
+ * clear_alpha (1 on the rank that owns the clear, 0 on the others). */
+int32_t lg_image_clear(lg_ctx *ctx, float clear_alpha);
+/* SubRenderPass::render for the device segment buffer. */
+int32_t lg_accumulate_traced(lg_ctx *ctx, LgTraceStats *stats);
+/* update_vertex_buffer + render for host lines. */
+int32_t lg_accumulate_segments(lg_ctx *ctx, const LgVertexPair *pairs,
+                               uint64_t n, LgTraceStats *stats);
+/* StringMod::draw (string_mod.rs:152-158) + render; chords [first, first+count)
+ * of the pattern (count = 0 means this context's shard of all chords). */
+int32_t lg_string_mod(lg_ctx *ctx, const LgStringMod *sm,
+                      const LgModRemColor *rules, uint32_t n_rules,
+                      uint64_t first, uint64_t count, LgTraceStats *stats);
+/* trace_all + render fused: rays are traced in waves through the bounded
+ * segment buffer and each wave is accumulated before the next is traced. */
+int32_t lg_render(lg_ctx *ctx, LgTraceStats *stats);
+/* Image out: LG_RGBA32F (16 B/px) or LG_RGBA16F (8 B/px, round to nearest
+ * even, what the ROP would have stored). pitch in bytes, 0 = tight. */
+int32_t lg_image_read(lg_ctx *ctx, int32_t format, void *dst, size_t pitch);
+
+/* ---- multi-GPU: one context per device ------------------------------------ */
+/* 128-byte ncclUniqueId produced on one rank and handed to all of them. */
+int32_t lg_comm_unique_id(void *id128);
+int32_t lg_comm_init_rank(lg_ctx *ctx, const void *id128, int32_t rank,
+                          int32_t world);
+/* Single process driving several devices (the Rust app's shape). */
+int32_t lg_comm_init_all(lg_ctx **ctxs, int32_t n);
+/* Sum of the partial fp32 images onto `root` (ncclReduce over NVLink). */
+int32_t lg_image_reduce(lg_ctx *ctx, int32_t root, float *reduce_ms);
+int32_t lg_comm_destroy(lg_ctx *ctx);
+
+/* ---- plumbing for hosts that own the process (bench, tests) --------------- */
+/* cudaStream_t the context launches on, as an integer handle. */
+int32_t lg_stream_handle(lg_ctx *ctx, uint64_t *stream);
+/* Device pointer of the fp32 RGBA working image (width*height*16 bytes). */
+int32_t lg_image_device_ptr(lg_ctx *ctx, uint64_t *ptr);
+/* Kernels launched by this context since creation. */
+int32_t lg_launch_count(lg_ctx *ctx, uint64_t *n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LIGHT_GARDEN_B200_H */

@@ -1,0 +1,261 @@
+// lg_accum.cuh — K3 (string-mod chords), K4 (line accumulation), K5 (finalize).
+//
+// Replaces, for the LineList pass of the reference:
+//   SubRenderPass::update_vertex_buffer  src/sub_render_pass.rs:188-203  (P2 f64 -> [f32;2])
+//   vs_main / fs_main                    src/shader.wgsl:14-28            (ortho transform, colour pass-through)
+//   Renderer::generate_matrix            src/renderer.rs:120-124          (OPENGL_TO_WGPU * ortho(-a,a,-1,1,0,1))
+//   pipeline state                       src/sub_render_pass.rs:43-101    (LineList, 1 px, no MSAA)
+//   default BlendState                   src/light_garden/mod.rs:57-73    (rgb: src+dst, a: src.a*src.a + dst.a)
+//   Rgba16Float target + clear           src/texture_renderer.rs:5,69-80, src/renderer.rs:174-177
+//   StringMod::draw                      src/light_garden/string_mod.rs:33-158 (Circle curve)
+// Coverage rule and arithmetic order: oracle/ORACLE.md §8 (one fragment per
+// major-axis pixel centre inside the segment, colour lerped between the ends).
+//
+// The working image is RGBA fp32 (16 B/pixel); one blended fragment is one
+// 16-byte vector reduction (red.global.add.v4.f32, SASS REDG.E.ADD.F32x4)
+// resolved in L2.  Compiled with -fmad=false: the only fused operations are the
+// explicit fmaf calls the spec names.
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/light_garden_b200.h"
+
+namespace lg {
+
+constexpr int kAccumBlock = 256;
+
+struct AccumArgs {
+  float *img; // RGBA fp32, row-major, y down
+  int W, H;
+  float m00, m11, hw, hh; // projection + viewport (ORACLE.md §8.1)
+  unsigned long long *pixel_updates;
+};
+
+__device__ __forceinline__ void red_add_v4(float *p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+// Rasterise one segment with the whole warp; all arguments are warp-uniform.
+// Returns this lane's number of blended fragments.
+__device__ __forceinline__ unsigned warp_raster(const AccumArgs &A, float ax, float ay, float bx, float by,
+                                                const float ca[4], const float cb[4], unsigned lane) {
+  // vs_main + viewport
+  const float x0 = __fmaf_rn(A.m00 * ax, A.hw, A.hw), y0 = __fmaf_rn(-(A.m11 * ay), A.hh, A.hh);
+  const float x1 = __fmaf_rn(A.m00 * bx, A.hw, A.hw), y1 = __fmaf_rn(-(A.m11 * by), A.hh, A.hh);
+  const float dx = x1 - x0, dy = y1 - y0;
+  if (!(fabsf(dx) < 1e30f) || !(fabsf(dy) < 1e30f)) return 0;
+  const bool xmajor = fabsf(dx) >= fabsf(dy);
+  const float m0 = xmajor ? x0 : y0, m1 = xmajor ? x1 : y1;
+  const float n0 = xmajor ? y0 : x0, n1 = xmajor ? y1 : x1;
+  const float dm = m1 - m0, dn = n1 - n0;
+  if (dm == 0.f) return 0;
+  const float lo = m0 < m1 ? m0 : m1, hi = m0 < m1 ? m1 : m0;
+  const int Nmaj = xmajor ? A.W : A.H, Nmin = xmajor ? A.H : A.W;
+  float flo = ceilf(lo - 0.5f), fhi = ceilf(hi - 0.5f);
+  if (flo < 0.f) flo = 0.f;
+  if (fhi > (float)Nmaj) fhi = (float)Nmaj;
+  if (!(flo < fhi)) return 0;
+  const int i0 = (int)flo, i1 = (int)fhi;
+  const float inv = __fdiv_rn(1.0f, dm);
+  const float dc0 = cb[0] - ca[0], dc1 = cb[1] - ca[1], dc2 = cb[2] - ca[2], dc3 = cb[3] - ca[3];
+  unsigned n = 0;
+  for (int i = i0 + (int)lane; i < i1; i += 32) {
+    const float mc = (float)i + 0.5f;
+    const float s = (mc - m0) * inv;
+    const float nv = __fmaf_rn(s, dn, n0);
+    const float fj = floorf(nv);
+    if (!(fj >= 0.f) || !(fj < (float)Nmin)) continue;
+    const int j = (int)fj;
+    const int px = xmajor ? i : j, py = xmajor ? j : i;
+    const float c0 = __fmaf_rn(s, dc0, ca[0]), c1 = __fmaf_rn(s, dc1, ca[1]);
+    const float c2 = __fmaf_rn(s, dc2, ca[2]), c3 = __fmaf_rn(s, dc3, ca[3]);
+    // blend: rgb = src*1 + dst*1 ; a = src.a*src.a + dst.a   (mod.rs:57-73)
+    red_add_v4(A.img + ((size_t)py * A.W + px) * 4, c0, c1, c2, c3 * c3);
+    ++n;
+  }
+  return n;
+}
+
+__device__ __forceinline__ void flush_count(const AccumArgs &A, unsigned long long n, unsigned lane) {
+  for (int off = 16; off > 0; off >>= 1) n += __shfl_down_sync(0xffffffffu, n, off);
+  if (lane == 0 && n) atomicAdd(A.pixel_updates, n);
+}
+
+// K4 over the compact device segments written by the trace kernel
+__global__ void __launch_bounds__(kAccumBlock) accumulate_segments_kernel(AccumArgs A, const LgSegment *seg,
+                                                                           unsigned long long n) {
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned long long warp = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const unsigned long long nwarps = ((unsigned long long)gridDim.x * blockDim.x) >> 5;
+  unsigned long long cnt = 0;
+  for (unsigned long long base = warp * 32ull; base < n; base += nwarps * 32ull) {
+    // one coalesced 32-byte load per lane, then broadcast segment by segment
+    float4 p = make_float4(0.f, 0.f, 0.f, 0.f), c = p;
+    if (base + lane < n) {
+      const float4 *s = reinterpret_cast<const float4 *>(seg + base + lane);
+      p = __ldg(s);
+      c = __ldg(s + 1);
+    }
+    const int m = (int)((n - base) < 32ull ? (n - base) : 32ull);
+    for (int k = 0; k < m; ++k) {
+      const float ax = __shfl_sync(0xffffffffu, p.x, k), ay = __shfl_sync(0xffffffffu, p.y, k);
+      const float bx = __shfl_sync(0xffffffffu, p.z, k), by = __shfl_sync(0xffffffffu, p.w, k);
+      float col[4];
+      col[0] = __shfl_sync(0xffffffffu, c.x, k);
+      col[1] = __shfl_sync(0xffffffffu, c.y, k);
+      col[2] = __shfl_sync(0xffffffffu, c.z, k);
+      col[3] = __shfl_sync(0xffffffffu, c.w, k);
+      cnt += warp_raster(A, ax, ay, bx, by, col, col, lane);
+    }
+  }
+  flush_count(A, cnt, lane);
+}
+
+// K4 over host supplied vertex pairs (two colours, f64 positions cast `as f32`)
+__global__ void __launch_bounds__(kAccumBlock) accumulate_pairs_kernel(AccumArgs A, const LgVertexPair *vp,
+                                                                        unsigned long long n) {
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned long long warp = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const unsigned long long nwarps = ((unsigned long long)gridDim.x * blockDim.x) >> 5;
+  unsigned long long cnt = 0;
+  for (unsigned long long base = warp * 32ull; base < n; base += nwarps * 32ull) {
+    float v[12];
+#pragma unroll
+    for (int q = 0; q < 12; ++q) v[q] = 0.f;
+    if (base + lane < n) {
+      const LgVertexPair &s = vp[base + lane];
+      v[0] = (float)s.a[0], v[1] = (float)s.a[1], v[2] = (float)s.b[0], v[3] = (float)s.b[1];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) v[4 + q] = s.color_a[q], v[8 + q] = s.color_b[q];
+    }
+    const int m = (int)((n - base) < 32ull ? (n - base) : 32ull);
+    for (int k = 0; k < m; ++k) {
+      float u[12];
+#pragma unroll
+      for (int q = 0; q < 12; ++q) u[q] = __shfl_sync(0xffffffffu, v[q], k);
+      cnt += warp_raster(A, u[0], u[1], u[2], u[3], u + 4, u + 8, lane);
+    }
+  }
+  flush_count(A, cnt, lane);
+}
+
+// ---- K3: string mod, fused into K4 (no chord list in memory) -----------------------
+struct StringModArgs {
+  LgStringMod sm;
+  const LgModRemColor *rules;
+  unsigned int n_rules;
+  unsigned long long first, count;
+};
+
+__device__ __forceinline__ unsigned long long wrapping_pow(unsigned long long base, unsigned int e) {
+  unsigned long long acc = 1ull; // Rust u64::pow in release builds wraps
+  while (e) {
+    if (e & 1u) acc *= base;
+    base *= base;
+    e >>= 1;
+  }
+  return acc;
+}
+__device__ __forceinline__ unsigned long long sm_target(const LgStringMod &sm, unsigned long long i) {
+  const unsigned long long m = sm.modulo; // string_mod.rs:111-116
+  switch (sm.mode) {
+  case LG_SM_ADD: return (i + sm.num) % m;
+  case LG_SM_MUL: return (i * sm.num) % m;
+  case LG_SM_POW: return wrapping_pow(i, (unsigned int)sm.num) % m;
+  default: return wrapping_pow(sm.num, (unsigned int)i) % m;
+  }
+}
+__device__ __forceinline__ void sm_point(const LgStringMod &sm, unsigned long long n, float &x, float &y) {
+  const double TAU = 6.28318530717958647692; // string_mod.rs:45-55
+  const double angle = __ddiv_rn(__dmul_rn((double)(sm.turns * n), TAU), (double)sm.modulo);
+  double s, c;
+  sincos(angle, &s, &c);
+  x = (float)c; // `p.x as f32`, sub_render_pass.rs:192
+  y = (float)s;
+}
+__device__ __forceinline__ void sm_color(const StringModArgs &S, unsigned long long ix, float out[4]) {
+  float c0 = 0.f, c1 = 0.f, c2 = 0.f, c3 = 0.f; // string_mod.rs:124-150
+  int cnt = 0;
+  for (unsigned int k = 0; k < S.n_rules; ++k) {
+    const LgModRemColor r = S.rules[k];
+    if (r.modulo != 0ull && (ix % r.modulo) == r.rem) {
+      c0 += r.color[0], c1 += r.color[1], c2 += r.color[2], c3 += r.color[3];
+      ++cnt;
+    }
+  }
+  if (cnt == 0) {
+    out[0] = S.sm.color[0], out[1] = S.sm.color[1], out[2] = S.sm.color[2], out[3] = S.sm.color[3];
+  } else {
+    const float f = (float)cnt;
+    out[0] = __fdiv_rn(c0, f), out[1] = __fdiv_rn(c1, f), out[2] = __fdiv_rn(c2, f), out[3] = __fdiv_rn(c3, f);
+  }
+}
+
+__global__ void __launch_bounds__(kAccumBlock) string_mod_kernel(AccumArgs A, StringModArgs S) {
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned long long warp = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const unsigned long long nwarps = ((unsigned long long)gridDim.x * blockDim.x) >> 5;
+  unsigned long long cnt = 0;
+  for (unsigned long long base = warp * 32ull; base < S.count; base += nwarps * 32ull) {
+    float v[12];
+#pragma unroll
+    for (int q = 0; q < 12; ++q) v[q] = 0.f;
+    if (base + lane < S.count) {
+      const unsigned long long iix = S.first + base + lane;
+      const unsigned long long ix = sm_target(S.sm, iix);
+      sm_point(S.sm, iix, v[0], v[1]);
+      sm_point(S.sm, ix, v[2], v[3]);
+      sm_color(S, iix, v + 4);
+      sm_color(S, ix, v + 8);
+    }
+    const int m = (int)((S.count - base) < 32ull ? (S.count - base) : 32ull);
+    for (int k = 0; k < m; ++k) {
+      float u[12];
+#pragma unroll
+      for (int q = 0; q < 12; ++q) u[q] = __shfl_sync(0xffffffffu, v[q], k);
+      cnt += warp_raster(A, u[0], u[1], u[2], u[3], u + 4, u + 8, lane);
+    }
+  }
+  flush_count(A, cnt, lane);
+}
+
+// chord list only (tests / lg_string_mod readback): StringMod::draw as vertex pairs
+__global__ void string_mod_list_kernel(StringModArgs S, LgVertexPair *dst) {
+  const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= S.count) return;
+  const unsigned long long iix = S.first + i, ix = sm_target(S.sm, iix);
+  const double TAU = 6.28318530717958647692;
+  LgVertexPair vp;
+  double s, c;
+  sincos(__ddiv_rn(__dmul_rn((double)(S.sm.turns * iix), TAU), (double)S.sm.modulo), &s, &c);
+  vp.a[0] = c, vp.a[1] = s;
+  sincos(__ddiv_rn(__dmul_rn((double)(S.sm.turns * ix), TAU), (double)S.sm.modulo), &s, &c);
+  vp.b[0] = c, vp.b[1] = s;
+  sm_color(S, iix, vp.color_a);
+  sm_color(S, ix, vp.color_b);
+  dst[i] = vp;
+}
+
+// ---- clear + K5 finalize -------------------------------------------------------------
+__global__ void clear_image_kernel(float4 *img, size_t n_px, float alpha) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_px; i += stride)
+    img[i] = make_float4(0.f, 0.f, 0.f, alpha); // LoadOp::Clear(BLACK), renderer.rs:174-177
+}
+
+// fp32 RGBA -> Rgba16Float (round to nearest even, what the ROP store does)
+__global__ void finalize_f16_kernel(const float4 *img, uint2 *dst, size_t n_px) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_px; i += stride) {
+    const float4 v = img[i];
+    const __half2 lo = __floats2half2_rn(v.x, v.y), hi = __floats2half2_rn(v.z, v.w);
+    uint2 o;
+    o.x = *reinterpret_cast<const unsigned int *>(&lo);
+    o.y = *reinterpret_cast<const unsigned int *>(&hi);
+    dst[i] = o;
+  }
+}
+
+} // namespace lg

@@ -1,0 +1,933 @@
+// lg_capi.cu — implementation of include/light_garden_b200.h.
+//
+// One lg_ctx = one device, one stream, one (optional) NCCL communicator.
+// See the header for the reference call sites each entry point replaces.
+// There is no CPU fallback anywhere in this file: every compute entry point
+// launches a kernel from lg_trace.cuh / lg_accum.cuh or fails.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <vector>
+
+#include "../../include/light_garden_b200.h"
+#include "lg_accum.cuh"
+#include "lg_scene.h"
+#include "lg_trace.cuh"
+
+static_assert(sizeof(LgGeoNode) == 112, "LgGeoNode ABI");
+static_assert(sizeof(LgObject) == 16, "LgObject ABI");
+static_assert(sizeof(LgTraceParams) == 56, "LgTraceParams ABI");
+static_assert(sizeof(LgLight) == 88, "LgLight ABI");
+static_assert(sizeof(LgRay) == 56, "LgRay ABI");
+static_assert(sizeof(LgSegment) == 32, "LgSegment ABI");
+static_assert(sizeof(LgVertexPair) == 64, "LgVertexPair ABI");
+static_assert(sizeof(LgSegmentTag) == 24, "LgSegmentTag ABI");
+static_assert(sizeof(LgSegmentF64) == 32, "LgSegmentF64 ABI");
+static_assert(sizeof(LgModRemColor) == 32, "LgModRemColor ABI");
+static_assert(sizeof(LgStringMod) == 48, "LgStringMod ABI");
+static_assert(sizeof(LgTraceStats) == 56, "LgTraceStats ABI");
+
+using namespace lg;
+
+// ---- NCCL through dlopen: no link-time dependency, the process-wide libnccl.so.2
+// (torch's or the system's) is the one that gets used -----------------------------------
+namespace {
+typedef struct {
+  char internal[128];
+} NcclUniqueId;
+typedef void *NcclComm;
+struct NcclApi {
+  void *handle = nullptr;
+  int (*GetUniqueId)(NcclUniqueId *) = nullptr;
+  int (*CommInitRank)(NcclComm *, int, NcclUniqueId, int) = nullptr;
+  int (*CommInitAll)(NcclComm *, int, const int *) = nullptr;
+  int (*CommDestroy)(NcclComm) = nullptr;
+  int (*Reduce)(const void *, void *, size_t, int, int, int, NcclComm, cudaStream_t) = nullptr;
+  const char *(*GetErrorString)(int) = nullptr;
+  bool tried = false;
+  std::string why;
+};
+NcclApi g_nccl;
+bool nccl_load() {
+  if (g_nccl.tried) return g_nccl.handle != nullptr;
+  g_nccl.tried = true;
+  const char *names[] = {"libnccl.so.2", "libnccl.so"};
+  for (const char *n : names) {
+    g_nccl.handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+    if (g_nccl.handle) break;
+  }
+  if (!g_nccl.handle) {
+    g_nccl.why = "libnccl.so.2 not found";
+    return false;
+  }
+  bool ok = true;
+  auto sym = [&](const char *s) {
+    void *p = dlsym(g_nccl.handle, s);
+    if (!p) {
+      ok = false;
+      g_nccl.why = std::string("missing symbol ") + s;
+    }
+    return p;
+  };
+  g_nccl.GetUniqueId = (decltype(g_nccl.GetUniqueId))sym("ncclGetUniqueId");
+  g_nccl.CommInitRank = (decltype(g_nccl.CommInitRank))sym("ncclCommInitRank");
+  g_nccl.CommInitAll = (decltype(g_nccl.CommInitAll))sym("ncclCommInitAll");
+  g_nccl.CommDestroy = (decltype(g_nccl.CommDestroy))sym("ncclCommDestroy");
+  g_nccl.Reduce = (decltype(g_nccl.Reduce))sym("ncclReduce");
+  g_nccl.GetErrorString = (decltype(g_nccl.GetErrorString))sym("ncclGetErrorString");
+  if (!ok) {
+    dlclose(g_nccl.handle);
+    g_nccl.handle = nullptr;
+  }
+  return ok;
+}
+constexpr int kNcclFloat32 = 7; // ncclFloat32
+constexpr int kNcclSum = 0;     // ncclSum
+} // namespace
+
+// ---- context -----------------------------------------------------------------------------
+struct DevBuf {
+  void *p = nullptr;
+  size_t bytes = 0;
+};
+
+struct lg_ctx {
+  int device = 0;
+  int precision = LG_PRECISION_F32;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  std::string err;
+  int sm_count = 0;
+  int slots = 2; // ray slots per thread (R)
+  size_t smem_optin = 0;
+
+  // scene
+  bool have_scene = false;
+  HostScene hs;
+  int n_circ = 0, n_seg = 0, n_rect = 0, n_bez = 0, n_csg = 0, n_obj = 0;
+  unsigned fast_bytes = 0;
+  DevBuf fast, toks, circ_obj, seg_obj, rect_obj, bez_obj, csg_obj, obj_first, obj_count, obj_n, ovl_start, ovl_list;
+  double canvas[8] = {0};
+
+  // lights / shard
+  std::vector<LgLight> lights;
+  std::vector<DevLight> dev_lights;
+  DevBuf d_lights;
+  uint32_t rank = 0, world = 1;
+  unsigned long long shard_rays = 0;
+
+  // segments
+  unsigned long long seg_cap = 64ull << 20;
+  bool tags_on = false;
+  DevBuf seg, tags, seg64;
+  unsigned long long seg_count = 0;
+  DevBuf ctr;
+  DevBuf stack;
+  DevBuf rays; // explicit primary rays
+  double segs_per_ray_est = 0;
+
+  // image
+  int W = 0, H = 0;
+  DevBuf img, img16, pixctr;
+
+  // comm
+  NcclComm comm = nullptr;
+  int comm_rank = 0, comm_world = 1;
+
+  unsigned long long launches = 0;
+};
+
+namespace {
+
+int fail(lg_ctx *c, int code, const std::string &msg) {
+  if (c) c->err = msg;
+  return code;
+}
+#define LG_CUDA(c, call)                                                                                  \
+  do {                                                                                                    \
+    cudaError_t e_ = (call);                                                                              \
+    if (e_ != cudaSuccess)                                                                                \
+      return fail((c), e_ == cudaErrorMemoryAllocation ? LG_ERR_NOMEM : LG_ERR_CUDA,                      \
+                  std::string(#call) + ": " + cudaGetErrorString(e_));                                    \
+  } while (0)
+
+int ensure(lg_ctx *c, DevBuf &b, size_t bytes) {
+  if (b.bytes >= bytes && b.p) return LG_OK;
+  if (b.p) cudaFree(b.p);
+  b.p = nullptr;
+  b.bytes = 0;
+  if (bytes == 0) bytes = 16;
+  cudaError_t e = cudaMalloc(&b.p, bytes);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return fail(c, LG_ERR_NOMEM, std::string("cudaMalloc(") + std::to_string(bytes) + "): " + cudaGetErrorString(e));
+  }
+  b.bytes = bytes;
+  return LG_OK;
+}
+void release(DevBuf &b) {
+  if (b.p) cudaFree(b.p);
+  b.p = nullptr;
+  b.bytes = 0;
+}
+template <class V> int upload(lg_ctx *c, DevBuf &b, const std::vector<V> &v) {
+  int rc = ensure(c, b, v.size() * sizeof(V));
+  if (rc) return rc;
+  if (!v.empty()) LG_CUDA(c, cudaMemcpyAsync(b.p, v.data(), v.size() * sizeof(V), cudaMemcpyHostToDevice, c->stream));
+  return LG_OK;
+}
+
+// device tables in precision T (ORACLE.md §2.2: cast to T, then derive in T)
+template <class T> int upload_scene(lg_ctx *c) {
+  const HostScene &hs = c->hs;
+  std::vector<Tok<T>> toks(hs.toks.size());
+  for (size_t i = 0; i < hs.toks.size(); ++i) {
+    const HostTok &h = hs.toks[i];
+    Tok<T> t{};
+    t.kind = h.kind, t.op = h.op, t.a_start = h.a_start, t.b_start = h.b_start;
+    switch (h.kind) {
+    case 0:
+      t.p[0] = (T)h.p[0], t.p[1] = (T)h.p[1], t.p[2] = (T)h.p[2];
+      t.p[3] = t.p[2] * t.p[2];
+      break;
+    case 1:
+      for (int k = 0; k < 6; ++k) t.p[k] = (T)h.p[k];
+      t.p[6] = std::fma(t.p[2], t.p[2], t.p[3] * t.p[3]);
+      t.p[7] = std::fma(t.p[4], t.p[4], t.p[5] * t.p[5]);
+      break;
+    case 2:
+      t.p[0] = (T)h.p[0], t.p[1] = (T)h.p[1];
+      t.p[2] = (T)h.p[2] - t.p[0];
+      t.p[3] = (T)h.p[3] - t.p[1];
+      break;
+    case 3:
+      for (int k = 0; k < 8; ++k) t.p[k] = (T)h.p[k];
+      break;
+    default: break;
+    }
+    toks[i] = t;
+  }
+  std::vector<T> circ, segs, rects;
+  std::vector<int> circ_obj, seg_obj, rect_obj, bez_obj, csg_obj, obj_first, obj_count;
+  std::vector<T> obj_n;
+  for (size_t i = 0; i < hs.objs.size(); ++i) {
+    const HostObj &o = hs.objs[i];
+    obj_first.push_back(o.first);
+    obj_count.push_back(o.count);
+    obj_n.push_back(o.has_material ? (T)o.n : std::numeric_limits<T>::quiet_NaN());
+    if (o.count == 1) {
+      const Tok<T> &t = toks[o.first];
+      if (t.kind == TOK_CIRCLE) {
+        circ.insert(circ.end(), t.p, t.p + 4);
+        circ_obj.push_back((int)i);
+      } else if (t.kind == TOK_SEGMENT) {
+        segs.insert(segs.end(), t.p, t.p + 4);
+        seg_obj.push_back((int)i);
+      } else if (t.kind == TOK_RECT) {
+        rects.insert(rects.end(), t.p, t.p + 8);
+        rect_obj.push_back((int)i);
+      } else {
+        bez_obj.push_back((int)i);
+      }
+    } else {
+      csg_obj.push_back((int)i);
+    }
+  }
+  c->n_circ = (int)circ_obj.size(), c->n_seg = (int)seg_obj.size(), c->n_rect = (int)rect_obj.size();
+  c->n_bez = (int)bez_obj.size(), c->n_csg = (int)csg_obj.size(), c->n_obj = (int)hs.objs.size();
+  std::vector<T> fast;
+  fast.insert(fast.end(), circ.begin(), circ.end());
+  fast.insert(fast.end(), segs.begin(), segs.end());
+  fast.insert(fast.end(), rects.begin(), rects.end());
+  c->fast_bytes = (unsigned)(fast.size() * sizeof(T));
+  int rc;
+  if ((rc = upload(c, c->fast, fast))) return rc;
+  if ((rc = upload(c, c->toks, toks))) return rc;
+  if ((rc = upload(c, c->circ_obj, circ_obj))) return rc;
+  if ((rc = upload(c, c->seg_obj, seg_obj))) return rc;
+  if ((rc = upload(c, c->rect_obj, rect_obj))) return rc;
+  if ((rc = upload(c, c->bez_obj, bez_obj))) return rc;
+  if ((rc = upload(c, c->csg_obj, csg_obj))) return rc;
+  if ((rc = upload(c, c->obj_first, obj_first))) return rc;
+  if ((rc = upload(c, c->obj_count, obj_count))) return rc;
+  if ((rc = upload(c, c->obj_n, obj_n))) return rc;
+  if ((rc = upload(c, c->ovl_start, hs.ovl_start))) return rc;
+  if ((rc = upload(c, c->ovl_list, hs.ovl_list))) return rc;
+  // canvas as a rect: Rect::from_tlbr(top, left, bottom, right), sub_render_pass.rs:156
+  const double top = hs.params.canvas_tlbr[0], left = hs.params.canvas_tlbr[1], bottom = hs.params.canvas_tlbr[2],
+               right = hs.params.canvas_tlbr[3];
+  T cv[8];
+  cv[0] = (T)((left + right) * 0.5);
+  cv[1] = (T)((top + bottom) * 0.5);
+  cv[2] = (T)((right - left) * 0.5);
+  cv[3] = (T)0;
+  cv[4] = (T)0;
+  cv[5] = (T)((top - bottom) * 0.5);
+  cv[6] = cv[2] * cv[2];
+  cv[7] = cv[5] * cv[5];
+  for (int k = 0; k < 8; ++k) c->canvas[k] = (double)cv[k];
+  LG_CUDA(c, cudaStreamSynchronize(c->stream)); // host vectors die here
+  return LG_OK;
+}
+
+void rebuild_dev_lights(lg_ctx *c) {
+  c->dev_lights.clear();
+  unsigned long long prefix = 0, id_base = 0;
+  for (const LgLight &l : c->lights) {
+    DevLight d{};
+    d.kind = l.kind;
+    const unsigned long long n = l.num_rays;
+    d.first = (unsigned long long)(((unsigned __int128)n * c->rank) / c->world);
+    const unsigned long long hi = (unsigned long long)(((unsigned __int128)n * (c->rank + 1)) / c->world);
+    d.count = hi - d.first;
+    d.prefix = prefix;
+    d.id_base = id_base;
+    d.n_rays = (double)n;
+    d.n0 = c->have_scene ? host_start_medium(c->hs, l.position[0], l.position[1]) : 1.0;
+    std::memcpy(d.color, l.color, 16);
+    d.px = l.position[0], d.py = l.position[1];
+    d.ex = l.b[0] - l.position[0], d.ey = l.b[1] - l.position[1];
+    if (l.kind == LG_LIGHT_SPOT) { // light.rs:230-243; EPSILON: ORACLE.md §6.2
+      const double PI = 3.14159265358979323846;
+      const double dx = l.spot_direction[0], dy = l.spot_direction[1];
+      const double da = std::fabs(dx) < 1e-10 ? (dy >= 0. ? PI * 0.5 : -PI * 0.5) : std::atan(dy / dx);
+      d.min_angle = da - 0.5 * l.spot_angle;
+      d.spot_angle = l.spot_angle;
+      d.sign = std::isnan(dx) ? dx : (std::signbit(dx) ? -1.0 : 1.0); // f64::signum
+    }
+    c->dev_lights.push_back(d);
+    prefix += d.count;
+    id_base += n;
+  }
+  c->shard_rays = prefix;
+}
+
+template <class T> void fill_args(lg_ctx *c, TraceArgs<T> &A) {
+  A.fast = (const T *)c->fast.p;
+  A.fast_bytes = c->fast_bytes;
+  A.n_circ = c->n_circ, A.n_seg = c->n_seg, A.n_rect = c->n_rect, A.n_bez = c->n_bez, A.n_csg = c->n_csg;
+  A.circ_obj = (const int *)c->circ_obj.p, A.seg_obj = (const int *)c->seg_obj.p;
+  A.rect_obj = (const int *)c->rect_obj.p, A.bez_obj = (const int *)c->bez_obj.p, A.csg_obj = (const int *)c->csg_obj.p;
+  A.toks = (const Tok<T> *)c->toks.p;
+  A.obj_first = (const int *)c->obj_first.p, A.obj_count = (const int *)c->obj_count.p;
+  A.obj_n = (const T *)c->obj_n.p;
+  A.ovl_start = (const int *)c->ovl_start.p, A.ovl_list = (const int *)c->ovl_list.p;
+  for (int k = 0; k < 8; ++k) A.canvas[k] = (T)c->canvas[k];
+  A.n_obj = c->n_obj;
+  A.max_bounce = c->hs.params.max_bounce;
+  std::memcpy(A.cutoff, c->hs.params.cutoff_color, 16);
+  A.lights = (const DevLight *)c->d_lights.p;
+  A.n_lights = (int)c->dev_lights.size();
+  A.rays = nullptr;
+  A.seg = (LgSegment *)c->seg.p;
+  A.tags = c->tags_on ? (LgSegmentTag *)c->tags.p : nullptr;
+  A.seg64 = (c->tags_on && c->precision == LG_PRECISION_F64) ? (LgSegmentF64 *)c->seg64.p : nullptr;
+  A.seg_cap = c->seg_cap;
+  A.ctr = (TraceCounters *)c->ctr.p;
+  A.stack = (uint4 *)c->stack.p;
+}
+
+template <class T> struct KernelOf;
+template <> struct KernelOf<float> {
+  static const void *get(int slots, bool smem) { return trace_kernel_f32(slots, smem); }
+  static int clamp(int slots) { return (slots == 1 || slots == 4) ? slots : 2; }
+};
+template <> struct KernelOf<double> {
+  static const void *get(int slots, bool smem) { return trace_kernel_f64(slots, smem); }
+  static int clamp(int slots) { return slots == 2 ? 2 : 1; }
+};
+
+template <class T> int launch_trace(lg_ctx *c, TraceArgs<T> &A) {
+  const int R = KernelOf<T>::clamp(c->slots);
+  const bool use_smem = (size_t)A.fast_bytes + 1024 <= c->smem_optin;
+  const void *kern = KernelOf<T>::get(R, use_smem);
+  const size_t smem = use_smem ? A.fast_bytes : 0;
+  if (smem > 48 * 1024) LG_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 0;
+  LG_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kTraceBlock, smem));
+  if (per_sm < 1) return fail(c, LG_ERR_CUDA, "trace kernel does not fit on an SM");
+  const int grid = c->sm_count * per_sm;
+  const size_t nthreads = (size_t)grid * kTraceBlock;
+  // split stack: one private stack per slot, depth <= max_bounce - 1 live branches
+  int cap = (int)std::min<unsigned>(A.max_bounce > 0 ? A.max_bounce - 1 : 0, 64u);
+  if (cap < 1) cap = 1;
+  A.stack_cap = cap;
+  int rc = ensure(c, c->stack, (size_t)cap * R * StackCodec<T>::kVecs * sizeof(uint4) * nthreads);
+  if (rc) return rc;
+  A.stack = (uint4 *)c->stack.p;
+  void *args[] = {(void *)&A};
+  LG_CUDA(c, cudaLaunchKernel(kern, dim3(grid), dim3(kTraceBlock), args, smem, c->stream));
+  c->launches++;
+  return LG_OK;
+}
+
+int prepare_trace_buffers(lg_ctx *c) {
+  int rc;
+  if ((rc = ensure(c, c->seg, c->seg_cap * sizeof(LgSegment)))) return rc;
+  if (c->tags_on) {
+    if ((rc = ensure(c, c->tags, c->seg_cap * sizeof(LgSegmentTag)))) return rc;
+    if (c->precision == LG_PRECISION_F64 && (rc = ensure(c, c->seg64, c->seg_cap * sizeof(LgSegmentF64)))) return rc;
+  }
+  if ((rc = ensure(c, c->ctr, sizeof(TraceCounters)))) return rc;
+  return LG_OK;
+}
+
+// one trace launch over [first, end) of the ray index space (or explicit rays);
+// returns with the stream drained and the counters on the host
+int trace_range(lg_ctx *c, const LgRay *d_rays, unsigned long long first, unsigned long long end, TraceCounters &out,
+                float *ms) {
+  LG_CUDA(c, cudaMemsetAsync(c->ctr.p, 0, sizeof(TraceCounters), c->stream));
+  LG_CUDA(c, cudaEventRecord(c->ev0, c->stream));
+  int rc;
+  if (c->precision == LG_PRECISION_F64) {
+    TraceArgs<double> A{};
+    fill_args(c, A);
+    A.rays = d_rays, A.ray_first = first, A.ray_end = end;
+    rc = launch_trace(c, A);
+  } else {
+    TraceArgs<float> A{};
+    fill_args(c, A);
+    A.rays = d_rays, A.ray_first = first, A.ray_end = end;
+    rc = launch_trace(c, A);
+  }
+  if (rc) return rc;
+  LG_CUDA(c, cudaEventRecord(c->ev1, c->stream));
+  LG_CUDA(c, cudaMemcpyAsync(&out, c->ctr.p, sizeof(TraceCounters), cudaMemcpyDeviceToHost, c->stream));
+  LG_CUDA(c, cudaStreamSynchronize(c->stream));
+  float t = 0.f;
+  LG_CUDA(c, cudaEventElapsedTime(&t, c->ev0, c->ev1));
+  if (ms) *ms += t;
+  if (out.stack_overflow) return fail(c, LG_ERR_OVERFLOW, "split stack overflow (max_bounce with refraction > 65)");
+  return LG_OK;
+}
+
+AccumArgs accum_args(lg_ctx *c) {
+  AccumArgs A;
+  A.img = (float *)c->img.p;
+  A.W = c->W, A.H = c->H;
+  const float aspect = (float)c->W / (float)c->H; // sub_render_pass.rs:146
+  A.m00 = 2.0f / (aspect - (-aspect));           // cgmath::ortho, renderer.rs:121
+  A.m11 = 2.0f / (1.0f - (-1.0f));
+  A.hw = (float)c->W * 0.5f;
+  A.hh = (float)c->H * 0.5f;
+  A.pixel_updates = (unsigned long long *)c->pixctr.p;
+  return A;
+}
+int accum_grid(lg_ctx *c) { return c->sm_count * 8; }
+
+int accumulate_device_segments(lg_ctx *c, unsigned long long n, float *ms, unsigned *launches) {
+  if (n == 0) return LG_OK;
+  LG_CUDA(c, cudaEventRecord(c->ev0, c->stream));
+  accumulate_segments_kernel<<<accum_grid(c), kAccumBlock, 0, c->stream>>>(accum_args(c), (const LgSegment *)c->seg.p, n);
+  LG_CUDA(c, cudaGetLastError());
+  c->launches++;
+  if (launches) (*launches)++;
+  LG_CUDA(c, cudaEventRecord(c->ev1, c->stream));
+  LG_CUDA(c, cudaStreamSynchronize(c->stream));
+  float t = 0.f;
+  LG_CUDA(c, cudaEventElapsedTime(&t, c->ev0, c->ev1));
+  if (ms) *ms += t;
+  return LG_OK;
+}
+
+int read_pixel_counter(lg_ctx *c, uint64_t *out) {
+  unsigned long long v = 0;
+  LG_CUDA(c, cudaMemcpyAsync(&v, c->pixctr.p, 8, cudaMemcpyDeviceToHost, c->stream));
+  LG_CUDA(c, cudaStreamSynchronize(c->stream));
+  *out = v;
+  return LG_OK;
+}
+
+int need_scene_lights(lg_ctx *c, bool lights) {
+  if (!c) return LG_ERR_INVALID;
+  if (!c->have_scene) return fail(c, LG_ERR_STATE, "lg_scene_set has not been called");
+  if (lights && c->dev_lights.empty()) return fail(c, LG_ERR_STATE, "lg_lights_set has not been called");
+  return LG_OK;
+}
+int need_image(lg_ctx *c) {
+  if (!c) return LG_ERR_INVALID;
+  if (!c->img.p || c->W <= 0) return fail(c, LG_ERR_STATE, "lg_image_configure has not been called");
+  return LG_OK;
+}
+
+} // namespace
+
+// ===========================================================================================
+extern "C" {
+
+int32_t lg_abi_version(void) { return LG_ABI_VERSION; }
+
+int32_t lg_device_count(int32_t *count) {
+  if (!count) return LG_ERR_INVALID;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    *count = 0;
+    return LG_ERR_CUDA;
+  }
+  *count = n;
+  return LG_OK;
+}
+
+int32_t lg_create(int32_t device, int32_t precision, lg_ctx **out) {
+  if (!out) return LG_ERR_INVALID;
+  *out = nullptr;
+  if (precision != LG_PRECISION_F32 && precision != LG_PRECISION_F64) return LG_ERR_INVALID;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) {
+    cudaGetLastError();
+    return LG_ERR_CUDA; // no CPU fallback
+  }
+  if (device < 0 || device >= n) return LG_ERR_INVALID;
+  lg_ctx *c = new lg_ctx();
+  c->device = device;
+  c->precision = precision;
+  cudaDeviceProp prop;
+  if (cudaSetDevice(device) != cudaSuccess || cudaGetDeviceProperties(&prop, device) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreate(&c->ev0) != cudaSuccess || cudaEventCreate(&c->ev1) != cudaSuccess) {
+    cudaGetLastError();
+    delete c;
+    return LG_ERR_CUDA;
+  }
+  c->sm_count = prop.multiProcessorCount;
+  c->smem_optin = prop.sharedMemPerBlockOptin;
+  c->slots = precision == LG_PRECISION_F64 ? 1 : 2;
+  if (const char *e = getenv("LG_TRACE_SLOTS")) {
+    int v = atoi(e);
+    if (v == 1 || v == 2 || v == 4) c->slots = v;
+  }
+  *out = c;
+  return LG_OK;
+}
+
+int32_t lg_destroy(lg_ctx *c) {
+  if (!c) return LG_ERR_INVALID;
+  cudaSetDevice(c->device);
+  if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
+  DevBuf *bufs[] = {&c->fast,      &c->toks,     &c->circ_obj, &c->seg_obj, &c->rect_obj, &c->bez_obj, &c->csg_obj,
+                    &c->obj_first, &c->obj_count, &c->obj_n,    &c->ovl_start, &c->ovl_list, &c->d_lights, &c->seg,
+                    &c->tags,      &c->seg64,    &c->ctr,      &c->stack,   &c->rays,     &c->img,     &c->img16,
+                    &c->pixctr};
+  for (DevBuf *b : bufs) release(*b);
+  if (c->ev0) cudaEventDestroy(c->ev0);
+  if (c->ev1) cudaEventDestroy(c->ev1);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+  return LG_OK;
+}
+
+const char *lg_last_error(const lg_ctx *c) { return c ? c->err.c_str() : "null context"; }
+
+int32_t lg_scene_set(lg_ctx *c, const LgObject *objects, uint32_t n_objects, const LgGeoNode *nodes, uint32_t n_nodes,
+                     const LgTraceParams *params) {
+  if (!c) return LG_ERR_INVALID;
+  if (!params || (n_objects && (!objects || !nodes))) return fail(c, LG_ERR_INVALID, "null scene arrays");
+  LG_CUDA(c, cudaSetDevice(c->device));
+  std::string err;
+  int rc = lower_scene(objects, n_objects, nodes, n_nodes, *params, c->hs, err);
+  if (rc) {
+    c->have_scene = false;
+    return fail(c, rc, err);
+  }
+  rc = c->precision == LG_PRECISION_F64 ? upload_scene<double>(c) : upload_scene<float>(c);
+  if (rc) return rc;
+  c->have_scene = true;
+  if (!c->lights.empty()) { // start media depend on the scene
+    rebuild_dev_lights(c);
+    if ((rc = upload(c, c->d_lights, c->dev_lights))) return rc;
+    LG_CUDA(c, cudaStreamSynchronize(c->stream));
+  }
+  return LG_OK;
+}
+
+int32_t lg_lights_set(lg_ctx *c, const LgLight *lights, uint32_t n) {
+  if (!c) return LG_ERR_INVALID;
+  if (n && !lights) return fail(c, LG_ERR_INVALID, "null lights");
+  for (uint32_t i = 0; i < n; ++i)
+    if (lights[i].kind < LG_LIGHT_POINT || lights[i].kind > LG_LIGHT_SPOT) return fail(c, LG_ERR_INVALID, "light kind");
+  LG_CUDA(c, cudaSetDevice(c->device));
+  c->lights.assign(lights, lights + n);
+  rebuild_dev_lights(c);
+  int rc = upload(c, c->d_lights, c->dev_lights);
+  if (rc) return rc;
+  LG_CUDA(c, cudaStreamSynchronize(c->stream));
+  return LG_OK;
+}
+
+int32_t lg_shard_set(lg_ctx *c, uint32_t rank, uint32_t world) {
+  if (!c) return LG_ERR_INVALID;
+  if (world == 0 || rank >= world) return fail(c, LG_ERR_INVALID, "rank/world");
+  LG_CUDA(c, cudaSetDevice(c->device));
+  c->rank = rank, c->world = world;
+  rebuild_dev_lights(c);
+  int rc = upload(c, c->d_lights, c->dev_lights);
+  if (rc) return rc;
+  LG_CUDA(c, cudaStreamSynchronize(c->stream));
+  return LG_OK;
+}
+
+int32_t lg_segment_capacity_set(lg_ctx *c, uint64_t n) {
+  if (!c) return LG_ERR_INVALID;
+  if (n == 0) return fail(c, LG_ERR_INVALID, "capacity 0");
+  LG_CUDA(c, cudaSetDevice(c->device));
+  c->seg_cap = n;
+  release(c->seg), release(c->tags), release(c->seg64);
+  c->seg_count = 0;
+  return LG_OK;
+}
+
+int32_t lg_tags_enable(lg_ctx *c, int32_t enable) {
+  if (!c) return LG_ERR_INVALID;
+  c->tags_on = enable != 0;
+  return LG_OK;
+}
+
+int32_t lg_emit_rays(lg_ctx *c, uint32_t light, uint64_t first, uint64_t count, LgRay *dst) {
+  if (!c) return LG_ERR_INVALID;
+  if (light >= c->dev_lights.size() || (count && !dst)) return fail(c, LG_ERR_INVALID, "light index / dst");
+  if (count == 0) return LG_OK;
+  LG_CUDA(c, cudaSetDevice(c->device));
+  int rc = ensure(c, c->rays, count * sizeof(LgRay));
+  if (rc) return rc;
+  const unsigned grid = (unsigned)((count + 255) / 256);
+  emit_rays_kernel<<<grid, 256, 0, c->stream>>>(c->dev_lights[light], first, count, (LgRay *)c->rays.p);
+  LG_CUDA(c, cudaGetLastError());
+  c->launches++;
+  LG_CUDA(c, cudaMemcpyAsync(dst, c->rays.p, count * sizeof(LgRay), cudaMemcpyDeviceToHost, c->stream));
+  LG_CUDA(c, cudaStreamSynchronize(c->stream));
+  return LG_OK;
+}
+
+static void fill_stats(lg_ctx *c, LgTraceStats *st, unsigned long long rays, unsigned long long steps,
+                       unsigned long long segs, float tms, unsigned tl) {
+  if (!st) return;
+  st->primary_rays += rays;
+  st->ray_steps += steps;
+  st->object_tests += steps * (unsigned long long)c->n_obj;
+  st->segments += segs;
+  st->trace_ms += tms;
+  st->trace_launches += tl;
+}
+
+int32_t lg_trace(lg_ctx *c, LgTraceStats *stats) {
+  int rc = need_scene_lights(c, true);
+  if (rc) return rc;
+  LG_CUDA(c, cudaSetDevice(c->device));
+  if (stats) std::memset(stats, 0, sizeof *stats);
+  if ((rc = prepare_trace_buffers(c))) return rc;
+  TraceCounters k{};
+  float ms = 0.f;
+  c->seg_count = 0;
+  if ((rc = trace_range(c, nullptr, 0, c->shard_rays, k, &ms))) return rc;
+  fill_stats(c, stats, c->shard_rays, k.ray_steps, k.seg_count, ms, 1);
+  if (k.seg_overflow) {
+    c->seg_count = 0;
+    return fail(c, LG_ERR_OVERFLOW,
+                "segment buffer too small: " + std::to_string(k.seg_count) + " segments, capacity " +
+                    std::to_string(c->seg_cap) + " (raise lg_segment_capacity_set or use lg_render)");
+  }
+  c->seg_count = k.seg_count;
+  return LG_OK;
+}
+
+int32_t lg_trace_rays(lg_ctx *c, const LgRay *rays, uint64_t n, LgTraceStats *stats) {
+  int rc = need_scene_lights(c, false);
+  if (rc) return rc;
+  if (n && !rays) return fail(c, LG_ERR_INVALID, "null rays");
+  LG_CUDA(c, cudaSetDevice(c->device));
+  if (stats) std::memset(stats, 0, sizeof *stats);
+  if ((rc = prepare_trace_buffers(c))) return rc;
+  if ((rc = ensure(c, c->rays, n * sizeof(LgRay)))) return rc;
+  if (n) LG_CUDA(c, cudaMemcpyAsync(c->rays.p, rays, n * sizeof(LgRay), cudaMemcpyHostToDevice, c->stream));
+  TraceCounters k{};
+  float ms = 0.f;
+  c->seg_count = 0;
+  if ((rc = trace_range(c, (const LgRay *)c->rays.p, 0, n, k, &ms))) return rc;
+  fill_stats(c, stats, n, k.ray_steps, k.seg_count, ms, 1);
+  if (k.seg_overflow) return fail(c, LG_ERR_OVERFLOW, "segment buffer too small");
+  c->seg_count = k.seg_count;
+  return LG_OK;
+}
+
+int32_t lg_segments_count(lg_ctx *c, uint64_t *n) {
+  if (!c || !n) return LG_ERR_INVALID;
+  *n = c->seg_count;
+  return LG_OK;
+}
+
+int32_t lg_segments_read(lg_ctx *c, LgSegment *dst, LgSegmentTag *tags, LgSegmentF64 *f64, uint64_t cap, uint64_t *n) {
+  if (!c || !n) return LG_ERR_INVALID;
+  LG_CUDA(c, cudaSetDevice(c->device));
+  const uint64_t m = std::min<uint64_t>(cap, c->seg_count);
+  *n = m;
+  if (m == 0) return LG_OK;
+  if (dst) LG_CUDA(c, cudaMemcpyAsync(dst, c->seg.p, m * sizeof(LgSegment), cudaMemcpyDeviceToHost, c->stream));
+  if (tags) {
+    if (!c->tags_on || !c->tags.p) return fail(c, LG_ERR_STATE, "tags were not enabled for the last trace");
+    LG_CUDA(c, cudaMemcpyAsync(tags, c->tags.p, m * sizeof(LgSegmentTag), cudaMemcpyDeviceToHost, c->stream));
+  }
+  if (f64) {
+    if (!c->tags_on || c->precision != LG_PRECISION_F64 || !c->seg64.p)
+      return fail(c, LG_ERR_STATE, "f64 endpoints need an F64 context with tags enabled");
+    LG_CUDA(c, cudaMemcpyAsync(f64, c->seg64.p, m * sizeof(LgSegmentF64), cudaMemcpyDeviceToHost, c->stream));
+  }
+  LG_CUDA(c, cudaStreamSynchronize(c->stream));
+  return LG_OK;
+}
+
+int32_t lg_image_configure(lg_ctx *c, uint32_t width, uint32_t height) {
+  if (!c) return LG_ERR_INVALID;
+  if (width == 0 || height == 0 || width > 32768 || height > 32768) return fail(c, LG_ERR_INVALID, "image size");
+  LG_CUDA(c, cudaSetDevice(c->device));
+  c->W = (int)width, c->H = (int)height;
+  int rc;
+  if ((rc = ensure(c, c->img, (size_t)width * height * 16))) return rc;
+  if ((rc = ensure(c, c->pixctr, 8))) return rc;
+  return lg_image_clear(c, 1.0f);
+}
+
+int32_t lg_image_clear(lg_ctx *c, float clear_alpha) {
+  int rc = need_image(c);
+  if (rc) return rc;
+  LG_CUDA(c, cudaSetDevice(c->device));
+  clear_image_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>((float4 *)c->img.p, (size_t)c->W * c->H, clear_alpha);
+  LG_CUDA(c, cudaGetLastError());
+  c->launches++;
+  LG_CUDA(c, cudaMemsetAsync(c->pixctr.p, 0, 8, c->stream));
+  LG_CUDA(c, cudaStreamSynchronize(c->stream));
+  return LG_OK;
+}
+
+int32_t lg_accumulate_traced(lg_ctx *c, LgTraceStats *stats) {
+  int rc = need_image(c);
+  if (rc) return rc;
+  LG_CUDA(c, cudaSetDevice(c->device));
+  float ms = 0.f;
+  unsigned l = 0;
+  if ((rc = accumulate_device_segments(c, c->seg_count, &ms, &l))) return rc;
+  if (stats) {
+    stats->accumulate_ms += ms;
+    stats->accumulate_launches += l;
+    if ((rc = read_pixel_counter(c, &stats->pixel_updates))) return rc;
+  }
+  return LG_OK;
+}
+
+int32_t lg_accumulate_segments(lg_ctx *c, const LgVertexPair *pairs, uint64_t n, LgTraceStats *stats) {
+  int rc = need_image(c);
+  if (rc) return rc;
+  if (n && !pairs) return fail(c, LG_ERR_INVALID, "null pairs");
+  if (n == 0) return LG_OK;
+  LG_CUDA(c, cudaSetDevice(c->device));
+  // reuse the ray staging buffer for the upload (update_vertex_buffer makes a NEW buffer per frame)
+  if ((rc = ensure(c, c->rays, n * sizeof(LgVertexPair)))) return rc;
+  LG_CUDA(c, cudaMemcpyAsync(c->rays.p, pairs, n * sizeof(LgVertexPair), cudaMemcpyHostToDevice, c->stream));
+  LG_CUDA(c, cudaEventRecord(c->ev0, c->stream));
+  accumulate_pairs_kernel<<<accum_grid(c), kAccumBlock, 0, c->stream>>>(accum_args(c), (const LgVertexPair *)c->rays.p, n);
+  LG_CUDA(c, cudaGetLastError());
+  c->launches++;
+  LG_CUDA(c, cudaEventRecord(c->ev1, c->stream));
+  LG_CUDA(c, cudaStreamSynchronize(c->stream));
+  if (stats) {
+    float t = 0.f;
+    LG_CUDA(c, cudaEventElapsedTime(&t, c->ev0, c->ev1));
+    stats->accumulate_ms += t;
+    stats->accumulate_launches += 1;
+    stats->segments += n;
+    if ((rc = read_pixel_counter(c, &stats->pixel_updates))) return rc;
+  }
+  return LG_OK;
+}
+
+int32_t lg_string_mod(lg_ctx *c, const LgStringMod *sm, const LgModRemColor *rules, uint32_t n_rules, uint64_t first,
+                      uint64_t count, LgTraceStats *stats) {
+  int rc = need_image(c);
+  if (rc) return rc;
+  if (!sm || (n_rules && !rules)) return fail(c, LG_ERR_INVALID, "null string mod");
+  if (sm->curve != LG_CURVE_CIRCLE) return fail(c, LG_ERR_UNSUPPORTED, "only Curve::Circle (SURVEY.md §8f)");
+  if (sm->mode < LG_SM_ADD || sm->mode > LG_SM_BASE) return fail(c, LG_ERR_INVALID, "StringModMode");
+  if (sm->modulo == 0) return LG_OK; // draw_init_points: points.is_empty() -> no lines (string_mod.rs:106-108)
+  LG_CUDA(c, cudaSetDevice(c->device));
+  if (count == 0) { // this context's shard of all chords
+    first = (uint64_t)(((unsigned __int128)sm->modulo * c->rank) / c->world);
+    count = (uint64_t)(((unsigned __int128)sm->modulo * (c->rank + 1)) / c->world) - first;
+  }
+  if (first + count > sm->modulo) return fail(c, LG_ERR_INVALID, "chord range beyond modulo");
+  std::vector<LgModRemColor> rv(rules, rules + n_rules);
+  if ((rc = upload(c, c->rays, rv))) return rc;
+  StringModArgs S;
+  S.sm = *sm;
+  S.rules = (const LgModRemColor *)c->rays.p;
+  S.n_rules = n_rules;
+  S.first = first, S.count = count;
+  LG_CUDA(c, cudaEventRecord(c->ev0, c->stream));
+  if (count) {
+    string_mod_kernel<<<accum_grid(c), kAccumBlock, 0, c->stream>>>(accum_args(c), S);
+    LG_CUDA(c, cudaGetLastError());
+    c->launches++;
+  }
+  LG_CUDA(c, cudaEventRecord(c->ev1, c->stream));
+  LG_CUDA(c, cudaStreamSynchronize(c->stream));
+  if (stats) {
+    float t = 0.f;
+    LG_CUDA(c, cudaEventElapsedTime(&t, c->ev0, c->ev1));
+    stats->accumulate_ms += t;
+    stats->accumulate_launches += count ? 1 : 0;
+    stats->segments += count;
+    if ((rc = read_pixel_counter(c, &stats->pixel_updates))) return rc;
+  }
+  return LG_OK;
+}
+
+int32_t lg_render(lg_ctx *c, LgTraceStats *stats) {
+  int rc = need_scene_lights(c, true);
+  if (rc) return rc;
+  if ((rc = need_image(c))) return rc;
+  LG_CUDA(c, cudaSetDevice(c->device));
+  LgTraceStats local;
+  if (!stats) stats = &local;
+  std::memset(stats, 0, sizeof *stats);
+  if ((rc = prepare_trace_buffers(c))) return rc;
+  // waves through the bounded segment buffer: a wave that overflows is traced
+  // again with half the rays (nothing of it has been accumulated yet)
+  const unsigned mb = c->hs.params.max_bounce;
+  double est = c->segs_per_ray_est > 0 ? c->segs_per_ray_est : std::min<double>(2.0 * (mb ? mb : 1), 64.0);
+  unsigned long long done = 0;
+  const unsigned long long total = c->shard_rays;
+  while (done < total) {
+    unsigned long long wave = (unsigned long long)((double)c->seg_cap / (est * 1.25 + 1.0));
+    if (wave < 1024) wave = 1024;
+    if (wave > total - done) wave = total - done;
+    TraceCounters k{};
+    float ms = 0.f;
+    if ((rc = trace_range(c, nullptr, done, done + wave, k, &ms))) return rc;
+    stats->trace_ms += ms;
+    stats->trace_launches += 1;
+    if (k.seg_overflow) {
+      if (wave <= 1) return fail(c, LG_ERR_OVERFLOW, "one ray does not fit the segment buffer");
+      est = std::max(est * 2.0, (double)k.seg_count / (double)wave);
+      continue;
+    }
+    est = std::max(1.0, (double)k.seg_count / (double)wave);
+    fill_stats(c, stats, wave, k.ray_steps, k.seg_count, 0.f, 0);
+    c->seg_count = k.seg_count;
+    if ((rc = accumulate_device_segments(c, k.seg_count, &stats->accumulate_ms, &stats->accumulate_launches))) return rc;
+    done += wave;
+  }
+  c->segs_per_ray_est = est;
+  return read_pixel_counter(c, &stats->pixel_updates);
+}
+
+int32_t lg_image_read(lg_ctx *c, int32_t format, void *dst, size_t pitch) {
+  int rc = need_image(c);
+  if (rc) return rc;
+  if (!dst) return fail(c, LG_ERR_INVALID, "null dst");
+  LG_CUDA(c, cudaSetDevice(c->device));
+  const size_t npx = (size_t)c->W * c->H;
+  if (format == LG_RGBA32F) {
+    const size_t row = (size_t)c->W * 16;
+    if (pitch == 0) pitch = row;
+    if (pitch < row) return fail(c, LG_ERR_INVALID, "pitch");
+    LG_CUDA(c, cudaMemcpy2DAsync(dst, pitch, c->img.p, row, row, c->H, cudaMemcpyDeviceToHost, c->stream));
+  } else if (format == LG_RGBA16F) {
+    const size_t row = (size_t)c->W * 8;
+    if (pitch == 0) pitch = row;
+    if (pitch < row) return fail(c, LG_ERR_INVALID, "pitch");
+    if ((rc = ensure(c, c->img16, npx * 8))) return rc;
+    finalize_f16_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>((const float4 *)c->img.p, (uint2 *)c->img16.p, npx);
+    LG_CUDA(c, cudaGetLastError());
+    c->launches++;
+    LG_CUDA(c, cudaMemcpy2DAsync(dst, pitch, c->img16.p, row, row, c->H, cudaMemcpyDeviceToHost, c->stream));
+  } else {
+    return fail(c, LG_ERR_INVALID, "format");
+  }
+  LG_CUDA(c, cudaStreamSynchronize(c->stream));
+  return LG_OK;
+}
+
+// ---- multi-GPU ---------------------------------------------------------------------------
+int32_t lg_comm_unique_id(void *id128) {
+  if (!id128) return LG_ERR_INVALID;
+  if (!nccl_load()) return LG_ERR_NCCL;
+  NcclUniqueId id;
+  if (g_nccl.GetUniqueId(&id) != 0) return LG_ERR_NCCL;
+  std::memcpy(id128, &id, 128);
+  return LG_OK;
+}
+
+int32_t lg_comm_init_rank(lg_ctx *c, const void *id128, int32_t rank, int32_t world) {
+  if (!c || !id128 || world < 1 || rank < 0 || rank >= world) return fail(c, LG_ERR_INVALID, "comm arguments");
+  if (!nccl_load()) return fail(c, LG_ERR_NCCL, g_nccl.why);
+  LG_CUDA(c, cudaSetDevice(c->device));
+  if (c->comm) g_nccl.CommDestroy(c->comm), c->comm = nullptr;
+  NcclUniqueId id;
+  std::memcpy(&id, id128, 128);
+  int r = g_nccl.CommInitRank(&c->comm, world, id, rank);
+  if (r != 0) return fail(c, LG_ERR_NCCL, std::string("ncclCommInitRank: ") + g_nccl.GetErrorString(r));
+  c->comm_rank = rank, c->comm_world = world;
+  return LG_OK;
+}
+
+int32_t lg_comm_init_all(lg_ctx **ctxs, int32_t n) {
+  if (!ctxs || n < 1) return LG_ERR_INVALID;
+  if (!nccl_load()) return fail(ctxs[0], LG_ERR_NCCL, g_nccl.why);
+  std::vector<int> devs(n);
+  std::vector<NcclComm> comms(n);
+  for (int i = 0; i < n; ++i) devs[i] = ctxs[i]->device;
+  int r = g_nccl.CommInitAll(comms.data(), n, devs.data());
+  if (r != 0) return fail(ctxs[0], LG_ERR_NCCL, std::string("ncclCommInitAll: ") + g_nccl.GetErrorString(r));
+  for (int i = 0; i < n; ++i) {
+    ctxs[i]->comm = comms[i];
+    ctxs[i]->comm_rank = i, ctxs[i]->comm_world = n;
+  }
+  return LG_OK;
+}
+
+int32_t lg_image_reduce(lg_ctx *c, int32_t root, float *reduce_ms) {
+  int rc = need_image(c);
+  if (rc) return rc;
+  if (reduce_ms) *reduce_ms = 0.f;
+  if (c->comm_world <= 1 || !c->comm) return LG_OK; // one partial image: nothing to sum
+  LG_CUDA(c, cudaSetDevice(c->device));
+  LG_CUDA(c, cudaEventRecord(c->ev0, c->stream));
+  int r = g_nccl.Reduce(c->img.p, c->img.p, (size_t)c->W * c->H * 4, kNcclFloat32, kNcclSum, root, c->comm, c->stream);
+  if (r != 0) return fail(c, LG_ERR_NCCL, std::string("ncclReduce: ") + g_nccl.GetErrorString(r));
+  LG_CUDA(c, cudaEventRecord(c->ev1, c->stream));
+  LG_CUDA(c, cudaStreamSynchronize(c->stream));
+  if (reduce_ms) LG_CUDA(c, cudaEventElapsedTime(reduce_ms, c->ev0, c->ev1));
+  return LG_OK;
+}
+
+int32_t lg_comm_destroy(lg_ctx *c) {
+  if (!c) return LG_ERR_INVALID;
+  if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
+  c->comm = nullptr;
+  c->comm_world = 1, c->comm_rank = 0;
+  return LG_OK;
+}
+
+int32_t lg_stream_handle(lg_ctx *c, uint64_t *s) {
+  if (!c || !s) return LG_ERR_INVALID;
+  *s = (uint64_t)(uintptr_t)c->stream;
+  return LG_OK;
+}
+int32_t lg_image_device_ptr(lg_ctx *c, uint64_t *p) {
+  if (!c || !p) return LG_ERR_INVALID;
+  *p = (uint64_t)(uintptr_t)c->img.p;
+  return LG_OK;
+}
+int32_t lg_launch_count(lg_ctx *c, uint64_t *n) {
+  if (!c || !n) return LG_ERR_INVALID;
+  *n = c->launches;
+  return LG_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,260 @@
+// lg_scene.h — host-side lowering of the reference's scene model to the flat
+// device tables the trace kernel reads.
+//
+// Input is what the Rust app holds in Tracer{objects, lights, ...}
+// (src/light_garden/tracer.rs:4-17) flattened to the PODs of
+// include/light_garden_b200.h.  Every Geo tree (object.rs:282-295; Lens =
+// Logic(And, circle, circle), object.rs:393-410) becomes a postfix program of
+// world-space leaves: the Logic nodes' local frames (origin + Rotation2,
+// default.ron:20-29) are composed in f64 here, once, instead of per ray.
+#pragma once
+#include <cmath>
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "../../include/light_garden_b200.h"
+
+namespace lg {
+
+struct HostTok {
+  int32_t kind, op, a_start, b_start;
+  double p[8]; // world-space: CIRCLE cx cy r | RECT cx cy ux uy vx vy | SEGMENT ax ay bx by | BEZIER 8
+};
+struct HostObj {
+  int32_t first, count;
+  int32_t has_material;
+  double n;
+  double aabb[4]; // xmin ymin xmax ymax of the leaves that can contain a point
+  bool can_contain;
+};
+
+struct HostScene {
+  std::vector<HostTok> toks;
+  std::vector<HostObj> objs;
+  // per object: indices (ascending) of the OTHER material objects whose
+  // containing region may overlap it — the only candidates of the
+  // "which medium does the ray leave into" scan of tracer.rs:432-439
+  std::vector<int32_t> ovl_start, ovl_list;
+  LgTraceParams params{};
+  double bound = 1.0; // max |coordinate| of anything in the scene or canvas
+};
+
+struct Affine {
+  double m11, m21, m12, m22, tx, ty; // column-major 2x2 like nalgebra + translation
+};
+inline Affine compose_rot(const Affine &P, const double rot[4]) {
+  Affine r = P;
+  r.m11 = P.m11 * rot[0] + P.m12 * rot[1];
+  r.m21 = P.m21 * rot[0] + P.m22 * rot[1];
+  r.m12 = P.m11 * rot[2] + P.m12 * rot[3];
+  r.m22 = P.m21 * rot[2] + P.m22 * rot[3];
+  return r;
+}
+inline void xform(const Affine &A, double x, double y, double *o) {
+  o[0] = A.m11 * x + A.m12 * y + A.tx;
+  o[1] = A.m21 * x + A.m22 * y + A.ty;
+}
+
+inline bool lower_geo(const LgGeoNode *nodes, uint32_t n_nodes, int32_t ix, const Affine &A,
+                      std::vector<HostTok> &out, size_t base, int depth, std::string &err) {
+  if (ix < 0 || (uint32_t)ix >= n_nodes) {
+    err = "geometry node index out of range";
+    return false;
+  }
+  if (depth > 32) {
+    err = "geometry tree deeper than 32 (cycle?)";
+    return false;
+  }
+  const LgGeoNode &g = nodes[ix];
+  HostTok t{};
+  t.a_start = t.b_start = -1;
+  switch (g.kind) {
+  case LG_GEO_CIRCLE:
+    t.kind = 0;
+    xform(A, g.p[0], g.p[1], t.p);
+    t.p[2] = g.p[2];
+    out.push_back(t);
+    return true;
+  case LG_GEO_RECT: {
+    t.kind = 1;
+    xform(A, g.p[0], g.p[1], t.p);
+    Affine W = compose_rot(A, g.rot);
+    double hw = g.p[2] * 0.5, hh = g.p[3] * 0.5;
+    t.p[2] = W.m11 * hw;
+    t.p[3] = W.m21 * hw;
+    t.p[4] = W.m12 * hh;
+    t.p[5] = W.m22 * hh;
+    out.push_back(t);
+    return true;
+  }
+  case LG_GEO_SEGMENT:
+    t.kind = 2;
+    xform(A, g.p[0], g.p[1], t.p);
+    xform(A, g.p[2], g.p[3], t.p + 2);
+    out.push_back(t);
+    return true;
+  case LG_GEO_BEZIER:
+    t.kind = 3;
+    for (int k = 0; k < 4; ++k) xform(A, g.p[2 * k], g.p[2 * k + 1], t.p + 2 * k);
+    out.push_back(t);
+    return true;
+  case LG_GEO_LOGIC: {
+    if (g.op < LG_OP_AND || g.op > LG_OP_ANDNOT) {
+      err = "unknown LogicOp";
+      return false;
+    }
+    Affine W = compose_rot(A, g.rot);
+    double tw[2];
+    xform(A, g.p[0], g.p[1], tw);
+    W.tx = tw[0];
+    W.ty = tw[1];
+    int32_t a0 = (int32_t)(out.size() - base);
+    if (!lower_geo(nodes, n_nodes, g.child_a, W, out, base, depth + 1, err)) return false;
+    int32_t b0 = (int32_t)(out.size() - base);
+    if (!lower_geo(nodes, n_nodes, g.child_b, W, out, base, depth + 1, err)) return false;
+    t.kind = 4;
+    t.op = g.op;
+    t.a_start = a0;
+    t.b_start = b0;
+    out.push_back(t);
+    return true;
+  }
+  default:
+    // ConvexPolygon / Ellipse / MCircle exist in collision2d's Geo
+    // (drawer.rs:57-98) but are outside the BASELINE configs: SURVEY.md §8f.
+    err = "unsupported Geo kind";
+    return false;
+  }
+}
+
+constexpr int kMaxTokensPerObject = 64;
+
+inline int32_t lower_scene(const LgObject *objects, uint32_t n_obj, const LgGeoNode *nodes, uint32_t n_nodes,
+                           const LgTraceParams &prm, HostScene &hs, std::string &err) {
+  hs = HostScene{};
+  hs.params = prm;
+  const Affine I{1, 0, 0, 1, 0, 0};
+  double bound = 0;
+  for (int k = 0; k < 4; ++k) bound = std::fmax(bound, std::fabs(prm.canvas_tlbr[k]));
+  for (uint32_t i = 0; i < n_obj; ++i) {
+    HostObj o{};
+    o.first = (int32_t)hs.toks.size();
+    if (!lower_geo(nodes, n_nodes, objects[i].root, I, hs.toks, (size_t)o.first, 0, err)) return LG_ERR_INVALID;
+    o.count = (int32_t)hs.toks.size() - o.first;
+    if (o.count > kMaxTokensPerObject) {
+      err = "geometry tree with more than 64 tokens";
+      return LG_ERR_UNSUPPORTED;
+    }
+    o.has_material = objects[i].has_material != 0;
+    o.n = objects[i].refractive_index;
+    if (o.has_material && !(o.n > 0.0)) {
+      // the GUI slider reaches <= 0 (gui/mod.rs:287-294); not a physical medium
+      err = "refractive index must be > 0";
+      return LG_ERR_UNSUPPORTED;
+    }
+    o.aabb[0] = o.aabb[1] = 1e300;
+    o.aabb[2] = o.aabb[3] = -1e300;
+    o.can_contain = false;
+    for (int k = 0; k < o.count; ++k) {
+      const HostTok &t = hs.toks[o.first + k];
+      int np = t.kind == 0 ? 1 : t.kind == 1 ? 1 : t.kind == 2 ? 2 : t.kind == 3 ? 4 : 0;
+      for (int q = 0; q < np; ++q) bound = std::fmax(bound, std::fmax(std::fabs(t.p[2 * q]), std::fabs(t.p[2 * q + 1])));
+      double ex = 0, ey = 0;
+      if (t.kind == 0) {
+        ex = ey = std::fabs(t.p[2]);
+      } else if (t.kind == 1) {
+        ex = std::fabs(t.p[2]) + std::fabs(t.p[4]);
+        ey = std::fabs(t.p[3]) + std::fabs(t.p[5]);
+      } else {
+        continue;
+      }
+      bound = std::fmax(bound, std::fmax(std::fabs(t.p[0]) + ex, std::fabs(t.p[1]) + ey));
+      o.can_contain = true;
+      o.aabb[0] = std::fmin(o.aabb[0], t.p[0] - ex);
+      o.aabb[1] = std::fmin(o.aabb[1], t.p[1] - ey);
+      o.aabb[2] = std::fmax(o.aabb[2], t.p[0] + ex);
+      o.aabb[3] = std::fmax(o.aabb[3], t.p[1] + ey);
+    }
+    hs.objs.push_back(o);
+  }
+  hs.bound = bound > 0 ? bound : 1.0;
+  // overlap candidates: conservative (AABBs inflated by 1e-4 of the scene bound,
+  // far above any rounding of a hit point) so the scan result is unchanged.
+  const double pad = 1e-4 * hs.bound;
+  hs.ovl_start.assign(n_obj + 1, 0);
+  for (uint32_t i = 0; i < n_obj; ++i) {
+    hs.ovl_start[i] = (int32_t)hs.ovl_list.size();
+    const HostObj &a = hs.objs[i];
+    if (!a.has_material) continue; // the scan only runs for material hits (tracer.rs:428)
+    // bounding box of everything a hit point on object i can lie on: all leaves
+    double bx0 = 1e300, by0 = 1e300, bx1 = -1e300, by1 = -1e300;
+    for (int k = 0; k < a.count; ++k) {
+      const HostTok &t = hs.toks[a.first + k];
+      if (t.kind == 4) continue;
+      if (t.kind == 0) {
+        bx0 = std::fmin(bx0, t.p[0] - t.p[2]), bx1 = std::fmax(bx1, t.p[0] + t.p[2]);
+        by0 = std::fmin(by0, t.p[1] - t.p[2]), by1 = std::fmax(by1, t.p[1] + t.p[2]);
+      } else if (t.kind == 1) {
+        double ex = std::fabs(t.p[2]) + std::fabs(t.p[4]), ey = std::fabs(t.p[3]) + std::fabs(t.p[5]);
+        bx0 = std::fmin(bx0, t.p[0] - ex), bx1 = std::fmax(bx1, t.p[0] + ex);
+        by0 = std::fmin(by0, t.p[1] - ey), by1 = std::fmax(by1, t.p[1] + ey);
+      } else {
+        int np = t.kind == 2 ? 2 : 4;
+        for (int q = 0; q < np; ++q) {
+          bx0 = std::fmin(bx0, t.p[2 * q]), bx1 = std::fmax(bx1, t.p[2 * q]);
+          by0 = std::fmin(by0, t.p[2 * q + 1]), by1 = std::fmax(by1, t.p[2 * q + 1]);
+        }
+      }
+    }
+    for (uint32_t j = 0; j < n_obj; ++j) {
+      if (j == i) continue;
+      const HostObj &b = hs.objs[j];
+      if (!b.has_material || !b.can_contain) continue;
+      if (b.aabb[0] - pad > bx1 || b.aabb[2] + pad < bx0 || b.aabb[1] - pad > by1 || b.aabb[3] + pad < by0) continue;
+      hs.ovl_list.push_back((int32_t)j);
+    }
+  }
+  hs.ovl_start[n_obj] = (int32_t)hs.ovl_list.size();
+  return LG_OK;
+}
+
+// postfix containment in f64 on the host: start medium of a light,
+// src/light_garden/tracer.rs:280-287 (`last match wins`, no break).
+inline bool host_contains_leaf(const HostTok &t, double x, double y) {
+  if (t.kind == 0) {
+    double qx = x - t.p[0], qy = y - t.p[1];
+    return std::fma(qx, qx, qy * qy) < t.p[2] * t.p[2];
+  }
+  if (t.kind == 1) {
+    double qx = x - t.p[0], qy = y - t.p[1];
+    double a = std::fma(qx, t.p[2], qy * t.p[3]), b = std::fma(qx, t.p[4], qy * t.p[5]);
+    double uu = std::fma(t.p[2], t.p[2], t.p[3] * t.p[3]), vv = std::fma(t.p[4], t.p[4], t.p[5] * t.p[5]);
+    return std::fabs(a) < uu && std::fabs(b) < vv;
+  }
+  return false;
+}
+inline bool host_contains(const HostScene &hs, int obj, double x, double y) {
+  const HostObj &o = hs.objs[obj];
+  uint64_t st = 0;
+  for (int i = 0; i < o.count; ++i) {
+    const HostTok &t = hs.toks[o.first + i];
+    if (t.kind == 4) {
+      bool b = st & 1, a = (st >> 1) & 1;
+      st >>= 2;
+      bool r = t.op == LG_OP_AND ? (a && b) : t.op == LG_OP_OR ? (a || b) : (a && !b);
+      st = (st << 1) | (r ? 1 : 0);
+    } else {
+      st = (st << 1) | (host_contains_leaf(t, x, y) ? 1 : 0);
+    }
+  }
+  return st & 1;
+}
+inline double host_start_medium(const HostScene &hs, double x, double y) {
+  double n = 1.0;
+  for (size_t i = 0; i < hs.objs.size(); ++i)
+    if (hs.objs[i].has_material && host_contains(hs, (int)i, x, y)) n = hs.objs[i].n;
+  return n;
+}
+
+} // namespace lg

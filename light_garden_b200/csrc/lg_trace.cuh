@@ -1,0 +1,628 @@
+// lg_trace.cuh — K1 (ray emission) + K2 (trace) for sm_100a.
+//
+// Replaces Tracer::trace_all / Tracer::trace (src/light_garden/tracer.rs:276-493)
+// and Light::set_num_rays (src/light_garden/light.rs:103-115,163-174,225-249).
+//
+// Shape of the kernel
+//   * persistent CTAs; every thread owns R ray slots.  A slot holds one ray of
+//     the reference's work list (tracer.rs:368-369).  The reference walks a
+//     primary ray's split tree breadth-first with two Vecs; here each slot
+//     walks it depth-first with a private stack in global memory — the set of
+//     processed rays (and therefore of emitted segments) is identical, the
+//     emission order is restored from the (ray, generation, path) tag.
+//   * the scene's object table is staged once per CTA into shared memory with
+//     one cp.async.bulk (TMA bulk copy, SASS UBLKCP) and every lane tests the
+//     same object at the same time (broadcast LDS, no bank conflicts, warp
+//     uniform control flow: tracer.rs:412-424 brute-force loop).
+//   * rays that die (left the canvas, culled by cutoff_color, generation
+//     limit) free their slot; idle slots are re-filled every iteration from the
+//     slot's stack or, warp-aggregated (ballot + one atomicAdd per warp), from
+//     the global primary-ray counter, so lanes stay packed with live rays
+//     however divergent the bounce depth is.
+//   * segments leave through warp-aggregated slot allocation (ballot + one
+//     atomicAdd per warp) as two 16-byte stores per segment.
+#pragma once
+#include "../../include/light_garden_b200.h"
+#include "lg_geom.cuh"
+
+namespace lg {
+
+constexpr int kTraceBlock = 256;
+
+struct DevLight {
+  int32_t kind;
+  int32_t _pad;
+  unsigned long long first;    // first ray index of this context's shard
+  unsigned long long count;    // rays in the shard
+  unsigned long long prefix;   // offset of the shard in this context's ray index space
+  unsigned long long id_base;  // global id of ray 0 of this light
+  double n_rays;
+  double n0; // start medium, tracer.rs:280-287
+  float color[4];
+  double px, py;               // position / segment a
+  double ex, ey;               // directional: b - a
+  double min_angle, spot_angle, sign; // spot: light.rs:230-243
+};
+
+struct TraceCounters {
+  unsigned long long next_ray;   // work counter
+  unsigned long long seg_count;  // segments emitted
+  unsigned long long ray_steps;  // popped rays that passed the cutoff test
+  unsigned int seg_overflow;     // a segment did not fit
+  unsigned int stack_overflow;   // a split did not fit the slot's stack
+};
+
+template <class T> struct TraceArgs {
+  // fast tables, contiguous: circles (4 T), segments (4 T), rects (8 T)
+  const T *fast;
+  unsigned int fast_bytes;
+  int n_circ, n_seg, n_rect, n_bez, n_csg;
+  const int *circ_obj, *seg_obj, *rect_obj, *bez_obj, *csg_obj;
+  const Tok<T> *toks;
+  const int *obj_first, *obj_count;
+  const T *obj_n; // refractive index, NaN = no material
+  const int *ovl_start, *ovl_list;
+  T canvas[8];
+  int n_obj;
+  unsigned int max_bounce;
+  float cutoff[4];
+  // rays
+  const DevLight *lights;
+  int n_lights;
+  const LgRay *rays;             // explicit primary rays (lg_trace_rays) or nullptr
+  unsigned long long ray_first;  // this launch covers [ray_first, ray_end) of the index space
+  unsigned long long ray_end;
+  // outputs
+  LgSegment *seg;
+  LgSegmentTag *tags;
+  LgSegmentF64 *seg64;
+  unsigned long long seg_cap;
+  TraceCounters *ctr;
+  uint4 *stack;
+  int stack_cap; // entries per slot
+};
+
+// ---- stack entry packing -------------------------------------------------------
+template <class T> struct StackCodec;
+template <> struct StackCodec<float> {
+  static constexpr int kVecs = 3;
+  static __device__ __forceinline__ void put(uint4 *s, size_t stride, V2<float> o, V2<float> d, float n, float r,
+                                             float g, float b, unsigned gen, unsigned long long path) {
+    s[0] = make_uint4(__float_as_uint(o.x), __float_as_uint(o.y), __float_as_uint(d.x), __float_as_uint(d.y));
+    s[stride] = make_uint4(__float_as_uint(n), __float_as_uint(r), __float_as_uint(g), __float_as_uint(b));
+    s[2 * stride] = make_uint4(gen, (unsigned)path, (unsigned)(path >> 32), 0u);
+  }
+  static __device__ __forceinline__ void get(const uint4 *s, size_t stride, V2<float> &o, V2<float> &d, float &n,
+                                             float &r, float &g, float &b, unsigned &gen, unsigned long long &path) {
+    uint4 a = s[0], c = s[stride], e = s[2 * stride];
+    o = {__uint_as_float(a.x), __uint_as_float(a.y)};
+    d = {__uint_as_float(a.z), __uint_as_float(a.w)};
+    n = __uint_as_float(c.x);
+    r = __uint_as_float(c.y);
+    g = __uint_as_float(c.z);
+    b = __uint_as_float(c.w);
+    gen = e.x;
+    path = (unsigned long long)e.y | ((unsigned long long)e.z << 32);
+  }
+};
+template <> struct StackCodec<double> {
+  static constexpr int kVecs = 4;
+  static __device__ __forceinline__ uint2 d2u(double v) {
+    long long x = __double_as_longlong(v);
+    return make_uint2((unsigned)x, (unsigned)((unsigned long long)x >> 32));
+  }
+  static __device__ __forceinline__ double u2d(unsigned lo, unsigned hi) {
+    return __longlong_as_double((long long)((unsigned long long)lo | ((unsigned long long)hi << 32)));
+  }
+  static __device__ __forceinline__ void put(uint4 *s, size_t stride, V2<double> o, V2<double> d, double n, float r,
+                                             float g, float b, unsigned gen, unsigned long long path) {
+    uint2 a = d2u(o.x), c = d2u(o.y), e = d2u(d.x), f = d2u(d.y), h = d2u(n);
+    s[0] = make_uint4(a.x, a.y, c.x, c.y);
+    s[stride] = make_uint4(e.x, e.y, f.x, f.y);
+    s[2 * stride] = make_uint4(h.x, h.y, __float_as_uint(r), __float_as_uint(g));
+    s[3 * stride] = make_uint4(__float_as_uint(b), gen, (unsigned)path, (unsigned)(path >> 32));
+  }
+  static __device__ __forceinline__ void get(const uint4 *s, size_t stride, V2<double> &o, V2<double> &d, double &n,
+                                             float &r, float &g, float &b, unsigned &gen, unsigned long long &path) {
+    uint4 a = s[0], c = s[stride], e = s[2 * stride], f = s[3 * stride];
+    o = {u2d(a.x, a.y), u2d(a.z, a.w)};
+    d = {u2d(c.x, c.y), u2d(c.z, c.w)};
+    n = u2d(e.x, e.y);
+    r = __uint_as_float(e.z);
+    g = __uint_as_float(e.w);
+    b = __uint_as_float(f.x);
+    gen = f.y;
+    path = (unsigned long long)f.z | ((unsigned long long)f.w << 32);
+  }
+};
+
+// ---- K1: ray emission (always f64, like the reference) ---------------------------
+__device__ __forceinline__ void unit_from(double x, double y, double &ux, double &uy) {
+  // Ray::from_origin -> nalgebra Unit::new_normalize: v / sqrt(x*x + y*y)
+  double n = __dsqrt_rn(__dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y)));
+  ux = __ddiv_rn(x, n);
+  uy = __ddiv_rn(y, n);
+}
+__device__ __forceinline__ void emit_ray(const DevLight &l, unsigned long long i, double &ox, double &oy, double &dx,
+                                         double &dy) {
+  const double PI = 3.14159265358979323846;
+  if (l.kind == LG_LIGHT_POINT) { // light.rs:163-174
+    double f = __ddiv_rn(__dmul_rn(__dmul_rn((double)i, PI), 2.0), l.n_rays);
+    double s, c;
+    sincos(f, &s, &c);
+    ox = l.px;
+    oy = l.py;
+    unit_from(c, s, dx, dy);
+  } else if (l.kind == LG_LIGHT_SPOT) { // light.rs:225-249
+    double step = (double)(i + 1ull);
+    double angle = __dadd_rn(l.min_angle, __dmul_rn(__ddiv_rn(step, l.n_rays), l.spot_angle));
+    double s, c;
+    sincos(angle, &s, &c);
+    ox = l.px;
+    oy = l.py;
+    unit_from(__dmul_rn(l.sign, c), __dmul_rn(l.sign, s), dx, dy);
+  } else { // directional, light.rs:103-115 (ORACLE.md §6.3)
+    double rr = __ddiv_rn((double)i, l.n_rays);
+    ox = __dadd_rn(l.px, __dmul_rn(rr, l.ex));
+    oy = __dadd_rn(l.py, __dmul_rn(rr, l.ey));
+    unit_from(-l.ey, l.ex, dx, dy);
+  }
+}
+
+static __global__ void emit_rays_kernel(DevLight l, unsigned long long first, unsigned long long count, LgRay *dst) {
+  unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  LgRay r;
+  emit_ray(l, first + i, r.origin[0], r.origin[1], r.direction[0], r.direction[1]);
+  r.color[0] = l.color[0];
+  r.color[1] = l.color[1];
+  r.color[2] = l.color[2];
+  r.color[3] = l.color[3];
+  r.refractive_index = l.n0;
+  dst[i] = r;
+}
+
+// ---- best-hit bookkeeping (tracer.rs:412-424) -------------------------------------
+template <class T> struct Best {
+  T d2;
+  T px, py, aux;
+  int obj, tok;
+};
+
+template <class T>
+__device__ __forceinline__ void take(Best<T> &b, V2<T> o, const Cand<T> &c, int obj, int tok) {
+  T dx = c.p.x - o.x, dy = c.p.y - o.y;
+  T d2 = dx * dx + dy * dy; // nalgebra distance_squared, no fused multiply-add
+  // strict `<`; the sweep visits objects grouped by type, so equal distances
+  // are resolved towards the lower object index, as the in-order loop would
+  if (d2 < b.d2 || (d2 == b.d2 && obj < b.obj)) {
+    b.d2 = d2;
+    b.px = c.p.x;
+    b.py = c.p.y;
+    b.aux = c.aux;
+    b.obj = obj;
+    b.tok = tok;
+  }
+}
+
+// Rare path of the sweep loops: a primitive passed its early-out test.  Kept
+// out of line so the hot loops stay a handful of instructions per test.
+template <class T>
+__device__ __noinline__ Best<T> cand_circle(Best<T> b, const T *c, V2<T> o, V2<T> d, int ob, int tok) {
+  CandList<T> hl;
+  hl.n = 0;
+  hit_circle(c, o, d, hl);
+  for (int q = 0; q < hl.n; ++q) take(b, o, hl.h[q], ob, tok);
+  return b;
+}
+template <class T>
+__device__ __noinline__ Best<T> cand_segment(Best<T> b, const T *s, V2<T> o, V2<T> d, int ob, int tok) {
+  CandList<T> hl;
+  hl.n = 0;
+  hit_segment(s, o, d, hl);
+  for (int q = 0; q < hl.n; ++q) take(b, o, hl.h[q], ob, tok);
+  return b;
+}
+template <class T>
+__device__ __noinline__ Best<T> cand_rect(Best<T> b, const T *r, V2<T> o, V2<T> d, int ob, int tok) {
+  CandList<T> hl;
+  hl.n = 0;
+  hit_rect(r, o, d, hl);
+  for (int q = 0; q < hl.n; ++q) take(b, o, hl.h[q], ob, tok);
+  return b;
+}
+template <class T>
+__device__ __noinline__ Best<T> cand_bezier(Best<T> b, const T *p, V2<T> o, V2<T> d, int ob, int tok) {
+  CandList<T> hl;
+  hl.n = 0;
+  hit_bezier(p, o, d, hl);
+  for (int q = 0; q < hl.n; ++q) take(b, o, hl.h[q], ob, tok);
+  return b;
+}
+
+// Ray::intersect(&Geo::GeoLogic): leaf hits in program order, each filtered by
+// the sibling subtrees on the way to the root (ORACLE.md §3.6)
+template <class T>
+__device__ __noinline__ void sweep_csg_object(const TraceArgs<T> &A, int obj, V2<T> o, V2<T> d, Best<T> &best) {
+  const int first = A.obj_first[obj], count = A.obj_count[obj];
+  const Tok<T> *tok = A.toks + first;
+  for (int k = 0; k < count; ++k) {
+    const Tok<T> &l = tok[k];
+    if (l.kind == TOK_OP) continue;
+    CandList<T> hl;
+    hl.n = 0;
+    if (l.kind == TOK_CIRCLE)
+      hit_circle(l.p, o, d, hl);
+    else if (l.kind == TOK_RECT)
+      hit_rect(l.p, o, d, hl);
+    else if (l.kind == TOK_SEGMENT)
+      hit_segment(l.p, o, d, hl);
+    else
+      hit_bezier(l.p, o, d, hl);
+    for (int j = 0; j < hl.n; ++j) {
+      bool keep = true;
+      for (int i = k + 1; i < count && keep; ++i) {
+        const Tok<T> &q = tok[i];
+        if (q.kind != TOK_OP || q.a_start > k) continue;
+        if (k < q.b_start) {
+          bool inb = contains_range(tok, q.b_start, i - 1, hl.h[j].p);
+          keep = (q.op == OP_AND) ? inb : !inb;
+        } else {
+          bool ina = contains_range(tok, q.a_start, q.b_start - 1, hl.h[j].p);
+          keep = (q.op == OP_OR) ? !ina : ina;
+        }
+      }
+      if (keep) take(best, o, hl.h[j], obj, first + k);
+    }
+  }
+}
+
+template <class T> __device__ __forceinline__ bool contains_object(const TraceArgs<T> &A, int obj, V2<T> p) {
+  return contains_range(A.toks + A.obj_first[obj], 0, A.obj_count[obj] - 1, p);
+}
+
+__device__ __forceinline__ bool culled(float r, float g, float b, float a, const float *cut) {
+  // tracer.rs:378-384
+  return (r < cut[0] && g < cut[1] && b < cut[2]) || a < cut[3];
+}
+
+// ---- K2 ---------------------------------------------------------------------------
+template <class T, int R, bool kSmem>
+__global__ void __launch_bounds__(kTraceBlock) trace_kernel(const __grid_constant__ TraceArgs<T> A) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ __align__(8) unsigned long long mbar;
+  const T *fast = A.fast;
+  if (kSmem) {
+    // stage the object table: one TMA bulk copy, completion on an mbarrier
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_raw);
+    const unsigned bar = (unsigned)__cvta_generic_to_shared(&mbar);
+    if (threadIdx.x == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+      asm volatile("fence.mbarrier_init.release.cluster;");
+    }
+    __syncthreads();
+    if (A.fast_bytes > 0) {
+      if (threadIdx.x == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(A.fast_bytes));
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         dst),
+                     "l"(A.fast), "r"(A.fast_bytes), "r"(bar)
+                     : "memory");
+      }
+      unsigned done = 0;
+      while (!done) {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(done)
+                     : "r"(bar), "r"(0u)
+                     : "memory");
+      }
+    }
+    fast = reinterpret_cast<const T *>(smem_raw);
+  }
+  const T *circ = fast;
+  const T *segs = circ + 4 * (size_t)A.n_circ;
+  const T *rects = segs + 4 * (size_t)A.n_seg;
+
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t nthreads = (size_t)gridDim.x * blockDim.x;
+  constexpr int kVecs = StackCodec<T>::kVecs;
+
+  // per-slot state (fully unrolled => registers)
+  V2<T> o[R], d[R];
+  T nmed[R];
+  float cr[R], cg[R], cb[R], ca[R];
+  unsigned gen[R];
+  unsigned long long path[R], rid[R];
+  int sp[R];
+  bool alive[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    alive[r] = false;
+    sp[r] = 0;
+    o[r] = {(T)0, (T)0};
+    d[r] = {(T)1, (T)0};
+    nmed[r] = (T)1;
+    cr[r] = cg[r] = cb[r] = ca[r] = 0.f;
+    gen[r] = 0;
+    path[r] = rid[r] = 0;
+  }
+  bool exhausted = false;
+  unsigned long long steps = 0;
+
+  while (true) {
+    // ---- 1. refill idle slots -----------------------------------------------------
+    bool any_alive = false;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      if (!alive[r] && sp[r] > 0) {
+        --sp[r];
+        const uint4 *s = A.stack + ((size_t)(sp[r] * R + r) * kVecs) * nthreads + tid;
+        StackCodec<T>::get(s, nthreads, o[r], d[r], nmed[r], cr[r], cg[r], cb[r], gen[r], path[r]);
+        alive[r] = true; // pushed rays already passed the cutoff test
+      }
+      const bool want = !alive[r] && !exhausted;
+      const unsigned m = __ballot_sync(0xffffffffu, want);
+      if (m) {
+        const int leader = __ffs(m) - 1;
+        unsigned long long base = 0;
+        if ((int)lane == leader) base = atomicAdd(&A.ctr->next_ray, (unsigned long long)__popc(m));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (want) {
+          const unsigned long long j = A.ray_first + base + __popc(m & lt_mask);
+          if (j < A.ray_end) {
+            double ox, oy, dx, dy, n0;
+            if (A.rays) {
+              const LgRay &ry = A.rays[j];
+              ox = ry.origin[0], oy = ry.origin[1], dx = ry.direction[0], dy = ry.direction[1];
+              cr[r] = ry.color[0], cg[r] = ry.color[1], cb[r] = ry.color[2], ca[r] = ry.color[3];
+              n0 = ry.refractive_index;
+              rid[r] = j;
+            } else {
+              int li = 0;
+              while (li + 1 < A.n_lights && j >= A.lights[li + 1].prefix) ++li;
+              const DevLight &l = A.lights[li];
+              const unsigned long long i = l.first + (j - l.prefix);
+              emit_ray(l, i, ox, oy, dx, dy);
+              cr[r] = l.color[0], cg[r] = l.color[1], cb[r] = l.color[2], ca[r] = l.color[3];
+              n0 = l.n0;
+              rid[r] = l.id_base + i;
+            }
+            o[r] = {(T)ox, (T)oy};
+            d[r] = {(T)dx, (T)dy};
+            nmed[r] = (T)n0;
+            gen[r] = 0;
+            path[r] = 0;
+            // generation 0 is popped like any other ray: cutoff test, tracer.rs:378-384
+            alive[r] = A.max_bounce > 0 && !culled(cr[r], cg[r], cb[r], ca[r], A.cutoff);
+          } else {
+            exhausted = true;
+          }
+        }
+      }
+      any_alive |= alive[r];
+    }
+    if (!__any_sync(0xffffffffu, any_alive || !exhausted)) break;
+
+    // ---- 2. nearest hit over all objects (tracer.rs:412-424) -----------------------
+    Best<T> best[R];
+    V2<T> so[R], sd[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      best[r].d2 = Real<T>::max_value();
+      best[r].obj = -1;
+      best[r].tok = -1;
+      best[r].px = best[r].py = best[r].aux = (T)0;
+      // idle slots sweep a ray that can hit nothing
+      so[r] = alive[r] ? o[r] : V2<T>{(T)1e30, (T)1e30};
+      sd[r] = alive[r] ? d[r] : V2<T>{(T)1, (T)0};
+      if (alive[r]) ++steps;
+    }
+    // circles: early-out is the discriminant test of ORACLE.md §3.1 itself
+#pragma unroll 4
+    for (int j = 0; j < A.n_circ; ++j) {
+      const T cx = circ[4 * j], cy = circ[4 * j + 1], r2 = circ[4 * j + 3];
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const T mx = cx - so[r].x, my = cy - so[r].y;
+        const T c = Real<T>::fma(mx, sd[r].y, -(my * sd[r].x));
+        const T disc = Real<T>::fma(-c, c, r2);
+        if (disc >= (T)0) {
+          const int ob = A.circ_obj[j];
+          best[r] = cand_circle(best[r], circ + 4 * j, so[r], sd[r], ob, A.obj_first[ob]);
+        }
+      }
+    }
+    // straight mirrors: early-out is the u-range test of ORACLE.md §3.2
+#pragma unroll 4
+    for (int j = 0; j < A.n_seg; ++j) {
+      const T ax = segs[4 * j], ay = segs[4 * j + 1], ex = segs[4 * j + 2], ey = segs[4 * j + 3];
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const T denom = Real<T>::fma(sd[r].x, ey, -(sd[r].y * ex));
+        const T wx = ax - so[r].x, wy = ay - so[r].y;
+        T s = Real<T>::fma(wx, sd[r].y, -(wy * sd[r].x));
+        if (denom < (T)0) s = -s;
+        const T ad = Real<T>::abs(denom);
+        if (ad > (T)kParEps && s >= (T)0 && s <= ad) {
+          const int ob = A.seg_obj[j];
+          best[r] = cand_segment(best[r], segs + 4 * j, so[r], sd[r], ob, A.obj_first[ob]);
+        }
+      }
+    }
+    // rects: early-out is the separating-axis test of ORACLE.md §3.3
+#pragma unroll 2
+    for (int j = 0; j < A.n_rect; ++j) {
+      const T *rc = rects + 8 * j;
+      const T cx = rc[0], cy = rc[1], ux = rc[2], uy = rc[3], vx = rc[4], vy = rc[5];
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const T mx = cx - so[r].x, my = cy - so[r].y;
+        const T s = Real<T>::fma(sd[r].x, my, -(sd[r].y * mx));
+        const T cu = Real<T>::fma(sd[r].x, uy, -(sd[r].y * ux));
+        const T cv = Real<T>::fma(sd[r].x, vy, -(sd[r].y * vx));
+        const T ext = Real<T>::abs(cu) + Real<T>::abs(cv);
+        if (Real<T>::abs(s) <= ext) {
+          const int ob = A.rect_obj[j];
+          best[r] = cand_rect(best[r], rc, so[r], sd[r], ob, A.obj_first[ob]);
+        }
+      }
+    }
+    // curved mirrors (few): tokens straight from global memory
+    for (int j = 0; j < A.n_bez; ++j) {
+      const int ob = A.bez_obj[j];
+      const int tk = A.obj_first[ob];
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        if (!alive[r]) continue;
+        best[r] = cand_bezier(best[r], A.toks[tk].p, so[r], sd[r], ob, tk);
+      }
+    }
+    // CSG objects
+    for (int j = 0; j < A.n_csg; ++j) {
+      const int ob = A.csg_obj[j];
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        if (!alive[r]) continue;
+        sweep_csg_object(A, ob, so[r], sd[r], best[r]);
+      }
+    }
+
+    // ---- 3. resolve: shade, emit, spawn (tracer.rs:426-489) ------------------------
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      bool do_emit = false;
+      V2<T> ea = o[r], eb = o[r];
+      float e_r = cr[r], e_g = cg[r], e_b = cb[r], e_a = ca[r];
+      unsigned e_gen = gen[r];
+      unsigned long long e_path = path[r];
+      int e_hit = -1;
+      if (alive[r]) {
+        const Best<T> &bh = best[r];
+        if (bh.obj >= 0) {
+          const V2<T> hp{bh.px, bh.py};
+          const V2<T> nrm = hit_normal(A.toks[bh.tok], hp, bh.aux);
+          const T mat_n = A.obj_n[bh.obj];
+          do_emit = true;
+          eb = hp;
+          e_hit = bh.obj;
+          const unsigned ngen = gen[r] + 1u;
+          const bool child_ok = ngen < A.max_bounce;
+          if (mat_n == mat_n) { // has a material, tracer.rs:428
+            T n2 = (T)1;       // air
+            // tracer.rs:431 obj.contains(&ray.get_origin()), sampled at the
+            // midpoint of (origin, hit): ORACLE.md §5.2
+            const V2<T> mid{(o[r].x + hp.x) * (T)0.5, (o[r].y + hp.y) * (T)0.5};
+            if (contains_object(A, bh.obj, mid)) {
+              // tracer.rs:432-439: first OTHER object containing the hit point
+              const int q0 = A.ovl_start[bh.obj], q1 = A.ovl_start[bh.obj + 1];
+              for (int q = q0; q < q1; ++q) {
+                const int ix = A.ovl_list[q];
+                if (contains_object(A, ix, hp)) {
+                  n2 = A.obj_n[ix];
+                  break;
+                }
+              }
+            } else {
+              n2 = mat_n; // tracer.rs:441
+            }
+            V2<T> rfl, rfr;
+            bool has;
+            const T Rf = refract_dir(d[r], nrm, nmed[r], n2, rfl, rfr, has); // tracer.rs:444-450
+            const float refl = (float)Rf;                                    // tracer.rs:454
+            const float om = 1.f - refl;
+            const float ar = cr[r] * refl, ag = cg[r] * refl, ab = cb[r] * refl; // reflected colour
+            const float br = cr[r] * om, bg = cg[r] * om, bb = cb[r] * om;       // refracted colour
+            const bool live_a = child_ok && !culled(ar, ag, ab, ca[r], A.cutoff);
+            const bool live_b = child_ok && has && !culled(br, bg, bb, ca[r], A.cutoff);
+            const unsigned long long pa = path[r] << 1, pb = (path[r] << 1) | 1ull;
+            if (live_a && live_b) {
+              // keep the refracted ray in the slot, park the reflected one
+              if (sp[r] < A.stack_cap) {
+                uint4 *s = A.stack + ((size_t)(sp[r] * R + r) * kVecs) * nthreads + tid;
+                StackCodec<T>::put(s, nthreads, hp, rfl, nmed[r], ar, ag, ab, ngen, pa);
+                ++sp[r];
+              } else {
+                atomicExch(&A.ctr->stack_overflow, 1u);
+              }
+            }
+            if (live_b) {
+              o[r] = hp, d[r] = rfr, nmed[r] = n2;
+              cr[r] = br, cg[r] = bg, cb[r] = bb;
+              gen[r] = ngen, path[r] = pb;
+            } else if (live_a) {
+              o[r] = hp, d[r] = rfl;
+              cr[r] = ar, cg[r] = ag, cb[r] = ab;
+              gen[r] = ngen, path[r] = pa;
+            } else {
+              alive[r] = false;
+            }
+          } else { // mirror, tracer.rs:473-481 (colour and medium unchanged)
+            if (child_ok) {
+              d[r] = reflect_dir(d[r], nrm);
+              o[r] = hp;
+              gen[r] = ngen;
+              path[r] = path[r] << 1;
+            } else {
+              alive[r] = false;
+            }
+          }
+        } else { // canvas, tracer.rs:482-488
+          CandList<T> hl;
+          hl.n = 0;
+          hit_rect(A.canvas, o[r], d[r], hl);
+          if (hl.n > 0) {
+            int f = 0;
+            for (int q = 1; q < hl.n; ++q)
+              if (hl.h[q].t < hl.h[f].t) f = q;
+            do_emit = true;
+            eb = hl.h[f].p;
+          }
+          alive[r] = false;
+        }
+      }
+      // warp-aggregated segment slot allocation, two 16-byte stores per segment
+      const unsigned em = __ballot_sync(0xffffffffu, do_emit);
+      if (em) {
+        const int leader = __ffs(em) - 1;
+        unsigned long long base = 0;
+        if ((int)lane == leader) base = atomicAdd(&A.ctr->seg_count, (unsigned long long)__popc(em));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (do_emit) {
+          const unsigned long long slot = base + __popc(em & lt_mask);
+          if (slot < A.seg_cap) {
+            float4 *dst = reinterpret_cast<float4 *>(A.seg + slot);
+            dst[0] = make_float4((float)ea.x, (float)ea.y, (float)eb.x, (float)eb.y); // `as f32`, sub_render_pass.rs:192
+            dst[1] = make_float4(e_r, e_g, e_b, e_a);
+            if (A.tags) {
+              LgSegmentTag tg;
+              tg.ray = rid[r];
+              tg.path = e_path;
+              tg.generation = e_gen;
+              tg.hit_object = e_hit;
+              A.tags[slot] = tg;
+            }
+            if (A.seg64) {
+              LgSegmentF64 s64;
+              s64.a[0] = (double)ea.x, s64.a[1] = (double)ea.y, s64.b[0] = (double)eb.x, s64.b[1] = (double)eb.y;
+              A.seg64[slot] = s64;
+            }
+          } else {
+            atomicExch(&A.ctr->seg_overflow, 1u);
+          }
+        }
+      }
+    }
+  }
+  // ray_steps: warp reduce, one atomic per warp
+  for (int off = 16; off > 0; off >>= 1) steps += __shfl_down_sync(0xffffffffu, steps, off);
+  if (lane == 0 && steps) atomicAdd(&A.ctr->ray_steps, steps);
+}
+
+// Type-erased access to the instantiations (one translation unit per precision,
+// lg_trace_f32.cu / lg_trace_f64.cu, so they compile in parallel).
+const void *trace_kernel_f32(int slots, bool smem);
+const void *trace_kernel_f64(int slots, bool smem);
+
+} // namespace lg

@@ -1,0 +1,252 @@
+"""Host-side mirror of the reference's Tracer (src/light_garden/tracer.rs) and of
+the LineList half of its Renderer (src/renderer.rs, src/sub_render_pass.rs) on
+top of the C ABI.  Same method names and argument meaning as the Rust code so
+that tests read like tests of the reference would; every computation happens in
+liblight_garden_b200.so on the GPU.
+"""
+import ctypes as C
+from typing import List, Optional
+
+import numpy as np
+
+from . import abi
+from ._lib import LightGardenError, check, load
+from .scene import (CubicBezier, DirectionalLight, Object, PointLight, Rect, SpotLight, StringMod, flatten_objects,
+                    lights_to_array, trace_params)
+
+
+class Context:
+    """Owns one lg_ctx (one device, one stream)."""
+
+    def __init__(self, device: int = 0, precision: int = abi.LG_PRECISION_F32):
+        self.lib = load()
+        self.h = C.c_void_p()
+        rc = self.lib.lg_create(int(device), int(precision), C.byref(self.h))
+        if rc != 0:
+            raise LightGardenError(rc, "lg_create failed (no CUDA device? this library has no CPU fallback)")
+        self.device = device
+        self.precision = precision
+
+    def close(self):
+        if self.h:
+            self.lib.lg_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def call(self, name, *args):
+        check(self.h, getattr(self.lib, name)(self.h, *args))
+
+    def launch_count(self) -> int:
+        n = C.c_uint64()
+        self.call("lg_launch_count", C.byref(n))
+        return n.value
+
+
+def sort_segments(seg, tags, f64=None):
+    """Device order -> the reference's order: light -> ray -> generation -> queue order."""
+    order = np.lexsort((tags["path"], tags["generation"], tags["ray"]))
+    return seg[order], tags[order], (f64[order] if f64 is not None else None)
+
+
+class Tracer:
+    """tracer.rs:4-17.  Scene-edit methods keep the reference's names; trace_all/trace run on the device."""
+
+    def __init__(self, canvas_bounds: Rect, device: int = 0, precision: int = abi.LG_PRECISION_F32,
+                 ctx: Optional[Context] = None):
+        self.ctx = ctx or Context(device, precision)
+        self.objects: List[Object] = []
+        self.lights: list = []
+        self.max_bounce = 5                              # tracer.rs:37
+        self.cutoff_color = [0.001, 0.001, 0.001, 0.001]  # tracer.rs:38
+        self.chunk_size = 100                            # tracer.rs:39 (rayon chunking; unused on the device)
+        self.canvas_bounds = canvas_bounds
+        self.last_stats = abi.LgTraceStats()
+        self._scene_dirty = True
+        self._lights_dirty = True
+        self._rank, self._world = 0, 1
+
+    # -- scene editing: tracer.rs:48-181 ------------------------------------------------------
+    def clear(self):
+        self.objects.clear()
+        self.lights.clear()
+        self._scene_dirty = self._lights_dirty = True
+
+    def clear_objects(self):
+        self.objects.clear()
+        self._scene_dirty = True
+
+    def push_object(self, obj: Object):
+        self.objects.append(obj)
+        self._scene_dirty = True
+
+    def push_light(self, light):
+        self.lights.append(light)
+        self._lights_dirty = True
+
+    def index_object(self, ix):
+        self._scene_dirty = True
+        return self.objects[ix]
+
+    def index_light(self, ix):
+        self._lights_dirty = True
+        return self.lights[ix]
+
+    def replace_object(self, ix, obj):
+        self.objects[ix] = obj
+        self._scene_dirty = True
+
+    def remove_object(self, ix):
+        del self.objects[ix]
+        self._scene_dirty = True
+
+    def remove_light(self, ix):
+        del self.lights[ix]
+        self._lights_dirty = True
+
+    def object_iterator(self):
+        return iter(self.objects)
+
+    def light_iterator(self):
+        return iter(self.lights)
+
+    def resize(self, bounds: Rect):
+        self.canvas_bounds = bounds
+        self._scene_dirty = True
+
+    def load(self, data: str):
+        """Tracer::load (tracer.rs:190-204): RON text of (Vec<Object>, Vec<Light>)."""
+        from .ron import load_scene
+        objects, lights = load_scene(data)
+        self.clear()
+        self.objects, self.lights = objects, lights
+
+    # -- device state -----------------------------------------------------------------------------
+    def set_shard(self, rank: int, world: int):
+        self._rank, self._world = rank, world
+        self.ctx.call("lg_shard_set", rank, world)
+
+    def sync_scene(self):
+        """lg_scene_set / lg_lights_set when the host copy changed (the reference's `moved` dirty bit, object.rs:54)."""
+        # scalar knobs (max_bounce, cutoff_color) are public fields in the reference: always re-sent
+        objs, n_obj, nodes, n_nodes = flatten_objects(self.objects)
+        prm = trace_params(self.max_bounce, self.cutoff_color, self.canvas_bounds)
+        self.ctx.call("lg_scene_set", C.cast(objs, C.c_void_p), n_obj, C.cast(nodes, C.c_void_p), n_nodes,
+                      C.byref(prm))
+        arr = lights_to_array(self.lights)
+        self.ctx.call("lg_lights_set", C.cast(arr, C.c_void_p), len(self.lights))
+        self._scene_dirty = self._lights_dirty = False
+
+    # -- tracing -----------------------------------------------------------------------------------
+    def emit_rays(self, light_index: int, first: int = 0, count: Optional[int] = None):
+        """Light::get_rays (light.rs:17-23) for one light, computed on the device."""
+        self.sync_scene()
+        if count is None:
+            count = int(self.lights[light_index].num_rays) - first
+        out = np.zeros(count, dtype=abi.RAY_DTYPE)
+        self.ctx.call("lg_emit_rays", light_index, first, count, abi.array_ptr(out))
+        return out
+
+    def _read_segments(self, tags: bool):
+        n = C.c_uint64()
+        self.ctx.call("lg_segments_count", C.byref(n))
+        seg = np.zeros(n.value, dtype=abi.SEGMENT_DTYPE)
+        tg = np.zeros(n.value, dtype=abi.SEGMENT_TAG_DTYPE) if tags else None
+        f64 = np.zeros(n.value, dtype=abi.SEGMENT_F64_DTYPE) if (
+            tags and self.ctx.precision == abi.LG_PRECISION_F64) else None
+        got = C.c_uint64()
+        self.ctx.call("lg_segments_read", abi.array_ptr(seg), abi.array_ptr(tg) if tags else None,
+                      abi.array_ptr(f64) if f64 is not None else None, n.value, C.byref(got))
+        return seg, tg, f64
+
+    def trace_all(self, ordered: bool = True, control_lines: bool = True, return_tags: bool = False):
+        """Tracer::trace_all (tracer.rs:276-358): all lights' rays -> segments, in the reference's order."""
+        self.ctx.call("lg_tags_enable", 1 if (ordered or return_tags) else 0)
+        self.sync_scene()
+        st = abi.LgTraceStats()
+        self.ctx.call("lg_trace", C.byref(st))
+        self.last_stats = st
+        seg, tg, f64 = self._read_segments(ordered or return_tags)
+        if ordered:
+            seg, tg, f64 = sort_segments(seg, tg, f64)
+        if control_lines:  # tracer.rs:342-346
+            extra = [cl for ob in self.objects for cl in ob.get_control_lines()]
+            if extra:
+                add = np.zeros(len(extra), dtype=abi.SEGMENT_DTYPE)
+                for i, (a, b, col) in enumerate(extra):
+                    add[i]["a"], add[i]["b"], add[i]["color"] = a, b, col
+                seg = np.concatenate([seg, add])
+        return (seg, tg, f64) if return_tags else seg
+
+    def trace(self, rays: np.ndarray, ordered: bool = True):
+        """Tracer::trace (tracer.rs:360-493) over caller supplied primary rays (abi.RAY_DTYPE)."""
+        rays = np.ascontiguousarray(rays, dtype=abi.RAY_DTYPE)
+        self.ctx.call("lg_tags_enable", 1)
+        self.sync_scene()
+        st = abi.LgTraceStats()
+        self.ctx.call("lg_trace_rays", abi.array_ptr(rays), len(rays), C.byref(st))
+        self.last_stats = st
+        seg, tg, f64 = self._read_segments(True)
+        if ordered:
+            seg, tg, f64 = sort_segments(seg, tg, f64)
+        return seg, tg, f64
+
+
+class Renderer:
+    """The LineList pass of renderer.rs into the Rgba16Float target (texture_renderer.rs:5), on the device."""
+
+    def __init__(self, ctx: Context, width: int, height: int):
+        self.ctx = ctx
+        self.width, self.height = int(width), int(height)
+        ctx.call("lg_image_configure", self.width, self.height)
+        self.last_stats = abi.LgTraceStats()
+
+    def clear(self, clear_alpha: float = 1.0):
+        """LoadOp::Clear(BLACK) (renderer.rs:174-177)."""
+        self.ctx.call("lg_image_clear", C.c_float(clear_alpha))
+
+    def render_traced(self):
+        """sub_rpass_lines.render for the segments of the last trace (sub_render_pass.rs:205-212)."""
+        st = abi.LgTraceStats()
+        self.ctx.call("lg_accumulate_traced", C.byref(st))
+        self.last_stats = st
+        return st
+
+    def render_lines(self, pairs: np.ndarray):
+        """update_vertex_buffer + render for host vertex pairs (abi.VERTEX_PAIR_DTYPE)."""
+        pairs = np.ascontiguousarray(pairs, dtype=abi.VERTEX_PAIR_DTYPE)
+        st = abi.LgTraceStats()
+        self.ctx.call("lg_accumulate_segments", abi.array_ptr(pairs), len(pairs), C.byref(st))
+        self.last_stats = st
+        return st
+
+    def render_string_mod(self, sm: StringMod, first: int = 0, count: int = 0):
+        """LightGarden::draw in Mode::StringMod (mod.rs:681-689) + the line pass."""
+        pod, rules, n = sm.to_pod()
+        st = abi.LgTraceStats()
+        self.ctx.call("lg_string_mod", C.byref(pod), C.cast(rules, C.c_void_p), n, first, count, C.byref(st))
+        self.last_stats = st
+        return st
+
+    def render(self, tracer: Tracer):
+        """Renderer::render's trace + line pass fused (waves through the bounded segment buffer)."""
+        tracer.ctx.call("lg_tags_enable", 0)
+        tracer.sync_scene()
+        st = abi.LgTraceStats()
+        self.ctx.call("lg_render", C.byref(st))
+        self.last_stats = st
+        return st
+
+    def read_rgba32f(self):
+        out = np.zeros((self.height, self.width, 4), dtype=np.float32)
+        self.ctx.call("lg_image_read", abi.LG_RGBA32F, abi.array_ptr(out), 0)
+        return out
+
+    def read_rgba16f(self):
+        out = np.zeros((self.height, self.width, 4), dtype=np.float16)
+        self.ctx.call("lg_image_read", abi.LG_RGBA16F, abi.array_ptr(out), 0)
+        return out
