@@ -1,0 +1,379 @@
+#!/usr/bin/env python
+"""bench.py — the headline benchmark of the Light Garden hot path on B200.
+
+Workload (BASELINE.json configs[4], the one the north-star target is quoted on): the synthetic 4096-object scene
+(2048 circles, 1024 straight mirrors, 1024 rects on a jittered 64x64 lattice), 32 M primary rays PER GPU
+(N point lights x 32 M rays, rank r of N traces the r-th N-th of every light: weak scaling; N = 8 is exactly
+C5 = 256 M rays), max_bounce 5, brute-force ray x object tests, 3840x2160 accumulation, NCCL image reduce.
+
+One step = one frame of the reference (framework.rs:200-234): clear, trace every ray of the shard, accumulate
+every segment, sum the partial images onto rank 0.
+  value : primary rays/s, whole job, scene + lights already resident on the device
+  e2e   : the same through the C ABI with host buffers: lg_scene_set + lg_lights_set (H2D) ... lg_image_read of
+          the Rgba16Float frame (D2H) inside the timed region
+  roofline : the trace kernel against the FP32 FMA peak measured in this run (16.5 algorithmic
+          flops per ray-object test for this mix); roofline_accumulate: the accumulate kernel's algorithmic bytes
+          against the measured HBM copy bandwidth
+  cpu_baseline : the oracle (restated reference, f64, chunks of 100 rays over all host cores) on a bounded sample
+
+`--impl reference` times that CPU restatement alone (the real rayon binary cannot be built offline: no Rust
+toolchain, collision2d not vendored).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FLOPS_PER_TEST = {"circle": 14.0, "segment": 14.0, "rect": 24.0}  # SURVEY.md §8d contract figures
+RAYS_PER_GPU = 32_000_000
+WIDTH, HEIGHT = 3840, 2160
+
+
+def algorithmic_flops_per_test(objects):
+    kinds = {"Circle": "circle", "StraightMirror": "segment", "Rect": "rect"}
+    tot = sum(FLOPS_PER_TEST[kinds[o.kind]] for o in objects)
+    return tot / len(objects)
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._pump, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+def run_reference(args):
+    """The reference arm: the CPU restatement of Tracer::trace_all + the line pass on the host cores."""
+    rank, world, _ = dist_env()
+    if rank != 0:
+        return 0
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import lg_oracle as oracle
+    from light_garden_b200 import abi, scenes
+    oracle.build()
+    n = args.gpus
+    spec = scenes.c5_large(n_lights=n, rays_per_light=RAYS_PER_GPU)
+    osc = oracle.OracleScene.from_spec(spec)
+    cores = oracle.num_threads()
+    # probe to size a bounded sample (~8 s of trace per step)
+    stride = max(1, spec.total_rays() // 4000)
+    t0 = time.perf_counter()
+    probe = osc.trace_all(spec.lights, abi.LG_PRECISION_F64, stride=stride, store=False)
+    dt = time.perf_counter() - t0
+    rps = probe.primary_rays / max(dt, 1e-6)
+    sample = int(min(spec.total_rays(), max(20_000, rps * args.ref_seconds)))
+    stride = max(1, spec.total_rays() // sample)
+    img = oracle.new_image(WIDTH, HEIGHT)
+    times, rays_done, segs = [], 0, 0
+    for it in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        res = osc.trace_all(spec.lights, abi.LG_PRECISION_F64, stride=stride, store=True)
+        img[...] = 0
+        img[..., 3] = 1
+        oracle.accumulate_segments(img, res.seg)
+        dt = time.perf_counter() - t0
+        if it >= args.warmup:
+            times.append(dt)
+            rays_done += res.primary_rays
+            segs += res.segments_emitted
+    total = sum(times)
+    value = rays_done / total
+    out = {
+        "impl": "reference", "metric": "rays_per_sec_traced_and_accumulated", "value": value, "unit": "rays/s",
+        "n_gpus": n, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(n),
+        "segments_per_s": segs / total,
+        "cpu_baseline": {"value": value, "unit": "rays/s", "cores": cores, "kind": "port",
+                         "sample": f"every {stride}-th primary ray of the workload per step "
+                                   f"({rays_done // len(times)} rays/step), f64 restated oracle, rayon-style chunks of 100"},
+        "e2e": {"value": value, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "restated reference (oracle/): the real rayon binary cannot be built offline (no Rust, collision2d unvendored)",
+    }
+    print(json.dumps(out), flush=True)
+    return 0
+
+
+def workload_config(n):
+    return {"workload": "C5: synthetic 4096-object scene (2048 circles, 1024 mirrors, 1024 rects), "
+                        f"{RAYS_PER_GPU} primary rays per GPU x {n} GPU(s), max_bounce 5, brute force, "
+                        f"{WIDTH}x{HEIGHT} RGBA accumulation, NCCL image reduce",
+            "objects": 4096, "rays_per_gpu": RAYS_PER_GPU, "max_bounce": 5, "width": WIDTH, "height": HEIGHT,
+            "parallelism": f"ray-shard x{n}",
+            "l2": "inputs larger than L2: GB-scale segment stream and a 132.7 MB image per step"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--rays-per-gpu", type=int, default=RAYS_PER_GPU)
+    ap.add_argument("--precision", default="f32", choices=["f32", "f64"])
+    ap.add_argument("--ref-seconds", type=float, default=8.0)
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    rank, world, local = dist_env()
+    n = args.gpus
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from light_garden_b200 import abi, scenes
+    from light_garden_b200._lib import check, load
+    from light_garden_b200.scene import flatten_objects, lights_to_array, trace_params
+    from light_garden_b200.tracer import Context, Renderer, Tracer
+
+    if world != n and world > 1:
+        n = world
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    rays_per_gpu = args.rays_per_gpu
+    prec = abi.LG_PRECISION_F64 if args.precision == "f64" else abi.LG_PRECISION_F32
+    spec = scenes.c5_large(n_lights=n, rays_per_light=rays_per_gpu)
+    ctx = Context(local, prec)
+    lib = load()
+    tracer = spec.apply(Tracer(spec.canvas_bounds, ctx=ctx))
+    rend = Renderer(ctx, WIDTH, HEIGHT)
+    ctx.call("lg_segment_capacity_set", 512 << 20)          # 16 GB of the 180 GB: one or two waves per step
+    tracer.sync_scene()
+    tracer.set_shard(rank, world)
+    ctx.call("lg_tags_enable", 0)
+
+    # communicator for the image reduce: the unique id travels over torch.distributed
+    if world > 1:
+        idbuf = torch.zeros(128, dtype=torch.uint8)
+        if rank == 0:
+            raw = (C.c_ubyte * 128)()
+            check(None, lib.lg_comm_unique_id(raw))
+            idbuf = torch.tensor(list(raw), dtype=torch.uint8)
+        idbuf = idbuf.cuda()
+        dist.broadcast(idbuf, 0)
+        raw = (C.c_ubyte * 128)(*idbuf.cpu().tolist())
+        ctx.call("lg_comm_init_rank", raw, rank, world)
+
+    sh = C.c_uint64()
+    ctx.call("lg_stream_handle", C.byref(sh))
+    stream = torch.cuda.ExternalStream(sh.value, device=torch.device("cuda", local))
+
+    objs, n_obj, nodes, n_nodes = flatten_objects(spec.objects)
+    prm = trace_params(spec.max_bounce, spec.cutoff_color, spec.canvas_bounds)
+    larr = lights_to_array(spec.lights)
+    h2d = C.sizeof(objs) + C.sizeof(nodes) + C.sizeof(larr) + C.sizeof(prm)
+    frame16 = np.zeros((HEIGHT, WIDTH, 4), dtype=np.float16)
+    d2h = frame16.nbytes
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step(e2e):
+        st = abi.LgTraceStats()
+        red = C.c_float()
+        if e2e:  # the frame as a host application drives it: scene in, Rgba16Float frame out
+            ctx.call("lg_scene_set", C.cast(objs, C.c_void_p), n_obj, C.cast(nodes, C.c_void_p), n_nodes, C.byref(prm))
+            ctx.call("lg_lights_set", C.cast(larr, C.c_void_p), len(spec.lights))
+        ctx.call("lg_image_clear", C.c_float(1.0 if rank == 0 else 0.0))
+        ctx.call("lg_render", C.byref(st))
+        ctx.call("lg_image_reduce", 0, C.byref(red))
+        if e2e and rank == 0:
+            ctx.call("lg_image_read", abi.LG_RGBA16F, abi.array_ptr(frame16), 0)
+        return st, red.value
+
+    def timed(steps, e2e):
+        """EXACTLY `steps` steps between barrier+sync, CUDA events on the library's stream, max over ranks."""
+        agg = {"ray_steps": 0, "segments": 0, "pixel_updates": 0, "trace_ms": 0.0, "accumulate_ms": 0.0,
+               "trace_launches": 0, "accumulate_launches": 0, "reduce_ms": 0.0}
+        l0 = ctx.launch_count()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(stream):
+            e0.record(stream)
+            for _ in range(steps):
+                st, red = step(e2e)
+                for k in ("ray_steps", "segments", "pixel_updates", "trace_ms", "accumulate_ms", "trace_launches",
+                          "accumulate_launches"):
+                    agg[k] += getattr(st, k)
+                agg["reduce_ms"] += red
+            e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+            for k in list(agg):
+                t = torch.tensor([float(agg[k])], device="cuda", dtype=torch.float64)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX if k.endswith("_ms") else dist.ReduceOp.SUM)
+                agg[k] = float(t.item())
+        agg["launches"] = ctx.launch_count() - l0
+        return ms, agg
+
+    # measured denominators (same device, same run)
+    fma = C.c_double()
+    ctx.call("lg_measure_fma_peak", prec, 3, C.byref(fma))
+    red_coal, red_rand = C.c_double(), C.c_double()
+    ctx.call("lg_measure_red_peak", WIDTH * HEIGHT, 0, 2, C.byref(red_coal))
+    ctx.call("lg_measure_red_peak", WIDTH * HEIGHT, 1, 2, C.byref(red_rand))
+
+    for _ in range(max(3, args.warmup)):
+        step(False)
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    ms, agg = timed(args.steps, False)
+    clocks = sampler.stop() if sampler else None
+    ms_e2e, agg_e2e = timed(args.steps, True)
+
+    total_rays = rays_per_gpu * world * args.steps
+    value = total_rays / (ms * 1e-3)
+    e2e_value = total_rays / (ms_e2e * 1e-3)
+    out = None
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak, hbm_src = (peaks.get("hbm_gbs"), "measured (MEASURED_PEAKS.json)") if peaks.get("hbm_gbs") else (6650.0, "fallback")
+        fpt = algorithmic_flops_per_test(spec.objects)
+        tests = agg["ray_steps"] * len(spec.objects)
+        # per-launch figures of the dominant kernel (trace), summed over ranks / launches
+        tr_launches = max(1.0, agg["trace_launches"])
+        tr_ms_per_launch = agg["trace_ms"] / (tr_launches / world)    # trace_ms is max over ranks of per-rank sums
+        flops_per_launch = tests * fpt / tr_launches
+        achieved_tflops = flops_per_launch / (tr_ms_per_launch * 1e-3) / 1e12
+        acc_launches = max(1.0, agg["accumulate_launches"])
+        acc_ms_per_launch = agg["accumulate_ms"] / (acc_launches / world)
+        acc_bytes = (32.0 * agg["segments"] + 16.0 * agg["pixel_updates"]) / acc_launches
+        acc_gbs = acc_bytes / (acc_ms_per_launch * 1e-3) / 1e9
+        out = {
+            "metric": "rays_per_sec_traced_and_accumulated", "value": value, "unit": "rays/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": args.precision, "data": "synthetic", "config": workload_config(world),
+            "segments_per_s": agg["segments"] / (ms * 1e-3),
+            "ray_object_tests_per_s": tests / (ms * 1e-3),
+            "ray_object_tests_per_s_per_gpu_in_kernel": tests / world / (agg["trace_ms"] * 1e-3),
+            "pixel_updates_per_s_in_kernel": agg["pixel_updates"] / world / max(1e-9, agg["accumulate_ms"] * 1e-3),
+            "segments_per_ray": agg["segments"] / total_rays,
+            "phase_ms_per_step": {"trace": agg["trace_ms"] / args.steps, "accumulate": agg["accumulate_ms"] / args.steps,
+                                  "nccl_reduce": agg["reduce_ms"] / args.steps},
+            "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": int(agg["launches"]),
+            "clocks": clocks,
+            "roofline": {"bound": "fp32", "kernel": "lg::trace_kernel", "achieved": achieved_tflops,
+                         "peak": fma.value, "unit": "TFLOP/s", "frac": achieved_tflops / fma.value if fma.value else None,
+                         "traffic": None,
+                         "note": f"algorithmic {fpt:.2f} flop per ray-object test (SURVEY.md §8d) x tests per launch / "
+                                 "CUDA-event launch time; peak = FMA microbenchmark of this run "
+                                 f"({'FP64' if args.precision == 'f64' else 'FP32'} pipe), not in MEASURED_PEAKS.json; "
+                                 "the contract's hbm/tensor bounds do not apply to the trace kernel: its table lives in "
+                                 "shared memory and it writes 32 B per segment"},
+            "roofline_accumulate": {"bound": "hbm", "kernel": "lg::accumulate_segments_kernel", "achieved": acc_gbs,
+                                    "peak": hbm_peak, "unit": "GB/s", "frac": acc_gbs / hbm_peak, "traffic": None,
+                                    "peak_source": hbm_src,
+                                    "red_v4_peak_gred_per_s": {"coalesced": red_coal.value, "random": red_rand.value},
+                                    "note": "algorithmic bytes = 32 B per segment read + 16 B per blended fragment"},
+        }
+    # CPU baseline: rank 0, N = 1 only, bounded sample
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import lg_oracle as oracle
+        oracle.build()
+        osc = oracle.OracleScene.from_spec(spec)
+        stride = max(1, spec.total_rays() // 4000)
+        t0 = time.perf_counter()
+        probe = osc.trace_all(spec.lights, abi.LG_PRECISION_F64, stride=stride, store=False)
+        rps = probe.primary_rays / max(time.perf_counter() - t0, 1e-6)
+        sample = int(min(spec.total_rays(), max(20_000, rps * args.cpu_seconds)))
+        stride = max(1, spec.total_rays() // sample)
+        t0 = time.perf_counter()
+        res = osc.trace_all(spec.lights, abi.LG_PRECISION_F64, stride=stride, store=True)
+        img = oracle.new_image(WIDTH, HEIGHT)
+        oracle.accumulate_segments(img, res.seg)
+        dt = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": res.primary_rays / dt, "unit": "rays/s", "cores": oracle.num_threads(),
+                               "kind": "port",
+                               "sample": f"every {stride}-th primary ray ({res.primary_rays} rays, {dt:.1f} s): f64 "
+                                         "restated oracle trace (chunks of 100 rays over all cores) + host accumulate"}
+    elif rank == 0:
+        out["cpu_baseline"] = None
+    if rank == 0:
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        ctx.call("lg_comm_destroy")
+        dist.barrier()
+        dist.destroy_process_group()
+    ctx.close()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

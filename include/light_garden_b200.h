@@ -281,6 +281,14 @@ int32_t lg_image_device_ptr(lg_ctx *ctx, uint64_t *ptr);
 /* Kernels launched by this context since creation. */
 int32_t lg_launch_count(lg_ctx *ctx, uint64_t *n);
 
+/* ---- measurement: the roofline denominators BASELINE.md leaves to the builder -- */
+/* FP32 (precision F32) or FP64 (F64) FMA throughput of the device in TFLOP/s,
+ * best of `reps` launches of a register-only FMA kernel. */
+int32_t lg_measure_fma_peak(lg_ctx *ctx, int32_t precision, int32_t reps, double *tflops);
+/* red.global.add.v4.f32 throughput in 1e9 reductions/s over an image of
+ * `span_px` RGBA fp32 pixels; pattern 0 = coalesced sweep, 1 = random pixels. */
+int32_t lg_measure_red_peak(lg_ctx *ctx, uint64_t span_px, int32_t pattern, int32_t reps, double *gred_per_s);
+
 #ifdef __cplusplus
 }
 #endif

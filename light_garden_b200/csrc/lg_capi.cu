@@ -18,6 +18,7 @@
 
 #include "../../include/light_garden_b200.h"
 #include "lg_accum.cuh"
+#include "lg_bench.cuh"
 #include "lg_scene.h"
 #include "lg_trace.cuh"
 
@@ -911,6 +912,60 @@ int32_t lg_comm_destroy(lg_ctx *c) {
   if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
   c->comm = nullptr;
   c->comm_world = 1, c->comm_rank = 0;
+  return LG_OK;
+}
+
+int32_t lg_measure_fma_peak(lg_ctx *c, int32_t precision, int32_t reps, double *tflops) {
+  if (!c || !tflops) return LG_ERR_INVALID;
+  LG_CUDA(c, cudaSetDevice(c->device));
+  DevBuf tmp;
+  int rc = ensure(c, tmp, 64);
+  if (rc) return rc;
+  const int grid = c->sm_count * 8, iters = 4096;
+  double best = 0;
+  for (int r = 0; r < std::max(1, reps) + 1; ++r) {
+    LG_CUDA(c, cudaEventRecord(c->ev0, c->stream));
+    if (precision == LG_PRECISION_F64)
+      dfma_peak_kernel<<<grid, 256, 0, c->stream>>>((double *)tmp.p, iters, 0.999, 0.001);
+    else
+      fma_peak_kernel<<<grid, 256, 0, c->stream>>>((float *)tmp.p, iters, 0.999f, 0.001f);
+    LG_CUDA(c, cudaGetLastError());
+    c->launches++;
+    LG_CUDA(c, cudaEventRecord(c->ev1, c->stream));
+    LG_CUDA(c, cudaStreamSynchronize(c->stream));
+    float ms = 0.f;
+    LG_CUDA(c, cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    const double fl = 2.0 * kFmaPerIter * (double)iters * (double)grid * 256.0;
+    if (r > 0 && ms > 0) best = std::max(best, fl / (ms * 1e-3) / 1e12);
+  }
+  release(tmp);
+  *tflops = best;
+  return LG_OK;
+}
+
+int32_t lg_measure_red_peak(lg_ctx *c, uint64_t span_px, int32_t pattern, int32_t reps, double *gred) {
+  if (!c || !gred || span_px == 0) return LG_ERR_INVALID;
+  LG_CUDA(c, cudaSetDevice(c->device));
+  DevBuf tmp;
+  int rc = ensure(c, tmp, span_px * 16);
+  if (rc) return rc;
+  LG_CUDA(c, cudaMemsetAsync(tmp.p, 0, span_px * 16, c->stream));
+  const int grid = c->sm_count * 8, iters = 2048;
+  double best = 0;
+  for (int r = 0; r < std::max(1, reps) + 1; ++r) {
+    LG_CUDA(c, cudaEventRecord(c->ev0, c->stream));
+    red_peak_kernel<<<grid, 256, 0, c->stream>>>((float *)tmp.p, span_px, iters, pattern);
+    LG_CUDA(c, cudaGetLastError());
+    c->launches++;
+    LG_CUDA(c, cudaEventRecord(c->ev1, c->stream));
+    LG_CUDA(c, cudaStreamSynchronize(c->stream));
+    float ms = 0.f;
+    LG_CUDA(c, cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    const double n = (double)iters * (double)grid * 256.0;
+    if (r > 0 && ms > 0) best = std::max(best, n / (ms * 1e-3) / 1e9);
+  }
+  release(tmp);
+  *gred = best;
   return LG_OK;
 }
 

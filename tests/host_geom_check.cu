@@ -1,0 +1,272 @@
+// tests/host_geom_check.cu — runs the product's geometry header
+// (light_garden_b200/csrc/lg_geom.cuh, host instantiation of its
+// __host__ __device__ functions) against the oracle (oracle/lg_oracle.hpp) on
+// random inputs and demands bit-identical results.  CPU only; built and run by
+// tests/test_geom_host.py.  Prints "OK <n>" or "MISMATCH ..." lines.
+#include <cstdio>
+#include <cstring>
+#include <cstdint>
+#include <cmath>
+#include <vector>
+#include <string>
+
+#include "../light_garden_b200/csrc/lg_geom.cuh"
+#include "../light_garden_b200/csrc/lg_scene.h"
+#include "../oracle/lg_oracle.hpp"
+
+static uint64_t s_state = 0x4C47BEEFull;
+static uint64_t nextu() {
+  s_state += 0x9E3779B97F4A7C15ull;
+  uint64_t z = s_state;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+static double uni(double lo, double hi) { return lo + (hi - lo) * ((nextu() >> 11) * (1.0 / 9007199254740992.0)); }
+
+template <class T> static bool same(T a, T b) { return std::memcmp(&a, &b, sizeof(T)) == 0 || (a != a && b != b); }
+
+static long g_bad = 0;
+#define CHECK(cond, what)                                  \
+  do {                                                     \
+    if (!(cond)) {                                         \
+      if (g_bad < 20) std::printf("MISMATCH %s (%s)\n", what, sizeof(T) == 4 ? "f32" : "f64"); \
+      ++g_bad;                                             \
+    }                                                      \
+  } while (0)
+
+template <class T> static void cmp_lists(const lg::CandList<T> &a, const lgo::HitList<T> &b, const char *what) {
+  CHECK(a.n == b.n, what);
+  for (int i = 0; i < a.n && i < b.n; ++i) {
+    CHECK(same(a.h[i].t, b.h[i].t), what);
+    CHECK(same(a.h[i].p.x, b.h[i].p.x) && same(a.h[i].p.y, b.h[i].p.y), what);
+  }
+}
+
+template <class T> static long run(int iters) {
+  long n = 0;
+  for (int it = 0; it < iters; ++it) {
+    // ray
+    double ang = uni(0, 6.283185307179586);
+    lg::V2<T> o{(T)uni(-1.5, 1.5), (T)uni(-1, 1)}, d{(T)std::cos(ang), (T)std::sin(ang)};
+    lgo::V2<T> oo{o.x, o.y}, od{d.x, d.y};
+    // circle
+    {
+      lg::Tok<T> k{};
+      k.kind = lg::TOK_CIRCLE;
+      k.p[0] = (T)uni(-1.5, 1.5), k.p[1] = (T)uni(-1, 1), k.p[2] = (T)uni(0.005, 0.6);
+      k.p[3] = k.p[2] * k.p[2];
+      lg::CandList<T> a;
+      a.n = 0;
+      lg::hit_circle(k.p, o, d, a);
+      lgo::HitList<T> b;
+      lgo::hit_circle(k.p, oo, od, b);
+      cmp_lists(a, b, "circle");
+      for (int i = 0; i < a.n && i < b.n; ++i) {
+        lg::V2<T> nn = lg::hit_normal(k, a.h[i].p, a.h[i].aux);
+        CHECK(same(nn.x, b.h[i].n.x) && same(nn.y, b.h[i].n.y), "circle normal");
+      }
+      lgo::LeafT<T> l{};
+      l.kind = lgo::TOK_CIRCLE;
+      std::memcpy(l.p, k.p, sizeof k.p);
+      lg::V2<T> q{(T)uni(-1.5, 1.5), (T)uni(-1, 1)};
+      CHECK(lg::contains_leaf(k, q) == lgo::contains_leaf(l, lgo::V2<T>{q.x, q.y}), "circle contains");
+      n += 1 + a.n;
+    }
+    // segment
+    {
+      lg::Tok<T> k{};
+      k.kind = lg::TOK_SEGMENT;
+      T ax = (T)uni(-1.5, 1.5), ay = (T)uni(-1, 1), bx = (T)uni(-1.5, 1.5), by = (T)uni(-1, 1);
+      k.p[0] = ax, k.p[1] = ay, k.p[2] = bx - ax, k.p[3] = by - ay;
+      lg::CandList<T> a;
+      a.n = 0;
+      lg::hit_segment(k.p, o, d, a);
+      lgo::HitList<T> b;
+      lgo::hit_segment(k.p, oo, od, b);
+      cmp_lists(a, b, "segment");
+      for (int i = 0; i < a.n && i < b.n; ++i) {
+        lg::V2<T> nn = lg::hit_normal(k, a.h[i].p, a.h[i].aux);
+        CHECK(same(nn.x, b.h[i].n.x) && same(nn.y, b.h[i].n.y), "segment normal");
+      }
+      n += 1 + a.n;
+    }
+    // rect
+    {
+      lg::Tok<T> k{};
+      k.kind = lg::TOK_RECT;
+      double ra = uni(0, 6.283185307179586), hw = uni(0.01, 0.5), hh = uni(0.01, 0.5);
+      k.p[0] = (T)uni(-1.5, 1.5), k.p[1] = (T)uni(-1, 1);
+      k.p[2] = (T)(std::cos(ra) * hw), k.p[3] = (T)(std::sin(ra) * hw);
+      k.p[4] = (T)(-std::sin(ra) * hh), k.p[5] = (T)(std::cos(ra) * hh);
+      k.p[6] = lg::dot(lg::V2<T>{k.p[2], k.p[3]}, lg::V2<T>{k.p[2], k.p[3]});
+      k.p[7] = lg::dot(lg::V2<T>{k.p[4], k.p[5]}, lg::V2<T>{k.p[4], k.p[5]});
+      lg::CandList<T> a;
+      a.n = 0;
+      lg::hit_rect(k.p, o, d, a);
+      lgo::HitList<T> b;
+      lgo::hit_rect(k.p, oo, od, b);
+      cmp_lists(a, b, "rect");
+      for (int i = 0; i < a.n && i < b.n; ++i) {
+        lg::V2<T> nn = lg::hit_normal(k, a.h[i].p, a.h[i].aux);
+        CHECK(same(nn.x, b.h[i].n.x) && same(nn.y, b.h[i].n.y), "rect normal");
+      }
+      lgo::LeafT<T> l{};
+      l.kind = lgo::TOK_RECT;
+      std::memcpy(l.p, k.p, sizeof k.p);
+      lg::V2<T> q{(T)(k.p[0] + uni(-0.6, 0.6)), (T)(k.p[1] + uni(-0.6, 0.6))};
+      CHECK(lg::contains_leaf(k, q) == lgo::contains_leaf(l, lgo::V2<T>{q.x, q.y}), "rect contains");
+      n += 1 + a.n;
+    }
+    // bezier
+    {
+      lg::Tok<T> k{};
+      k.kind = lg::TOK_BEZIER;
+      double cx = uni(-1, 1), cy = uni(-0.7, 0.7);
+      for (int i = 0; i < 4; ++i) k.p[2 * i] = (T)(cx + uni(-0.6, 0.6)), k.p[2 * i + 1] = (T)(cy + uni(-0.6, 0.6));
+      lg::CandList<T> a;
+      a.n = 0;
+      lg::hit_bezier(k.p, o, d, a);
+      lgo::HitList<T> b;
+      lgo::hit_bezier(k.p, oo, od, b);
+      cmp_lists(a, b, "bezier");
+      for (int i = 0; i < a.n && i < b.n; ++i) {
+        lg::V2<T> nn = lg::hit_normal(k, a.h[i].p, a.h[i].aux);
+        CHECK(same(nn.x, b.h[i].n.x) && same(nn.y, b.h[i].n.y), "bezier normal");
+      }
+      n += 1 + a.n;
+    }
+    // reflect / refract
+    {
+      double na = uni(0, 6.283185307179586);
+      lg::V2<T> nn{(T)std::cos(na), (T)std::sin(na)};
+      lg::V2<T> r = lg::reflect_dir(d, nn);
+      lgo::V2<T> r2 = lgo::reflect_dir(od, lgo::V2<T>{nn.x, nn.y});
+      CHECK(same(r.x, r2.x) && same(r.y, r2.y), "reflect");
+      T n1 = (T)uni(1.0, 2.4), n2 = (T)uni(1.0, 2.4);
+      lg::V2<T> fl, fr{0, 0};
+      bool has;
+      T R = lg::refract_dir(d, nn, n1, n2, fl, fr, has);
+      lgo::V2<T> gl, gr{0, 0};
+      bool has2;
+      T R2 = lgo::refract_dir(od, lgo::V2<T>{nn.x, nn.y}, n1, n2, gl, gr, has2);
+      CHECK(has == has2 && same(R, R2), "refract reflectance");
+      CHECK(same(fl.x, gl.x) && same(fl.y, gl.y), "refract reflected");
+      if (has && has2) CHECK(same(fr.x, gr.x) && same(fr.y, gr.y), "refract refracted");
+      n += 2;
+    }
+  }
+  return n;
+}
+
+// random Geo trees: product lowering (lg_scene.h) vs oracle lowering, bit for bit
+static int rand_geo(std::vector<LgGeoNode> &nodes, int depth) {
+  LgGeoNode g{};
+  g.child_a = g.child_b = -1;
+  g.rot[0] = 1, g.rot[3] = 1;
+  int kind = depth >= 3 ? (int)(nextu() % 4) : (int)(nextu() % 5);
+  g.kind = kind;
+  double ra = uni(0, 6.283185307179586);
+  switch (kind) {
+  case LG_GEO_CIRCLE: g.p[0] = uni(-1, 1), g.p[1] = uni(-1, 1), g.p[2] = uni(0.05, 0.5); break;
+  case LG_GEO_RECT:
+    g.p[0] = uni(-1, 1), g.p[1] = uni(-1, 1), g.p[2] = uni(0.05, 0.8), g.p[3] = uni(0.05, 0.8);
+    g.rot[0] = std::cos(ra), g.rot[1] = std::sin(ra), g.rot[2] = -std::sin(ra), g.rot[3] = std::cos(ra);
+    break;
+  case LG_GEO_SEGMENT: for (int k = 0; k < 4; ++k) g.p[k] = uni(-1, 1); break;
+  case LG_GEO_BEZIER: for (int k = 0; k < 8; ++k) g.p[k] = uni(-1, 1); break;
+  default: {
+    g.op = (int)(nextu() % 3);
+    g.p[0] = uni(-0.5, 0.5), g.p[1] = uni(-0.5, 0.5);
+    g.rot[0] = std::cos(ra), g.rot[1] = std::sin(ra), g.rot[2] = -std::sin(ra), g.rot[3] = std::cos(ra);
+    int ix = (int)nodes.size();
+    nodes.push_back(g);
+    int a = rand_geo(nodes, depth + 1);
+    int b = rand_geo(nodes, depth + 1);
+    nodes[ix].child_a = a, nodes[ix].child_b = b;
+    return ix;
+  }
+  }
+  nodes.push_back(g);
+  return (int)nodes.size() - 1;
+}
+
+static long check_lowering(int n_scenes) {
+  long n = 0;
+  for (int sidx = 0; sidx < n_scenes; ++sidx) {
+    std::vector<LgGeoNode> nodes;
+    std::vector<LgObject> objs;
+    int nobj = 1 + (int)(nextu() % 6);
+    for (int i = 0; i < nobj; ++i) {
+      LgObject o{};
+      o.root = rand_geo(nodes, 0);
+      o.has_material = (int)(nextu() % 2);
+      o.refractive_index = uni(1.05, 2.4);
+      objs.push_back(o);
+    }
+    LgTraceParams prm{};
+    prm.max_bounce = 5;
+    prm.canvas_tlbr[0] = 1, prm.canvas_tlbr[1] = -1.7, prm.canvas_tlbr[2] = -1, prm.canvas_tlbr[3] = 1.7;
+    lg::HostScene hs;
+    std::string err;
+    int rc = lg::lower_scene(objs.data(), (uint32_t)objs.size(), nodes.data(), (uint32_t)nodes.size(), prm, hs, err);
+    lgo::Scene os = lgo::make_scene(objs.data(), (uint32_t)objs.size(), nodes.data(), (uint32_t)nodes.size(), &prm);
+    if ((rc == 0) != os.ok) { std::printf("MISMATCH lowering status\n"); ++g_bad; continue; }
+    if (rc) continue;
+    if (hs.toks.size() != os.tokens.size() || hs.objs.size() != os.objects.size()) { std::printf("MISMATCH lowering size\n"); ++g_bad; continue; }
+    for (size_t i = 0; i < hs.toks.size(); ++i) {
+      const lg::HostTok &a = hs.toks[i];
+      const lgo::Token &b = os.tokens[i];
+      bool ok = a.kind == b.kind && (a.kind != 4 || (a.op == b.op && a.a_start == b.a_start && a.b_start == b.b_start));
+      int np = a.kind == 0 ? 3 : a.kind == 1 ? 6 : a.kind == 2 ? 4 : a.kind == 3 ? 8 : 0;
+      for (int k = 0; k < np; ++k) ok = ok && std::memcmp(&a.p[k], &b.p[k], 8) == 0;
+      if (!ok) { if (g_bad < 20) std::printf("MISMATCH lowering token %zu kind %d\n", i, a.kind); ++g_bad; }
+      ++n;
+    }
+    for (size_t i = 0; i < hs.objs.size(); ++i)
+      if (hs.objs[i].first != os.objects[i].first || hs.objs[i].count != os.objects[i].count) { std::printf("MISMATCH object range\n"); ++g_bad; }
+    // start medium + overlap-candidate completeness: any other material object containing a
+    // point near object i's boundary must be in i's candidate list
+    lgo::SceneT<double> sd = lgo::cast_scene<double>(os);
+    for (int q = 0; q < 50; ++q) {
+      double x = uni(-1.7, 1.7), y = uni(-1, 1);
+      LgLight l{};
+      l.position[0] = x, l.position[1] = y;
+      double m1 = lg::host_start_medium(hs, x, y), m2 = lgo::start_medium(sd, l);
+      if (std::memcmp(&m1, &m2, 8) != 0) { if (g_bad < 20) std::printf("MISMATCH start medium\n"); ++g_bad; }
+      ++n;
+    }
+    for (size_t i = 0; i < hs.objs.size(); ++i) {
+      if (!hs.objs[i].has_material) continue;
+      for (int q = 0; q < 200; ++q) {
+        double ang = uni(0, 6.283185307179586);
+        lgo::V2<double> o{uni(-1.7, 1.7), uni(-1, 1)}, d{std::cos(ang), std::sin(ang)};
+        lgo::ObjHits<double> oh;
+        lgo::intersect_object(sd, (int)i, o, d, oh);
+        for (int h = 0; h < oh.n; ++h) {
+          for (size_t j = 0; j < hs.objs.size(); ++j) {
+            if (j == i || !hs.objs[j].has_material) continue;
+            if (!lgo::contains_object(sd, (int)j, oh.h[h].p)) continue;
+            bool listed = false;
+            for (int e = hs.ovl_start[i]; e < hs.ovl_start[i + 1]; ++e) listed = listed || hs.ovl_list[e] == (int)j;
+            if (!listed) { if (g_bad < 20) std::printf("MISMATCH overlap list misses %zu in %zu\n", j, i); ++g_bad; }
+            ++n;
+          }
+        }
+      }
+    }
+  }
+  return n;
+}
+
+int main(int argc, char **argv) {
+  int iters = argc > 1 ? std::atoi(argv[1]) : 200000;
+  long n = run<float>(iters) + run<double>(iters);
+  n += check_lowering(iters / 500 + 10);
+  if (g_bad) {
+    std::printf("FAILED %ld mismatches\n", g_bad);
+    return 1;
+  }
+  std::printf("OK %ld\n", n);
+  return 0;
+}

@@ -1,0 +1,193 @@
+"""Parity of the CUDA accumulation path (K3 string mod, K4 accumulate, K5 finalize) with the oracle.
+
+Coverage (which pixels, how many fragments) is integer work: bit-exact.  Sums are fp32 reductions whose
+order is not defined on the device (red.global.add): with power-of-two colours every partial sum is exact,
+so those images are compared bit for bit; with arbitrary colours the tolerance is stated in the test.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from light_garden_b200 import abi, scenes
+from light_garden_b200.scene import ModRemColor, StringMod, StringModMode
+from util import have_cuda, primary_rays, small_specs
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not have_cuda(), reason="no CUDA device")]
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from light_garden_b200.tracer import Context
+    c = Context(0, abi.LG_PRECISION_F32)
+    yield c
+    c.close()
+
+
+def random_pairs(n, seed, span=2.2, pow2=True):
+    rng = np.random.default_rng(seed)
+    p = np.zeros(n, dtype=abi.VERTEX_PAIR_DTYPE)
+    p["a"] = rng.uniform(-span, span, (n, 2))
+    p["b"] = rng.uniform(-span, span, (n, 2))
+    if pow2:
+        p["color_a"] = 2.0 ** -rng.integers(4, 9, (n, 4))
+        p["color_b"] = p["color_a"]
+    else:
+        p["color_a"] = rng.uniform(0, 0.02, (n, 4))
+        p["color_b"] = rng.uniform(0, 0.02, (n, 4))
+    return p
+
+
+@pytest.mark.parametrize("size", [(96, 54), (257, 131), (64, 64), (33, 200)])
+def test_pairs_exact_coverage_and_sums(oracle, ctx, size):
+    from light_garden_b200.tracer import Renderer
+    W, H = size
+    r = Renderer(ctx, W, H)
+    p = random_pairs(3000, seed=W * 1000 + H)
+    # degenerate and hostile inputs: zero length, fully outside, huge, axis-aligned on pixel centres
+    p["b"][0] = p["a"][0]
+    p["a"][1], p["b"][1] = (10.0, 10.0), (12.0, 11.0)
+    p["a"][2], p["b"][2] = (-1e6, -1e6), (1e6, 1e6)
+    p["a"][3], p["b"][3] = (0.0, 0.0), (0.5, 0.0)
+    p["a"][4], p["b"][4] = (0.25, -3.0), (0.25, 3.0)
+    st = r.render_lines(p)
+    got = r.read_rgba32f()
+    exp = oracle.new_image(W, H)
+    n = oracle.accumulate_pairs(exp, p)
+    assert st.pixel_updates == n
+    assert np.array_equal(got, exp)
+
+
+def test_two_colour_lerp_matches_oracle(oracle, ctx):
+    """Arbitrary per-endpoint colours: same fragments; sums within fp32 reordering error."""
+    from light_garden_b200.tracer import Renderer
+    W, H = 160, 90
+    r = Renderer(ctx, W, H)
+    p = random_pairs(5000, seed=11, pow2=False)
+    st = r.render_lines(p)
+    got = r.read_rgba32f()
+    exp = oracle.new_image(W, H)
+    assert st.pixel_updates == oracle.accumulate_pairs(exp, p)
+    # <= ~60 adds of O(0.02) per pixel: reordering error far below 1e-6 absolute; stated tolerance 2e-6
+    assert np.abs(got - exp).max() < 2e-6
+    assert np.array_equal(got == (0, 0, 0, 1), exp == (0, 0, 0, 1))          # identical coverage
+
+
+@pytest.mark.parametrize("name", ["C1", "C5-16"])
+def test_traced_segments_image(oracle, ctx, name):
+    """trace -> accumulate on the device vs the oracle accumulating the device's own segments, and
+    lg_render (waves through a small segment buffer) vs the one-shot path."""
+    from light_garden_b200.tracer import Renderer, Tracer
+    spec = small_specs()[name]
+    t = spec.apply(Tracer(spec.canvas_bounds, ctx=ctx))
+    r = Renderer(ctx, spec.width, spec.height)
+    seg = t.trace_all(ordered=False, control_lines=False)
+    st = r.render_traced()
+    got = r.read_rgba32f()
+    exp = oracle.new_image(spec.width, spec.height)
+    n = oracle.accumulate_segments(exp, seg)
+    assert st.pixel_updates == n
+    assert np.array_equal(got[..., 3] > 1, exp[..., 3] > 1)                    # same covered pixels
+    err = np.abs(got - exp)
+    # hot pixels next to a light sum thousands of fragments: relative bound 1e-5 of the pixel value
+    assert (err <= 1e-5 * np.maximum(1.0, np.abs(exp))).all(), err.max()
+    mse = float(np.mean((got - exp) ** 2))
+    psnr = 10 * np.log10(float(exp.max()) ** 2 / mse) if mse > 0 else np.inf
+    assert psnr > 100
+    # waves: capacity for only a fraction of the segments
+    ctx.call("lg_segment_capacity_set", max(2048, len(seg) // 5))
+    try:
+        r.clear()
+        st2 = r.render(t)
+        assert st2.segments == len(seg) and st2.pixel_updates == n and st2.trace_launches >= 4
+        got2 = r.read_rgba32f()
+        assert (np.abs(got2 - exp) <= 1e-5 * np.maximum(1.0, np.abs(exp))).all()
+    finally:
+        ctx.call("lg_segment_capacity_set", 64 << 20)
+
+
+def test_string_mod_matches_oracle(oracle, ctx):
+    from light_garden_b200.tracer import Renderer
+    W = H = 256
+    k = 2.0 ** -8
+    rules = [ModRemColor(3, 0, (k, 0, 0, k)), ModRemColor(3, 1, (0, k, 0, k)), ModRemColor(3, 2, (0, 0, k, k))]
+    for mode, num, m in ((StringModMode.Mul, 2, 3001), (StringModMode.Add, 977, 2048), (StringModMode.Pow, 3, 1000),
+                         (StringModMode.Base, 3, 500), (StringModMode.Mul, 7919, 4099)):
+        sm = StringMod(modulo=m, num=num, mode=mode, color=(k, k, k, k), modulo_colors=rules)
+        r = Renderer(ctx, W, H)
+        st = r.render_string_mod(sm)
+        got = r.read_rgba32f()
+        exp = oracle.new_image(W, H)
+        n = oracle.accumulate_pairs(exp, oracle.string_mod(sm))
+        # chord end points come from sincos on both sides (device vs libm: last-place differences in f64
+        # that survive the cast to f32 only rarely) -> allow a handful of fragments to move
+        assert abs(int(st.pixel_updates) - int(n)) <= 8, (mode, st.pixel_updates, n)
+        diff = np.nonzero((got != exp).any(axis=2))
+        assert len(diff[0]) <= 16, (mode, len(diff[0]))
+        assert st.segments == m
+    # sub-range + shard semantics: two halves add up to the whole (colours are powers of two: exact)
+    sm = StringMod(modulo=3001, num=2, mode=StringModMode.Mul, color=(k, k, k, k), modulo_colors=rules)
+    r = Renderer(ctx, W, H)
+    r.render_string_mod(sm)
+    whole = r.read_rgba32f()
+    r.clear()
+    r.render_string_mod(sm, first=0, count=1500)
+    r.render_string_mod(sm, first=1500, count=1501)
+    assert np.array_equal(r.read_rgba32f(), whole)
+    # modulo = 0 draws nothing (string_mod.rs:106-108)
+    r.clear()
+    assert r.render_string_mod(StringMod(modulo=0)).segments == 0
+
+
+def test_finalize_rgba16f(oracle, ctx):
+    """K5: the Rgba16Float image is the fp32 image rounded to nearest even, bit for bit."""
+    from light_garden_b200.tracer import Renderer
+    W, H = 128, 72
+    r = Renderer(ctx, W, H)
+    p = random_pairs(4000, seed=5, pow2=False)
+    p["color_a"] *= 50       # push some pixels past fp16's integer range
+    p["color_b"] *= 50
+    r.render_lines(p)
+    f32 = r.read_rgba32f()
+    f16 = r.read_rgba16f()
+    assert np.array_equal(f16.view(np.uint16), oracle.to_f16(f32).view(np.uint16))
+    assert np.array_equal(f16.view(np.uint16), f32.astype(np.float16).view(np.uint16))
+
+
+def test_clear_value_and_partial_alpha(ctx):
+    from light_garden_b200.tracer import Renderer
+    r = Renderer(ctx, 40, 30)
+    img = r.read_rgba32f()
+    assert np.all(img[..., :3] == 0) and np.all(img[..., 3] == 1)       # LoadOp::Clear(BLACK)
+    r.clear(0.0)                                                          # non-owning ranks of a multi-GPU frame
+    assert np.all(r.read_rgba32f() == 0)
+
+
+@pytest.mark.parametrize("wh", [(4096, 4096)])
+def test_full_size_string_mod_properties(ctx, wh):
+    """C4 at BASELINE size (10 M chords, 4096 x 4096) through size-independent properties: with a
+    power-of-two colour every pixel holds count * colour exactly, so the image sums are a checksum of the
+    fragment counter; the two halves of the chord range add up to the whole."""
+    from light_garden_b200.tracer import Renderer
+    W, H = wh
+    k = 2.0 ** -12
+    sm = StringMod(modulo=10_000_000, num=2, mode=StringModMode.Mul, color=(k, k, k, k))
+    r = Renderer(ctx, W, H)
+    r.clear(0.0)        # alpha starts at 0 so that count * 2^-24 stays exact (1 + 2^-24 is not an fp32 number)
+    st = r.render_string_mod(sm)
+    img = r.read_rgba32f()
+    n = int(st.pixel_updates)
+    assert st.segments == 10_000_000
+    # mean chord of the unit circle is 4/pi world units = 4/pi * 2048 px; DDA steps ~ x (2 sqrt2 / pi)
+    assert 2.2e10 < n < 2.5e10
+    for ch in range(3):
+        assert int(round(float(img[..., ch].astype(np.float64).sum()) / k)) == n
+    assert int(round(float(img[..., 3].astype(np.float64).sum()) / (k * k))) == n
+    assert float(img[..., 0].max()) / k < 2 ** 24                       # counts stayed exactly representable
+    # 4-fold symmetry of the pattern is not exact in pixels, but the left/right halves must balance closely
+    left, right = img[:, : W // 2, 0].sum(dtype=np.float64), img[:, W // 2:, 0].sum(dtype=np.float64)
+    assert abs(left - right) / (left + right) < 0.02
+    r.clear(0.0)
+    r.render_string_mod(sm, first=0, count=5_000_000)
+    r.render_string_mod(sm, first=5_000_000, count=5_000_000)
+    assert np.array_equal(r.read_rgba32f(), img)

@@ -1,0 +1,55 @@
+"""Multi-GPU: ray shards on several devices, partial images summed with the NCCL reduce.
+Needs >= 2 visible GPUs (gpurun --gpus 2); skipped otherwise."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from light_garden_b200 import abi
+from util import have_cuda, small_specs
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not have_cuda(), reason="no CUDA device")]
+
+
+def device_count():
+    from light_garden_b200 import _lib
+    n = C.c_int32(0)
+    _lib.load().lg_device_count(C.byref(n))
+    return n.value
+
+
+@pytest.mark.skipif(not have_cuda() or device_count() < 2, reason="needs 2 GPUs")
+def test_two_device_render_equals_one_device(oracle):
+    from light_garden_b200 import _lib
+    from light_garden_b200.tracer import Context, Renderer, Tracer
+    spec = small_specs()["C1"]
+    world = 2
+    ctxs = [Context(d, abi.LG_PRECISION_F32) for d in range(world)]
+    try:
+        arr = (C.c_void_p * world)(*[c.h for c in ctxs])
+        _lib.check(ctxs[0].h, _lib.load().lg_comm_init_all(arr, world))
+        rends = []
+        for rk, c in enumerate(ctxs):
+            t = spec.apply(Tracer(spec.canvas_bounds, ctx=c))
+            t.set_shard(rk, world)
+            r = Renderer(c, spec.width, spec.height)
+            r.clear(1.0 if rk == 0 else 0.0)          # only the root owns the clear alpha
+            r.render(t)
+            rends.append(r)
+        import threading
+        ms = [C.c_float() for _ in ctxs]
+        th = [threading.Thread(target=lambda i=i: ctxs[i].call("lg_image_reduce", 0, C.byref(ms[i])))
+              for i in range(world)]
+        [x.start() for x in th]
+        [x.join() for x in th]
+        total = rends[0].read_rgba32f()
+        one = Context(0, abi.LG_PRECISION_F32)
+        t = spec.apply(Tracer(spec.canvas_bounds, ctx=one))
+        r1 = Renderer(one, spec.width, spec.height)
+        r1.render(t)
+        ref = r1.read_rgba32f()
+        assert (np.abs(total - ref) <= 1e-5 * np.maximum(1.0, np.abs(ref))).all()
+        one.close()
+    finally:
+        for c in ctxs:
+            c.close()

@@ -1,0 +1,240 @@
+"""Parity of the CUDA trace path (K1 emit + K2 trace) with the oracle, through the C ABI.
+
+Bar (BASELINE.json north_star): hit-object sequences and segment counts bit-exact; here the device and
+the oracle implement the same ORACLE.md formulas with IEEE-exact operations only, so for identical
+primary rays EVERYTHING (tags, endpoints, colours) is compared bit for bit, in both precisions.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from light_garden_b200 import abi, scenes
+from light_garden_b200.scene import (AND_NOT, Circle, CubicBezier, Logic, Material, Object, PointLight, Rect,
+                                     SpotLight)
+from util import assert_same_segments, have_cuda, primary_rays, small_specs, ulp_diff64
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not have_cuda(), reason="no CUDA device")]
+
+SPECS = small_specs()
+
+
+@pytest.fixture(scope="module")
+def ctx64():
+    from light_garden_b200.tracer import Context
+    c = Context(0, abi.LG_PRECISION_F64)
+    yield c
+    c.close()
+
+
+@pytest.fixture(scope="module")
+def ctx32():
+    from light_garden_b200.tracer import Context
+    c = Context(0, abi.LG_PRECISION_F32)
+    yield c
+    c.close()
+
+
+def make_tracer(spec, ctx):
+    from light_garden_b200.tracer import Tracer
+    return spec.apply(Tracer(spec.canvas_bounds, ctx=ctx))
+
+
+@pytest.mark.parametrize("name", list(SPECS))
+def test_trace_f64_bit_exact(oracle, ctx64, name):
+    spec = SPECS[name]
+    osc = oracle.OracleScene.from_spec(spec)
+    rays = primary_rays(oracle, spec, osc)
+    exp = osc.trace_rays(rays, abi.LG_PRECISION_F64)
+    t = make_tracer(spec, ctx64)
+    got = t.trace(rays)
+    assert exp.segments_emitted > len(rays) // 2
+    assert_same_segments(got, exp, f64=True)
+    assert t.last_stats.ray_steps == exp.ray_steps
+    assert t.last_stats.segments == exp.segments_emitted
+    assert t.last_stats.object_tests == exp.ray_steps * len(spec.objects)
+
+
+@pytest.mark.parametrize("name", list(SPECS))
+def test_trace_f32_bit_exact(oracle, ctx32, name):
+    spec = SPECS[name]
+    osc = oracle.OracleScene.from_spec(spec)
+    rays = primary_rays(oracle, spec, osc)
+    exp = osc.trace_rays(rays, abi.LG_PRECISION_F32)
+    t = make_tracer(spec, ctx32)
+    got = t.trace(rays)
+    assert_same_segments(got, exp)
+    assert t.last_stats.ray_steps == exp.ray_steps
+
+
+@pytest.mark.parametrize("slots", ["1", "2", "4"])
+def test_slot_counts_give_identical_results(oracle, slots):
+    """R ray slots per thread is a scheduling choice: results must not depend on it."""
+    from light_garden_b200.tracer import Context
+    spec = SPECS["C3"]
+    osc = oracle.OracleScene.from_spec(spec)
+    rays = primary_rays(oracle, spec, osc)
+    for prec in (abi.LG_PRECISION_F32, abi.LG_PRECISION_F64):
+        os.environ["LG_TRACE_SLOTS"] = slots
+        try:
+            c = Context(0, prec)
+        finally:
+            del os.environ["LG_TRACE_SLOTS"]
+        try:
+            got = make_tracer(spec, c).trace(rays)
+            assert_same_segments(got, osc.trace_rays(rays, prec), f64=prec == abi.LG_PRECISION_F64)
+        finally:
+            c.close()
+
+
+def test_emission_matches_reference_formulas(oracle, ctx64):
+    """K1: device sincos vs libm sincos may differ in the last place; everything else is exact."""
+    spec = SPECS["C3"]   # point, spot and directional lights
+    t = make_tracer(spec, ctx64)
+    osc = oracle.OracleScene.from_spec(spec)
+    for i, l in enumerate(spec.lights):
+        got = t.emit_rays(i)
+        exp = oracle.emit_rays(l)
+        assert np.array_equal(got["origin"], exp["origin"])
+        assert np.array_equal(got["color"], exp["color"])
+        assert ulp_diff64(got["direction"], exp["direction"]).max() <= 4
+        # near the axes a component is ~1e-17 and 4 ulp of it is nothing: also bound the absolute error
+        assert np.abs(got["direction"] - exp["direction"]).max() < 1e-15
+        assert np.all(got["refractive_index"] == osc.start_medium(l))
+    # ragged sub-range
+    got = t.emit_rays(0, first=7, count=33)
+    exp = oracle.emit_rays(spec.lights[0], first=7, count=33)
+    assert np.abs(got["direction"] - exp["direction"]).max() < 1e-15
+
+
+@pytest.mark.parametrize("name", ["C1", "C5-16"])
+def test_trace_all_device_emission_end_to_end(oracle, ctx64, name):
+    """Tracer::trace_all with rays emitted on the device: same segments up to the last-place emission
+    difference (segment endpoints within 1e-9 relative, identical hit sequences)."""
+    spec = SPECS[name]
+    osc = oracle.OracleScene.from_spec(spec)
+    exp = osc.trace_all(spec.lights, abi.LG_PRECISION_F64)
+    t = make_tracer(spec, ctx64)
+    seg, tags, f64 = t.trace_all(control_lines=False, return_tags=True)
+    assert t.last_stats.primary_rays == spec.total_rays()
+    # rays whose whole tag sequence is identical
+    same_len = len(seg) == len(exp.seg)
+    if same_len and all(np.array_equal(tags[n], exp.tags[n]) for n in ("ray", "generation", "path", "hit_object")):
+        scale = np.maximum(1.0, np.abs(exp.f64["b"]))
+        assert (np.abs(f64["b"] - exp.f64["b"]) / scale).max() < 1e-9
+        assert np.array_equal(seg["color"], exp.seg["color"])
+    else:
+        # a last-place direction difference flipped a grazing hit somewhere: bound how many rays differ
+        got_keys = set(zip(tags["ray"].tolist(), tags["generation"].tolist(), tags["path"].tolist(),
+                           tags["hit_object"].tolist()))
+        exp_keys = set(zip(exp.tags["ray"].tolist(), exp.tags["generation"].tolist(), exp.tags["path"].tolist(),
+                           exp.tags["hit_object"].tolist()))
+        diff_rays = {k[0] for k in got_keys ^ exp_keys}
+        assert len(diff_rays) <= max(1, spec.total_rays() // 2000), len(diff_rays)
+
+
+def test_trace_all_appends_control_lines(ctx32):
+    """tracer.rs:342-346: the curved mirror's control polygon (3 red segments) follows the traced lines."""
+    spec = SPECS["C1"]
+    t = make_tracer(spec, ctx32)
+    seg = t.trace_all()
+    assert np.all(seg["color"][-3:] == np.float32([1, 0, 0, 1]))
+    p = spec.objects[1].geo.points
+    np.testing.assert_allclose(seg["a"][-3], p[0], rtol=1e-7)
+    np.testing.assert_allclose(seg["b"][-1], p[3], rtol=1e-7)
+
+
+def test_shards_partition_the_rays(oracle, ctx32):
+    """rank r of R takes rays [r*n/R, (r+1)*n/R) of every light; the union is the whole trace."""
+    spec = SPECS["C1"]
+    t = make_tracer(spec, ctx32)
+    osc = oracle.OracleScene.from_spec(spec)
+    full = osc.trace_all(spec.lights, abi.LG_PRECISION_F32)
+    seen = []
+    for r in range(3):
+        t.set_shard(r, 3)
+        seg, tags, _ = t.trace_all(control_lines=False, return_tags=True)
+        part = osc.trace_all(spec.lights, abi.LG_PRECISION_F32, rank=r, world=3)
+        assert len(seg) == part.segments_emitted
+        seen.append(tags["ray"])
+    t.set_shard(0, 1)
+    allr = np.sort(np.concatenate(seen))
+    assert np.array_equal(allr, np.sort(full.tags["ray"]))
+
+
+# ---- edge cases ---------------------------------------------------------------------------------------
+def test_empty_and_ragged_inputs(oracle, ctx32):
+    from light_garden_b200.tracer import Tracer
+    t = Tracer(scenes.canvas(16 / 9), ctx=ctx32)
+    # empty scene, no lights
+    seg = t.trace_all()
+    assert len(seg) == 0
+    # empty scene, rays leave through the canvas: one segment each; 33 rays = one full warp + 1
+    t.push_light(PointLight((0.1, 0.2), 33, (0.5, 0.5, 0.5, 0.5)))
+    seg, tags, _ = t.trace_all(return_tags=True)
+    assert len(seg) == 33 and np.all(tags["hit_object"] == -1) and np.array_equal(tags["ray"], np.arange(33))
+    # zero rays
+    seg, _, _ = t.trace(np.zeros(0, dtype=abi.RAY_DTYPE))
+    assert len(seg) == 0
+    # max_bounce = 0: nothing is traced (tracer.rs:373)
+    t.max_bounce = 0
+    assert len(t.trace_all()) == 0
+    # a light below the cutoff emits nothing (tracer.rs:378-384)
+    t.max_bounce = 5
+    t.index_light(0).color = (0.0005, 0.0005, 0.0005, 0.5)
+    assert len(t.trace_all()) == 0
+
+
+def test_deep_split_tree_matches_oracle(oracle, ctx64):
+    """max_bounce = 12 with refraction and a zero cutoff: the full binary split tree (stack depth 11)."""
+    from light_garden_b200.tracer import Tracer
+    objs = [Object.new_circle((0.0, 0.0), 0.5).with_index(1.5), Object.new_rect((1.0, 0.1), 0.4, 0.9).with_index(1.3),
+            Object.new_mirror((-1.2, -0.9), (-1.0, 0.9))]
+    t = Tracer(scenes.canvas(16 / 9), ctx=ctx64)
+    for o in objs:
+        t.push_object(o)
+    t.max_bounce = 12
+    t.cutoff_color = [0.0, 0.0, 0.0, 0.0]
+    light = PointLight((-0.9, 0.05), 40, (0.5, 0.4, 0.3, 0.2))
+    osc = oracle.OracleScene(objs, 12, [0.0] * 4, scenes.canvas(16 / 9))
+    rays = oracle.emit_rays(light)
+    exp = osc.trace_rays(rays, abi.LG_PRECISION_F64)
+    got = t.trace(rays)
+    assert exp.segments_emitted > 40 * 30
+    assert_same_segments(got, exp, f64=True)
+
+
+def test_errors_are_reported_not_hidden(ctx32):
+    from light_garden_b200._lib import LightGardenError
+    from light_garden_b200.tracer import Context, Tracer
+    c = Context(0, abi.LG_PRECISION_F32)
+    try:
+        with pytest.raises(LightGardenError) as e:       # trace before any scene
+            c.call("lg_trace", None)
+        assert e.value.code == abi.LG_ERR_STATE
+        objs = (abi.LgObject * 1)()
+        objs[0].root = 5                                  # node index out of range
+        nodes = (abi.LgGeoNode * 1)()
+        prm = abi.LgTraceParams()
+        with pytest.raises(LightGardenError) as e:
+            c.call("lg_scene_set", C.cast(objs, C.c_void_p), 1, C.cast(nodes, C.c_void_p), 1, C.byref(prm))
+        assert e.value.code == abi.LG_ERR_INVALID and "range" in e.value.message
+    finally:
+        c.close()
+    # segment buffer too small for lg_trace: LG_ERR_OVERFLOW, not silent truncation
+    spec = SPECS["C1"]
+    t = make_tracer(spec, ctx32)
+    ctx32.call("lg_segment_capacity_set", 1000)
+    try:
+        with pytest.raises(LightGardenError) as e:
+            t.trace_all()
+        assert e.value.code == abi.LG_ERR_OVERFLOW
+    finally:
+        ctx32.call("lg_segment_capacity_set", 64 << 20)
+    # negative refractive index (reachable from the GUI slider, gui/mod.rs:287-294) is rejected
+    t2 = Tracer(scenes.canvas(1.0), ctx=ctx32)
+    t2.push_object(Object.new_circle((0, 0), 0.5).with_index(-1.0))
+    with pytest.raises(LightGardenError) as e:
+        t2.sync_scene()
+    assert e.value.code == abi.LG_ERR_UNSUPPORTED
