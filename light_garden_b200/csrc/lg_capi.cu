@@ -803,9 +803,11 @@ int32_t lg_render(lg_ctx *c, LgTraceStats *stats) {
   double est = c->segs_per_ray_est > 0 ? c->segs_per_ray_est : std::min<double>(2.0 * (mb ? mb : 1), 64.0);
   unsigned long long done = 0;
   const unsigned long long total = c->shard_rays;
+  unsigned long long limit = ~0ull; // shrinks when a wave overflowed
   while (done < total) {
     unsigned long long wave = (unsigned long long)((double)c->seg_cap / (est * 1.25 + 1.0));
-    if (wave < 1024) wave = 1024;
+    if (wave < 1) wave = 1;
+    if (wave > limit) wave = limit;
     if (wave > total - done) wave = total - done;
     TraceCounters k{};
     float ms = 0.f;
@@ -814,9 +816,11 @@ int32_t lg_render(lg_ctx *c, LgTraceStats *stats) {
     stats->trace_launches += 1;
     if (k.seg_overflow) {
       if (wave <= 1) return fail(c, LG_ERR_OVERFLOW, "one ray does not fit the segment buffer");
-      est = std::max(est * 2.0, (double)k.seg_count / (double)wave);
+      est = std::max(est, (double)k.seg_count / (double)wave);
+      limit = wave / 2; // guaranteed progress: the retry traces at most half as many rays
       continue;
     }
+    limit = ~0ull;
     est = std::max(1.0, (double)k.seg_count / (double)wave);
     fill_stats(c, stats, wave, k.ray_steps, k.seg_count, 0.f, 0);
     c->seg_count = k.seg_count;

@@ -1,0 +1,34 @@
+#!/bin/bash
+# One GPU-box round trip: parity tests, smoke, bench, ncu launch list + full captures of the two hot kernels.
+# Usage (under gpurun): bash tools/gpu_round.sh [tests|bench|prof]...   (default: all)
+set -u
+mkdir -p gpurun_out
+what="${*:-tests bench prof}"
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.limit --format=csv > gpurun_out/smi.log 2>&1
+for w in $what; do
+  case $w in
+    tests)
+      timeout 900 python -m pytest tests -m gpu -q -x --durations=15 --timeout=240 --timeout-method=thread \
+        > gpurun_out/pytest_gpu.log 2>&1
+      echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
+      timeout 200 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1
+      ;;
+    bench)
+      timeout 600 python bench.py > gpurun_out/bench.log 2>&1
+      timeout 300 python bench.py --precision f64 --rays-per-gpu 8000000 --no-cpu-baseline > gpurun_out/bench_f64.log 2>&1
+      ;;
+    prof)
+      timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv \
+        --log-file gpurun_out/launches.csv python bench.py --rays-per-gpu 4000000 --steps 2 --warmup 3 --no-cpu-baseline \
+        > gpurun_out/bench_under_ncu.log 2>&1
+      timeout 600 ncu --set full --clock-control none --import-source on -k regex:trace_kernel -s 1 -c 1 \
+        -f -o gpurun_out/prof_trace python bench.py --rays-per-gpu 2000000 --steps 1 --warmup 3 --no-cpu-baseline \
+        > gpurun_out/prof_trace.log 2>&1
+      timeout 600 ncu --set full --clock-control none --import-source on -k regex:accumulate_segments -s 1 -c 1 \
+        -f -o gpurun_out/prof_accum python bench.py --rays-per-gpu 2000000 --steps 1 --warmup 3 --no-cpu-baseline \
+        > gpurun_out/prof_accum.log 2>&1
+      ;;
+  esac
+done
+tail -3 gpurun_out/pytest_gpu.log 2>/dev/null
+tail -c 600 gpurun_out/bench.log 2>/dev/null
