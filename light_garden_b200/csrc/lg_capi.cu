@@ -112,10 +112,13 @@ struct lg_ctx {
   // scene
   bool have_scene = false;
   HostScene hs;
-  int n_circ = 0, n_seg = 0, n_rect = 0, n_bez = 0, n_csg = 0, n_obj = 0;
-  unsigned fast_bytes = 0;
-  DevBuf fast, toks, circ_obj, seg_obj, rect_obj, bez_obj, csg_obj, obj_first, obj_count, obj_n, ovl_start, ovl_list;
+  int n_obj = 0, n_pad = 0;
+  unsigned bounds_bytes = 0;
+  DevBuf bounds, toks, obj_first, obj_count, obj_n, ovl_start, ovl_list;
   double canvas[8] = {0};
+  std::vector<double> bound_c; // per object: bounding circle cx, cy, radius (f64)
+  double coord_bound = 0;      // max |coordinate| the broad-phase margin was built for
+  double delta = 0;
 
   // lights / shard
   std::vector<LgLight> lights;
@@ -215,47 +218,17 @@ template <class T> int upload_scene(lg_ctx *c) {
     }
     toks[i] = t;
   }
-  std::vector<T> circ, segs, rects;
-  std::vector<int> circ_obj, seg_obj, rect_obj, bez_obj, csg_obj, obj_first, obj_count;
+  std::vector<int> obj_first, obj_count;
   std::vector<T> obj_n;
   for (size_t i = 0; i < hs.objs.size(); ++i) {
     const HostObj &o = hs.objs[i];
     obj_first.push_back(o.first);
     obj_count.push_back(o.count);
     obj_n.push_back(o.has_material ? (T)o.n : std::numeric_limits<T>::quiet_NaN());
-    if (o.count == 1) {
-      const Tok<T> &t = toks[o.first];
-      if (t.kind == TOK_CIRCLE) {
-        circ.insert(circ.end(), t.p, t.p + 4);
-        circ_obj.push_back((int)i);
-      } else if (t.kind == TOK_SEGMENT) {
-        segs.insert(segs.end(), t.p, t.p + 4);
-        seg_obj.push_back((int)i);
-      } else if (t.kind == TOK_RECT) {
-        rects.insert(rects.end(), t.p, t.p + 8);
-        rect_obj.push_back((int)i);
-      } else {
-        bez_obj.push_back((int)i);
-      }
-    } else {
-      csg_obj.push_back((int)i);
-    }
   }
-  c->n_circ = (int)circ_obj.size(), c->n_seg = (int)seg_obj.size(), c->n_rect = (int)rect_obj.size();
-  c->n_bez = (int)bez_obj.size(), c->n_csg = (int)csg_obj.size(), c->n_obj = (int)hs.objs.size();
-  std::vector<T> fast;
-  fast.insert(fast.end(), circ.begin(), circ.end());
-  fast.insert(fast.end(), segs.begin(), segs.end());
-  fast.insert(fast.end(), rects.begin(), rects.end());
-  c->fast_bytes = (unsigned)(fast.size() * sizeof(T));
+  c->n_obj = (int)hs.objs.size();
   int rc;
-  if ((rc = upload(c, c->fast, fast))) return rc;
   if ((rc = upload(c, c->toks, toks))) return rc;
-  if ((rc = upload(c, c->circ_obj, circ_obj))) return rc;
-  if ((rc = upload(c, c->seg_obj, seg_obj))) return rc;
-  if ((rc = upload(c, c->rect_obj, rect_obj))) return rc;
-  if ((rc = upload(c, c->bez_obj, bez_obj))) return rc;
-  if ((rc = upload(c, c->csg_obj, csg_obj))) return rc;
   if ((rc = upload(c, c->obj_first, obj_first))) return rc;
   if ((rc = upload(c, c->obj_count, obj_count))) return rc;
   if ((rc = upload(c, c->obj_n, obj_n))) return rc;
@@ -274,8 +247,87 @@ template <class T> int upload_scene(lg_ctx *c) {
   cv[6] = cv[2] * cv[2];
   cv[7] = cv[5] * cv[5];
   for (int k = 0; k < 8; ++k) c->canvas[k] = (double)cv[k];
+  // broad phase: one bounding circle per object, in f64 (every hit point of an object lies on one
+  // of its leaves, so the union of the leaves' bounding circles bounds all of them)
+  c->bound_c.assign(3 * hs.objs.size(), 0.0);
+  for (size_t i = 0; i < hs.objs.size(); ++i) {
+    const HostObj &o = hs.objs[i];
+    double x0 = 1e300, y0 = 1e300, x1 = -1e300, y1 = -1e300;
+    auto leaf_circle = [&](const HostTok &t, double &cx, double &cy, double &rr) {
+      if (t.kind == 0) {
+        cx = t.p[0], cy = t.p[1], rr = std::fabs(t.p[2]);
+      } else if (t.kind == 1) {
+        cx = t.p[0], cy = t.p[1], rr = std::hypot(std::hypot(t.p[2], t.p[3]), std::hypot(t.p[4], t.p[5]));
+      } else {
+        const int np = t.kind == 2 ? 2 : 4;
+        cx = cy = 0;
+        for (int q = 0; q < np; ++q) cx += t.p[2 * q] / np, cy += t.p[2 * q + 1] / np;
+        rr = 0;
+        for (int q = 0; q < np; ++q) rr = std::fmax(rr, std::hypot(t.p[2 * q] - cx, t.p[2 * q + 1] - cy));
+      }
+    };
+    for (int k = 0; k < o.count; ++k) {
+      const HostTok &t = hs.toks[o.first + k];
+      if (t.kind == 4) continue;
+      double cx, cy, rr;
+      leaf_circle(t, cx, cy, rr);
+      x0 = std::fmin(x0, cx - rr), x1 = std::fmax(x1, cx + rr), y0 = std::fmin(y0, cy - rr), y1 = std::fmax(y1, cy + rr);
+    }
+    const double mx = 0.5 * (x0 + x1), my = 0.5 * (y0 + y1);
+    double rad = 0;
+    for (int k = 0; k < o.count; ++k) {
+      const HostTok &t = hs.toks[o.first + k];
+      if (t.kind == 4) continue;
+      double cx, cy, rr;
+      leaf_circle(t, cx, cy, rr);
+      rad = std::fmax(rad, std::hypot(cx - mx, cy - my) + rr);
+    }
+    c->bound_c[3 * i] = mx, c->bound_c[3 * i + 1] = my, c->bound_c[3 * i + 2] = rad;
+  }
+  c->coord_bound = 0; // forces the broad-phase table to be rebuilt at the next launch
   LG_CUDA(c, cudaStreamSynchronize(c->stream)); // host vectors die here
   return LG_OK;
+}
+
+// Broad-phase table for coordinate bound B (scene, canvas, lights, explicit ray origins): the margin
+// delta = 64 eps B covers every rounding difference between the 3-FFMA line test and the exact tests.
+template <class T> int upload_bounds(lg_ctx *c, double B) {
+  const size_t n = c->bound_c.size() / 3;
+  const int n_pad = (int)((n + 31) / 32 * 32);
+  const double eps = std::numeric_limits<T>::epsilon();
+  const double delta = 64.0 * eps * B;
+  std::vector<T> tab(4 * (size_t)n_pad);
+  T *bx = tab.data(), *by = bx + n_pad, *br2 = by + n_pad, *brb = br2 + n_pad;
+  for (int i = 0; i < n_pad; ++i) {
+    if ((size_t)i < n) {
+      bx[i] = (T)c->bound_c[3 * i];
+      by[i] = (T)c->bound_c[3 * i + 1];
+      const double rb = (c->bound_c[3 * i + 2] * (1.0 + 1e-6) + delta) * (1.0 + 4 * eps);
+      brb[i] = std::nextafter((T)rb, std::numeric_limits<T>::max());
+      br2[i] = std::nextafter((T)((double)brb[i] * (double)brb[i] * (1.0 + 4 * eps)), std::numeric_limits<T>::max());
+    } else {
+      bx[i] = by[i] = (T)0;
+      br2[i] = (T)-1; // never a candidate
+      brb[i] = (T)0;
+    }
+  }
+  c->n_pad = n_pad;
+  c->bounds_bytes = (unsigned)(tab.size() * sizeof(T));
+  c->coord_bound = B;
+  c->delta = delta;
+  int rc = upload(c, c->bounds, tab);
+  if (rc) return rc;
+  LG_CUDA(c, cudaStreamSynchronize(c->stream));
+  return LG_OK;
+}
+int ensure_bounds(lg_ctx *c, double ray_bound) {
+  double B = std::fmax(c->hs.bound, ray_bound);
+  for (const LgLight &l : c->lights) {
+    B = std::fmax(B, std::fmax(std::fabs(l.position[0]), std::fabs(l.position[1])));
+    if (l.kind == LG_LIGHT_DIRECTIONAL) B = std::fmax(B, std::fmax(std::fabs(l.b[0]), std::fabs(l.b[1])));
+  }
+  if (c->bounds.p && c->coord_bound >= B && c->coord_bound > 0) return LG_OK;
+  return c->precision == LG_PRECISION_F64 ? upload_bounds<double>(c, B) : upload_bounds<float>(c, B);
 }
 
 void rebuild_dev_lights(lg_ctx *c) {
@@ -311,11 +363,10 @@ void rebuild_dev_lights(lg_ctx *c) {
 }
 
 template <class T> void fill_args(lg_ctx *c, TraceArgs<T> &A) {
-  A.fast = (const T *)c->fast.p;
-  A.fast_bytes = c->fast_bytes;
-  A.n_circ = c->n_circ, A.n_seg = c->n_seg, A.n_rect = c->n_rect, A.n_bez = c->n_bez, A.n_csg = c->n_csg;
-  A.circ_obj = (const int *)c->circ_obj.p, A.seg_obj = (const int *)c->seg_obj.p;
-  A.rect_obj = (const int *)c->rect_obj.p, A.bez_obj = (const int *)c->bez_obj.p, A.csg_obj = (const int *)c->csg_obj.p;
+  A.bounds = (const T *)c->bounds.p;
+  A.bounds_bytes = c->bounds_bytes;
+  A.n_pad = c->n_pad;
+  A.delta = (T)c->delta;
   A.toks = (const Tok<T> *)c->toks.p;
   A.obj_first = (const int *)c->obj_first.p, A.obj_count = (const int *)c->obj_count.p;
   A.obj_n = (const T *)c->obj_n.p;
@@ -347,9 +398,9 @@ template <> struct KernelOf<double> {
 
 template <class T> int launch_trace(lg_ctx *c, TraceArgs<T> &A) {
   const int R = KernelOf<T>::clamp(c->slots);
-  const bool use_smem = (size_t)A.fast_bytes + 1024 <= c->smem_optin;
+  const bool use_smem = (size_t)A.bounds_bytes + 1024 <= c->smem_optin;
   const void *kern = KernelOf<T>::get(R, use_smem);
-  const size_t smem = use_smem ? A.fast_bytes : 0;
+  const size_t smem = use_smem ? A.bounds_bytes : 0;
   if (smem > 48 * 1024) LG_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
   LG_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kTraceBlock, smem));
@@ -383,7 +434,9 @@ int prepare_trace_buffers(lg_ctx *c) {
 // one trace launch over [first, end) of the ray index space (or explicit rays);
 // returns with the stream drained and the counters on the host
 int trace_range(lg_ctx *c, const LgRay *d_rays, unsigned long long first, unsigned long long end, TraceCounters &out,
-                float *ms) {
+                float *ms, double ray_bound = 0.0) {
+  int rb = ensure_bounds(c, ray_bound);
+  if (rb) return rb;
   LG_CUDA(c, cudaMemsetAsync(c->ctr.p, 0, sizeof(TraceCounters), c->stream));
   LG_CUDA(c, cudaEventRecord(c->ev0, c->stream));
   int rc;
@@ -513,7 +566,7 @@ int32_t lg_destroy(lg_ctx *c) {
   if (!c) return LG_ERR_INVALID;
   cudaSetDevice(c->device);
   if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
-  DevBuf *bufs[] = {&c->fast,      &c->toks,     &c->circ_obj, &c->seg_obj, &c->rect_obj, &c->bez_obj, &c->csg_obj,
+  DevBuf *bufs[] = {&c->bounds,    &c->toks,
                     &c->obj_first, &c->obj_count, &c->obj_n,    &c->ovl_start, &c->ovl_list, &c->d_lights, &c->seg,
                     &c->tags,      &c->seg64,    &c->ctr,      &c->stack,   &c->rays,     &c->img,     &c->img16,
                     &c->pixctr};
@@ -651,7 +704,11 @@ int32_t lg_trace_rays(lg_ctx *c, const LgRay *rays, uint64_t n, LgTraceStats *st
   TraceCounters k{};
   float ms = 0.f;
   c->seg_count = 0;
-  if ((rc = trace_range(c, (const LgRay *)c->rays.p, 0, n, k, &ms))) return rc;
+  double ray_bound = 0;
+  for (uint64_t i = 0; i < n; ++i)
+    ray_bound = std::fmax(ray_bound, std::fmax(std::fabs(rays[i].origin[0]), std::fabs(rays[i].origin[1])));
+  if (!(ray_bound < 1e30)) return fail(c, LG_ERR_INVALID, "ray origin is not finite");
+  if ((rc = trace_range(c, (const LgRay *)c->rays.p, 0, n, k, &ms, ray_bound))) return rc;
   fill_stats(c, stats, n, k.ray_steps, k.seg_count, ms, 1);
   if (k.seg_overflow) return fail(c, LG_ERR_OVERFLOW, "segment buffer too small");
   c->seg_count = k.seg_count;

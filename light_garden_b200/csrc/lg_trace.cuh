@@ -10,10 +10,16 @@
 //     walks it depth-first with a private stack in global memory — the set of
 //     processed rays (and therefore of emitted segments) is identical, the
 //     emission order is restored from the (ray, generation, path) tag.
-//   * the scene's object table is staged once per CTA into shared memory with
-//     one cp.async.bulk (TMA bulk copy, SASS UBLKCP) and every lane tests the
-//     same object at the same time (broadcast LDS, no bank conflicts, warp
-//     uniform control flow: tracer.rs:412-424 brute-force loop).
+//   * brute force over every object (tracer.rs:412-424) in two phases.  Broad
+//     phase: the object table — one conservative bounding circle per object,
+//     SoA, staged once per CTA into shared memory with one cp.async.bulk (TMA
+//     bulk copy, SASS UBLKCP) — is swept by all lanes in lock step (broadcast
+//     LDS.128 of 4 objects, no bank conflicts, no branches): 3 FFMA + 1 funnel
+//     shift per ray x object decide "the ray's line misses this object for
+//     sure" and collect the outcome in a bit mask.  Narrow phase: the rare
+//     survivors run the exact ORACLE.md test.  The broad phase only discards
+//     provable misses (its radius carries the rounding margin), so results are
+//     bit-identical to testing every object exactly.
 //   * rays that die (left the canvas, culled by cutoff_color, generation
 //     limit) free their slot; idle slots are re-filled every iteration from the
 //     slot's stack or, warp-aggregated (ballot + one atomicAdd per warp), from
@@ -53,11 +59,13 @@ struct TraceCounters {
 };
 
 template <class T> struct TraceArgs {
-  // fast tables, contiguous: circles (4 T), segments (4 T), rects (8 T)
-  const T *fast;
-  unsigned int fast_bytes;
-  int n_circ, n_seg, n_rect, n_bez, n_csg;
-  const int *circ_obj, *seg_obj, *rect_obj, *bez_obj, *csg_obj;
+  // broad-phase table, contiguous SoA of n_pad entries each: centre x, centre y,
+  // (radius + margin)^2, radius + margin.  n_pad is a multiple of 32; padding
+  // entries have a negative squared radius and can never become candidates.
+  const T *bounds;
+  unsigned int bounds_bytes;
+  int n_pad;
+  T delta; // rounding margin of the broad phase (64 eps x coordinate bound)
   const Tok<T> *toks;
   const int *obj_first, *obj_count;
   const T *obj_n; // refractive index, NaN = no material
@@ -205,41 +213,6 @@ __device__ __forceinline__ void take(Best<T> &b, V2<T> o, const Cand<T> &c, int 
   }
 }
 
-// Rare path of the sweep loops: a primitive passed its early-out test.  Kept
-// out of line so the hot loops stay a handful of instructions per test.
-template <class T>
-__device__ __noinline__ Best<T> cand_circle(Best<T> b, const T *c, V2<T> o, V2<T> d, int ob, int tok) {
-  CandList<T> hl;
-  hl.n = 0;
-  hit_circle(c, o, d, hl);
-  for (int q = 0; q < hl.n; ++q) take(b, o, hl.h[q], ob, tok);
-  return b;
-}
-template <class T>
-__device__ __noinline__ Best<T> cand_segment(Best<T> b, const T *s, V2<T> o, V2<T> d, int ob, int tok) {
-  CandList<T> hl;
-  hl.n = 0;
-  hit_segment(s, o, d, hl);
-  for (int q = 0; q < hl.n; ++q) take(b, o, hl.h[q], ob, tok);
-  return b;
-}
-template <class T>
-__device__ __noinline__ Best<T> cand_rect(Best<T> b, const T *r, V2<T> o, V2<T> d, int ob, int tok) {
-  CandList<T> hl;
-  hl.n = 0;
-  hit_rect(r, o, d, hl);
-  for (int q = 0; q < hl.n; ++q) take(b, o, hl.h[q], ob, tok);
-  return b;
-}
-template <class T>
-__device__ __noinline__ Best<T> cand_bezier(Best<T> b, const T *p, V2<T> o, V2<T> d, int ob, int tok) {
-  CandList<T> hl;
-  hl.n = 0;
-  hit_bezier(p, o, d, hl);
-  for (int q = 0; q < hl.n; ++q) take(b, o, hl.h[q], ob, tok);
-  return b;
-}
-
 // Ray::intersect(&Geo::GeoLogic): leaf hits in program order, each filtered by
 // the sibling subtrees on the way to the root (ORACLE.md §3.6)
 template <class T>
@@ -277,6 +250,45 @@ __device__ __noinline__ void sweep_csg_object(const TraceArgs<T> &A, int obj, V2
   }
 }
 
+// Narrow phase: the exact Ray::intersect of ORACLE.md §3 for one object.  Out of
+// line so that the broad-phase loop stays a handful of instructions per test.
+template <class T>
+__device__ __noinline__ Best<T> narrow_phase(const TraceArgs<T> &A, Best<T> b, int obj, V2<T> o, V2<T> d) {
+  const int first = A.obj_first[obj];
+  if (A.obj_count[obj] == 1) {
+    const Tok<T> &k = A.toks[first];
+    CandList<T> hl;
+    hl.n = 0;
+    if (k.kind == TOK_CIRCLE)
+      hit_circle(k.p, o, d, hl);
+    else if (k.kind == TOK_SEGMENT)
+      hit_segment(k.p, o, d, hl);
+    else if (k.kind == TOK_RECT)
+      hit_rect(k.p, o, d, hl);
+    else
+      hit_bezier(k.p, o, d, hl);
+    for (int q = 0; q < hl.n; ++q) take(b, o, hl.h[q], obj, first);
+  } else {
+    sweep_csg_object(A, obj, o, d, b);
+  }
+  return b;
+}
+
+template <class T> struct SignBits;
+template <> struct SignBits<float> {
+  static __device__ __forceinline__ unsigned get(float v) { return __float_as_uint(v); }
+};
+template <> struct SignBits<double> {
+  static __device__ __forceinline__ unsigned get(double v) { return (unsigned)__double2hiint(v); }
+};
+template <class T> struct Vec4;
+template <> struct Vec4<float> {
+  typedef float4 type;
+};
+template <> struct Vec4<double> {
+  typedef double4 type;
+};
+
 template <class T> __device__ __forceinline__ bool contains_object(const TraceArgs<T> &A, int obj, V2<T> p) {
   return contains_range(A.toks + A.obj_first[obj], 0, A.obj_count[obj] - 1, p);
 }
@@ -288,10 +300,11 @@ __device__ __forceinline__ bool culled(float r, float g, float b, float a, const
 
 // ---- K2 ---------------------------------------------------------------------------
 template <class T, int R, bool kSmem>
-__global__ void __launch_bounds__(kTraceBlock) trace_kernel(const __grid_constant__ TraceArgs<T> A) {
+__global__ void __launch_bounds__(kTraceBlock, (R >= 4 || sizeof(T) == 8) ? 2 : 3)
+    trace_kernel(const __grid_constant__ TraceArgs<T> A) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ __align__(8) unsigned long long mbar;
-  const T *fast = A.fast;
+  const T *tab = A.bounds;
   if (kSmem) {
     // stage the object table: one TMA bulk copy, completion on an mbarrier
     const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_raw);
@@ -301,12 +314,12 @@ __global__ void __launch_bounds__(kTraceBlock) trace_kernel(const __grid_constan
       asm volatile("fence.mbarrier_init.release.cluster;");
     }
     __syncthreads();
-    if (A.fast_bytes > 0) {
+    if (A.bounds_bytes > 0) {
       if (threadIdx.x == 0) {
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(A.fast_bytes));
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(A.bounds_bytes));
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                          dst),
-                     "l"(A.fast), "r"(A.fast_bytes), "r"(bar)
+                     "l"(A.bounds), "r"(A.bounds_bytes), "r"(bar)
                      : "memory");
       }
       unsigned done = 0;
@@ -317,11 +330,13 @@ __global__ void __launch_bounds__(kTraceBlock) trace_kernel(const __grid_constan
                      : "memory");
       }
     }
-    fast = reinterpret_cast<const T *>(smem_raw);
+    tab = reinterpret_cast<const T *>(smem_raw);
   }
-  const T *circ = fast;
-  const T *segs = circ + 4 * (size_t)A.n_circ;
-  const T *rects = segs + 4 * (size_t)A.n_seg;
+  const T *bx = tab;
+  const T *by = bx + A.n_pad;
+  const T *br2 = by + A.n_pad;
+  const T *brb = br2 + A.n_pad;
+  typedef typename Vec4<T>::type T4;
 
   const unsigned lane = threadIdx.x & 31u;
   const unsigned lt_mask = (1u << lane) - 1u;
@@ -407,85 +422,65 @@ __global__ void __launch_bounds__(kTraceBlock) trace_kernel(const __grid_constan
 
     // ---- 2. nearest hit over all objects (tracer.rs:412-424) -----------------------
     Best<T> best[R];
-    V2<T> so[R], sd[R];
+    T sdx[R], sdy[R], nk[R], nkd[R], tb[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) {
       best[r].d2 = Real<T>::max_value();
       best[r].obj = -1;
       best[r].tok = -1;
       best[r].px = best[r].py = best[r].aux = (T)0;
-      // idle slots sweep a ray that can hit nothing
-      so[r] = alive[r] ? o[r] : V2<T>{(T)1e30, (T)1e30};
-      sd[r] = alive[r] ? d[r] : V2<T>{(T)1, (T)0};
-      if (alive[r]) ++steps;
-    }
-    // circles: early-out is the discriminant test of ORACLE.md §3.1 itself
-#pragma unroll 4
-    for (int j = 0; j < A.n_circ; ++j) {
-      const T cx = circ[4 * j], cy = circ[4 * j + 1], r2 = circ[4 * j + 3];
-#pragma unroll
-      for (int r = 0; r < R; ++r) {
-        const T mx = cx - so[r].x, my = cy - so[r].y;
-        const T c = Real<T>::fma(mx, sd[r].y, -(my * sd[r].x));
-        const T disc = Real<T>::fma(-c, c, r2);
-        if (disc >= (T)0) {
-          const int ob = A.circ_obj[j];
-          best[r] = cand_circle(best[r], circ + 4 * j, so[r], sd[r], ob, A.obj_first[ob]);
-        }
+      tb[r] = Real<T>::max_value();
+      if (alive[r]) {
+        ++steps;
+        sdx[r] = d[r].x, sdy[r] = d[r].y;
+        nk[r] = -cross(o[r], d[r]);  // cross(c - o, d) = cx*dy - cy*dx - cross(o, d)
+        nkd[r] = -dot(o[r], d[r]);   // dot(c - o, d)   = cx*dx + cy*dy - dot(o, d)
+      } else {                       // an idle slot sweeps a line that misses everything
+        sdx[r] = sdy[r] = (T)0;
+        nk[r] = (T)-1e30;
+        nkd[r] = (T)0;
       }
     }
-    // straight mirrors: early-out is the u-range test of ORACLE.md §3.2
-#pragma unroll 4
-    for (int j = 0; j < A.n_seg; ++j) {
-      const T ax = segs[4 * j], ay = segs[4 * j + 1], ex = segs[4 * j + 2], ey = segs[4 * j + 3];
+    for (int c0 = 0; c0 < A.n_pad; c0 += 32) {
+      // broad phase over 32 objects: bit (31 - i) of m[r] = "object c0 + i cannot be hit"
+      unsigned m[R];
 #pragma unroll
-      for (int r = 0; r < R; ++r) {
-        const T denom = Real<T>::fma(sd[r].x, ey, -(sd[r].y * ex));
-        const T wx = ax - so[r].x, wy = ay - so[r].y;
-        T s = Real<T>::fma(wx, sd[r].y, -(wy * sd[r].x));
-        if (denom < (T)0) s = -s;
-        const T ad = Real<T>::abs(denom);
-        if (ad > (T)kParEps && s >= (T)0 && s <= ad) {
-          const int ob = A.seg_obj[j];
-          best[r] = cand_segment(best[r], segs + 4 * j, so[r], sd[r], ob, A.obj_first[ob]);
-        }
-      }
-    }
-    // rects: early-out is the separating-axis test of ORACLE.md §3.3
+      for (int r = 0; r < R; ++r) m[r] = 0u;
 #pragma unroll 2
-    for (int j = 0; j < A.n_rect; ++j) {
-      const T *rc = rects + 8 * j;
-      const T cx = rc[0], cy = rc[1], ux = rc[2], uy = rc[3], vx = rc[4], vy = rc[5];
+      for (int q = 0; q < 32; q += 4) {
+        const T4 x4 = *reinterpret_cast<const T4 *>(bx + c0 + q);
+        const T4 y4 = *reinterpret_cast<const T4 *>(by + c0 + q);
+        const T4 r4 = *reinterpret_cast<const T4 *>(br2 + c0 + q);
+        const T xs[4] = {x4.x, x4.y, x4.z, x4.w}, ys[4] = {y4.x, y4.y, y4.z, y4.w}, rs[4] = {r4.x, r4.y, r4.z, r4.w};
 #pragma unroll
-      for (int r = 0; r < R; ++r) {
-        const T mx = cx - so[r].x, my = cy - so[r].y;
-        const T s = Real<T>::fma(sd[r].x, my, -(sd[r].y * mx));
-        const T cu = Real<T>::fma(sd[r].x, uy, -(sd[r].y * ux));
-        const T cv = Real<T>::fma(sd[r].x, vy, -(sd[r].y * vx));
-        const T ext = Real<T>::abs(cu) + Real<T>::abs(cv);
-        if (Real<T>::abs(s) <= ext) {
-          const int ob = A.rect_obj[j];
-          best[r] = cand_rect(best[r], rc, so[r], sd[r], ob, A.obj_first[ob]);
+        for (int e = 0; e < 4; ++e) {
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            const T t = Real<T>::fma(xs[e], sdy[r], nk[r]);
+            const T c = Real<T>::fma(-ys[e], sdx[r], t);
+            const T disc = Real<T>::fma(-c, c, rs[e]);
+            m[r] = __funnelshift_l(SignBits<T>::get(disc), m[r], 1);
+          }
         }
       }
-    }
-    // curved mirrors (few): tokens straight from global memory
-    for (int j = 0; j < A.n_bez; ++j) {
-      const int ob = A.bez_obj[j];
-      const int tk = A.obj_first[ob];
+      // narrow phase: survivors in ascending object order, so the strict `<` of
+      // tracer.rs:417 resolves equal distances exactly like the in-order loop
 #pragma unroll
       for (int r = 0; r < R; ++r) {
-        if (!alive[r]) continue;
-        best[r] = cand_bezier(best[r], A.toks[tk].p, so[r], sd[r], ob, tk);
-      }
-    }
-    // CSG objects
-    for (int j = 0; j < A.n_csg; ++j) {
-      const int ob = A.csg_obj[j];
-#pragma unroll
-      for (int r = 0; r < R; ++r) {
-        if (!alive[r]) continue;
-        sweep_csg_object(A, ob, so[r], sd[r], best[r]);
+        unsigned cand = ~m[r];
+        while (cand) {
+          const int bit = 31 - __clz(cand);
+          cand ^= 1u << bit;
+          const int j = c0 + 31 - bit;
+          // all hits of object j have t in [tca - rb, tca + rb]: skip it when that lies
+          // behind the origin or beyond the nearest hit found so far
+          const T tca = Real<T>::fma(bx[j], sdx[r], Real<T>::fma(by[j], sdy[r], nkd[r]));
+          const T rb = brb[j];
+          if (tca < -rb || tca - rb > tb[r]) continue;
+          const T before = best[r].d2;
+          best[r] = narrow_phase(A, best[r], j, o[r], d[r]);
+          if (best[r].d2 != before) tb[r] = Real<T>::sqrt(best[r].d2) * (T)1.000001 + A.delta;
+        }
       }
     }
 

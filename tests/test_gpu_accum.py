@@ -120,9 +120,10 @@ def test_string_mod_matches_oracle(oracle, ctx):
         exp = oracle.new_image(W, H)
         n = oracle.accumulate_pairs(exp, oracle.string_mod(sm))
         # chord end points come from sincos on both sides (device vs libm: last-place differences in f64
-        # that survive the cast to f32 only rarely) -> allow a handful of fragments to move
+        # that survive the cast to f32 only rarely) -> allow a handful of fragments to move; the two end
+        # points of a chord have different colours, so the lerped sums differ by fp32 reordering only
         assert abs(int(st.pixel_updates) - int(n)) <= 8, (mode, st.pixel_updates, n)
-        diff = np.nonzero((got != exp).any(axis=2))
+        diff = np.nonzero((np.abs(got - exp) > 1e-6 * np.maximum(1.0, np.abs(exp))).any(axis=2))
         assert len(diff[0]) <= 16, (mode, len(diff[0]))
         assert st.segments == m
     # sub-range + shard semantics: two halves add up to the whole (colours are powers of two: exact)
