@@ -126,8 +126,8 @@ def test_string_mod_matches_oracle(oracle, ctx):
         diff = np.nonzero((np.abs(got - exp) > 1e-6 * np.maximum(1.0, np.abs(exp))).any(axis=2))
         assert len(diff[0]) <= 16, (mode, len(diff[0]))
         assert st.segments == m
-    # sub-range + shard semantics: two halves add up to the whole (colours are powers of two: exact)
-    sm = StringMod(modulo=3001, num=2, mode=StringModMode.Mul, color=(k, k, k, k), modulo_colors=rules)
+    # sub-range + shard semantics: two halves add up to the whole (one colour, a power of two: exact sums)
+    sm = StringMod(modulo=3001, num=2, mode=StringModMode.Mul, color=(k, k, k, k))
     r = Renderer(ctx, W, H)
     r.render_string_mod(sm)
     whole = r.read_rgba32f()

@@ -8,7 +8,7 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.limit --format=csv > g
 for w in $what; do
   case $w in
     tests)
-      timeout 900 python -m pytest tests -m gpu -q -x --durations=15 --timeout=240 --timeout-method=thread \
+      timeout 900 python -m pytest tests -m gpu -q --durations=15 --timeout=240 --timeout-method=thread \
         > gpurun_out/pytest_gpu.log 2>&1
       echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
       timeout 200 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1
@@ -16,6 +16,12 @@ for w in $what; do
     bench)
       timeout 600 python bench.py > gpurun_out/bench.log 2>&1
       timeout 300 python bench.py --precision f64 --rays-per-gpu 8000000 --no-cpu-baseline > gpurun_out/bench_f64.log 2>&1
+      ;;
+    slots)
+      for s in 1 2 4; do
+        LG_TRACE_SLOTS=$s timeout 300 python bench.py --rays-per-gpu 8000000 --steps 2 --no-cpu-baseline > gpurun_out/bench_slots$s.log 2>&1
+      done
+      LG_TRACE_SLOTS=2 timeout 300 python bench.py --precision f64 --rays-per-gpu 4000000 --steps 2 --no-cpu-baseline > gpurun_out/bench_f64_slots2.log 2>&1
       ;;
     prof)
       timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv \
