@@ -185,7 +185,7 @@ def main():
     from light_garden_b200 import abi, scenes
     from light_garden_b200._lib import check, load
     from light_garden_b200.scene import flatten_objects, lights_to_array, trace_params
-    from light_garden_b200.tracer import Context, Renderer, Tracer
+    from light_garden_b200.tracer import Context, Renderer, Tracer, pinned_array
 
     if world != n and world > 1:
         n = world
@@ -224,7 +224,7 @@ def main():
     prm = trace_params(spec.max_bounce, spec.cutoff_color, spec.canvas_bounds)
     larr = lights_to_array(spec.lights)
     h2d = C.sizeof(objs) + C.sizeof(nodes) + C.sizeof(larr) + C.sizeof(prm)
-    frame16 = np.zeros((HEIGHT, WIDTH, 4), dtype=np.float16)
+    frame16 = pinned_array((HEIGHT, WIDTH, 4), np.float16)   # page-locked: the D2H runs at PCIe speed
     d2h = frame16.nbytes
 
     def barrier():

@@ -280,6 +280,11 @@ int32_t lg_stream_handle(lg_ctx *ctx, uint64_t *stream);
 int32_t lg_image_device_ptr(lg_ctx *ctx, uint64_t *ptr);
 /* Kernels launched by this context since creation. */
 int32_t lg_launch_count(lg_ctx *ctx, uint64_t *n);
+/* Page-locked host memory for frames / ray / segment buffers: lg_image_read and the
+ * other copies run at full PCIe speed into it (any host pointer is accepted, pageable
+ * ones go through the driver's staging copy). */
+int32_t lg_host_alloc(size_t bytes, void **out);
+int32_t lg_host_free(void *p);
 
 /* ---- measurement: the roofline denominators BASELINE.md leaves to the builder -- */
 /* FP32 (precision F32) or FP64 (F64) FMA throughput of the device in TFLOP/s,

@@ -118,6 +118,8 @@ PROTOTYPES = {
     "lg_stream_handle": [_ctx, C.POINTER(C.c_uint64)],
     "lg_image_device_ptr": [_ctx, C.POINTER(C.c_uint64)],
     "lg_launch_count": [_ctx, C.POINTER(C.c_uint64)],
+    "lg_host_alloc": [C.c_size_t, C.POINTER(C.c_void_p)],
+    "lg_host_free": [C.c_void_p],
     "lg_measure_fma_peak": [_ctx, C.c_int32, C.c_int32, C.POINTER(C.c_double)],
     "lg_measure_red_peak": [_ctx, C.c_uint64, C.c_int32, C.c_int32, C.POINTER(C.c_double)],
 }

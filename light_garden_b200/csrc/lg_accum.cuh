@@ -37,40 +37,65 @@ __device__ __forceinline__ void red_add_v4(float *p, float a, float b, float c, 
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
-// Rasterise one segment with the whole warp; all arguments are warp-uniform.
-// Returns this lane's number of blended fragments.
-__device__ __forceinline__ unsigned warp_raster(const AccumArgs &A, float ax, float ay, float bx, float by,
-                                                const float ca[4], const float cb[4], unsigned lane) {
+// Per-segment raster setup (ORACLE.md §8.1-8.2), computed by ONE lane for its own segment and
+// parked in shared memory; the warp then walks the 32 parked segments and every lane takes one
+// major-axis step of the current one.  A segment with nothing to draw has i0 >= i1.
+struct RasterSetup {
+  float m0, inv, dn, n0; // major start, 1/(m1 - m0), minor delta, minor start
+  int i0, i1, xmajor, _pad;
+};
+
+__device__ __forceinline__ RasterSetup raster_setup(const AccumArgs &A, float ax, float ay, float bx, float by) {
+  RasterSetup S;
+  S.m0 = S.inv = S.dn = S.n0 = 0.f;
+  S.i0 = S.i1 = 0;
+  S.xmajor = 1;
+  S._pad = 0;
   // vs_main + viewport
   const float x0 = __fmaf_rn(A.m00 * ax, A.hw, A.hw), y0 = __fmaf_rn(-(A.m11 * ay), A.hh, A.hh);
   const float x1 = __fmaf_rn(A.m00 * bx, A.hw, A.hw), y1 = __fmaf_rn(-(A.m11 * by), A.hh, A.hh);
   const float dx = x1 - x0, dy = y1 - y0;
-  if (!(fabsf(dx) < 1e30f) || !(fabsf(dy) < 1e30f)) return 0;
+  if (!(fabsf(dx) < 1e30f) || !(fabsf(dy) < 1e30f)) return S;
   const bool xmajor = fabsf(dx) >= fabsf(dy);
   const float m0 = xmajor ? x0 : y0, m1 = xmajor ? x1 : y1;
   const float n0 = xmajor ? y0 : x0, n1 = xmajor ? y1 : x1;
-  const float dm = m1 - m0, dn = n1 - n0;
-  if (dm == 0.f) return 0;
+  const float dm = m1 - m0;
+  if (dm == 0.f) return S;
   const float lo = m0 < m1 ? m0 : m1, hi = m0 < m1 ? m1 : m0;
-  const int Nmaj = xmajor ? A.W : A.H, Nmin = xmajor ? A.H : A.W;
+  const int Nmaj = xmajor ? A.W : A.H;
   float flo = ceilf(lo - 0.5f), fhi = ceilf(hi - 0.5f);
   if (flo < 0.f) flo = 0.f;
   if (fhi > (float)Nmaj) fhi = (float)Nmaj;
-  if (!(flo < fhi)) return 0;
-  const int i0 = (int)flo, i1 = (int)fhi;
-  const float inv = __fdiv_rn(1.0f, dm);
-  const float dc0 = cb[0] - ca[0], dc1 = cb[1] - ca[1], dc2 = cb[2] - ca[2], dc3 = cb[3] - ca[3];
+  if (!(flo < fhi)) return S;
+  S.m0 = m0;
+  S.inv = __fdiv_rn(1.0f, dm);
+  S.dn = n1 - n0;
+  S.n0 = n0;
+  S.i0 = (int)flo;
+  S.i1 = (int)fhi;
+  S.xmajor = xmajor ? 1 : 0;
+  return S;
+}
+
+// One warp rasterises one parked segment; returns this lane's number of blended fragments.
+template <bool kLerp>
+__device__ __forceinline__ unsigned raster_walk(const AccumArgs &A, const RasterSetup &S, const float4 ca,
+                                                const float4 dc, unsigned lane) {
+  const int Nmin = S.xmajor ? A.H : A.W;
   unsigned n = 0;
-  for (int i = i0 + (int)lane; i < i1; i += 32) {
+  for (int i = S.i0 + (int)lane; i < S.i1; i += 32) {
     const float mc = (float)i + 0.5f;
-    const float s = (mc - m0) * inv;
-    const float nv = __fmaf_rn(s, dn, n0);
+    const float s = (mc - S.m0) * S.inv;
+    const float nv = __fmaf_rn(s, S.dn, S.n0);
     const float fj = floorf(nv);
     if (!(fj >= 0.f) || !(fj < (float)Nmin)) continue;
     const int j = (int)fj;
-    const int px = xmajor ? i : j, py = xmajor ? j : i;
-    const float c0 = __fmaf_rn(s, dc0, ca[0]), c1 = __fmaf_rn(s, dc1, ca[1]);
-    const float c2 = __fmaf_rn(s, dc2, ca[2]), c3 = __fmaf_rn(s, dc3, ca[3]);
+    const int px = S.xmajor ? i : j, py = S.xmajor ? j : i;
+    float c0 = ca.x, c1 = ca.y, c2 = ca.z, c3 = ca.w;
+    if (kLerp) { // fmaf(s, 0, c) == c: single-colour segments skip the arithmetic, not the semantics
+      c0 = __fmaf_rn(s, dc.x, ca.x), c1 = __fmaf_rn(s, dc.y, ca.y);
+      c2 = __fmaf_rn(s, dc.z, ca.z), c3 = __fmaf_rn(s, dc.w, ca.w);
+    }
     // blend: rgb = src*1 + dst*1 ; a = src.a*src.a + dst.a   (mod.rs:57-73)
     red_add_v4(A.img + ((size_t)py * A.W + px) * 4, c0, c1, c2, c3 * c3);
     ++n;
@@ -78,37 +103,52 @@ __device__ __forceinline__ unsigned warp_raster(const AccumArgs &A, float ax, fl
   return n;
 }
 
+struct WarpScratch { // one per warp, in shared memory
+  RasterSetup s[32];
+  float4 ca[32];
+  float4 dc[32];
+};
+constexpr int kWarpsPerBlock = kAccumBlock / 32;
+
 __device__ __forceinline__ void flush_count(const AccumArgs &A, unsigned long long n, unsigned lane) {
   for (int off = 16; off > 0; off >>= 1) n += __shfl_down_sync(0xffffffffu, n, off);
   if (lane == 0 && n) atomicAdd(A.pixel_updates, n);
 }
 
+// walk the m parked segments of this warp
+template <bool kLerp>
+__device__ __forceinline__ unsigned long long walk_parked(const AccumArgs &A, const WarpScratch &W, int m,
+                                                          unsigned lane) {
+  unsigned long long cnt = 0;
+  for (int k = 0; k < m; ++k) {
+    const RasterSetup S = W.s[k]; // broadcast loads
+    if (S.i0 >= S.i1) continue;   // warp-uniform
+    cnt += raster_walk<kLerp>(A, S, W.ca[k], kLerp ? W.dc[k] : make_float4(0.f, 0.f, 0.f, 0.f), lane);
+  }
+  return cnt;
+}
+
 // K4 over the compact device segments written by the trace kernel
 __global__ void __launch_bounds__(kAccumBlock) accumulate_segments_kernel(AccumArgs A, const LgSegment *seg,
                                                                            unsigned long long n) {
+  __shared__ WarpScratch scratch[kWarpsPerBlock];
+  WarpScratch &W = scratch[threadIdx.x >> 5];
   const unsigned lane = threadIdx.x & 31u;
   const unsigned long long warp = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const unsigned long long nwarps = ((unsigned long long)gridDim.x * blockDim.x) >> 5;
   unsigned long long cnt = 0;
   for (unsigned long long base = warp * 32ull; base < n; base += nwarps * 32ull) {
-    // one coalesced 32-byte load per lane, then broadcast segment by segment
-    float4 p = make_float4(0.f, 0.f, 0.f, 0.f), c = p;
+    // one coalesced 32-byte load and one setup per lane
     if (base + lane < n) {
       const float4 *s = reinterpret_cast<const float4 *>(seg + base + lane);
-      p = __ldg(s);
-      c = __ldg(s + 1);
+      const float4 p = __ldg(s);
+      W.s[lane] = raster_setup(A, p.x, p.y, p.z, p.w);
+      W.ca[lane] = __ldg(s + 1);
     }
+    __syncwarp();
     const int m = (int)((n - base) < 32ull ? (n - base) : 32ull);
-    for (int k = 0; k < m; ++k) {
-      const float ax = __shfl_sync(0xffffffffu, p.x, k), ay = __shfl_sync(0xffffffffu, p.y, k);
-      const float bx = __shfl_sync(0xffffffffu, p.z, k), by = __shfl_sync(0xffffffffu, p.w, k);
-      float col[4];
-      col[0] = __shfl_sync(0xffffffffu, c.x, k);
-      col[1] = __shfl_sync(0xffffffffu, c.y, k);
-      col[2] = __shfl_sync(0xffffffffu, c.z, k);
-      col[3] = __shfl_sync(0xffffffffu, c.w, k);
-      cnt += warp_raster(A, ax, ay, bx, by, col, col, lane);
-    }
+    cnt += walk_parked<false>(A, W, m, lane);
+    __syncwarp();
   }
   flush_count(A, cnt, lane);
 }
@@ -116,27 +156,24 @@ __global__ void __launch_bounds__(kAccumBlock) accumulate_segments_kernel(AccumA
 // K4 over host supplied vertex pairs (two colours, f64 positions cast `as f32`)
 __global__ void __launch_bounds__(kAccumBlock) accumulate_pairs_kernel(AccumArgs A, const LgVertexPair *vp,
                                                                         unsigned long long n) {
+  __shared__ WarpScratch scratch[kWarpsPerBlock];
+  WarpScratch &W = scratch[threadIdx.x >> 5];
   const unsigned lane = threadIdx.x & 31u;
   const unsigned long long warp = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const unsigned long long nwarps = ((unsigned long long)gridDim.x * blockDim.x) >> 5;
   unsigned long long cnt = 0;
   for (unsigned long long base = warp * 32ull; base < n; base += nwarps * 32ull) {
-    float v[12];
-#pragma unroll
-    for (int q = 0; q < 12; ++q) v[q] = 0.f;
     if (base + lane < n) {
       const LgVertexPair &s = vp[base + lane];
-      v[0] = (float)s.a[0], v[1] = (float)s.a[1], v[2] = (float)s.b[0], v[3] = (float)s.b[1];
-#pragma unroll
-      for (int q = 0; q < 4; ++q) v[4 + q] = s.color_a[q], v[8 + q] = s.color_b[q];
+      W.s[lane] = raster_setup(A, (float)s.a[0], (float)s.a[1], (float)s.b[0], (float)s.b[1]);
+      const float4 ca = make_float4(s.color_a[0], s.color_a[1], s.color_a[2], s.color_a[3]);
+      W.ca[lane] = ca;
+      W.dc[lane] = make_float4(s.color_b[0] - ca.x, s.color_b[1] - ca.y, s.color_b[2] - ca.z, s.color_b[3] - ca.w);
     }
+    __syncwarp();
     const int m = (int)((n - base) < 32ull ? (n - base) : 32ull);
-    for (int k = 0; k < m; ++k) {
-      float u[12];
-#pragma unroll
-      for (int q = 0; q < 12; ++q) u[q] = __shfl_sync(0xffffffffu, v[q], k);
-      cnt += warp_raster(A, u[0], u[1], u[2], u[3], u + 4, u + 8, lane);
-    }
+    cnt += walk_parked<true>(A, W, m, lane);
+    __syncwarp();
   }
   flush_count(A, cnt, lane);
 }
@@ -194,29 +231,29 @@ __device__ __forceinline__ void sm_color(const StringModArgs &S, unsigned long l
 }
 
 __global__ void __launch_bounds__(kAccumBlock) string_mod_kernel(AccumArgs A, StringModArgs S) {
+  __shared__ WarpScratch scratch[kWarpsPerBlock];
+  WarpScratch &W = scratch[threadIdx.x >> 5];
   const unsigned lane = threadIdx.x & 31u;
   const unsigned long long warp = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const unsigned long long nwarps = ((unsigned long long)gridDim.x * blockDim.x) >> 5;
   unsigned long long cnt = 0;
   for (unsigned long long base = warp * 32ull; base < S.count; base += nwarps * 32ull) {
-    float v[12];
-#pragma unroll
-    for (int q = 0; q < 12; ++q) v[q] = 0.f;
-    if (base + lane < S.count) {
+    if (base + lane < S.count) { // lane = one chord: end points (f64 sincos), colours, raster setup
       const unsigned long long iix = S.first + base + lane;
       const unsigned long long ix = sm_target(S.sm, iix);
-      sm_point(S.sm, iix, v[0], v[1]);
-      sm_point(S.sm, ix, v[2], v[3]);
-      sm_color(S, iix, v + 4);
-      sm_color(S, ix, v + 8);
+      float ax, ay, bx, by, ca[4], cb[4];
+      sm_point(S.sm, iix, ax, ay);
+      sm_point(S.sm, ix, bx, by);
+      sm_color(S, iix, ca);
+      sm_color(S, ix, cb);
+      W.s[lane] = raster_setup(A, ax, ay, bx, by);
+      W.ca[lane] = make_float4(ca[0], ca[1], ca[2], ca[3]);
+      W.dc[lane] = make_float4(cb[0] - ca[0], cb[1] - ca[1], cb[2] - ca[2], cb[3] - ca[3]);
     }
+    __syncwarp();
     const int m = (int)((S.count - base) < 32ull ? (S.count - base) : 32ull);
-    for (int k = 0; k < m; ++k) {
-      float u[12];
-#pragma unroll
-      for (int q = 0; q < 12; ++q) u[q] = __shfl_sync(0xffffffffu, v[q], k);
-      cnt += warp_raster(A, u[0], u[1], u[2], u[3], u + 4, u + 8, lane);
-    }
+    cnt += walk_parked<true>(A, W, m, lane);
+    __syncwarp();
   }
   flush_count(A, cnt, lane);
 }

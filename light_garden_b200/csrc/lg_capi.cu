@@ -122,6 +122,7 @@ struct lg_ctx {
 
   // lights / shard
   std::vector<LgLight> lights;
+  bool have_lights = false; // lg_lights_set was called (possibly with zero lights)
   std::vector<DevLight> dev_lights;
   DevBuf d_lights;
   uint32_t rank = 0, world = 1;
@@ -502,7 +503,7 @@ int read_pixel_counter(lg_ctx *c, uint64_t *out) {
 int need_scene_lights(lg_ctx *c, bool lights) {
   if (!c) return LG_ERR_INVALID;
   if (!c->have_scene) return fail(c, LG_ERR_STATE, "lg_scene_set has not been called");
-  if (lights && c->dev_lights.empty()) return fail(c, LG_ERR_STATE, "lg_lights_set has not been called");
+  if (lights && !c->have_lights) return fail(c, LG_ERR_STATE, "lg_lights_set has not been called");
   return LG_OK;
 }
 int need_image(lg_ctx *c) {
@@ -609,6 +610,7 @@ int32_t lg_lights_set(lg_ctx *c, const LgLight *lights, uint32_t n) {
     if (lights[i].kind < LG_LIGHT_POINT || lights[i].kind > LG_LIGHT_SPOT) return fail(c, LG_ERR_INVALID, "light kind");
   LG_CUDA(c, cudaSetDevice(c->device));
   c->lights.assign(lights, lights + n);
+  c->have_lights = true;
   rebuild_dev_lights(c);
   int rc = upload(c, c->d_lights, c->dev_lights);
   if (rc) return rc;
@@ -1039,6 +1041,19 @@ int32_t lg_image_device_ptr(lg_ctx *c, uint64_t *p) {
   if (!c || !p) return LG_ERR_INVALID;
   *p = (uint64_t)(uintptr_t)c->img.p;
   return LG_OK;
+}
+int32_t lg_host_alloc(size_t bytes, void **out) {
+  if (!out || bytes == 0) return LG_ERR_INVALID;
+  *out = nullptr;
+  if (cudaHostAlloc(out, bytes, cudaHostAllocDefault) != cudaSuccess) {
+    cudaGetLastError();
+    return LG_ERR_NOMEM;
+  }
+  return LG_OK;
+}
+int32_t lg_host_free(void *p) {
+  if (!p) return LG_ERR_INVALID;
+  return cudaFreeHost(p) == cudaSuccess ? LG_OK : LG_ERR_CUDA;
 }
 int32_t lg_launch_count(lg_ctx *c, uint64_t *n) {
   if (!c || !n) return LG_ERR_INVALID;

@@ -8,6 +8,7 @@
 // world-space leaves: the Logic nodes' local frames (origin + Rotation2,
 // default.ron:20-29) are composed in f64 here, once, instead of per ray.
 #pragma once
+#include <algorithm>
 #include <cmath>
 #include <cstdint>
 #include <string>
@@ -181,39 +182,62 @@ inline int32_t lower_scene(const LgObject *objects, uint32_t n_obj, const LgGeoN
   hs.bound = bound > 0 ? bound : 1.0;
   // overlap candidates: conservative (AABBs inflated by 1e-4 of the scene bound,
   // far above any rounding of a hit point) so the scan result is unchanged.
+  // Sweep and prune along x instead of all pairs: O(n log n + overlaps).
   const double pad = 1e-4 * hs.bound;
-  hs.ovl_start.assign(n_obj + 1, 0);
+  struct Box {
+    double x0, y0, x1, y1;
+  };
+  std::vector<Box> hull(n_obj); // everything a hit point on object i can lie on: all leaves
   for (uint32_t i = 0; i < n_obj; ++i) {
-    hs.ovl_start[i] = (int32_t)hs.ovl_list.size();
     const HostObj &a = hs.objs[i];
-    if (!a.has_material) continue; // the scan only runs for material hits (tracer.rs:428)
-    // bounding box of everything a hit point on object i can lie on: all leaves
-    double bx0 = 1e300, by0 = 1e300, bx1 = -1e300, by1 = -1e300;
+    Box bx{1e300, 1e300, -1e300, -1e300};
     for (int k = 0; k < a.count; ++k) {
       const HostTok &t = hs.toks[a.first + k];
       if (t.kind == 4) continue;
       if (t.kind == 0) {
-        bx0 = std::fmin(bx0, t.p[0] - t.p[2]), bx1 = std::fmax(bx1, t.p[0] + t.p[2]);
-        by0 = std::fmin(by0, t.p[1] - t.p[2]), by1 = std::fmax(by1, t.p[1] + t.p[2]);
+        bx.x0 = std::fmin(bx.x0, t.p[0] - t.p[2]), bx.x1 = std::fmax(bx.x1, t.p[0] + t.p[2]);
+        bx.y0 = std::fmin(bx.y0, t.p[1] - t.p[2]), bx.y1 = std::fmax(bx.y1, t.p[1] + t.p[2]);
       } else if (t.kind == 1) {
         double ex = std::fabs(t.p[2]) + std::fabs(t.p[4]), ey = std::fabs(t.p[3]) + std::fabs(t.p[5]);
-        bx0 = std::fmin(bx0, t.p[0] - ex), bx1 = std::fmax(bx1, t.p[0] + ex);
-        by0 = std::fmin(by0, t.p[1] - ey), by1 = std::fmax(by1, t.p[1] + ey);
+        bx.x0 = std::fmin(bx.x0, t.p[0] - ex), bx.x1 = std::fmax(bx.x1, t.p[0] + ex);
+        bx.y0 = std::fmin(bx.y0, t.p[1] - ey), bx.y1 = std::fmax(bx.y1, t.p[1] + ey);
       } else {
         int np = t.kind == 2 ? 2 : 4;
         for (int q = 0; q < np; ++q) {
-          bx0 = std::fmin(bx0, t.p[2 * q]), bx1 = std::fmax(bx1, t.p[2 * q]);
-          by0 = std::fmin(by0, t.p[2 * q + 1]), by1 = std::fmax(by1, t.p[2 * q + 1]);
+          bx.x0 = std::fmin(bx.x0, t.p[2 * q]), bx.x1 = std::fmax(bx.x1, t.p[2 * q]);
+          bx.y0 = std::fmin(bx.y0, t.p[2 * q + 1]), bx.y1 = std::fmax(bx.y1, t.p[2 * q + 1]);
         }
       }
     }
-    for (uint32_t j = 0; j < n_obj; ++j) {
-      if (j == i) continue;
-      const HostObj &b = hs.objs[j];
-      if (!b.has_material || !b.can_contain) continue;
-      if (b.aabb[0] - pad > bx1 || b.aabb[2] + pad < bx0 || b.aabb[1] - pad > by1 || b.aabb[3] + pad < by0) continue;
-      hs.ovl_list.push_back((int32_t)j);
+    hull[i] = bx;
+  }
+  // i lists j  <=>  i has a material (the scan only runs for material hits, tracer.rs:428), j has a
+  // material and can contain a point, and hull(i) meets j's padded containing box
+  std::vector<uint32_t> order;
+  for (uint32_t i = 0; i < n_obj; ++i)
+    if (hs.objs[i].has_material) order.push_back(i);
+  std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return hull[a].x0 < hull[b].x0; });
+  std::vector<std::vector<int32_t>> lists(n_obj);
+  auto lists_j = [&](uint32_t i, uint32_t j) {
+    const HostObj &b = hs.objs[j];
+    if (!b.can_contain) return false;
+    const Box &h = hull[i];
+    return !(b.aabb[0] - pad > h.x1 || b.aabb[2] + pad < h.x0 || b.aabb[1] - pad > h.y1 || b.aabb[3] + pad < h.y0);
+  };
+  for (size_t a = 0; a < order.size(); ++a) {
+    const uint32_t i = order[a];
+    for (size_t b = a + 1; b < order.size(); ++b) {
+      const uint32_t j = order[b];
+      if (hull[j].x0 - pad > hull[i].x1 + pad) break; // hull(j) contains j's containing box: nothing further overlaps
+      if (lists_j(i, j)) lists[i].push_back((int32_t)j);
+      if (lists_j(j, i)) lists[j].push_back((int32_t)i);
     }
+  }
+  hs.ovl_start.assign(n_obj + 1, 0);
+  for (uint32_t i = 0; i < n_obj; ++i) {
+    hs.ovl_start[i] = (int32_t)hs.ovl_list.size();
+    std::sort(lists[i].begin(), lists[i].end());
+    hs.ovl_list.insert(hs.ovl_list.end(), lists[i].begin(), lists[i].end());
   }
   hs.ovl_start[n_obj] = (int32_t)hs.ovl_list.size();
   return LG_OK;

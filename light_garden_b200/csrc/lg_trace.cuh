@@ -446,7 +446,7 @@ __global__ void __launch_bounds__(kTraceBlock, (R >= 4 || sizeof(T) == 8) ? 2 : 
       unsigned m[R];
 #pragma unroll
       for (int r = 0; r < R; ++r) m[r] = 0u;
-#pragma unroll 2
+#pragma unroll 4
       for (int q = 0; q < 32; q += 4) {
         const T4 x4 = *reinterpret_cast<const T4 *>(bx + c0 + q);
         const T4 y4 = *reinterpret_cast<const T4 *>(by + c0 + q);

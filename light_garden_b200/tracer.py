@@ -47,6 +47,33 @@ class Context:
         return n.value
 
 
+def pinned_array(shape, dtype):
+    """numpy array over page-locked host memory (lg_host_alloc); keeps the allocation alive with the array."""
+    lib = load()
+    dt = np.dtype(dtype)
+    n = int(np.prod(shape)) * dt.itemsize
+    p = C.c_void_p()
+    check(None, lib.lg_host_alloc(n, C.byref(p)))
+    buf = (C.c_ubyte * n).from_address(p.value)
+    arr = np.frombuffer(buf, dtype=dt).reshape(shape)
+
+    class _Owner:
+        def __init__(self, ptr):
+            self.ptr = ptr
+
+        def __del__(self):
+            try:
+                lib.lg_host_free(self.ptr)
+            except Exception:
+                pass
+
+    _PINNED[id(buf)] = (buf, _Owner(p))
+    return arr
+
+
+_PINNED = {}
+
+
 def sort_segments(seg, tags, f64=None):
     """Device order -> the reference's order: light -> ray -> generation -> queue order."""
     order = np.lexsort((tags["path"], tags["generation"], tags["ray"]))
@@ -246,7 +273,8 @@ class Renderer:
         self.ctx.call("lg_image_read", abi.LG_RGBA32F, abi.array_ptr(out), 0)
         return out
 
-    def read_rgba16f(self):
-        out = np.zeros((self.height, self.width, 4), dtype=np.float16)
+    def read_rgba16f(self, out=None):
+        if out is None:
+            out = np.zeros((self.height, self.width, 4), dtype=np.float16)
         self.ctx.call("lg_image_read", abi.LG_RGBA16F, abi.array_ptr(out), 0)
         return out
