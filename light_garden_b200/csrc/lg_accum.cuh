@@ -115,15 +115,23 @@ __device__ __forceinline__ void flush_count(const AccumArgs &A, unsigned long lo
   if (lane == 0 && n) atomicAdd(A.pixel_updates, n);
 }
 
-// walk the m parked segments of this warp
+// walk the m parked segments of this warp; the next segment's parameters are fetched from shared
+// memory while the current one is being rasterised (hides the LDS latency between short segments)
 template <bool kLerp>
 __device__ __forceinline__ unsigned long long walk_parked(const AccumArgs &A, const WarpScratch &W, int m,
                                                           unsigned lane) {
   unsigned long long cnt = 0;
+  if (m <= 0) return 0;
+  RasterSetup S = W.s[0]; // broadcast loads
+  float4 ca = W.ca[0];
+  float4 dc = kLerp ? W.dc[0] : make_float4(0.f, 0.f, 0.f, 0.f);
   for (int k = 0; k < m; ++k) {
-    const RasterSetup S = W.s[k]; // broadcast loads
-    if (S.i0 >= S.i1) continue;   // warp-uniform
-    cnt += raster_walk<kLerp>(A, S, W.ca[k], kLerp ? W.dc[k] : make_float4(0.f, 0.f, 0.f, 0.f), lane);
+    const int kn = k + 1 < m ? k + 1 : k;
+    const RasterSetup Sn = W.s[kn];
+    const float4 can = W.ca[kn];
+    const float4 dcn = kLerp ? W.dc[kn] : dc;
+    if (S.i0 < S.i1) cnt += raster_walk<kLerp>(A, S, ca, dc, lane); // warp-uniform condition
+    S = Sn, ca = can, dc = dcn;
   }
   return cnt;
 }
@@ -137,13 +145,22 @@ __global__ void __launch_bounds__(kAccumBlock) accumulate_segments_kernel(AccumA
   const unsigned long long warp = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const unsigned long long nwarps = ((unsigned long long)gridDim.x * blockDim.x) >> 5;
   unsigned long long cnt = 0;
-  for (unsigned long long base = warp * 32ull; base < n; base += nwarps * 32ull) {
-    // one coalesced 32-byte load and one setup per lane
-    if (base + lane < n) {
-      const float4 *s = reinterpret_cast<const float4 *>(seg + base + lane);
-      const float4 p = __ldg(s);
+  // the next batch's 32-byte segment is loaded while the current batch is rasterised
+  float4 p = make_float4(0.f, 0.f, 0.f, 0.f), c = p;
+  unsigned long long base = warp * 32ull;
+  if (base + lane < n) {
+    const float4 *s = reinterpret_cast<const float4 *>(seg + base + lane);
+    p = __ldg(s), c = __ldg(s + 1);
+  }
+  for (; base < n; base += nwarps * 32ull) {
+    if (base + lane < n) { // one raster setup per lane
       W.s[lane] = raster_setup(A, p.x, p.y, p.z, p.w);
-      W.ca[lane] = __ldg(s + 1);
+      W.ca[lane] = c;
+    }
+    const unsigned long long nb = base + nwarps * 32ull;
+    if (nb + lane < n) {
+      const float4 *s = reinterpret_cast<const float4 *>(seg + nb + lane);
+      p = __ldg(s), c = __ldg(s + 1);
     }
     __syncwarp();
     const int m = (int)((n - base) < 32ull ? (n - base) : 32ull);

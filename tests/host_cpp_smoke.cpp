@@ -1,0 +1,48 @@
+// tests/host_cpp_smoke.cpp — the C++ host mirror (light_garden_b200/host/lg_tracer.hpp) driving the C ABI:
+// builds default.ron's scene through the reference's constructor names, traces it, renders it, prints a digest
+// that tests/test_host_cpp.py compares with the Python host layer.  Needs a GPU.
+#include <cstdio>
+
+#include "../light_garden_b200/host/lg_tracer.hpp"
+
+int main() {
+  try {
+    const double aspect = (double)(480.0f / 270.0f);
+    lg::Tracer t(lg::Rect::from_tlbr(1., -aspect, -1., aspect));
+    lg::Object lens = lg::Object::new_lens({-0.022772240638732733, -0.09999999999999998}, 2.0, 3.8);
+    lens.geo.rot = {0.00000000000000006123233995736766, -1.0, 1.0, 0.00000000000000006123233995736766};
+    lens.material_opt = lg::Material{1.05};
+    t.push_object(lens);
+    t.push_object(lg::Object::new_curved_mirror({lg::P2{-0.622772240638733, 0.40000000000000013}, lg::P2{-0.3227722406387328, 0.8},
+                                                  lg::P2{0.2772277593612673, 0.8}, lg::P2{0.5772277593612682, 0.40000000000000013}}));
+    lg::Object rect = lg::Object::new_rect({-0.022772240638732733, -0.5}, 0.40000000000000036, 0.3999999999999999);
+    rect.material_opt = lg::Material{1.73};
+    t.push_object(rect);
+    t.push_light(lg::Light::point({-0.022772240638732733, -0.5}, 5000, {0.009721218f, 0.009721218f, 0.009721218f, 0.011764706f}));
+    t.push_light(lg::Light::spot({1.0772277593612674, -0.09999999999999998}, 0.17453292519943295,
+                                 {-0.9999922358557027, 0.003940587305547067}, 1000,
+                                 {0.0036765062f, 0.020288562f, 0.016807375f, 0.03529412f}));
+    auto lines = t.trace_all();
+    double sx = 0, sy = 0, sc = 0;
+    for (auto &v : lines) sx += v.first.x, sy += v.first.y, sc += v.second[0] + v.second[1] + v.second[2];
+    std::printf("vertices %zu segments %llu ray_steps %llu\n", lines.size(), (unsigned long long)t.last_stats.segments,
+                (unsigned long long)t.last_stats.ray_steps);
+    std::printf("checksum %.9e %.9e %.9e\n", sx, sy, sc);
+    // error behaviour: the reference panics on a bad scene, here the error crosses the boundary as a status
+    lg::Tracer bad(lg::Rect::from_tlbr(1, -1, -1, 1));
+    lg::Object neg = lg::Object::new_circle({0, 0}, 0.5);
+    neg.material_opt = lg::Material{-1.0};
+    bad.push_object(neg);
+    try {
+      bad.trace_all();
+      std::printf("error NOT raised\n");
+      return 1;
+    } catch (const lg::Error &e) {
+      std::printf("error %d %s\n", e.code, e.what());
+    }
+    return 0;
+  } catch (const lg::Error &e) {
+    std::printf("FAILED %d %s\n", e.code, e.what());
+    return 2;
+  }
+}
