@@ -289,6 +289,58 @@ template <> struct Vec4<double> {
   typedef double4 type;
 };
 
+// Broad phase for 4 consecutive table entries and one ray slot: appends 4 "certainly missed" bits to m.
+// cr = cross(c - o, d) = cx*dy - cy*dx - cross(o, d); the object can only be hit if cr^2 <= (radius + margin)^2.
+template <class T> struct Broad {
+  static __device__ __forceinline__ unsigned test4(const typename Vec4<T>::type &x4, const typename Vec4<T>::type &y4,
+                                                   const typename Vec4<T>::type &r4, T sdx, T sdy, T nk, unsigned m) {
+    const T xs[4] = {x4.x, x4.y, x4.z, x4.w}, ys[4] = {y4.x, y4.y, y4.z, y4.w}, rs[4] = {r4.x, r4.y, r4.z, r4.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const T t = Real<T>::fma(xs[e], sdy, nk);
+      const T c = Real<T>::fma(-ys[e], sdx, t);
+      const T disc = Real<T>::fma(-c, c, rs[e]);
+      m = __funnelshift_l(SignBits<T>::get(disc), m, 1);
+    }
+    return m;
+  }
+};
+// f32: Blackwell's packed fma.rn.f32x2 (SASS FFMA2) does two tests per instruction.  Each half is an
+// IEEE fused multiply-add, so the bits are those of the scalar form.
+__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(unsigned long long v, float &lo, float &hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+template <> struct Broad<float> {
+  static __device__ __forceinline__ unsigned pair(float x0, float x1, float y0, float y1, float r0, float r1, float sdx,
+                                                  float sdy, float nk, unsigned m) {
+    const unsigned long long t = fma2(pack2(x0, x1), pack2(sdy, sdy), pack2(nk, nk));
+    const unsigned long long c = fma2(pack2(-y0, -y1), pack2(sdx, sdx), t);
+    float c0, c1;
+    unpack2(c, c0, c1);
+    const unsigned long long d = fma2(pack2(-c0, -c1), c, pack2(r0, r1));
+    float d0, d1;
+    unpack2(d, d0, d1);
+    m = __funnelshift_l(__float_as_uint(d0), m, 1);
+    return __funnelshift_l(__float_as_uint(d1), m, 1);
+  }
+  static __device__ __forceinline__ unsigned test4(const float4 &x4, const float4 &y4, const float4 &r4, float sdx,
+                                                   float sdy, float nk, unsigned m) {
+    m = pair(x4.x, x4.y, y4.x, y4.y, r4.x, r4.y, sdx, sdy, nk, m);
+    return pair(x4.z, x4.w, y4.z, y4.w, r4.z, r4.w, sdx, sdy, nk, m);
+  }
+};
+
+
 template <class T> __device__ __forceinline__ bool contains_object(const TraceArgs<T> &A, int obj, V2<T> p) {
   return contains_range(A.toks + A.obj_first[obj], 0, A.obj_count[obj] - 1, p);
 }
@@ -451,17 +503,8 @@ __global__ void __launch_bounds__(kTraceBlock, (R >= 4 || sizeof(T) == 8) ? 2 : 
         const T4 x4 = *reinterpret_cast<const T4 *>(bx + c0 + q);
         const T4 y4 = *reinterpret_cast<const T4 *>(by + c0 + q);
         const T4 r4 = *reinterpret_cast<const T4 *>(br2 + c0 + q);
-        const T xs[4] = {x4.x, x4.y, x4.z, x4.w}, ys[4] = {y4.x, y4.y, y4.z, y4.w}, rs[4] = {r4.x, r4.y, r4.z, r4.w};
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-#pragma unroll
-          for (int r = 0; r < R; ++r) {
-            const T t = Real<T>::fma(xs[e], sdy[r], nk[r]);
-            const T c = Real<T>::fma(-ys[e], sdx[r], t);
-            const T disc = Real<T>::fma(-c, c, rs[e]);
-            m[r] = __funnelshift_l(SignBits<T>::get(disc), m[r], 1);
-          }
-        }
+        for (int r = 0; r < R; ++r) m[r] = Broad<T>::test4(x4, y4, r4, sdx[r], sdy[r], nk[r], m[r]);
       }
       // narrow phase: survivors in ascending object order, so the strict `<` of
       // tracer.rs:417 resolves equal distances exactly like the in-order loop
