@@ -48,7 +48,12 @@ def test_two_device_render_equals_one_device(oracle):
         r1 = Renderer(one, spec.width, spec.height)
         r1.render(t)
         ref = r1.read_rgba32f()
-        assert (np.abs(total - ref) <= 1e-5 * np.maximum(1.0, np.abs(ref))).all()
+        # same fragments, different fp32 summation trees (two partial images + ncclReduce vs one image): hot pixels
+        # next to a light sum ~1e4 fragments, so the stated bound is 1e-4 relative to the pixel value
+        assert np.array_equal(total[..., 3] > 1, ref[..., 3] > 1)
+        rel = np.abs(total - ref) / np.maximum(1.0, np.abs(ref))
+        assert rel.max() < 1e-4, rel.max()
+        assert np.median(rel) < 1e-7
         one.close()
     finally:
         for c in ctxs:

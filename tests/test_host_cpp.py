@@ -46,4 +46,4 @@ def test_cpp_host_mirror_matches_python_host(tmp_path, product_lib):
     sx = float(seg["a"][:, 0].astype(np.float64).sum() + seg["b"][:, 0].astype(np.float64).sum())
     sy = float(seg["a"][:, 1].astype(np.float64).sum() + seg["b"][:, 1].astype(np.float64).sum())
     sc = 2 * float(seg["color"][:, :3].astype(np.float64).sum())
-    np.testing.assert_allclose(cs, [sx, sy, sc], rtol=1e-9)
+    np.testing.assert_allclose(cs, [sx, sy, sc], rtol=1e-7)   # the digest is printed with 10 significant digits
