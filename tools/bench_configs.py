@@ -1,0 +1,82 @@
+#!/usr/bin/env python
+"""Times BASELINE.json configs C1..C4 at their full sizes on one GPU (bench.py covers C5, the headline):
+C1 default.ron 1 M rays 1920x1080; C2 mirror cavity 4 M rays x 64 bounces; C3 256 CSG/refractive objects 16 M rays;
+C4 string mod 10 M chords at 4096x4096 (no tracing).  One JSON line per config to stdout.
+    python tools/bench_configs.py [--precision f32|f64] [--repeat 3]
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--precision", default="f32")
+    ap.add_argument("--repeat", type=int, default=3)
+    ap.add_argument("--scale", type=float, default=1.0, help="scale ray / chord counts (smoke runs)")
+    args = ap.parse_args()
+    from light_garden_b200 import abi, scenes
+    from light_garden_b200.tracer import Context, Renderer, Tracer
+    prec = abi.LG_PRECISION_F64 if args.precision == "f64" else abi.LG_PRECISION_F32
+    k = args.scale
+    specs = [
+        ("C1", scenes.c1_default(total_rays=int(1_000_000 * k), width=1920, height=1080)),
+        ("C2", scenes.c2_cavity(total_rays=int(4_000_000 * k), max_bounce=64, width=1920, height=1080)),
+        ("C3", scenes.c3_refraction(total_rays=int(16_000_000 * k), width=1920, height=1080)),
+    ]
+    ctx = Context(0, prec)
+    ctx.call("lg_segment_capacity_set", 512 << 20)
+    for name, spec in specs:
+        t = spec.apply(Tracer(spec.canvas_bounds, ctx=ctx))
+        r = Renderer(ctx, spec.width, spec.height)
+        best = None
+        for it in range(args.repeat + 1):
+            r.clear()
+            t0 = time.perf_counter()
+            st = r.render(t)
+            dt = time.perf_counter() - t0
+            if it == 0:
+                continue  # warm-up
+            if best is None or dt < best[0]:
+                best = (dt, st.as_dict())
+        dt, st = best
+        print(json.dumps({
+            "config": name, "scene": spec.name, "precision": args.precision, "objects": len(spec.objects),
+            "primary_rays": st["primary_rays"], "max_bounce": spec.max_bounce, "image": [spec.width, spec.height],
+            "wall_ms": dt * 1e3, "trace_ms": st["trace_ms"], "accumulate_ms": st["accumulate_ms"],
+            "rays_per_s": st["primary_rays"] / dt, "ray_steps": st["ray_steps"], "segments": st["segments"],
+            "segments_per_s_in_kernel": st["segments"] / max(1e-9, st["accumulate_ms"] * 1e-3),
+            "ray_object_tests_per_s_in_kernel": st["object_tests"] / max(1e-9, st["trace_ms"] * 1e-3),
+            "pixel_updates": st["pixel_updates"],
+            "pixel_updates_per_s_in_kernel": st["pixel_updates"] / max(1e-9, st["accumulate_ms"] * 1e-3),
+            "launches": st["trace_launches"] + st["accumulate_launches"]}), flush=True)
+    # C4: string mod, pure accumulation
+    for num in (2, 7919):
+        sm = scenes.c4_string_mod(modulo=int(10_000_000 * k), num=num)
+        r = Renderer(ctx, 4096, 4096)
+        best = None
+        for it in range(args.repeat + 1):
+            r.clear()
+            t0 = time.perf_counter()
+            st = r.render_string_mod(sm)
+            dt = time.perf_counter() - t0
+            if it and (best is None or dt < best[0]):
+                best = (dt, st.as_dict())
+        dt, st = best
+        print(json.dumps({
+            "config": "C4", "scene": f"string mod modulo={sm.modulo} num={num} Mul", "image": [4096, 4096],
+            "chords": st["segments"], "wall_ms": dt * 1e3, "accumulate_ms": st["accumulate_ms"],
+            "chords_per_s": st["segments"] / dt, "pixel_updates": st["pixel_updates"],
+            "pixel_updates_per_s_in_kernel": st["pixel_updates"] / max(1e-9, st["accumulate_ms"] * 1e-3),
+            "algorithmic_GBps": 16.0 * st["pixel_updates"] / max(1e-9, st["accumulate_ms"] * 1e-3) / 1e9}), flush=True)
+    ctx.close()
+
+
+if __name__ == "__main__":
+    main()

@@ -17,6 +17,16 @@ for w in $what; do
       timeout 600 python bench.py > gpurun_out/bench.log 2>&1
       timeout 300 python bench.py --precision f64 --rays-per-gpu 8000000 --no-cpu-baseline > gpurun_out/bench_f64.log 2>&1
       ;;
+    configs)
+      timeout 900 python tools/bench_configs.py > gpurun_out/configs.jsonl 2> gpurun_out/configs.err
+      timeout 900 python tools/bench_configs.py --precision f64 > gpurun_out/configs_f64.jsonl 2>> gpurun_out/configs.err
+      ;;
+    sanitize)
+      timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 python __graft_entry__.py smoke > gpurun_out/sanitize_memcheck.log 2>&1
+      echo "memcheck rc=$?" >> gpurun_out/sanitize_memcheck.log
+      timeout 900 compute-sanitizer --tool racecheck --error-exitcode 9 python __graft_entry__.py smoke > gpurun_out/sanitize_racecheck.log 2>&1
+      echo "racecheck rc=$?" >> gpurun_out/sanitize_racecheck.log
+      ;;
     slots)
       for s in 1 2 4; do
         LG_TRACE_SLOTS=$s timeout 300 python bench.py --rays-per-gpu 8000000 --steps 2 --no-cpu-baseline > gpurun_out/bench_slots$s.log 2>&1
