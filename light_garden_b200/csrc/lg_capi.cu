@@ -114,7 +114,7 @@ struct lg_ctx {
   HostScene hs;
   int n_obj = 0, n_pad = 0;
   unsigned bounds_bytes = 0;
-  DevBuf bounds, perm, toks, obj_first, obj_count, obj_n, ovl_start, ovl_list;
+  DevBuf bounds, toks, obj_first, obj_count, obj_n, ovl_start, ovl_list;
   double canvas[8] = {0};
   std::vector<double> bound_c; // per object: bounding circle cx, cy, radius (f64)
   double coord_bound = 0;      // max |coordinate| the broad-phase margin was built for
@@ -297,46 +297,19 @@ template <class T> int upload_bounds(lg_ctx *c, double B) {
   const int n_pad = (int)((n + 31) / 32 * 32);
   const double eps = std::numeric_limits<T>::epsilon();
   const double delta = 64.0 * eps * B;
-  // table order: Morton curve over the bounding-circle centres (objects a ray passes are then
-  // neighbours in the table and fall into few 32-entry chunks)
-  std::vector<int> perm(n_pad, 0);
-  {
-    double x0 = 1e300, y0 = 1e300, x1 = -1e300, y1 = -1e300;
-    for (size_t i = 0; i < n; ++i) {
-      x0 = std::fmin(x0, c->bound_c[3 * i]), x1 = std::fmax(x1, c->bound_c[3 * i]);
-      y0 = std::fmin(y0, c->bound_c[3 * i + 1]), y1 = std::fmax(y1, c->bound_c[3 * i + 1]);
-    }
-    const double sx = x1 > x0 ? 65535.0 / (x1 - x0) : 0.0, sy = y1 > y0 ? 65535.0 / (y1 - y0) : 0.0;
-    auto spread = [](uint32_t v) {
-      uint64_t x = v & 0xffffu;
-      x = (x | (x << 8)) & 0x00ff00ffu;
-      x = (x | (x << 4)) & 0x0f0f0f0fu;
-      x = (x | (x << 2)) & 0x33333333u;
-      x = (x | (x << 1)) & 0x55555555u;
-      return x;
-    };
-    std::vector<std::pair<uint64_t, int>> keys(n);
-    for (size_t i = 0; i < n; ++i) {
-      const uint32_t qx = (uint32_t)((c->bound_c[3 * i] - x0) * sx), qy = (uint32_t)((c->bound_c[3 * i + 1] - y0) * sy);
-      keys[i] = {spread(qx) | (spread(qy) << 1), (int)i};
-    }
-    std::sort(keys.begin(), keys.end());
-    for (size_t i = 0; i < n; ++i) perm[i] = keys[i].second;
-  }
   std::vector<T> tab(4 * (size_t)n_pad);
   T *bx = tab.data(), *by = bx + n_pad, *br2 = by + n_pad, *brb = br2 + n_pad;
-  for (int s = 0; s < n_pad; ++s) {
-    if ((size_t)s < n) {
-      const int i = perm[s];
-      bx[s] = (T)c->bound_c[3 * i];
-      by[s] = (T)c->bound_c[3 * i + 1];
+  for (int i = 0; i < n_pad; ++i) {
+    if ((size_t)i < n) {
+      bx[i] = (T)c->bound_c[3 * i];
+      by[i] = (T)c->bound_c[3 * i + 1];
       const double rb = (c->bound_c[3 * i + 2] * (1.0 + 1e-6) + delta) * (1.0 + 4 * eps);
-      brb[s] = std::nextafter((T)rb, std::numeric_limits<T>::max());
-      br2[s] = std::nextafter((T)((double)brb[s] * (double)brb[s] * (1.0 + 4 * eps)), std::numeric_limits<T>::max());
+      brb[i] = std::nextafter((T)rb, std::numeric_limits<T>::max());
+      br2[i] = std::nextafter((T)((double)brb[i] * (double)brb[i] * (1.0 + 4 * eps)), std::numeric_limits<T>::max());
     } else {
-      bx[s] = by[s] = (T)0;
-      br2[s] = (T)-1; // never a candidate
-      brb[s] = (T)0;
+      bx[i] = by[i] = (T)0;
+      br2[i] = (T)-1; // never a candidate
+      brb[i] = (T)0;
     }
   }
   c->n_pad = n_pad;
@@ -345,7 +318,6 @@ template <class T> int upload_bounds(lg_ctx *c, double B) {
   c->delta = delta;
   int rc = upload(c, c->bounds, tab);
   if (rc) return rc;
-  if ((rc = upload(c, c->perm, perm))) return rc;
   LG_CUDA(c, cudaStreamSynchronize(c->stream));
   return LG_OK;
 }
@@ -393,7 +365,6 @@ void rebuild_dev_lights(lg_ctx *c) {
 
 template <class T> void fill_args(lg_ctx *c, TraceArgs<T> &A) {
   A.bounds = (const T *)c->bounds.p;
-  A.perm = (const int *)c->perm.p;
   A.bounds_bytes = c->bounds_bytes;
   A.n_pad = c->n_pad;
   A.delta = (T)c->delta;
@@ -596,7 +567,7 @@ int32_t lg_destroy(lg_ctx *c) {
   if (!c) return LG_ERR_INVALID;
   cudaSetDevice(c->device);
   if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
-  DevBuf *bufs[] = {&c->bounds,    &c->perm,     &c->toks,
+  DevBuf *bufs[] = {&c->bounds,    &c->toks,
                     &c->obj_first, &c->obj_count, &c->obj_n,    &c->ovl_start, &c->ovl_list, &c->d_lights, &c->seg,
                     &c->tags,      &c->seg64,    &c->ctr,      &c->stack,   &c->rays,     &c->img,     &c->img16,
                     &c->pixctr};

@@ -63,7 +63,6 @@ template <class T> struct TraceArgs {
   // (radius + margin)^2, radius + margin.  n_pad is a multiple of 32; padding
   // entries have a negative squared radius and can never become candidates.
   const T *bounds;
-  const int *perm; // table slot -> object index (slots follow a Morton curve so a ray's candidates cluster)
   unsigned int bounds_bytes;
   int n_pad;
   T delta; // rounding margin of the broad phase (64 eps x coordinate bound)
@@ -507,8 +506,8 @@ __global__ void __launch_bounds__(kTraceBlock, (R >= 4 || sizeof(T) == 8) ? 2 : 
 #pragma unroll
         for (int r = 0; r < R; ++r) m[r] = Broad<T>::test4(x4, y4, r4, sdx[r], sdy[r], nk[r], m[r]);
       }
-      // narrow phase on the survivors; take() resolves equal distances towards the lower object
-      // index, which is what the in-order loop with the strict `<` of tracer.rs:417 yields
+      // narrow phase: survivors in ascending object order, so the strict `<` of
+      // tracer.rs:417 resolves equal distances exactly like the in-order loop
 #pragma unroll
       for (int r = 0; r < R; ++r) {
         unsigned cand = ~m[r];
@@ -522,7 +521,7 @@ __global__ void __launch_bounds__(kTraceBlock, (R >= 4 || sizeof(T) == 8) ? 2 : 
           const T rb = brb[j];
           if (tca < -rb || tca - rb > tb[r]) continue;
           const T before = best[r].d2;
-          best[r] = narrow_phase(A, best[r], A.perm[j], o[r], d[r]);
+          best[r] = narrow_phase(A, best[r], j, o[r], d[r]);
           if (best[r].d2 != before) tb[r] = Real<T>::sqrt(best[r].d2) * (T)1.000001 + A.delta;
         }
       }
