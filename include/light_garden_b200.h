@@ -217,6 +217,10 @@ int32_t lg_lights_set(lg_ctx *ctx, const LgLight *lights, uint32_t n_lights);
 int32_t lg_shard_set(lg_ctx *ctx, uint32_t rank, uint32_t world);
 /* Capacity of the device segment buffer in segments (default 64 Mi). */
 int32_t lg_segment_capacity_set(lg_ctx *ctx, uint64_t n_segments);
+/* Where the additive blend is resolved: 0 = automatic (by segment count), 1 = direct
+ * (one red.global.add.v4.f32 per fragment), 2 = tile-binned (fragments are summed in
+ * shared-memory tiles first). Same image either way up to fp32 summation order. */
+int32_t lg_accumulate_mode_set(lg_ctx *ctx, int32_t mode);
 /* Keep LgSegmentTag (and LgSegmentF64 on F64 contexts) per segment. */
 int32_t lg_tags_enable(lg_ctx *ctx, int32_t enable);
 

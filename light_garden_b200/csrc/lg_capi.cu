@@ -19,6 +19,7 @@
 #include "../../include/light_garden_b200.h"
 #include "lg_accum.cuh"
 #include "lg_bench.cuh"
+#include "lg_tiles.cuh"
 #include "lg_scene.h"
 #include "lg_trace.cuh"
 
@@ -141,6 +142,9 @@ struct lg_ctx {
   // image
   int W = 0, H = 0;
   DevBuf img, img16, pixctr;
+  // tile-binned accumulation (lg_tiles.cuh)
+  int accum_mode = 0; // 0 = auto, 1 = direct (one L2 reduction per fragment), 2 = tile-binned
+  DevBuf tile_count, tile_cursor, tile_offset, item_prefix, tile_totals, item_counter, tile_list, seg2;
 
   // comm
   NcclComm comm = nullptr;
@@ -477,13 +481,73 @@ AccumArgs accum_args(lg_ctx *c) {
 }
 int accum_grid(lg_ctx *c) { return c->sm_count * 8; }
 
+constexpr unsigned long long kTiledMinSegments = 1ull << 17; // below this the direct kernels win
+
+bool use_tiled(lg_ctx *c, unsigned long long n) {
+  if (n == 0 || n >= (1ull << 32)) return false; // the tile lists hold 32-bit segment indices
+  if (c->accum_mode == 1) return false;
+  if (c->accum_mode == 2) return true;
+  return n >= kTiledMinSegments;
+}
+
+// count -> scan -> fill -> raster over device segments of type Seg (LgSegment or Seg2)
+template <class Seg> int accumulate_tiled(lg_ctx *c, const Seg *d_seg, unsigned long long n, unsigned *launches) {
+  TileArgs T;
+  T.A = accum_args(c);
+  T.tiles_x = (c->W + kTile - 1) / kTile, T.tiles_y = (c->H + kTile - 1) / kTile;
+  T.n_tiles = T.tiles_x * T.tiles_y;
+  int rc;
+  if ((rc = ensure(c, c->tile_count, (size_t)T.n_tiles * 4))) return rc;
+  if ((rc = ensure(c, c->tile_cursor, (size_t)T.n_tiles * 4))) return rc;
+  if ((rc = ensure(c, c->tile_offset, ((size_t)T.n_tiles + 1) * 8))) return rc;
+  if ((rc = ensure(c, c->item_prefix, ((size_t)T.n_tiles + 1) * 4))) return rc;
+  if ((rc = ensure(c, c->tile_totals, 16))) return rc;
+  if ((rc = ensure(c, c->item_counter, 4))) return rc;
+  T.tile_count = (unsigned *)c->tile_count.p, T.tile_cursor = (unsigned *)c->tile_cursor.p;
+  T.tile_offset = (unsigned long long *)c->tile_offset.p, T.item_prefix = (unsigned *)c->item_prefix.p;
+  T.totals = (unsigned long long *)c->tile_totals.p, T.item_counter = (unsigned *)c->item_counter.p;
+  T.list = nullptr;
+  LG_CUDA(c, cudaMemsetAsync(T.tile_count, 0, (size_t)T.n_tiles * 4, c->stream));
+  const int grid = c->sm_count * 8;
+  tile_count_kernel<Seg><<<grid, 256, 0, c->stream>>>(T, d_seg, n);
+  LG_CUDA(c, cudaGetLastError());
+  tile_scan_kernel<<<1, 1024, 0, c->stream>>>(T);
+  LG_CUDA(c, cudaGetLastError());
+  unsigned long long totals[2] = {0, 0};
+  LG_CUDA(c, cudaMemcpyAsync(totals, T.totals, 16, cudaMemcpyDeviceToHost, c->stream));
+  LG_CUDA(c, cudaStreamSynchronize(c->stream));
+  c->launches += 2;
+  if (launches) *launches += 2;
+  if (totals[0] == 0) return LG_OK; // nothing on the canvas
+  if ((rc = ensure(c, c->tile_list, (size_t)totals[0] * 4))) return rc;
+  T.list = (unsigned *)c->tile_list.p;
+  tile_fill_kernel<Seg><<<grid, 256, 0, c->stream>>>(T, d_seg, n);
+  LG_CUDA(c, cudaGetLastError());
+  const size_t smem = (size_t)kRasterWarps * ((size_t)kTileFloat4 * sizeof(float4) + sizeof(RasterScratch));
+  auto kern = tile_raster_kernel<Seg>;
+  LG_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 0;
+  LG_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kRasterWarps * 32, smem));
+  if (per_sm < 1) return fail(c, LG_ERR_CUDA, "tile raster kernel does not fit on an SM");
+  kern<<<c->sm_count * per_sm, kRasterWarps * 32, smem, c->stream>>>(T, d_seg);
+  LG_CUDA(c, cudaGetLastError());
+  c->launches += 2;
+  if (launches) *launches += 2;
+  return LG_OK;
+}
+
 int accumulate_device_segments(lg_ctx *c, unsigned long long n, float *ms, unsigned *launches) {
   if (n == 0) return LG_OK;
   LG_CUDA(c, cudaEventRecord(c->ev0, c->stream));
-  accumulate_segments_kernel<<<accum_grid(c), kAccumBlock, 0, c->stream>>>(accum_args(c), (const LgSegment *)c->seg.p, n);
-  LG_CUDA(c, cudaGetLastError());
-  c->launches++;
-  if (launches) (*launches)++;
+  if (use_tiled(c, n)) {
+    int rc = accumulate_tiled<LgSegment>(c, (const LgSegment *)c->seg.p, n, launches);
+    if (rc) return rc;
+  } else {
+    accumulate_segments_kernel<<<accum_grid(c), kAccumBlock, 0, c->stream>>>(accum_args(c), (const LgSegment *)c->seg.p, n);
+    LG_CUDA(c, cudaGetLastError());
+    c->launches++;
+    if (launches) (*launches)++;
+  }
   LG_CUDA(c, cudaEventRecord(c->ev1, c->stream));
   LG_CUDA(c, cudaStreamSynchronize(c->stream));
   float t = 0.f;
@@ -555,6 +619,10 @@ int32_t lg_create(int32_t device, int32_t precision, lg_ctx **out) {
   c->sm_count = prop.multiProcessorCount;
   c->smem_optin = prop.sharedMemPerBlockOptin;
   c->slots = precision == LG_PRECISION_F64 ? 1 : 2;
+  if (const char *e = getenv("LG_ACCUM_MODE")) {
+    int v = atoi(e);
+    if (v >= 0 && v <= 2) c->accum_mode = v;
+  }
   if (const char *e = getenv("LG_TRACE_SLOTS")) {
     int v = atoi(e);
     if (v == 1 || v == 2 || v == 4) c->slots = v;
@@ -570,7 +638,8 @@ int32_t lg_destroy(lg_ctx *c) {
   DevBuf *bufs[] = {&c->bounds,    &c->toks,
                     &c->obj_first, &c->obj_count, &c->obj_n,    &c->ovl_start, &c->ovl_list, &c->d_lights, &c->seg,
                     &c->tags,      &c->seg64,    &c->ctr,      &c->stack,   &c->rays,     &c->img,     &c->img16,
-                    &c->pixctr};
+                    &c->pixctr,    &c->tile_count, &c->tile_cursor, &c->tile_offset, &c->item_prefix,
+                    &c->tile_totals, &c->item_counter, &c->tile_list, &c->seg2};
   for (DevBuf *b : bufs) release(*b);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
@@ -637,6 +706,13 @@ int32_t lg_segment_capacity_set(lg_ctx *c, uint64_t n) {
   c->seg_cap = n;
   release(c->seg), release(c->tags), release(c->seg64);
   c->seg_count = 0;
+  return LG_OK;
+}
+
+int32_t lg_accumulate_mode_set(lg_ctx *c, int32_t mode) {
+  if (!c) return LG_ERR_INVALID;
+  if (mode < 0 || mode > 2) return fail(c, LG_ERR_INVALID, "accumulate mode");
+  c->accum_mode = mode;
   return LG_OK;
 }
 
@@ -791,16 +867,25 @@ int32_t lg_accumulate_segments(lg_ctx *c, const LgVertexPair *pairs, uint64_t n,
   if ((rc = ensure(c, c->rays, n * sizeof(LgVertexPair)))) return rc;
   LG_CUDA(c, cudaMemcpyAsync(c->rays.p, pairs, n * sizeof(LgVertexPair), cudaMemcpyHostToDevice, c->stream));
   LG_CUDA(c, cudaEventRecord(c->ev0, c->stream));
-  accumulate_pairs_kernel<<<accum_grid(c), kAccumBlock, 0, c->stream>>>(accum_args(c), (const LgVertexPair *)c->rays.p, n);
-  LG_CUDA(c, cudaGetLastError());
-  c->launches++;
+  unsigned nl = 0;
+  if (use_tiled(c, n)) {
+    if ((rc = ensure(c, c->seg2, n * sizeof(Seg2)))) return rc;
+    pairs_to_seg2_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>((const LgVertexPair *)c->rays.p, (Seg2 *)c->seg2.p, n);
+    LG_CUDA(c, cudaGetLastError());
+    c->launches++, nl++;
+    if ((rc = accumulate_tiled<Seg2>(c, (const Seg2 *)c->seg2.p, n, &nl))) return rc;
+  } else {
+    accumulate_pairs_kernel<<<accum_grid(c), kAccumBlock, 0, c->stream>>>(accum_args(c), (const LgVertexPair *)c->rays.p, n);
+    LG_CUDA(c, cudaGetLastError());
+    c->launches++, nl++;
+  }
   LG_CUDA(c, cudaEventRecord(c->ev1, c->stream));
   LG_CUDA(c, cudaStreamSynchronize(c->stream));
   if (stats) {
     float t = 0.f;
     LG_CUDA(c, cudaEventElapsedTime(&t, c->ev0, c->ev1));
     stats->accumulate_ms += t;
-    stats->accumulate_launches += 1;
+    stats->accumulate_launches += nl;
     stats->segments += n;
     if ((rc = read_pixel_counter(c, &stats->pixel_updates))) return rc;
   }
@@ -829,10 +914,18 @@ int32_t lg_string_mod(lg_ctx *c, const LgStringMod *sm, const LgModRemColor *rul
   S.n_rules = n_rules;
   S.first = first, S.count = count;
   LG_CUDA(c, cudaEventRecord(c->ev0, c->stream));
-  if (count) {
+  unsigned nl = 0;
+  if (count && use_tiled(c, count)) {
+    // the tiled path needs the chords in memory; the direct path generates them in-kernel
+    if ((rc = ensure(c, c->seg2, count * sizeof(Seg2)))) return rc;
+    string_mod_seg2_kernel<<<(unsigned)((count + 255) / 256), 256, 0, c->stream>>>(S, (Seg2 *)c->seg2.p);
+    LG_CUDA(c, cudaGetLastError());
+    c->launches++, nl++;
+    if ((rc = accumulate_tiled<Seg2>(c, (const Seg2 *)c->seg2.p, count, &nl))) return rc;
+  } else if (count) {
     string_mod_kernel<<<accum_grid(c), kAccumBlock, 0, c->stream>>>(accum_args(c), S);
     LG_CUDA(c, cudaGetLastError());
-    c->launches++;
+    c->launches++, nl++;
   }
   LG_CUDA(c, cudaEventRecord(c->ev1, c->stream));
   LG_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -840,7 +933,7 @@ int32_t lg_string_mod(lg_ctx *c, const LgStringMod *sm, const LgModRemColor *rul
     float t = 0.f;
     LG_CUDA(c, cudaEventElapsedTime(&t, c->ev0, c->ev1));
     stats->accumulate_ms += t;
-    stats->accumulate_launches += count ? 1 : 0;
+    stats->accumulate_launches += nl;
     stats->segments += count;
     if ((rc = read_pixel_counter(c, &stats->pixel_updates))) return rc;
   }

@@ -24,6 +24,16 @@ def ctx():
     c.close()
 
 
+DIRECT, TILED = 1, 2   # lg_accumulate_mode_set: one L2 reduction per fragment / shared-memory tile bins
+MODES = [pytest.param(DIRECT, id="direct"), pytest.param(TILED, id="tiled")]
+
+
+@pytest.fixture(autouse=True)
+def _auto_mode_after(ctx):
+    yield
+    ctx.call("lg_accumulate_mode_set", 0)
+
+
 def random_pairs(n, seed, span=2.2, pow2=True):
     rng = np.random.default_rng(seed)
     p = np.zeros(n, dtype=abi.VERTEX_PAIR_DTYPE)
@@ -38,9 +48,11 @@ def random_pairs(n, seed, span=2.2, pow2=True):
     return p
 
 
+@pytest.mark.parametrize("mode", MODES)
 @pytest.mark.parametrize("size", [(96, 54), (257, 131), (64, 64), (33, 200)])
-def test_pairs_exact_coverage_and_sums(oracle, ctx, size):
+def test_pairs_exact_coverage_and_sums(oracle, ctx, size, mode):
     from light_garden_b200.tracer import Renderer
+    ctx.call("lg_accumulate_mode_set", mode)
     W, H = size
     r = Renderer(ctx, W, H)
     p = random_pairs(3000, seed=W * 1000 + H)
@@ -58,9 +70,11 @@ def test_pairs_exact_coverage_and_sums(oracle, ctx, size):
     assert np.array_equal(got, exp)
 
 
-def test_two_colour_lerp_matches_oracle(oracle, ctx):
+@pytest.mark.parametrize("mode", MODES)
+def test_two_colour_lerp_matches_oracle(oracle, ctx, mode):
     """Arbitrary per-endpoint colours: same fragments; sums within fp32 reordering error."""
     from light_garden_b200.tracer import Renderer
+    ctx.call("lg_accumulate_mode_set", mode)
     W, H = 160, 90
     r = Renderer(ctx, W, H)
     p = random_pairs(5000, seed=11, pow2=False)
@@ -73,11 +87,13 @@ def test_two_colour_lerp_matches_oracle(oracle, ctx):
     assert np.array_equal(got == (0, 0, 0, 1), exp == (0, 0, 0, 1))          # identical coverage
 
 
+@pytest.mark.parametrize("mode", MODES)
 @pytest.mark.parametrize("name", ["C1", "C5-16"])
-def test_traced_segments_image(oracle, ctx, name):
+def test_traced_segments_image(oracle, ctx, name, mode):
     """trace -> accumulate on the device vs the oracle accumulating the device's own segments, and
     lg_render (waves through a small segment buffer) vs the one-shot path."""
     from light_garden_b200.tracer import Renderer, Tracer
+    ctx.call("lg_accumulate_mode_set", mode)
     spec = small_specs()[name]
     t = spec.apply(Tracer(spec.canvas_bounds, ctx=ctx))
     r = Renderer(ctx, spec.width, spec.height)
@@ -106,8 +122,10 @@ def test_traced_segments_image(oracle, ctx, name):
         ctx.call("lg_segment_capacity_set", 64 << 20)
 
 
-def test_string_mod_matches_oracle(oracle, ctx):
+@pytest.mark.parametrize("mode", MODES)
+def test_string_mod_matches_oracle(oracle, ctx, mode):
     from light_garden_b200.tracer import Renderer
+    ctx.call("lg_accumulate_mode_set", mode)
     W = H = 256
     k = 2.0 ** -8
     rules = [ModRemColor(3, 0, (k, 0, 0, k)), ModRemColor(3, 1, (0, k, 0, k)), ModRemColor(3, 2, (0, 0, k, k))]
@@ -192,3 +210,10 @@ def test_full_size_string_mod_properties(ctx, wh):
     r.render_string_mod(sm, first=0, count=5_000_000)
     r.render_string_mod(sm, first=5_000_000, count=5_000_000)
     assert np.array_equal(r.read_rgba32f(), img)
+    # the direct and the tile-binned resolve agree bit for bit (every partial sum is exact with this colour)
+    for mode in (DIRECT, TILED):
+        ctx.call("lg_accumulate_mode_set", mode)
+        r.clear(0.0)
+        st2 = r.render_string_mod(sm)
+        assert int(st2.pixel_updates) == n
+        assert np.array_equal(r.read_rgba32f(), img), mode
