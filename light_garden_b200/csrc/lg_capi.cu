@@ -144,7 +144,7 @@ struct lg_ctx {
   DevBuf img, img16, pixctr;
   // tile-binned accumulation (lg_tiles.cuh)
   int accum_mode = 0; // 0 = auto, 1 = direct (one L2 reduction per fragment), 2 = tile-binned
-  DevBuf tile_count, tile_cursor, tile_offset, item_prefix, tile_totals, item_counter, tile_list, seg2;
+  DevBuf tile_count, tile_cursor, tile_offset, item_prefix, tile_totals, item_counter, tile_list, seg2, tile_hist;
 
   // comm
   NcclComm comm = nullptr;
@@ -485,6 +485,8 @@ constexpr unsigned long long kTiledMinSegments = 1ull << 17; // below this the d
 
 bool use_tiled(lg_ctx *c, unsigned long long n) {
   if (n == 0 || n >= (1ull << 32)) return false; // the tile lists hold 32-bit segment indices
+  const size_t n_tiles = (size_t)((c->W + kTile - 1) / kTile) * ((c->H + kTile - 1) / kTile);
+  if (n_tiles * 4 + 1024 > c->smem_optin) return false; // the per-CTA histogram must fit in shared memory
   if (c->accum_mode == 1) return false;
   if (c->accum_mode == 2) return true;
   return n >= kTiledMinSegments;
@@ -507,21 +509,32 @@ template <class Seg> int accumulate_tiled(lg_ctx *c, const Seg *d_seg, unsigned 
   T.tile_offset = (unsigned long long *)c->tile_offset.p, T.item_prefix = (unsigned *)c->item_prefix.p;
   T.totals = (unsigned long long *)c->tile_totals.p, T.item_counter = (unsigned *)c->item_counter.p;
   T.list = nullptr;
-  LG_CUDA(c, cudaMemsetAsync(T.tile_count, 0, (size_t)T.n_tiles * 4, c->stream));
-  const int grid = c->sm_count * 8;
-  tile_count_kernel<Seg><<<grid, 256, 0, c->stream>>>(T, d_seg, n);
+  const int grid = c->sm_count * 4; // CTAs of the count and fill passes (same split of the segments in both)
+  T.n_ctas = grid;
+  if ((rc = ensure(c, c->tile_hist, (size_t)grid * T.n_tiles * 4))) return rc;
+  T.hist = (unsigned *)c->tile_hist.p;
+  const size_t hist_smem = (size_t)T.n_tiles * 4;
+  auto count_k = tile_count_kernel<Seg>;
+  auto fill_k = tile_fill_kernel<Seg>;
+  if (hist_smem > 48 * 1024) {
+    LG_CUDA(c, cudaFuncSetAttribute(count_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_smem));
+    LG_CUDA(c, cudaFuncSetAttribute(fill_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_smem));
+  }
+  count_k<<<grid, 256, hist_smem, c->stream>>>(T, d_seg, n);
+  LG_CUDA(c, cudaGetLastError());
+  tile_rowscan_kernel<<<(T.n_tiles + 255) / 256, 256, 0, c->stream>>>(T);
   LG_CUDA(c, cudaGetLastError());
   tile_scan_kernel<<<1, 1024, 0, c->stream>>>(T);
   LG_CUDA(c, cudaGetLastError());
   unsigned long long totals[2] = {0, 0};
   LG_CUDA(c, cudaMemcpyAsync(totals, T.totals, 16, cudaMemcpyDeviceToHost, c->stream));
   LG_CUDA(c, cudaStreamSynchronize(c->stream));
-  c->launches += 2;
-  if (launches) *launches += 2;
+  c->launches += 3;
+  if (launches) *launches += 3;
   if (totals[0] == 0) return LG_OK; // nothing on the canvas
   if ((rc = ensure(c, c->tile_list, (size_t)totals[0] * 4))) return rc;
   T.list = (unsigned *)c->tile_list.p;
-  tile_fill_kernel<Seg><<<grid, 256, 0, c->stream>>>(T, d_seg, n);
+  fill_k<<<grid, 256, hist_smem, c->stream>>>(T, d_seg, n);
   LG_CUDA(c, cudaGetLastError());
   const size_t smem = (size_t)kRasterWarps * ((size_t)kTileFloat4 * sizeof(float4) + sizeof(RasterScratch));
   auto kern = tile_raster_kernel<Seg>;
@@ -639,7 +652,7 @@ int32_t lg_destroy(lg_ctx *c) {
                     &c->obj_first, &c->obj_count, &c->obj_n,    &c->ovl_start, &c->ovl_list, &c->d_lights, &c->seg,
                     &c->tags,      &c->seg64,    &c->ctr,      &c->stack,   &c->rays,     &c->img,     &c->img16,
                     &c->pixctr,    &c->tile_count, &c->tile_cursor, &c->tile_offset, &c->item_prefix,
-                    &c->tile_totals, &c->item_counter, &c->tile_list, &c->seg2};
+                    &c->tile_totals, &c->item_counter, &c->tile_list, &c->seg2,       &c->tile_hist};
   for (DevBuf *b : bufs) release(*b);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);

@@ -5,9 +5,12 @@
 // send one 16-byte red.global.add per fragment to L2; at 500..70 000 fragments per pixel (BASELINE configs C1..C5)
 // that is the bottleneck.  Here fragments are summed in SHARED MEMORY first:
 //
-//   1. tile_count : lane = segment; walk the 32x32-pixel tiles the segment's fragments fall into, count per tile
-//   2. tile_scan  : exclusive scan -> list offsets; work items = (tile, chunk of <= kChunk list entries)
-//   3. tile_fill  : same walk, writes the segment index into the tile's list
+//   1. tile_count : lane = segment; walk the 32x32-pixel tiles the segment's fragments fall into and count them in
+//                   a per-CTA SHARED-MEMORY histogram (hot tiles next to a light take millions of hits: global
+//                   atomics on one address would serialise), written out as hist[cta][tile]
+//   2. tile_rowscan + tile_scan: exclusive scans -> every CTA's write position in every tile's list; work items =
+//                   (tile, chunk of <= kChunk list entries)
+//   3. tile_fill  : same walk by the same CTA over the same segments, positions from a shared-memory cursor
 //   4. tile_raster: persistent warps; a warp owns a PRIVATE 32x32 RGBA fp32 tile in shared memory (33-pixel pitch:
 //                   conflict-free for x-major and y-major lines), adds every fragment of its work item with plain
 //                   LDS.128 / FADD / STS.128 — lanes are distinct major-axis steps of one segment, so there are no
@@ -45,6 +48,8 @@ struct TileArgs {
   unsigned long long *totals; // [0] = pairs, [1] = items
   unsigned int *list;         // segment index per pair
   unsigned int *item_counter;
+  unsigned int *hist;         // [n_ctas][n_tiles] per-CTA counts, then per-CTA exclusive offsets within a tile
+  int n_ctas;
 };
 
 template <class Seg> struct SegIO;
@@ -96,12 +101,58 @@ template <class F> __device__ __forceinline__ void for_each_tile(const RasterSet
   }
 }
 
+// segments [lo, hi) of CTA b out of g: the SAME split in the count and the fill pass
+__device__ __forceinline__ void cta_range(unsigned long long n, unsigned b, unsigned g, unsigned long long &lo,
+                                          unsigned long long &hi) {
+  const unsigned long long per = (n + g - 1) / g;
+  lo = per * b < n ? per * b : n;
+  hi = lo + per < n ? lo + per : n;
+}
+
 template <class Seg> __global__ void __launch_bounds__(256) tile_count_kernel(TileArgs T, const Seg *seg, unsigned long long n) {
-  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
-  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+  extern __shared__ unsigned int s_hist[];
+  for (int t = threadIdx.x; t < T.n_tiles; t += blockDim.x) s_hist[t] = 0u;
+  __syncthreads();
+  unsigned long long lo, hi;
+  cta_range(n, blockIdx.x, gridDim.x, lo, hi);
+  for (unsigned long long i = lo + threadIdx.x; i < hi; i += blockDim.x) {
     const float4 ab = SegIO<Seg>::load_ab(seg, i);
     const RasterSetup S = raster_setup(T.A, ab.x, ab.y, ab.z, ab.w);
-    for_each_tile(S, T.A.W, T.A.H, T.tiles_x, [&](int tile) { atomicAdd(&T.tile_count[tile], 1u); });
+    for_each_tile(S, T.A.W, T.A.H, T.tiles_x, [&](int tile) { atomicAdd(&s_hist[tile], 1u); });
+  }
+  __syncthreads();
+  unsigned int *out = T.hist + (size_t)blockIdx.x * T.n_tiles;
+  for (int t = threadIdx.x; t < T.n_tiles; t += blockDim.x) out[t] = s_hist[t];
+}
+
+// thread = tile: exclusive scan down the CTA dimension; hist[c][t] becomes CTA c's offset inside tile t's list
+__global__ void __launch_bounds__(256) tile_rowscan_kernel(TileArgs T) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= T.n_tiles) return;
+  unsigned int run = 0;
+  for (int c = 0; c < T.n_ctas; ++c) {
+    unsigned int *p = T.hist + (size_t)c * T.n_tiles + t; // coalesced across the warp's tiles
+    const unsigned int v = *p;
+    *p = run;
+    run += v;
+  }
+  T.tile_count[t] = run;
+}
+
+template <class Seg> __global__ void __launch_bounds__(256) tile_fill_kernel(TileArgs T, const Seg *seg, unsigned long long n) {
+  extern __shared__ unsigned int s_cur[]; // this CTA's next slot in every tile's list, relative to the tile's offset
+  const unsigned int *mine = T.hist + (size_t)blockIdx.x * T.n_tiles;
+  for (int t = threadIdx.x; t < T.n_tiles; t += blockDim.x) s_cur[t] = mine[t];
+  __syncthreads();
+  unsigned long long lo, hi;
+  cta_range(n, blockIdx.x, gridDim.x, lo, hi);
+  for (unsigned long long i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+    const float4 ab = SegIO<Seg>::load_ab(seg, i);
+    const RasterSetup S = raster_setup(T.A, ab.x, ab.y, ab.z, ab.w);
+    for_each_tile(S, T.A.W, T.A.H, T.tiles_x, [&](int tile) {
+      const unsigned int pos = atomicAdd(&s_cur[tile], 1u);
+      T.list[T.tile_offset[tile] + pos] = (unsigned int)i;
+    });
   }
 }
 
@@ -143,18 +194,6 @@ __global__ void __launch_bounds__(1024) tile_scan_kernel(TileArgs T) {
     T.totals[0] = carry_pairs;
     T.totals[1] = carry_items;
     *T.item_counter = 0u;
-  }
-}
-
-template <class Seg> __global__ void __launch_bounds__(256) tile_fill_kernel(TileArgs T, const Seg *seg, unsigned long long n) {
-  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
-  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    const float4 ab = SegIO<Seg>::load_ab(seg, i);
-    const RasterSetup S = raster_setup(T.A, ab.x, ab.y, ab.z, ab.w);
-    for_each_tile(S, T.A.W, T.A.H, T.tiles_x, [&](int tile) {
-      const unsigned int pos = atomicAdd(&T.tile_cursor[tile], 1u);
-      T.list[T.tile_offset[tile] + pos] = (unsigned int)i;
-    });
   }
 }
 

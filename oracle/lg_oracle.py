@@ -66,6 +66,8 @@ def lib():
         L.lgo_image_clear.argtypes = [vp, C.c_int32, C.c_int32, C.c_float]
         L.lgo_accumulate_segments.restype = C.c_uint64
         L.lgo_accumulate_segments.argtypes = [vp, C.c_int32, C.c_int32, vp, C.c_uint64, C.c_int32]
+        L.lgo_accumulate_segments_f64.restype = C.c_uint64
+        L.lgo_accumulate_segments_f64.argtypes = [vp, C.c_int32, C.c_int32, vp, C.c_uint64]
         L.lgo_accumulate_pairs.restype = C.c_uint64
         L.lgo_accumulate_pairs.argtypes = [vp, C.c_int32, C.c_int32, vp, C.c_uint64, C.c_int32]
         L.lgo_image_to_f16.argtypes = [vp, C.c_uint64, vp]
@@ -189,6 +191,13 @@ def accumulate_segments(img, seg, threads=0):
     seg = np.ascontiguousarray(seg, dtype=abi.SEGMENT_DTYPE)
     h, w = img.shape[:2]
     return lib().lgo_accumulate_segments(abi.array_ptr(img), w, h, abi.array_ptr(seg), len(seg), threads)
+
+
+def accumulate_segments_f64(img, seg):
+    """Same fragments, f64 sums (img: float64 H x W x 4)."""
+    seg = np.ascontiguousarray(seg, dtype=abi.SEGMENT_DTYPE)
+    h, w = img.shape[:2]
+    return lib().lgo_accumulate_segments_f64(abi.array_ptr(img), w, h, abi.array_ptr(seg), len(seg))
 
 
 def accumulate_pairs(img, pairs, threads=0):

@@ -287,6 +287,21 @@ uint64_t lgo_accumulate_segments(float *img, int32_t W, int32_t H, const LgSegme
   });
 }
 
+// the same fragments summed in f64: the exact value both device resolves are bounded against
+uint64_t lgo_accumulate_segments_f64(double *img, int32_t W, int32_t H, const LgSegment *seg, uint64_t n) {
+  Proj pr = make_proj(W, H);
+  uint64_t total = 0;
+  for (uint64_t i = 0; i < n; ++i) {
+    const LgSegment &s = seg[i];
+    total += raster_segment(pr, s.a, s.b, s.color, s.color, 0, H, [&](int px, int py, const float c[4]) {
+      double *p = img + ((size_t)py * W + px) * 4;
+      p[0] += c[0], p[1] += c[1], p[2] += c[2];
+      p[3] += (double)(c[3] * c[3]);
+    });
+  }
+  return total;
+}
+
 uint64_t lgo_accumulate_pairs(float *img, int32_t W, int32_t H, const LgVertexPair *vp, uint64_t n,
                               int32_t threads) {
   return accumulate_t(img, W, H, n, threads, [&](uint64_t i, float a[2], float b[2], float ca[4], float cb[4]) {

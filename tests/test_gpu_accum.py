@@ -105,8 +105,16 @@ def test_traced_segments_image(oracle, ctx, name, mode):
     assert st.pixel_updates == n
     assert np.array_equal(got[..., 3] > 1, exp[..., 3] > 1)                    # same covered pixels
     err = np.abs(got - exp)
-    # hot pixels next to a light sum thousands of fragments: relative bound 1e-5 of the pixel value
-    assert (err <= 1e-5 * np.maximum(1.0, np.abs(exp))).all(), err.max()
+    # hot pixels next to a light sum thousands of equal fragments.  The direct resolve adds them one by one like
+    # the oracle's fp32 loop (same rounding pattern: 1e-5 of the pixel value); the tiled resolve adds per-tile
+    # partial sums, a different (more accurate) summation tree: it is bounded against the f64 sum instead.
+    tol = 1e-5 if mode == DIRECT else 3e-4
+    assert (err <= tol * np.maximum(1.0, np.abs(exp))).all(), err.max()
+    exact = np.zeros((spec.height, spec.width, 4), dtype=np.float64)
+    exact[..., 3] = 1.0
+    oracle.accumulate_segments_f64(exact, seg)
+    rel64 = np.abs(got - exact) / np.maximum(1.0, np.abs(exact))
+    assert rel64.max() < (3e-4 if mode == DIRECT else 2e-5), rel64.max()
     mse = float(np.mean((got - exp) ** 2))
     psnr = 10 * np.log10(float(exp.max()) ** 2 / mse) if mse > 0 else np.inf
     assert psnr > 100
@@ -117,7 +125,7 @@ def test_traced_segments_image(oracle, ctx, name, mode):
         st2 = r.render(t)
         assert st2.segments == len(seg) and st2.pixel_updates == n and st2.trace_launches >= 4
         got2 = r.read_rgba32f()
-        assert (np.abs(got2 - exp) <= 1e-5 * np.maximum(1.0, np.abs(exp))).all()
+        assert (np.abs(got2 - exp) <= tol * np.maximum(1.0, np.abs(exp))).all()
     finally:
         ctx.call("lg_segment_capacity_set", 64 << 20)
 
