@@ -27,6 +27,14 @@ for w in $what; do
       timeout 900 compute-sanitizer --tool racecheck --error-exitcode 9 python __graft_entry__.py smoke > gpurun_out/sanitize_racecheck.log 2>&1
       echo "racecheck rc=$?" >> gpurun_out/sanitize_racecheck.log
       ;;
+    proftiles)
+      timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 100 --csv \
+        --log-file gpurun_out/launches_tiles.csv python tools/bench_configs.py --scale 0.25 --repeat 1 \
+        > gpurun_out/configs_under_ncu.log 2>&1
+      timeout 600 ncu --set full --clock-control none --import-source on -k regex:tile_raster -s 2 -c 1 \
+        -f -o gpurun_out/prof_tile_raster python bench.py --rays-per-gpu 2000000 --steps 1 --warmup 3 --no-cpu-baseline \
+        > gpurun_out/prof_tile_raster.log 2>&1
+      ;;
     slots)
       for s in 1 2 4; do
         LG_TRACE_SLOTS=$s timeout 300 python bench.py --rays-per-gpu 8000000 --steps 2 --no-cpu-baseline > gpurun_out/bench_slots$s.log 2>&1
