@@ -242,35 +242,69 @@ template <class Seg> __global__ void __launch_bounds__(kRasterWarps * 32) tile_r
       }
       __syncwarp();
       const int m = (int)min(32u, last - base);
-      for (int k = 0; k < m; ++k) {
-        const RasterSetup S = P.s[k];
-        const float4 ca = P.ca[k];
-        // this tile's stretch of the segment: one major-axis step per lane
-        const int i = ((S.xmajor ? tx : ty) << kTileShift) + (int)lane;
-        if (i >= S.i0 && i < S.i1) {
+      // Two parked segments are in flight at a time: their coordinate math is independent (ILP hides the
+      // shared-memory latency), the two read-modify-writes then happen in list order (a lane may hit the same
+      // pixel in both).  The next two are fetched from shared memory before the current two are blended.
+      RasterSetup Sa = P.s[0], Sb = P.s[m > 1 ? 1 : 0];
+      float4 ca_a = P.ca[0], ca_b = P.ca[m > 1 ? 1 : 0];
+      float4 dc_a = kLerp ? P.dc[0] : make_float4(0.f, 0.f, 0.f, 0.f);
+      float4 dc_b = kLerp ? P.dc[m > 1 ? 1 : 0] : dc_a;
+      for (int k = 0; k < m; k += 2) {
+        const bool has_b = k + 1 < m;
+        const int kn0 = k + 2 < m ? k + 2 : k, kn1 = k + 3 < m ? k + 3 : k;
+        const RasterSetup Na = P.s[kn0], Nb = P.s[kn1];
+        const float4 nca_a = P.ca[kn0], nca_b = P.ca[kn1];
+        const float4 ndc_a = kLerp ? P.dc[kn0] : dc_a, ndc_b = kLerp ? P.dc[kn1] : dc_a;
+        // this tile's stretch of each segment: one major-axis step per lane (arithmetic of raster_walk)
+        int off_a, off_b;
+        float s_a, s_b;
+        bool act_a, act_b;
+        {
+          const int i = ((Sa.xmajor ? tx : ty) << kTileShift) + (int)lane;
           const float mc = (float)i + 0.5f;
-          const float s = (mc - S.m0) * S.inv;
-          const float nv = __fmaf_rn(s, S.dn, S.n0);
-          const float fj = floorf(nv);
-          const int Nmin = S.xmajor ? T.A.H : T.A.W;
-          if (fj >= 0.f && fj < (float)Nmin) {
-            const int j = (int)fj;
-            if ((j >> kTileShift) == (S.xmajor ? ty : tx)) {
-              const int lx = S.xmajor ? (int)lane : (j & (kTile - 1)), ly = S.xmajor ? (j & (kTile - 1)) : (int)lane;
-              float c0 = ca.x, c1 = ca.y, c2 = ca.z, c3 = ca.w;
-              if (kLerp) {
-                const float4 dc = P.dc[k];
-                c0 = __fmaf_rn(s, dc.x, ca.x), c1 = __fmaf_rn(s, dc.y, ca.y);
-                c2 = __fmaf_rn(s, dc.z, ca.z), c3 = __fmaf_rn(s, dc.w, ca.w);
-              }
-              float4 *px = tile + ly * kTilePitch + lx;
-              float4 v = *px; // private tile, distinct pixel per lane: plain read-modify-write
-              v.x += c0, v.y += c1, v.z += c2, v.w += c3 * c3; // mod.rs:57-73
-              *px = v;
-              ++cnt;
-            }
-          }
+          s_a = (mc - Sa.m0) * Sa.inv;
+          const float fj = floorf(__fmaf_rn(s_a, Sa.dn, Sa.n0));
+          const int Nmin = Sa.xmajor ? T.A.H : T.A.W;
+          const int j = (int)fmaxf(fminf(fj, 1e9f), -1e9f);
+          act_a = i >= Sa.i0 && i < Sa.i1 && fj >= 0.f && fj < (float)Nmin && (j >> kTileShift) == (Sa.xmajor ? ty : tx);
+          const int jl = j & (kTile - 1);
+          off_a = Sa.xmajor ? jl * kTilePitch + (int)lane : (int)lane * kTilePitch + jl;
         }
+        {
+          const int i = ((Sb.xmajor ? tx : ty) << kTileShift) + (int)lane;
+          const float mc = (float)i + 0.5f;
+          s_b = (mc - Sb.m0) * Sb.inv;
+          const float fj = floorf(__fmaf_rn(s_b, Sb.dn, Sb.n0));
+          const int Nmin = Sb.xmajor ? T.A.H : T.A.W;
+          const int j = (int)fmaxf(fminf(fj, 1e9f), -1e9f);
+          act_b = has_b && i >= Sb.i0 && i < Sb.i1 && fj >= 0.f && fj < (float)Nmin &&
+                  (j >> kTileShift) == (Sb.xmajor ? ty : tx);
+          const int jl = j & (kTile - 1);
+          off_b = Sb.xmajor ? jl * kTilePitch + (int)lane : (int)lane * kTilePitch + jl;
+        }
+        if (act_a) {
+          float c0 = ca_a.x, c1 = ca_a.y, c2 = ca_a.z, c3 = ca_a.w;
+          if (kLerp) {
+            c0 = __fmaf_rn(s_a, dc_a.x, ca_a.x), c1 = __fmaf_rn(s_a, dc_a.y, ca_a.y);
+            c2 = __fmaf_rn(s_a, dc_a.z, ca_a.z), c3 = __fmaf_rn(s_a, dc_a.w, ca_a.w);
+          }
+          float4 v = tile[off_a]; // private tile, distinct pixel per lane: plain read-modify-write
+          v.x += c0, v.y += c1, v.z += c2, v.w += c3 * c3; // mod.rs:57-73
+          tile[off_a] = v;
+          ++cnt;
+        }
+        if (act_b) {
+          float c0 = ca_b.x, c1 = ca_b.y, c2 = ca_b.z, c3 = ca_b.w;
+          if (kLerp) {
+            c0 = __fmaf_rn(s_b, dc_b.x, ca_b.x), c1 = __fmaf_rn(s_b, dc_b.y, ca_b.y);
+            c2 = __fmaf_rn(s_b, dc_b.z, ca_b.z), c3 = __fmaf_rn(s_b, dc_b.w, ca_b.w);
+          }
+          float4 v = tile[off_b];
+          v.x += c0, v.y += c1, v.z += c2, v.w += c3 * c3;
+          tile[off_b] = v;
+          ++cnt;
+        }
+        Sa = Na, Sb = Nb, ca_a = nca_a, ca_b = nca_b, dc_a = ndc_a, dc_b = ndc_b;
       }
       __syncwarp();
     }
