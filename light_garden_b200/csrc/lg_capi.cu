@@ -144,6 +144,9 @@ struct lg_ctx {
   DevBuf img, img16, pixctr;
   // tile-binned accumulation (lg_tiles.cuh)
   int accum_mode = 0; // 0 = auto, 1 = direct (one L2 reduction per fragment), 2 = tile-binned
+  // auto mode: measured cost of each resolve on this context's recent work (ns per fragment, 0 = no sample yet)
+  double ns_per_frag[3] = {0, 0, 0};
+  unsigned long long auto_calls = 0;
   DevBuf tile_count, tile_cursor, tile_offset, item_prefix, tile_totals, item_counter, tile_list, seg2, tile_hist;
 
   // comm
@@ -483,13 +486,34 @@ int accum_grid(lg_ctx *c) { return c->sm_count * 8; }
 
 constexpr unsigned long long kTiledMinSegments = 1ull << 17; // below this the direct kernels win
 
-bool use_tiled(lg_ctx *c, unsigned long long n) {
+bool tiled_possible(lg_ctx *c, unsigned long long n) {
   if (n == 0 || n >= (1ull << 32)) return false; // the tile lists hold 32-bit segment indices
   const size_t n_tiles = (size_t)((c->W + kTile - 1) / kTile) * ((c->H + kTile - 1) / kTile);
-  if (n_tiles * 4 + 1024 > c->smem_optin) return false; // the per-CTA histogram must fit in shared memory
+  return n_tiles * 4 + 1024 <= c->smem_optin; // the per-CTA histogram must fit in shared memory
+}
+
+// Which resolve to use.  Forced modes aside, small inputs go direct; large ones use whichever of the two has been
+// cheaper per fragment on this context so far (both are sampled first, the loser is re-probed every 64th call):
+// long coalescing segments favour the direct kernel, short or scattered ones the tile bins.
+bool use_tiled(lg_ctx *c, unsigned long long n) {
+  if (!tiled_possible(c, n)) return false;
   if (c->accum_mode == 1) return false;
   if (c->accum_mode == 2) return true;
-  return n >= kTiledMinSegments;
+  if (n < kTiledMinSegments) return false;
+  ++c->auto_calls;
+  if (c->ns_per_frag[2] == 0) return true;
+  if (c->ns_per_frag[1] == 0) return false;
+  const bool tiled_better = c->ns_per_frag[2] <= c->ns_per_frag[1];
+  if (c->auto_calls % 64 == 0) return !tiled_better;
+  return tiled_better;
+}
+
+// feed the auto mode: elapsed time of one resolve over `frags` fragments
+void note_accum_cost(lg_ctx *c, bool tiled, float ms, unsigned long long frags, unsigned long long n) {
+  if (frags == 0 || n < kTiledMinSegments) return;
+  const double v = (double)ms * 1e6 / (double)frags;
+  double &slot = c->ns_per_frag[tiled ? 2 : 1];
+  slot = slot == 0 ? v : 0.5 * slot + 0.5 * v;
 }
 
 // count -> scan -> fill -> raster over device segments of type Seg (LgSegment or Seg2)
@@ -549,12 +573,17 @@ template <class Seg> int accumulate_tiled(lg_ctx *c, const Seg *d_seg, unsigned 
   return LG_OK;
 }
 
+int read_pixel_counter(lg_ctx *c, uint64_t *out);
+
 int accumulate_device_segments(lg_ctx *c, unsigned long long n, float *ms, unsigned *launches) {
   if (n == 0) return LG_OK;
+  const bool tiled = use_tiled(c, n);
+  uint64_t before = 0, after = 0;
+  int rc;
+  if (c->accum_mode == 0 && n >= kTiledMinSegments && (rc = read_pixel_counter(c, &before))) return rc;
   LG_CUDA(c, cudaEventRecord(c->ev0, c->stream));
-  if (use_tiled(c, n)) {
-    int rc = accumulate_tiled<LgSegment>(c, (const LgSegment *)c->seg.p, n, launches);
-    if (rc) return rc;
+  if (tiled) {
+    if ((rc = accumulate_tiled<LgSegment>(c, (const LgSegment *)c->seg.p, n, launches))) return rc;
   } else {
     accumulate_segments_kernel<<<accum_grid(c), kAccumBlock, 0, c->stream>>>(accum_args(c), (const LgSegment *)c->seg.p, n);
     LG_CUDA(c, cudaGetLastError());
@@ -566,6 +595,10 @@ int accumulate_device_segments(lg_ctx *c, unsigned long long n, float *ms, unsig
   float t = 0.f;
   LG_CUDA(c, cudaEventElapsedTime(&t, c->ev0, c->ev1));
   if (ms) *ms += t;
+  if (c->accum_mode == 0 && n >= kTiledMinSegments) {
+    if ((rc = read_pixel_counter(c, &after))) return rc;
+    note_accum_cost(c, tiled, t, after - before, n);
+  }
   return LG_OK;
 }
 
@@ -879,9 +912,12 @@ int32_t lg_accumulate_segments(lg_ctx *c, const LgVertexPair *pairs, uint64_t n,
   // reuse the ray staging buffer for the upload (update_vertex_buffer makes a NEW buffer per frame)
   if ((rc = ensure(c, c->rays, n * sizeof(LgVertexPair)))) return rc;
   LG_CUDA(c, cudaMemcpyAsync(c->rays.p, pairs, n * sizeof(LgVertexPair), cudaMemcpyHostToDevice, c->stream));
+  const bool tiled = use_tiled(c, n);
+  uint64_t frag0 = 0;
+  if ((rc = read_pixel_counter(c, &frag0))) return rc;
   LG_CUDA(c, cudaEventRecord(c->ev0, c->stream));
   unsigned nl = 0;
-  if (use_tiled(c, n)) {
+  if (tiled) {
     if ((rc = ensure(c, c->seg2, n * sizeof(Seg2)))) return rc;
     pairs_to_seg2_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>((const LgVertexPair *)c->rays.p, (Seg2 *)c->seg2.p, n);
     LG_CUDA(c, cudaGetLastError());
@@ -894,13 +930,16 @@ int32_t lg_accumulate_segments(lg_ctx *c, const LgVertexPair *pairs, uint64_t n,
   }
   LG_CUDA(c, cudaEventRecord(c->ev1, c->stream));
   LG_CUDA(c, cudaStreamSynchronize(c->stream));
+  float t = 0.f;
+  LG_CUDA(c, cudaEventElapsedTime(&t, c->ev0, c->ev1));
+  uint64_t frag1 = 0;
+  if ((rc = read_pixel_counter(c, &frag1))) return rc;
+  if (c->accum_mode == 0) note_accum_cost(c, tiled, t, frag1 - frag0, n);
   if (stats) {
-    float t = 0.f;
-    LG_CUDA(c, cudaEventElapsedTime(&t, c->ev0, c->ev1));
     stats->accumulate_ms += t;
     stats->accumulate_launches += nl;
     stats->segments += n;
-    if ((rc = read_pixel_counter(c, &stats->pixel_updates))) return rc;
+    stats->pixel_updates = frag1;
   }
   return LG_OK;
 }
@@ -926,9 +965,12 @@ int32_t lg_string_mod(lg_ctx *c, const LgStringMod *sm, const LgModRemColor *rul
   S.rules = (const LgModRemColor *)c->rays.p;
   S.n_rules = n_rules;
   S.first = first, S.count = count;
+  const bool tiled = count && use_tiled(c, count);
+  uint64_t frag0 = 0;
+  if ((rc = read_pixel_counter(c, &frag0))) return rc;
   LG_CUDA(c, cudaEventRecord(c->ev0, c->stream));
   unsigned nl = 0;
-  if (count && use_tiled(c, count)) {
+  if (tiled) {
     // the tiled path needs the chords in memory; the direct path generates them in-kernel
     if ((rc = ensure(c, c->seg2, count * sizeof(Seg2)))) return rc;
     string_mod_seg2_kernel<<<(unsigned)((count + 255) / 256), 256, 0, c->stream>>>(S, (Seg2 *)c->seg2.p);
@@ -942,13 +984,16 @@ int32_t lg_string_mod(lg_ctx *c, const LgStringMod *sm, const LgModRemColor *rul
   }
   LG_CUDA(c, cudaEventRecord(c->ev1, c->stream));
   LG_CUDA(c, cudaStreamSynchronize(c->stream));
+  float t = 0.f;
+  LG_CUDA(c, cudaEventElapsedTime(&t, c->ev0, c->ev1));
+  uint64_t frag1 = 0;
+  if ((rc = read_pixel_counter(c, &frag1))) return rc;
+  if (c->accum_mode == 0 && count) note_accum_cost(c, tiled, t, frag1 - frag0, count);
   if (stats) {
-    float t = 0.f;
-    LG_CUDA(c, cudaEventElapsedTime(&t, c->ev0, c->ev1));
     stats->accumulate_ms += t;
     stats->accumulate_launches += nl;
     stats->segments += count;
-    if ((rc = read_pixel_counter(c, &stats->pixel_updates))) return rc;
+    stats->pixel_updates = frag1;
   }
   return LG_OK;
 }

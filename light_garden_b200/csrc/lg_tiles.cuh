@@ -232,14 +232,16 @@ template <class Seg> __global__ void __launch_bounds__(kRasterWarps * 32) tile_r
     const int tx = t % T.tiles_x, ty = t / T.tiles_x;
     for (int k = lane; k < kTileFloat4; k += 32) tile[k] = make_float4(0.f, 0.f, 0.f, 0.f);
     __syncwarp();
+    // the gather of the NEXT 32 list entries (index, then segment) is in flight while the current 32 are blended
+    float4 g_ab = make_float4(0.f, 0.f, 0.f, 0.f), g_ca = g_ab, g_dc = g_ab;
+    if (first + lane < last) SegIO<Seg>::load(seg, lst[first + lane], g_ab, g_ca, g_dc);
     for (unsigned int base = first; base < last; base += 32) {
-      if (base + lane < last) { // lane = one list entry: load its segment, park its raster setup
-        float4 ab, ca, dc;
-        SegIO<Seg>::load(seg, lst[base + lane], ab, ca, dc);
-        P.s[lane] = raster_setup(T.A, ab.x, ab.y, ab.z, ab.w);
-        P.ca[lane] = ca;
-        if (kLerp) P.dc[lane] = dc;
+      if (base + lane < last) { // lane = one list entry: park its raster setup
+        P.s[lane] = raster_setup(T.A, g_ab.x, g_ab.y, g_ab.z, g_ab.w);
+        P.ca[lane] = g_ca;
+        if (kLerp) P.dc[lane] = g_dc;
       }
+      if (base + 32 + lane < last) SegIO<Seg>::load(seg, lst[base + 32 + lane], g_ab, g_ca, g_dc);
       __syncwarp();
       const int m = (int)min(32u, last - base);
       // Two parked segments are in flight at a time: their coordinate math is independent (ILP hides the

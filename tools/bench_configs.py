@@ -18,7 +18,7 @@ sys.path.insert(0, ROOT)
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--precision", default="f32")
-    ap.add_argument("--repeat", type=int, default=3)
+    ap.add_argument("--repeat", type=int, default=4)
     ap.add_argument("--scale", type=float, default=1.0, help="scale ray / chord counts (smoke runs)")
     args = ap.parse_args()
     from light_garden_b200 import abi, scenes
