@@ -213,7 +213,9 @@ int32_t lg_scene_set(lg_ctx *ctx, const LgObject *objects, uint32_t n_objects,
  * evaluated here. */
 int32_t lg_lights_set(lg_ctx *ctx, const LgLight *lights, uint32_t n_lights);
 /* Data-parallel shard of the primary rays: rank r of `world` takes the rays
- * [r*n/world, (r+1)*n/world) of every light. Default 0 of 1. */
+ * r, r + world, r + 2*world, ... of every light (interleaved, so that every rank
+ * sees every direction of every light and the ranks' work is balanced;
+ * SURVEY.md §8e). Default 0 of 1. */
 int32_t lg_shard_set(lg_ctx *ctx, uint32_t rank, uint32_t world);
 /* Capacity of the device segment buffer in segments (default 64 Mi). */
 int32_t lg_segment_capacity_set(lg_ctx *ctx, uint64_t n_segments);

@@ -345,9 +345,11 @@ void rebuild_dev_lights(lg_ctx *c) {
     DevLight d{};
     d.kind = l.kind;
     const unsigned long long n = l.num_rays;
-    d.first = (unsigned long long)(((unsigned __int128)n * c->rank) / c->world);
-    const unsigned long long hi = (unsigned long long)(((unsigned __int128)n * (c->rank + 1)) / c->world);
-    d.count = hi - d.first;
+    // interleaved shard: ray i belongs to rank i mod world (every rank sees every direction of every light, so
+    // the ranks' work is balanced whatever the scene looks like around the light)
+    d.first = c->rank;
+    d.stride = c->world;
+    d.count = n > c->rank ? (n - c->rank + c->world - 1) / c->world : 0;
     d.prefix = prefix;
     d.id_base = id_base;
     d.n_rays = (double)n;
@@ -953,7 +955,7 @@ int32_t lg_string_mod(lg_ctx *c, const LgStringMod *sm, const LgModRemColor *rul
   if (sm->mode < LG_SM_ADD || sm->mode > LG_SM_BASE) return fail(c, LG_ERR_INVALID, "StringModMode");
   if (sm->modulo == 0) return LG_OK; // draw_init_points: points.is_empty() -> no lines (string_mod.rs:106-108)
   LG_CUDA(c, cudaSetDevice(c->device));
-  if (count == 0) { // this context's shard of all chords
+  if (count == 0) { // this context's shard of all chords: a contiguous block (chords are uniform work)
     first = (uint64_t)(((unsigned __int128)sm->modulo * c->rank) / c->world);
     count = (uint64_t)(((unsigned __int128)sm->modulo * (c->rank + 1)) / c->world) - first;
   }

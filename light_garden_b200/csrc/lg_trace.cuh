@@ -38,7 +38,8 @@ constexpr int kTraceBlock = 256;
 struct DevLight {
   int32_t kind;
   int32_t _pad;
-  unsigned long long first;    // first ray index of this context's shard
+  unsigned long long first;    // this context's shard of the light: rays first, first + stride, ...
+  unsigned long long stride;
   unsigned long long count;    // rays in the shard
   unsigned long long prefix;   // offset of the shard in this context's ray index space
   unsigned long long id_base;  // global id of ray 0 of this light
@@ -450,7 +451,7 @@ __global__ void __launch_bounds__(kTraceBlock, (R >= 4 || sizeof(T) == 8) ? 2 : 
               int li = 0;
               while (li + 1 < A.n_lights && j >= A.lights[li + 1].prefix) ++li;
               const DevLight &l = A.lights[li];
-              const unsigned long long i = l.first + (j - l.prefix);
+              const unsigned long long i = l.first + (j - l.prefix) * l.stride;
               emit_ray(l, i, ox, oy, dx, dy);
               cr[r] = l.color[0], cg[r] = l.color[1], cb[r] = l.color[2], ca[r] = l.color[3];
               n0 = l.n0;

@@ -7,11 +7,16 @@ inside the C library.
 import ctypes as C
 
 
-def shard_range(n: int, rank: int, world: int):
-    """Rays [lo, hi) of a light with n rays that rank `rank` of `world` traces (same formula as lg_shard_set)."""
+def shard_count(n: int, rank: int, world: int) -> int:
+    """Number of rays of a light with n rays that rank `rank` of `world` traces: the rays rank, rank + world, ...
+    (same interleaved split as lg_shard_set)."""
     if world < 1 or not (0 <= rank < world):
         raise ValueError("rank/world")
-    return (n * rank) // world, (n * (rank + 1)) // world
+    return (n - rank + world - 1) // world if n > rank else 0
+
+
+def shard_indices(n: int, rank: int, world: int):
+    return range(rank, n, world) if shard_count(n, rank, world) else range(0)
 
 
 def broadcast_bytes(payload: bytes, n: int, rank: int, src: int = 0, device=None) -> bytes:

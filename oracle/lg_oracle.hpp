@@ -747,11 +747,8 @@ inline double start_medium(const SceneT<double> &s, const LgLight &l) {
   return n;
 }
 
-// shard [lo, hi) of n rays for rank r of w
-inline void shard_range(uint64_t n, uint32_t r, uint32_t w, uint64_t &lo, uint64_t &hi) {
-  lo = (uint64_t)(((unsigned __int128)n * r) / w);
-  hi = (uint64_t)(((unsigned __int128)n * (r + 1)) / w);
-}
+// shard of n rays for rank r of w: the rays r, r + w, r + 2w, ...
+inline uint64_t shard_count(uint64_t n, uint32_t r, uint32_t w) { return n > r ? (n - r + w - 1) / w : 0; }
 
 // ---------------------------------------------------------------------------
 // §7 string mod — src/light_garden/string_mod.rs:33-158 (Circle curve)

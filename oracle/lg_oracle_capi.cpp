@@ -180,9 +180,10 @@ void *lgo_trace_all(void *h, int32_t precision, const LgLight *lights, uint32_t 
   for (uint32_t li = 0; li < n_lights; ++li) {
     const LgLight &l = lights[li];
     double n0 = start_medium(s->d, l);
-    uint64_t lo, hi;
-    shard_range(l.num_rays, rank, world, lo, hi);
-    uint64_t cnt = (hi - lo + stride - 1) / stride;
+    // local ray k of the shard is ray rank + k*world of the light; `stride` samples every stride-th local ray
+    const uint64_t local = shard_count(l.num_rays, rank, world);
+    const uint64_t cnt = (local + stride - 1) / stride;
+    const uint64_t step = (uint64_t)world * stride;
     // materialise in blocks to bound memory
     const uint64_t BLK = 1u << 20;
     std::vector<LgRay> rays;
@@ -191,24 +192,17 @@ void *lgo_trace_all(void *h, int32_t precision, const LgLight *lights, uint32_t 
       rays.resize(m);
 #pragma omp parallel for schedule(static)
       for (int64_t i = 0; i < (int64_t)m; ++i) {
-        emit_ray(l, lo + (b + i) * stride, rays[i]);
+        emit_ray(l, rank + (b + i) * step, rays[i]);
         rays[i].refractive_index = n0;
       }
-      if (stride == 1) {
-        if (precision == LG_PRECISION_F64)
-          trace_block<double>(*s, rays.data(), m, id_base + lo + b, chunk, threads, store != 0, *r);
-        else
-          trace_block<float>(*s, rays.data(), m, id_base + lo + b, chunk, threads, store != 0, *r);
-      } else {
-        // ids are not contiguous: trace block with id0 = 0 and fix up after
-        size_t before = r->segs.size();
-        if (precision == LG_PRECISION_F64)
-          trace_block<double>(*s, rays.data(), m, 0, chunk, threads, store != 0, *r);
-        else
-          trace_block<float>(*s, rays.data(), m, 0, chunk, threads, store != 0, *r);
-        for (size_t k = before; k < r->segs.size(); ++k)
-          r->segs[k].tag.ray = id_base + lo + (b + r->segs[k].tag.ray) * stride;
-      }
+      // ids are not contiguous: trace the block with local ids and map them back
+      size_t before = r->segs.size();
+      if (precision == LG_PRECISION_F64)
+        trace_block<double>(*s, rays.data(), m, 0, chunk, threads, store != 0, *r);
+      else
+        trace_block<float>(*s, rays.data(), m, 0, chunk, threads, store != 0, *r);
+      for (size_t k = before; k < r->segs.size(); ++k)
+        r->segs[k].tag.ray = id_base + rank + (b + r->segs[k].tag.ray) * step;
     }
     id_base += l.num_rays;
   }

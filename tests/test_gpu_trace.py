@@ -146,7 +146,7 @@ def test_trace_all_appends_control_lines(ctx32):
 
 
 def test_shards_partition_the_rays(oracle, ctx32):
-    """rank r of R takes rays [r*n/R, (r+1)*n/R) of every light; the union is the whole trace."""
+    """rank r of R takes the rays r, r + R, ... of every light; the union is the whole trace."""
     spec = SPECS["C1"]
     t = make_tracer(spec, ctx32)
     osc = oracle.OracleScene.from_spec(spec)
@@ -157,6 +157,7 @@ def test_shards_partition_the_rays(oracle, ctx32):
         seg, tags, _ = t.trace_all(control_lines=False, return_tags=True)
         part = osc.trace_all(spec.lights, abi.LG_PRECISION_F32, rank=r, world=3)
         assert len(seg) == part.segments_emitted
+        assert np.array_equal(np.unique(tags["ray"]), np.unique(part.tags["ray"]))
         seen.append(tags["ray"])
     t.set_shard(0, 1)
     allr = np.sort(np.concatenate(seen))
@@ -203,6 +204,34 @@ def test_deep_split_tree_matches_oracle(oracle, ctx64):
     got = t.trace(rays)
     assert exp.segments_emitted > 40 * 30
     assert_same_segments(got, exp, f64=True)
+
+
+def test_table_larger_than_shared_memory(oracle, ctx32):
+    """20 000 objects: the broad-phase table (320 KB) no longer fits the 227 KB of shared memory and is read from
+    global memory instead; results must not change."""
+    from light_garden_b200.tracer import Tracer
+    rng = scenes.SplitMix64(0x4C47B16)
+    objs = []
+    for k in range(20000):
+        cx, cy = rng.uniform(-1.7, 1.7), rng.uniform(-0.95, 0.95)
+        r = rng.uniform(0.002, 0.004)
+        if k % 3 == 0:
+            objs.append(Object.new_mirror((cx - r, cy - r), (cx + r, cy + r)))
+        elif k % 3 == 1:
+            objs.append(Object.new_circle((cx, cy), r).with_index(rng.uniform(1.1, 1.8)))
+        else:
+            objs.append(Object.new_rect((cx, cy), 2 * r, 1.5 * r).with_index(rng.uniform(1.1, 1.8)))
+    light = PointLight((0.01, 0.02), 300, (0.01, 0.008, 0.006, 0.02))
+    t = Tracer(scenes.canvas(16 / 9), ctx=ctx32)
+    for o in objs:
+        t.push_object(o)
+    osc = oracle.OracleScene(objs, 5, [0.001] * 4, scenes.canvas(16 / 9))
+    rays = oracle.emit_rays(light)
+    rays["refractive_index"] = osc.start_medium(light)
+    exp = osc.trace_rays(rays, abi.LG_PRECISION_F32)
+    got = t.trace(rays)
+    assert exp.segments_emitted > 600
+    assert_same_segments(got, exp)
 
 
 def test_errors_are_reported_not_hidden(ctx32):
