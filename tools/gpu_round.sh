@@ -48,9 +48,12 @@ for w in $what; do
       timeout 600 ncu --set full --clock-control none --import-source on -k regex:trace_kernel -s 1 -c 1 \
         -f -o gpurun_out/prof_trace python bench.py --rays-per-gpu 2000000 --steps 1 --warmup 3 --no-cpu-baseline \
         > gpurun_out/prof_trace.log 2>&1
-      timeout 600 ncu --set full --clock-control none --import-source on -k regex:accumulate_segments -s 1 -c 1 \
+      LG_ACCUM_MODE=1 timeout 600 ncu --set full --clock-control none --import-source on -k regex:accumulate_segments -s 1 -c 1 \
         -f -o gpurun_out/prof_accum python bench.py --rays-per-gpu 2000000 --steps 1 --warmup 3 --no-cpu-baseline \
         > gpurun_out/prof_accum.log 2>&1
+      LG_ACCUM_MODE=2 timeout 600 ncu --set full --clock-control none --import-source on -k regex:tile_raster -s 1 -c 1 \
+        -f -o gpurun_out/prof_tile_raster python bench.py --rays-per-gpu 2000000 --steps 1 --warmup 3 --no-cpu-baseline \
+        > gpurun_out/prof_tile_raster.log 2>&1
       ;;
   esac
 done
