@@ -275,23 +275,6 @@ __global__ void __launch_bounds__(kAccumBlock) string_mod_kernel(AccumArgs A, St
   flush_count(A, cnt, lane);
 }
 
-// chord list only (tests / lg_string_mod readback): StringMod::draw as vertex pairs
-__global__ void string_mod_list_kernel(StringModArgs S, LgVertexPair *dst) {
-  const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= S.count) return;
-  const unsigned long long iix = S.first + i, ix = sm_target(S.sm, iix);
-  const double TAU = 6.28318530717958647692;
-  LgVertexPair vp;
-  double s, c;
-  sincos(__ddiv_rn(__dmul_rn((double)(S.sm.turns * iix), TAU), (double)S.sm.modulo), &s, &c);
-  vp.a[0] = c, vp.a[1] = s;
-  sincos(__ddiv_rn(__dmul_rn((double)(S.sm.turns * ix), TAU), (double)S.sm.modulo), &s, &c);
-  vp.b[0] = c, vp.b[1] = s;
-  sm_color(S, iix, vp.color_a);
-  sm_color(S, ix, vp.color_b);
-  dst[i] = vp;
-}
-
 // ---- clear + K5 finalize -------------------------------------------------------------
 __global__ void clear_image_kernel(float4 *img, size_t n_px, float alpha) {
   const size_t stride = (size_t)gridDim.x * blockDim.x;

@@ -278,21 +278,21 @@ def _rays(n, seed=1):
 
 
 def test_csg_identities(oracle):
+    """A∧A = A, A∨A = A, A∧¬A = ∅ as point sets (contains)."""
     A = Circle((0.2, 0.1), 0.7)
     plain = scene(oracle, [Object.new_geo(A)])
     a_and_a = scene(oracle, [Object.new_geo(Logic(AND, A, A))])
     a_or_a = scene(oracle, [Object.new_geo(Logic(OR, A, A))])
     a_not_a = scene(oracle, [Object.new_geo(Logic(AND_NOT, A, A))])
-    o, d = _rays(300)
-    for i in range(len(o)):
-        ref = plain.intersect(0, o[i], d[i])
-        # A∧A: boundary points of one copy are ON the other copy's boundary, strictly-inside fails -> compare contains only
-        assert a_not_a.intersect(0, o[i], d[i]).shape[0] == 0 or True
-        p = o[i]
-        assert a_and_a.contains(0, p) == plain.contains(0, p)
-        assert a_or_a.contains(0, p) == plain.contains(0, p)
+    pts, _ = _rays(600)
+    inside = 0
+    for p in pts:
+        c = plain.contains(0, p)
+        inside += c
+        assert a_and_a.contains(0, p) == c
+        assert a_or_a.contains(0, p) == c
         assert not a_not_a.contains(0, p)
-        assert ref.shape[0] in (0, 1, 2)
+    assert 20 < inside < 580
 
 
 def test_csg_hit_sets(oracle):
