@@ -275,8 +275,14 @@ int32_t lg_comm_init_rank(lg_ctx *ctx, const void *id128, int32_t rank,
                           int32_t world);
 /* Single process driving several devices (the Rust app's shape). */
 int32_t lg_comm_init_all(lg_ctx **ctxs, int32_t n);
-/* Sum of the partial fp32 images onto `root` (ncclReduce over NVLink). */
+/* Sum of the partial fp32 images onto `root` (collective: every rank calls it).
+ * Default: one kernel per rank over NVLink peer memory that sums its band of rows
+ * of every rank's image in rank order and stores the fp32 sum and the Rgba16Float
+ * frame into the root's buffers (reduce-scatter + finalize + gather fused); falls
+ * back to ncclReduce when a peer cannot be mapped. */
 int32_t lg_image_reduce(lg_ctx *ctx, int32_t root, float *reduce_ms);
+/* 0 = automatic, 1 = ncclReduce, 2 = peer-memory fused (error if unreachable). */
+int32_t lg_reduce_mode_set(lg_ctx *ctx, int32_t mode);
 int32_t lg_comm_destroy(lg_ctx *ctx);
 
 /* ---- plumbing for hosts that own the process (bench, tests) --------------- */

@@ -115,6 +115,7 @@ PROTOTYPES = {
     "lg_comm_init_rank": [_ctx, _p, C.c_int32, C.c_int32],
     "lg_comm_init_all": [C.POINTER(_ctx), C.c_int32],
     "lg_image_reduce": [_ctx, C.c_int32, C.POINTER(C.c_float)],
+    "lg_reduce_mode_set": [_ctx, C.c_int32],
     "lg_comm_destroy": [_ctx],
     "lg_stream_handle": [_ctx, C.POINTER(C.c_uint64)],
     "lg_image_device_ptr": [_ctx, C.POINTER(C.c_uint64)],

@@ -20,6 +20,8 @@
 #include "lg_accum.cuh"
 #include "lg_bench.cuh"
 #include "lg_tiles.cuh"
+#include "lg_reduce.cuh"
+#include <unistd.h>
 #include "lg_scene.h"
 #include "lg_trace.cuh"
 
@@ -52,6 +54,8 @@ struct NcclApi {
   int (*CommInitAll)(NcclComm *, int, const int *) = nullptr;
   int (*CommDestroy)(NcclComm) = nullptr;
   int (*Reduce)(const void *, void *, size_t, int, int, int, NcclComm, cudaStream_t) = nullptr;
+  int (*AllReduce)(const void *, void *, size_t, int, int, NcclComm, cudaStream_t) = nullptr;
+  int (*AllGather)(const void *, void *, size_t, int, NcclComm, cudaStream_t) = nullptr;
   const char *(*GetErrorString)(int) = nullptr;
   bool tried = false;
   std::string why;
@@ -83,6 +87,8 @@ bool nccl_load() {
   g_nccl.CommInitAll = (decltype(g_nccl.CommInitAll))sym("ncclCommInitAll");
   g_nccl.CommDestroy = (decltype(g_nccl.CommDestroy))sym("ncclCommDestroy");
   g_nccl.Reduce = (decltype(g_nccl.Reduce))sym("ncclReduce");
+  g_nccl.AllReduce = (decltype(g_nccl.AllReduce))sym("ncclAllReduce");
+  g_nccl.AllGather = (decltype(g_nccl.AllGather))sym("ncclAllGather");
   g_nccl.GetErrorString = (decltype(g_nccl.GetErrorString))sym("ncclGetErrorString");
   if (!ok) {
     dlclose(g_nccl.handle);
@@ -92,6 +98,10 @@ bool nccl_load() {
 }
 constexpr int kNcclFloat32 = 7; // ncclFloat32
 constexpr int kNcclSum = 0;     // ncclSum
+constexpr int kNcclMax = 2;     // ncclMax
+constexpr int kNcclInt32 = 2;   // ncclInt32
+constexpr int kNcclUint8 = 1;   // ncclUint8
+constexpr int kMaxPeers = 16;
 } // namespace
 
 // ---- context -----------------------------------------------------------------------------
@@ -152,11 +162,24 @@ struct lg_ctx {
   // comm
   NcclComm comm = nullptr;
   int comm_rank = 0, comm_world = 1;
+  // peer-memory reduce (lg_reduce.cuh): every rank's fp32 image and the root's fp16 frame, mapped here
+  int reduce_mode = 0; // 0 = auto (peer-fused when every peer is reachable), 1 = ncclReduce, 2 = peer-fused only
+  bool peers_ready = false;
+  int peers_root = -1;
+  void *peer_img[kMaxPeers] = {nullptr};
+  void *peer_img16[kMaxPeers] = {nullptr};
+  bool peer_opened[kMaxPeers] = {false};   // mapped through cudaIpcOpenMemHandle (another process)
+  bool peer_opened16[kMaxPeers] = {false};
+  bool peer_fused_ok = true;
+  DevBuf sync_buf, peer_xchg;
+  bool img16_valid = false; // the fp16 frame already holds the finalized image
 
   unsigned long long launches = 0;
 };
 
 namespace {
+
+void close_peers(lg_ctx *c);
 
 int fail(lg_ctx *c, int code, const std::string &msg) {
   if (c) c->err = msg;
@@ -579,6 +602,7 @@ int read_pixel_counter(lg_ctx *c, uint64_t *out);
 
 int accumulate_device_segments(lg_ctx *c, unsigned long long n, float *ms, unsigned *launches) {
   if (n == 0) return LG_OK;
+  c->img16_valid = false;
   const bool tiled = use_tiled(c, n);
   uint64_t before = 0, after = 0;
   int rc;
@@ -682,12 +706,14 @@ int32_t lg_create(int32_t device, int32_t precision, lg_ctx **out) {
 int32_t lg_destroy(lg_ctx *c) {
   if (!c) return LG_ERR_INVALID;
   cudaSetDevice(c->device);
+  close_peers(c);
   if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
   DevBuf *bufs[] = {&c->bounds,    &c->toks,
                     &c->obj_first, &c->obj_count, &c->obj_n,    &c->ovl_start, &c->ovl_list, &c->d_lights, &c->seg,
                     &c->tags,      &c->seg64,    &c->ctr,      &c->stack,   &c->rays,     &c->img,     &c->img16,
                     &c->pixctr,    &c->tile_count, &c->tile_cursor, &c->tile_offset, &c->item_prefix,
-                    &c->tile_totals, &c->item_counter, &c->tile_list, &c->seg2,       &c->tile_hist};
+                    &c->tile_totals, &c->item_counter, &c->tile_list, &c->seg2,       &c->tile_hist,
+                    &c->sync_buf,  &c->peer_xchg};
   for (DevBuf *b : bufs) release(*b);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
@@ -872,6 +898,8 @@ int32_t lg_image_configure(lg_ctx *c, uint32_t width, uint32_t height) {
   if (width == 0 || height == 0 || width > 32768 || height > 32768) return fail(c, LG_ERR_INVALID, "image size");
   LG_CUDA(c, cudaSetDevice(c->device));
   c->W = (int)width, c->H = (int)height;
+  c->peers_ready = false; // the buffers may move: the next lg_image_reduce re-exchanges the peer mappings
+  c->img16_valid = false;
   int rc;
   if ((rc = ensure(c, c->img, (size_t)width * height * 16))) return rc;
   if ((rc = ensure(c, c->pixctr, 8))) return rc;
@@ -882,6 +910,7 @@ int32_t lg_image_clear(lg_ctx *c, float clear_alpha) {
   int rc = need_image(c);
   if (rc) return rc;
   LG_CUDA(c, cudaSetDevice(c->device));
+  c->img16_valid = false;
   clear_image_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>((float4 *)c->img.p, (size_t)c->W * c->H, clear_alpha);
   LG_CUDA(c, cudaGetLastError());
   c->launches++;
@@ -910,6 +939,7 @@ int32_t lg_accumulate_segments(lg_ctx *c, const LgVertexPair *pairs, uint64_t n,
   if (rc) return rc;
   if (n && !pairs) return fail(c, LG_ERR_INVALID, "null pairs");
   if (n == 0) return LG_OK;
+  c->img16_valid = false;
   LG_CUDA(c, cudaSetDevice(c->device));
   // reuse the ray staging buffer for the upload (update_vertex_buffer makes a NEW buffer per frame)
   if ((rc = ensure(c, c->rays, n * sizeof(LgVertexPair)))) return rc;
@@ -954,6 +984,7 @@ int32_t lg_string_mod(lg_ctx *c, const LgStringMod *sm, const LgModRemColor *rul
   if (sm->curve != LG_CURVE_CIRCLE) return fail(c, LG_ERR_UNSUPPORTED, "only Curve::Circle (SURVEY.md §8f)");
   if (sm->mode < LG_SM_ADD || sm->mode > LG_SM_BASE) return fail(c, LG_ERR_INVALID, "StringModMode");
   if (sm->modulo == 0) return LG_OK; // draw_init_points: points.is_empty() -> no lines (string_mod.rs:106-108)
+  c->img16_valid = false;
   LG_CUDA(c, cudaSetDevice(c->device));
   if (count == 0) { // this context's shard of all chords: a contiguous block (chords are uniform work)
     first = (uint64_t)(((unsigned __int128)sm->modulo * c->rank) / c->world);
@@ -1059,9 +1090,11 @@ int32_t lg_image_read(lg_ctx *c, int32_t format, void *dst, size_t pitch) {
     if (pitch == 0) pitch = row;
     if (pitch < row) return fail(c, LG_ERR_INVALID, "pitch");
     if ((rc = ensure(c, c->img16, npx * 8))) return rc;
-    finalize_f16_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>((const float4 *)c->img.p, (uint2 *)c->img16.p, npx);
-    LG_CUDA(c, cudaGetLastError());
-    c->launches++;
+    if (!c->img16_valid) { // the peer-fused reduce already left the finalized frame here
+      finalize_f16_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>((const float4 *)c->img.p, (uint2 *)c->img16.p, npx);
+      LG_CUDA(c, cudaGetLastError());
+      c->launches++;
+    }
     LG_CUDA(c, cudaMemcpy2DAsync(dst, pitch, c->img16.p, row, row, c->H, cudaMemcpyDeviceToHost, c->stream));
   } else {
     return fail(c, LG_ERR_INVALID, "format");
@@ -1108,15 +1141,164 @@ int32_t lg_comm_init_all(lg_ctx **ctxs, int32_t n) {
   return LG_OK;
 }
 
+} // extern "C"
+
+namespace {
+
+struct PeerInfo { // what every rank tells the others about its buffers
+  cudaIpcMemHandle_t h_img, h_img16;
+  unsigned long long ptr_img, ptr_img16;
+  long long pid;
+  int device, has16;
+  unsigned long long bytes_img;
+};
+
+void close_peers(lg_ctx *c) {
+  for (int p = 0; p < kMaxPeers; ++p) {
+    if (c->peer_opened[p] && c->peer_img[p]) cudaIpcCloseMemHandle(c->peer_img[p]);
+    if (c->peer_opened16[p] && c->peer_img16[p]) cudaIpcCloseMemHandle(c->peer_img16[p]);
+    c->peer_img[p] = c->peer_img16[p] = nullptr;
+    c->peer_opened[p] = c->peer_opened16[p] = false;
+  }
+  c->peers_ready = false;
+  cudaGetLastError();
+}
+
+// stream-ordered barrier + consensus: max over ranks of `value` (also orders all ranks' earlier work on their streams)
+int comm_max(lg_ctx *c, int value, int *out) {
+  int rc = ensure(c, c->sync_buf, 16);
+  if (rc) return rc;
+  LG_CUDA(c, cudaMemcpyAsync(c->sync_buf.p, &value, 4, cudaMemcpyHostToDevice, c->stream));
+  int r = g_nccl.AllReduce(c->sync_buf.p, (char *)c->sync_buf.p + 8, 1, kNcclInt32, kNcclMax, c->comm, c->stream);
+  if (r != 0) return fail(c, LG_ERR_NCCL, std::string("ncclAllReduce: ") + g_nccl.GetErrorString(r));
+  LG_CUDA(c, cudaMemcpyAsync(out, (char *)c->sync_buf.p + 8, 4, cudaMemcpyDeviceToHost, c->stream));
+  LG_CUDA(c, cudaStreamSynchronize(c->stream));
+  return LG_OK;
+}
+
+// all ranks exchange their buffer handles and map each other's images (collective)
+int exchange_peers(lg_ctx *c, int root) {
+  close_peers(c);
+  const int n = c->comm_world;
+  int rc;
+  if (c->comm_rank == root && (rc = ensure(c, c->img16, (size_t)c->W * c->H * 8))) return rc;
+  PeerInfo mine{};
+  mine.pid = (long long)getpid();
+  mine.device = c->device;
+  mine.ptr_img = (unsigned long long)(uintptr_t)c->img.p;
+  mine.bytes_img = (unsigned long long)c->W * c->H * 16;
+  bool ok = cudaIpcGetMemHandle(&mine.h_img, c->img.p) == cudaSuccess;
+  if (c->comm_rank == root) {
+    mine.has16 = 1;
+    mine.ptr_img16 = (unsigned long long)(uintptr_t)c->img16.p;
+    ok = ok && cudaIpcGetMemHandle(&mine.h_img16, c->img16.p) == cudaSuccess;
+  }
+  cudaGetLastError();
+  if ((rc = ensure(c, c->peer_xchg, sizeof(PeerInfo) * (size_t)(n + 1)))) return rc;
+  PeerInfo *d_mine = (PeerInfo *)c->peer_xchg.p, *d_all = d_mine + 1;
+  LG_CUDA(c, cudaMemcpyAsync(d_mine, &mine, sizeof mine, cudaMemcpyHostToDevice, c->stream));
+  int r = g_nccl.AllGather(d_mine, d_all, sizeof(PeerInfo), kNcclUint8, c->comm, c->stream);
+  if (r != 0) return fail(c, LG_ERR_NCCL, std::string("ncclAllGather: ") + g_nccl.GetErrorString(r));
+  std::vector<PeerInfo> all(n);
+  LG_CUDA(c, cudaMemcpyAsync(all.data(), d_all, sizeof(PeerInfo) * n, cudaMemcpyDeviceToHost, c->stream));
+  LG_CUDA(c, cudaStreamSynchronize(c->stream));
+  for (int p = 0; p < n && ok; ++p) {
+    if (all[p].bytes_img != mine.bytes_img) ok = false; // ranks disagree on the image size
+    if (p == c->comm_rank) {
+      c->peer_img[p] = c->img.p;
+      if (p == root) c->peer_img16[p] = c->img16.p;
+      continue;
+    }
+    if (all[p].pid == mine.pid) { // same process (lg_comm_init_all): plain peer access
+      int can = 0;
+      if (cudaDeviceCanAccessPeer(&can, c->device, all[p].device) != cudaSuccess || !can) {
+        ok = false;
+        break;
+      }
+      cudaError_t e = cudaDeviceEnablePeerAccess(all[p].device, 0);
+      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) ok = false;
+      cudaGetLastError();
+      c->peer_img[p] = (void *)(uintptr_t)all[p].ptr_img;
+      if (p == root) c->peer_img16[p] = (void *)(uintptr_t)all[p].ptr_img16;
+    } else { // another process (one rank per GPU under torchrun): CUDA IPC
+      if (cudaIpcOpenMemHandle(&c->peer_img[p], all[p].h_img, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+        c->peer_img[p] = nullptr;
+        ok = false;
+      } else {
+        c->peer_opened[p] = true;
+      }
+      if (ok && p == root) {
+        if (cudaIpcOpenMemHandle(&c->peer_img16[p], all[p].h_img16, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+          c->peer_img16[p] = nullptr;
+          ok = false;
+        } else {
+          c->peer_opened16[p] = true;
+        }
+      }
+      cudaGetLastError();
+    }
+  }
+  // every rank must take the same path: consensus on "somebody could not map a peer"
+  int any_bad = 0;
+  if ((rc = comm_max(c, ok ? 0 : 1, &any_bad))) return rc;
+  c->peer_fused_ok = any_bad == 0;
+  if (!c->peer_fused_ok) close_peers(c);
+  c->peers_ready = true; // the exchange happened (even if it ended in the NCCL fallback)
+  c->peers_root = root;
+  return LG_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+int32_t lg_reduce_mode_set(lg_ctx *c, int32_t mode) {
+  if (!c) return LG_ERR_INVALID;
+  if (mode < 0 || mode > 2) return fail(c, LG_ERR_INVALID, "reduce mode");
+  c->reduce_mode = mode;
+  return LG_OK;
+}
+
 int32_t lg_image_reduce(lg_ctx *c, int32_t root, float *reduce_ms) {
   int rc = need_image(c);
   if (rc) return rc;
   if (reduce_ms) *reduce_ms = 0.f;
   if (c->comm_world <= 1 || !c->comm) return LG_OK; // one partial image: nothing to sum
+  if (root < 0 || root >= c->comm_world) return fail(c, LG_ERR_INVALID, "root");
   LG_CUDA(c, cudaSetDevice(c->device));
   LG_CUDA(c, cudaEventRecord(c->ev0, c->stream));
-  int r = g_nccl.Reduce(c->img.p, c->img.p, (size_t)c->W * c->H * 4, kNcclFloat32, kNcclSum, root, c->comm, c->stream);
-  if (r != 0) return fail(c, LG_ERR_NCCL, std::string("ncclReduce: ") + g_nccl.GetErrorString(r));
+  bool fused = c->reduce_mode != 1 && c->comm_world <= kMaxPeers;
+  if (fused) {
+    // barrier (every rank's accumulation is complete) + consensus: does anybody need the handle exchange?
+    int need = 0;
+    const int mine = (!c->peers_ready || c->peers_root != root) ? 1 : 0;
+    if ((rc = comm_max(c, mine, &need))) return rc;
+    if (need && (rc = exchange_peers(c, root))) return rc;
+    fused = c->peer_fused_ok;
+    if (!fused && c->reduce_mode == 2) return fail(c, LG_ERR_UNSUPPORTED, "peer memory is not reachable from every rank");
+  }
+  if (fused) {
+    PeerPtrs P{};
+    P.n = c->comm_world;
+    for (int p = 0; p < P.n; ++p) P.img[p] = (const float4 *)c->peer_img[p];
+    P.root_img = (float4 *)c->peer_img[root];
+    P.root_img16 = (uint2 *)c->peer_img16[root];
+    const size_t rows0 = (size_t)c->H * c->comm_rank / c->comm_world, rows1 = (size_t)c->H * (c->comm_rank + 1) / c->comm_world;
+    const size_t px0 = rows0 * c->W, px1 = rows1 * c->W;
+    if (px1 > px0) {
+      reduce_finalize_peer_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(P, px0, px1);
+      LG_CUDA(c, cudaGetLastError());
+      c->launches++;
+    }
+    // barrier: every band has landed in the root's buffers, nobody touches its partial image before that
+    int dummy = 0;
+    if ((rc = comm_max(c, 0, &dummy))) return rc;
+    if (c->comm_rank == root) c->img16_valid = true;
+  } else {
+    int r = g_nccl.Reduce(c->img.p, c->img.p, (size_t)c->W * c->H * 4, kNcclFloat32, kNcclSum, root, c->comm, c->stream);
+    if (r != 0) return fail(c, LG_ERR_NCCL, std::string("ncclReduce: ") + g_nccl.GetErrorString(r));
+    c->img16_valid = false;
+  }
   LG_CUDA(c, cudaEventRecord(c->ev1, c->stream));
   LG_CUDA(c, cudaStreamSynchronize(c->stream));
   if (reduce_ms) LG_CUDA(c, cudaEventElapsedTime(reduce_ms, c->ev0, c->ev1));
@@ -1125,6 +1307,8 @@ int32_t lg_image_reduce(lg_ctx *c, int32_t root, float *reduce_ms) {
 
 int32_t lg_comm_destroy(lg_ctx *c) {
   if (!c) return LG_ERR_INVALID;
+  cudaSetDevice(c->device);
+  close_peers(c);
   if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
   c->comm = nullptr;
   c->comm_world = 1, c->comm_rank = 0;

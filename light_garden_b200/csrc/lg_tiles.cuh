@@ -204,11 +204,11 @@ struct RasterScratch { // per warp
 };
 
 template <class Seg> __global__ void __launch_bounds__(kRasterWarps * 32) tile_raster_kernel(TileArgs T, const Seg *seg) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(16) unsigned char tile_smem_raw[];
   const int warp_in_block = threadIdx.x >> 5;
   const unsigned lane = threadIdx.x & 31u;
-  float4 *tile = reinterpret_cast<float4 *>(smem_raw) + (size_t)warp_in_block * kTileFloat4;
-  RasterScratch &P = reinterpret_cast<RasterScratch *>(reinterpret_cast<float4 *>(smem_raw) +
+  float4 *tile = reinterpret_cast<float4 *>(tile_smem_raw) + (size_t)warp_in_block * kTileFloat4;
+  RasterScratch &P = reinterpret_cast<RasterScratch *>(reinterpret_cast<float4 *>(tile_smem_raw) +
                                                        (size_t)kRasterWarps * kTileFloat4)[warp_in_block];
   constexpr bool kLerp = SegIO<Seg>::kLerp;
   const unsigned int n_items = (unsigned int)T.totals[1];

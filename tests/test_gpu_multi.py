@@ -1,6 +1,8 @@
-"""Multi-GPU: ray shards on several devices, partial images summed with the NCCL reduce.
+"""Multi-GPU: ray shards on several devices, partial images summed onto the root — with the peer-memory kernel
+that fuses reduce-scatter, fp16 finalize and gather (default) and with ncclReduce (fallback).
 Needs >= 2 visible GPUs (gpurun --gpus 2); skipped otherwise."""
 import ctypes as C
+import threading
 
 import numpy as np
 import pytest
@@ -10,6 +12,8 @@ from util import have_cuda, small_specs
 
 pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not have_cuda(), reason="no CUDA device")]
 
+NCCL, PEER = 1, 2   # lg_reduce_mode_set
+
 
 def device_count():
     from light_garden_b200 import _lib
@@ -18,43 +22,68 @@ def device_count():
     return n.value
 
 
+def reduce_all(ctxs, root=0):
+    errs = []
+
+    def run(i):
+        try:
+            ms = C.c_float()
+            ctxs[i].call("lg_image_reduce", root, C.byref(ms))
+        except Exception as e:   # noqa: BLE001
+            errs.append(e)
+    th = [threading.Thread(target=run, args=(i,)) for i in range(len(ctxs))]
+    [x.start() for x in th]
+    [x.join() for x in th]
+    assert not errs, errs
+
+
 @pytest.mark.skipif(not have_cuda() or device_count() < 2, reason="needs 2 GPUs")
 def test_two_device_render_equals_one_device(oracle):
     from light_garden_b200 import _lib
     from light_garden_b200.tracer import Context, Renderer, Tracer
     spec = small_specs()["C1"]
-    world = 2
+    world = min(device_count(), 4)
     ctxs = [Context(d, abi.LG_PRECISION_F32) for d in range(world)]
+    one = Context(0, abi.LG_PRECISION_F32)
     try:
         arr = (C.c_void_p * world)(*[c.h for c in ctxs])
         _lib.check(ctxs[0].h, _lib.load().lg_comm_init_all(arr, world))
-        rends = []
+        t1 = spec.apply(Tracer(spec.canvas_bounds, ctx=one))
+        r1 = Renderer(one, spec.width, spec.height)
+        r1.render(t1)
+        ref = r1.read_rgba32f()
+        tracers, rends = [], []
         for rk, c in enumerate(ctxs):
             t = spec.apply(Tracer(spec.canvas_bounds, ctx=c))
             t.set_shard(rk, world)
-            r = Renderer(c, spec.width, spec.height)
-            r.clear(1.0 if rk == 0 else 0.0)          # only the root owns the clear alpha
-            r.render(t)
-            rends.append(r)
-        import threading
-        ms = [C.c_float() for _ in ctxs]
-        th = [threading.Thread(target=lambda i=i: ctxs[i].call("lg_image_reduce", 0, C.byref(ms[i])))
-              for i in range(world)]
-        [x.start() for x in th]
-        [x.join() for x in th]
-        total = rends[0].read_rgba32f()
-        one = Context(0, abi.LG_PRECISION_F32)
-        t = spec.apply(Tracer(spec.canvas_bounds, ctx=one))
-        r1 = Renderer(one, spec.width, spec.height)
-        r1.render(t)
-        ref = r1.read_rgba32f()
-        # same fragments, different fp32 summation trees (two partial images + ncclReduce vs one image): hot pixels
-        # next to a light sum ~1e4 fragments, so the stated bound is 1e-4 relative to the pixel value
-        assert np.array_equal(total[..., 3] > 1, ref[..., 3] > 1)
-        rel = np.abs(total - ref) / np.maximum(1.0, np.abs(ref))
-        assert rel.max() < 1e-4, rel.max()
-        assert np.median(rel) < 1e-7
-        one.close()
+            tracers.append(t)
+            rends.append(Renderer(c, spec.width, spec.height))
+        results = {}
+        for mode in (PEER, NCCL, PEER):
+            for rk, c in enumerate(ctxs):
+                c.call("lg_reduce_mode_set", mode)
+                rends[rk].clear(1.0 if rk == 0 else 0.0)     # only the root owns the clear alpha
+                rends[rk].render(tracers[rk])
+            parts = [r.read_rgba32f() for r in rends] if mode == PEER else None
+            reduce_all(ctxs, 0)
+            total = rends[0].read_rgba32f()
+            half = rends[0].read_rgba16f()
+            # same fragments, different fp32 summation trees (partial images + reduce vs one image): hot pixels next
+            # to a light sum ~1e4 fragments, so the stated bound is 1e-4 relative to the pixel value
+            assert np.array_equal(total[..., 3] > 1, ref[..., 3] > 1)
+            rel = np.abs(total - ref) / np.maximum(1.0, np.abs(ref))
+            assert rel.max() < 1e-4, (mode, rel.max())
+            assert np.median(rel) < 1e-7
+            # the Rgba16Float frame is the rounded fp32 sum, whichever kernel produced it
+            assert np.array_equal(half.view(np.uint16), total.astype(np.float16).view(np.uint16)), mode
+            if mode == PEER:   # deterministic: partial images added in rank order
+                acc = parts[0].copy()
+                for p in parts[1:]:
+                    acc += p
+                assert np.array_equal(total, acc)
+            results[mode] = total
+        assert (np.abs(results[PEER] - results[NCCL]) <= 1e-5 * np.maximum(1.0, np.abs(ref))).all()
     finally:
+        one.close()
         for c in ctxs:
             c.close()
