@@ -180,7 +180,9 @@ typedef struct LgStringMod {
 } LgStringMod; /* 48 bytes */
 
 /* ---- accumulation target -------------------------------------------------- */
-enum { LG_RGBA32F = 0, LG_RGBA16F = 1 };
+/* LG_BGRA8_GAMMA is the reference's screenshot conversion (src/renderer.rs:313-328):
+ * every Rgba16Float channel -> (f.powf(1/2.2) * 255) as u8, stored [b, g, r, a]. */
+enum { LG_RGBA32F = 0, LG_RGBA16F = 1, LG_BGRA8_GAMMA = 2 };
 
 typedef struct LgTraceStats {
   uint64_t primary_rays;    /* rays this context traced (its shard)          */
@@ -264,8 +266,10 @@ int32_t lg_string_mod(lg_ctx *ctx, const LgStringMod *sm,
 /* trace_all + render fused: rays are traced in waves through the bounded
  * segment buffer and each wave is accumulated before the next is traced. */
 int32_t lg_render(lg_ctx *ctx, LgTraceStats *stats);
-/* Image out: LG_RGBA32F (16 B/px) or LG_RGBA16F (8 B/px, round to nearest
- * even, what the ROP would have stored). pitch in bytes, 0 = tight. */
+/* Image out: LG_RGBA32F (16 B/px), LG_RGBA16F (8 B/px, round to nearest even,
+ * what the ROP would have stored) or LG_BGRA8_GAMMA (4 B/px, the screenshot
+ * path). pitch in bytes, 0 = tight (wgpu's readback pads rows to 256 bytes,
+ * renderer.rs:250-255: pass that pitch to get the same layout). */
 int32_t lg_image_read(lg_ctx *ctx, int32_t format, void *dst, size_t pitch);
 
 /* ---- multi-GPU: one context per device ------------------------------------ */

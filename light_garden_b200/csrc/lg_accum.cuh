@@ -295,4 +295,23 @@ __global__ void finalize_f16_kernel(const float4 *img, uint2 *dst, size_t n_px) 
   }
 }
 
+// Screenshot conversion of the reference (src/renderer.rs:313-328): every Rgba16Float channel becomes
+// `(f.powf(1. / 2.2) * 255.) as u8` (saturating cast, NaN -> 0) and the pixel is stored as [b, g, r, a].
+// powf is evaluated in f64 and rounded once, which reproduces a correctly rounded f32 powf.
+__device__ __forceinline__ unsigned char f16_to_u8(float v) {
+  const float f = __half2float(__float2half_rn(v)); // the value the fp16 texture holds
+  const float g = (float)pow((double)f, (double)(1.f / 2.2f)) * 255.f;
+  if (!(g == g)) return 0;
+  if (g <= 0.f) return 0;
+  if (g >= 255.f) return 255;
+  return (unsigned char)g; // truncation, as `as u8`
+}
+__global__ void screenshot_bgra8_kernel(const float4 *img, uchar4 *dst, size_t n_px) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_px; i += stride) {
+    const float4 v = img[i];
+    dst[i] = make_uchar4(f16_to_u8(v.z), f16_to_u8(v.y), f16_to_u8(v.x), f16_to_u8(v.w));
+  }
+}
+
 } // namespace lg

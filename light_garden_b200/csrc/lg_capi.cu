@@ -151,7 +151,7 @@ struct lg_ctx {
 
   // image
   int W = 0, H = 0;
-  DevBuf img, img16, pixctr;
+  DevBuf img, img16, img8, pixctr;
   // tile-binned accumulation (lg_tiles.cuh)
   int accum_mode = 0; // 0 = auto, 1 = direct (one L2 reduction per fragment), 2 = tile-binned
   // auto mode: measured cost of each resolve on this context's recent work (ns per fragment, 0 = no sample yet)
@@ -713,7 +713,7 @@ int32_t lg_destroy(lg_ctx *c) {
                     &c->tags,      &c->seg64,    &c->ctr,      &c->stack,   &c->rays,     &c->img,     &c->img16,
                     &c->pixctr,    &c->tile_count, &c->tile_cursor, &c->tile_offset, &c->item_prefix,
                     &c->tile_totals, &c->item_counter, &c->tile_list, &c->seg2,       &c->tile_hist,
-                    &c->sync_buf,  &c->peer_xchg};
+                    &c->sync_buf,  &c->peer_xchg,  &c->img8};
   for (DevBuf *b : bufs) release(*b);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
@@ -1096,6 +1096,15 @@ int32_t lg_image_read(lg_ctx *c, int32_t format, void *dst, size_t pitch) {
       c->launches++;
     }
     LG_CUDA(c, cudaMemcpy2DAsync(dst, pitch, c->img16.p, row, row, c->H, cudaMemcpyDeviceToHost, c->stream));
+  } else if (format == LG_BGRA8_GAMMA) {
+    const size_t row = (size_t)c->W * 4;
+    if (pitch == 0) pitch = row;
+    if (pitch < row) return fail(c, LG_ERR_INVALID, "pitch");
+    if ((rc = ensure(c, c->img8, npx * 4))) return rc;
+    screenshot_bgra8_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>((const float4 *)c->img.p, (uchar4 *)c->img8.p, npx);
+    LG_CUDA(c, cudaGetLastError());
+    c->launches++;
+    LG_CUDA(c, cudaMemcpy2DAsync(dst, pitch, c->img8.p, row, row, c->H, cudaMemcpyDeviceToHost, c->stream));
   } else {
     return fail(c, LG_ERR_INVALID, "format");
   }

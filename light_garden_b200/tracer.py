@@ -273,6 +273,14 @@ class Renderer:
         self.ctx.call("lg_image_read", abi.LG_RGBA32F, abi.array_ptr(out), 0)
         return out
 
+    def make_screenshot(self, pitch: int = 0):
+        """Renderer::make_screenshot's pixel conversion (renderer.rs:294-328): H x W x 4 uint8 in [b, g, r, a] order.
+        `pitch` > 0 pads every row (wgpu's COPY_BYTES_PER_ROW_ALIGNMENT layout, renderer.rs:250-255)."""
+        row = pitch if pitch else self.width * 4
+        out = np.zeros((self.height, row), dtype=np.uint8)
+        self.ctx.call("lg_image_read", abi.LG_BGRA8_GAMMA, abi.array_ptr(out), row)
+        return out[:, : self.width * 4].reshape(self.height, self.width, 4)
+
     def read_rgba16f(self, out=None):
         if out is None:
             out = np.zeros((self.height, self.width, 4), dtype=np.float16)

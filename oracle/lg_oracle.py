@@ -71,6 +71,7 @@ def lib():
         L.lgo_accumulate_pairs.restype = C.c_uint64
         L.lgo_accumulate_pairs.argtypes = [vp, C.c_int32, C.c_int32, vp, C.c_uint64, C.c_int32]
         L.lgo_image_to_f16.argtypes = [vp, C.c_uint64, vp]
+        L.lgo_image_to_bgra8.argtypes = [vp, C.c_uint64, vp]
         L.lgo_num_threads.restype = C.c_int32
         _lib = L
     return _lib
@@ -209,6 +210,14 @@ def accumulate_pairs(img, pairs, threads=0):
 def to_f16(img):
     out = np.zeros(img.shape, dtype=np.float16)
     lib().lgo_image_to_f16(abi.array_ptr(np.ascontiguousarray(img)), img.size, abi.array_ptr(out))
+    return out
+
+
+def to_bgra8(img):
+    """Renderer::make_screenshot's conversion of the Rgba16Float frame (renderer.rs:313-328)."""
+    img = np.ascontiguousarray(img, dtype=np.float32)
+    out = np.zeros(img.shape[:2] + (4,), dtype=np.uint8)
+    lib().lgo_image_to_bgra8(abi.array_ptr(img), img.shape[0] * img.shape[1], abi.array_ptr(out))
     return out
 
 

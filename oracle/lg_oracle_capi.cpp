@@ -330,6 +330,40 @@ static uint16_t f2h(float f) {
   if (rem > 0x1000u || (rem == 0x1000u && (half & 1))) half++;
   return (uint16_t)(sign | half);
 }
+static float h2f(uint16_t h) {
+  uint32_t sign = (uint32_t)(h & 0x8000u) << 16, ex = (h >> 10) & 0x1f, man = h & 0x3ffu, x;
+  if (ex == 0) {
+    if (man == 0) {
+      x = sign;
+    } else {
+      int e = -1;
+      do {
+        man <<= 1;
+        ++e;
+      } while (!(man & 0x400u));
+      x = sign | ((uint32_t)(127 - 15 - e) << 23) | ((man & 0x3ffu) << 13);
+    }
+  } else if (ex == 31) {
+    x = sign | 0x7f800000u | (man << 13);
+  } else {
+    x = sign | ((ex + 112) << 23) | (man << 13);
+  }
+  float f;
+  std::memcpy(&f, &x, 4);
+  return f;
+}
+// Renderer::f16_to_u8 + convert_pixel_rgbaf16_to_bgra8 (src/renderer.rs:313-328)
+void lgo_image_to_bgra8(const float *img, uint64_t n_px, uint8_t *dst) {
+  for (uint64_t i = 0; i < n_px; ++i) {
+    uint8_t c[4];
+    for (int k = 0; k < 4; ++k) {
+      float f = h2f(f2h(img[4 * i + k]));
+      float g = std::pow(f, 1.f / 2.2f) * 255.f; // f32 powf, like Rust's f32::powf
+      c[k] = !(g == g) ? 0 : g <= 0.f ? 0 : g >= 255.f ? 255 : (uint8_t)g; // `as u8`: saturating, NaN -> 0
+    }
+    dst[4 * i] = c[2], dst[4 * i + 1] = c[1], dst[4 * i + 2] = c[0], dst[4 * i + 3] = c[3];
+  }
+}
 void lgo_image_to_f16(const float *img, uint64_t n_floats, uint16_t *dst) {
   for (uint64_t i = 0; i < n_floats; ++i) dst[i] = f2h(img[i]);
 }

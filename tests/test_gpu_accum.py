@@ -181,6 +181,28 @@ def test_finalize_rgba16f(oracle, ctx):
     assert np.array_equal(f16.view(np.uint16), f32.astype(np.float16).view(np.uint16))
 
 
+def test_screenshot_bgra8(oracle, ctx):
+    """SURVEY.md §8f rank 3: Renderer::make_screenshot's fp16 -> gamma u8 conversion (renderer.rs:313-328) and the
+    256-byte padded row layout of its readback (renderer.rs:250-255)."""
+    from light_garden_b200.tracer import Renderer
+    W, H = 100, 40          # 400-byte rows: padded to 512
+    r = Renderer(ctx, W, H)
+    p = random_pairs(3000, seed=21, pow2=False)
+    p["color_a"] *= 20
+    p["color_b"] *= 20
+    r.render_lines(p)
+    f32 = r.read_rgba32f()
+    exp = oracle.to_bgra8(f32)
+    got = r.make_screenshot()
+    # powf in f64-then-rounded (device) vs libm powf (oracle): identical except when f^(1/2.2)*255 sits within an
+    # ulp of an integer
+    diff = np.abs(got.astype(np.int32) - exp.astype(np.int32))
+    assert diff.max() <= 1 and (diff != 0).mean() < 1e-3
+    assert got[..., 3].min() == 255                  # alpha >= 1 saturates
+    padded = r.make_screenshot(pitch=512)
+    assert np.array_equal(padded, got)
+
+
 def test_clear_value_and_partial_alpha(ctx):
     from light_garden_b200.tracer import Renderer
     r = Renderer(ctx, 40, 30)

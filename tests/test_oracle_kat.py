@@ -495,3 +495,15 @@ def test_f16_conversion_matches_numpy(oracle):
                         2.0 ** -24, 2.0 ** -25, 3 * 2.0 ** -25]]).astype(np.float32).reshape(-1, 4)
     with np.errstate(over="ignore"):
         assert np.array_equal(oracle.to_f16(x).view(np.uint16), x.astype(np.float16).view(np.uint16))
+
+
+def test_screenshot_conversion_known_values(oracle):
+    """renderer.rs:325-328: u8 = (f^(1/2.2) * 255) as u8 on the fp16 value; pixel order [b, g, r, a]."""
+    img = np.zeros((1, 6, 4), dtype=np.float32)
+    img[0, :, 0] = [0.0, 1.0, 0.5, 2.0, -1.0, 0.25]
+    img[0, :, 1] = 1.0
+    img[0, :, 3] = 0.0
+    out = oracle.to_bgra8(img)
+    exp_r = [0, 255, int(0.5 ** (1 / 2.2) * 255), 255, 0, int(0.25 ** (1 / 2.2) * 255)]   # saturates; NaN -> 0
+    assert out[0, :, 2].tolist() == exp_r          # red lands in byte 2
+    assert np.all(out[0, :, 1] == 255) and np.all(out[0, :, 0] == 0) and np.all(out[0, :, 3] == 0)
