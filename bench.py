@@ -323,7 +323,7 @@ def main():
             "pixel_updates_per_s_in_kernel": agg["pixel_updates"] / world / max(1e-9, agg["accumulate_ms"] * 1e-3),
             "segments_per_ray": agg["segments"] / total_rays,
             "phase_ms_per_step": {"trace": agg["trace_ms"] / args.steps, "accumulate": agg["accumulate_ms"] / args.steps,
-                                  "nccl_reduce": agg["reduce_ms"] / args.steps},
+                                  "image_reduce": agg["reduce_ms"] / args.steps},
             "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(agg["launches"]),

@@ -66,7 +66,8 @@ enum {
   LG_GEO_RECT = 1,    /* Geo::GeoRect         p = {ox, oy, width, height}, rot */
   LG_GEO_SEGMENT = 2, /* Geo::GeoLineSegment  p = {ax, ay, bx, by}            */
   LG_GEO_BEZIER = 3,  /* Geo::GeoCubicBezier  p = {x0,y0,x1,y1,x2,y2,x3,y3}   */
-  LG_GEO_LOGIC = 4    /* Geo::GeoLogic        p = {ox, oy}, rot, op, a, b     */
+  LG_GEO_LOGIC = 4,   /* Geo::GeoLogic        p = {ox, oy}, rot, op, a, b     */
+  LG_GEO_ELLIPSE = 5  /* Geo::GeoEllipse      p = {ox, oy, a, b}, rot         */
 };
 /* collision2d LogicOp (src/light_garden/mod.rs:368-372) */
 enum { LG_OP_AND = 0, LG_OP_OR = 1, LG_OP_ANDNOT = 2 };
@@ -164,7 +165,9 @@ typedef struct LgSegmentF64 {
 
 /* ---- string mod (src/light_garden/string_mod.rs:4-15) -------------------- */
 enum { LG_SM_ADD = 0, LG_SM_MUL = 1, LG_SM_POW = 2, LG_SM_BASE = 3 };
-enum { LG_CURVE_CIRCLE = 0 };
+/* Curve (string_mod.rs:182-188); curve_p: COMPLEX_EXP {re, im}; HYPOTROCHOID {r, s, d};
+ * LISSAJOUS {a, b, delta} */
+enum { LG_CURVE_CIRCLE = 0, LG_CURVE_COMPLEX_EXP = 1, LG_CURVE_HYPOTROCHOID = 2, LG_CURVE_LISSAJOUS = 3 };
 typedef struct LgModRemColor {
   uint64_t modulo;
   uint64_t rem;
@@ -177,7 +180,8 @@ typedef struct LgStringMod {
   int32_t mode;  /* LG_SM_*                                                  */
   int32_t curve; /* LG_CURVE_*                                               */
   float color[4];
-} LgStringMod; /* 48 bytes */
+  double curve_p[4];
+} LgStringMod; /* 80 bytes */
 
 /* ---- accumulation target -------------------------------------------------- */
 /* LG_BGRA8_GAMMA is the reference's screenshot conversion (src/renderer.rs:313-328):

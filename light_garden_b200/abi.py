@@ -18,11 +18,11 @@ ERROR_NAMES = {
 }
 
 LG_PRECISION_F32, LG_PRECISION_F64 = 0, 1
-LG_GEO_CIRCLE, LG_GEO_RECT, LG_GEO_SEGMENT, LG_GEO_BEZIER, LG_GEO_LOGIC = 0, 1, 2, 3, 4
+LG_GEO_CIRCLE, LG_GEO_RECT, LG_GEO_SEGMENT, LG_GEO_BEZIER, LG_GEO_LOGIC, LG_GEO_ELLIPSE = 0, 1, 2, 3, 4, 5
 LG_OP_AND, LG_OP_OR, LG_OP_ANDNOT = 0, 1, 2
 LG_LIGHT_POINT, LG_LIGHT_DIRECTIONAL, LG_LIGHT_SPOT = 0, 1, 2
 LG_SM_ADD, LG_SM_MUL, LG_SM_POW, LG_SM_BASE = 0, 1, 2, 3
-LG_CURVE_CIRCLE = 0
+LG_CURVE_CIRCLE, LG_CURVE_COMPLEX_EXP, LG_CURVE_HYPOTROCHOID, LG_CURVE_LISSAJOUS = 0, 1, 2, 3
 LG_RGBA32F, LG_RGBA16F, LG_BGRA8_GAMMA = 0, 1, 2
 
 
@@ -57,7 +57,7 @@ class LgTraceStats(C.Structure):
 
 class LgStringMod(C.Structure):
     _fields_ = [("modulo", C.c_uint64), ("num", C.c_uint64), ("turns", C.c_uint64), ("mode", C.c_int32),
-                ("curve", C.c_int32), ("color", C.c_float * 4)]
+                ("curve", C.c_int32), ("color", C.c_float * 4), ("curve_p", C.c_double * 4)]
 
 
 class LgModRemColor(C.Structure):
@@ -80,7 +80,7 @@ SIZES = {
     "LgRay": (RAY_DTYPE.itemsize, 56), "LgSegment": (SEGMENT_DTYPE.itemsize, 32),
     "LgVertexPair": (VERTEX_PAIR_DTYPE.itemsize, 64), "LgSegmentTag": (SEGMENT_TAG_DTYPE.itemsize, 24),
     "LgSegmentF64": (SEGMENT_F64_DTYPE.itemsize, 32), "LgModRemColor": (C.sizeof(LgModRemColor), 32),
-    "LgStringMod": (C.sizeof(LgStringMod), 48), "LgTraceStats": (C.sizeof(LgTraceStats), 56),
+    "LgStringMod": (C.sizeof(LgStringMod), 80), "LgTraceStats": (C.sizeof(LgTraceStats), 56),
 }
 
 _ctx = C.c_void_p

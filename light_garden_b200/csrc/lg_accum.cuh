@@ -221,13 +221,57 @@ __device__ __forceinline__ unsigned long long sm_target(const LgStringMod &sm, u
   default: return wrapping_pow(sm.num, (unsigned int)i) % m;
   }
 }
+// StringMod::init_points (string_mod.rs:33-85), f64 like the reference, then `as f32` (sub_render_pass.rs:192)
 __device__ __forceinline__ void sm_point(const LgStringMod &sm, unsigned long long n, float &x, float &y) {
-  const double TAU = 6.28318530717958647692; // string_mod.rs:45-55
-  const double angle = __ddiv_rn(__dmul_rn((double)(sm.turns * n), TAU), (double)sm.modulo);
-  double s, c;
-  sincos(angle, &s, &c);
-  x = (float)c; // `p.x as f32`, sub_render_pass.rs:192
-  y = (float)s;
+  const double TAU = 6.28318530717958647692;
+  const unsigned long long tn = sm.turns * n; // u64 product, wraps
+  double px, py;
+  if (sm.curve == LG_CURVE_COMPLEX_EXP) {
+    // complex.powu((turns * n) as u32): num_traits::pow, exponentiation by squaring with plain complex products
+    unsigned int e = (unsigned int)tn;
+    double br = sm.curve_p[0], bi = sm.curve_p[1];
+    if (e == 0) {
+      px = 1.0, py = 0.0;
+    } else {
+      while ((e & 1u) == 0u) {
+        const double r = __dsub_rn(__dmul_rn(br, br), __dmul_rn(bi, bi)), i = __dadd_rn(__dmul_rn(br, bi), __dmul_rn(bi, br));
+        br = r, bi = i;
+        e >>= 1;
+      }
+      double ar = br, ai = bi;
+      while (e > 1u) {
+        e >>= 1;
+        const double r = __dsub_rn(__dmul_rn(br, br), __dmul_rn(bi, bi)), i = __dadd_rn(__dmul_rn(br, bi), __dmul_rn(bi, br));
+        br = r, bi = i;
+        if (e & 1u) {
+          const double cr = __dsub_rn(__dmul_rn(ar, br), __dmul_rn(ai, bi)), ci = __dadd_rn(__dmul_rn(ar, bi), __dmul_rn(ai, br));
+          ar = cr, ai = ci;
+        }
+      }
+      px = ar, py = ai;
+    }
+  } else {
+    const double angle = __ddiv_rn(__dmul_rn((double)tn, TAU), (double)sm.modulo);
+    if (sm.curve == LG_CURVE_HYPOTROCHOID) { // string_mod.rs:56-71
+      const double small_r = (double)(unsigned long long)sm.curve_p[0], big_r = (double)(unsigned long long)sm.curve_p[1];
+      const double off = (double)(unsigned long long)sm.curve_p[2];
+      const double smr = __dsub_rn(big_r, small_r), ratio = __dadd_rn(smr, off);
+      const double inner = __ddiv_rn(__dmul_rn(angle, smr), small_r);
+      const double xx = __dadd_rn(__dmul_rn(smr, cos(angle)), __dmul_rn(off, cos(inner)));
+      const double yy = __dsub_rn(__dmul_rn(smr, sin(angle)), __dmul_rn(off, sin(inner)));
+      px = __ddiv_rn(xx, ratio), py = __ddiv_rn(yy, ratio);
+    } else if (sm.curve == LG_CURVE_LISSAJOUS) { // string_mod.rs:73-83
+      const double a = (double)(unsigned long long)sm.curve_p[0], b = (double)(unsigned long long)sm.curve_p[1];
+      px = sin(__dadd_rn(__dmul_rn(a, angle), sm.curve_p[2]));
+      py = sin(__dmul_rn(b, angle));
+    } else { // Circle, string_mod.rs:45-55
+      double s, c;
+      sincos(angle, &s, &c);
+      px = c, py = s;
+    }
+  }
+  x = (float)px;
+  y = (float)py;
 }
 __device__ __forceinline__ void sm_color(const StringModArgs &S, unsigned long long ix, float out[4]) {
   float c0 = 0.f, c1 = 0.f, c2 = 0.f, c3 = 0.f; // string_mod.rs:124-150

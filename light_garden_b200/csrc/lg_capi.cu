@@ -35,7 +35,7 @@ static_assert(sizeof(LgVertexPair) == 64, "LgVertexPair ABI");
 static_assert(sizeof(LgSegmentTag) == 24, "LgSegmentTag ABI");
 static_assert(sizeof(LgSegmentF64) == 32, "LgSegmentF64 ABI");
 static_assert(sizeof(LgModRemColor) == 32, "LgModRemColor ABI");
-static_assert(sizeof(LgStringMod) == 48, "LgStringMod ABI");
+static_assert(sizeof(LgStringMod) == 80, "LgStringMod ABI");
 static_assert(sizeof(LgTraceStats) == 56, "LgTraceStats ABI");
 
 using namespace lg;
@@ -245,6 +245,11 @@ template <class T> int upload_scene(lg_ctx *c) {
     case 3:
       for (int k = 0; k < 8; ++k) t.p[k] = (T)h.p[k];
       break;
+    case 5:
+      for (int k = 0; k < 6; ++k) t.p[k] = (T)h.p[k];
+      t.p[6] = (T)1 / t.p[4];
+      t.p[7] = (T)1 / t.p[5];
+      break;
     default: break;
     }
     toks[i] = t;
@@ -287,6 +292,8 @@ template <class T> int upload_scene(lg_ctx *c) {
     auto leaf_circle = [&](const HostTok &t, double &cx, double &cy, double &rr) {
       if (t.kind == 0) {
         cx = t.p[0], cy = t.p[1], rr = std::fabs(t.p[2]);
+      } else if (t.kind == 5) {
+        cx = t.p[0], cy = t.p[1], rr = std::fmax(t.p[4], t.p[5]);
       } else if (t.kind == 1) {
         cx = t.p[0], cy = t.p[1], rr = std::hypot(std::hypot(t.p[2], t.p[3]), std::hypot(t.p[4], t.p[5]));
       } else {
@@ -981,7 +988,7 @@ int32_t lg_string_mod(lg_ctx *c, const LgStringMod *sm, const LgModRemColor *rul
   int rc = need_image(c);
   if (rc) return rc;
   if (!sm || (n_rules && !rules)) return fail(c, LG_ERR_INVALID, "null string mod");
-  if (sm->curve != LG_CURVE_CIRCLE) return fail(c, LG_ERR_UNSUPPORTED, "only Curve::Circle (SURVEY.md §8f)");
+  if (sm->curve < LG_CURVE_CIRCLE || sm->curve > LG_CURVE_LISSAJOUS) return fail(c, LG_ERR_INVALID, "Curve");
   if (sm->mode < LG_SM_ADD || sm->mode > LG_SM_BASE) return fail(c, LG_ERR_INVALID, "StringModMode");
   if (sm->modulo == 0) return LG_OK; // draw_init_points: points.is_empty() -> no lines (string_mod.rs:106-108)
   c->img16_valid = false;

@@ -21,7 +21,7 @@ namespace lg {
 constexpr double kTMin = 1e-5;    // ORACLE.md §1: accept a hit iff t > T_MIN
 constexpr double kParEps = 1e-12; // ORACLE.md §1: |cross(d,e)| <= PAR_EPS is parallel
 
-enum : int32_t { TOK_CIRCLE = 0, TOK_RECT = 1, TOK_SEGMENT = 2, TOK_BEZIER = 3, TOK_OP = 4 };
+enum : int32_t { TOK_CIRCLE = 0, TOK_RECT = 1, TOK_SEGMENT = 2, TOK_BEZIER = 3, TOK_OP = 4, TOK_ELLIPSE = 5 };
 enum : int32_t { OP_AND = 0, OP_OR = 1, OP_ANDNOT = 2 };
 
 // ---- real-type wrappers ----------------------------------------------------
@@ -80,6 +80,7 @@ template <class T> struct Tok {
   T p[8];
   // CIRCLE : cx cy r r2          SEGMENT: ax ay ex ey
   // RECT   : cx cy ux uy vx vy uu vv     BEZIER : x0 y0 .. x3 y3
+  // ELLIPSE: cx cy ux uy a b 1/a 1/b  (u = unit x axis of the ellipse in world space)
 };
 
 // A candidate hit: ray parameter, point, and what is needed to rebuild the
@@ -242,6 +243,29 @@ template <class T> LG_HD V2<T> bezier_normal(const T *b, T tt) {
   return unit(V2<T>{-tg.y, tg.x});
 }
 
+// ---- ORACLE.md §3.7 ellipse: the ray in the frame where the ellipse is the unit circle ------------
+template <class T> LG_HD V2<T> ellipse_frame(const T *e, V2<T> w) {
+  V2<T> u{e[2], e[3]}, up{-e[3], e[2]};
+  return {dot(w, u) * e[6], dot(w, up) * e[7]};
+}
+template <class T> LG_HD V2<T> ellipse_normal(const T *e, V2<T> p) {
+  V2<T> u{e[2], e[3]}, up{-e[3], e[2]};
+  V2<T> l = ellipse_frame(e, V2<T>{p.x - e[0], p.y - e[1]});
+  T gx = l.x * e[6], gy = l.y * e[7];
+  return unit(V2<T>{Real<T>::fma(gx, u.x, gy * up.x), Real<T>::fma(gx, u.y, gy * up.y)});
+}
+template <class T> LG_HD void hit_ellipse(const T *e, V2<T> o, V2<T> d, CandList<T> &out) {
+  V2<T> lo = ellipse_frame(e, V2<T>{o.x - e[0], o.y - e[1]});
+  V2<T> ld = ellipse_frame(e, d);
+  T A = dot(ld, ld), B = dot(lo, ld), C = dot(lo, lo) - (T)1;
+  T disc = Real<T>::fma(B, B, -(A * C));
+  if (!(disc >= (T)0) || !(A > (T)0)) return;
+  T sq = Real<T>::sqrt(disc);
+  T t0 = Real<T>::div(-B - sq, A), t1 = Real<T>::div(-B + sq, A);
+  if (t0 > (T)kTMin) out.h[out.n++] = {t0, ray_at(o, t0, d), (T)0};
+  if (t1 > (T)kTMin) out.h[out.n++] = {t1, ray_at(o, t1, d), (T)1};
+}
+
 // unit normal of the hit (token, point, aux); orientation is fixed later
 template <class T> LG_HD V2<T> hit_normal(const Tok<T> &k, V2<T> p, T aux) {
   switch (k.kind) {
@@ -252,6 +276,7 @@ template <class T> LG_HD V2<T> hit_normal(const Tok<T> &k, V2<T> p, T aux) {
     rect_edge(k.p, (int)aux, a, e);
     return unit(V2<T>{-e.y, e.x});
   }
+  case TOK_ELLIPSE: return ellipse_normal(k.p, p);
   default: return bezier_normal(k.p, aux);
   }
 }
@@ -267,6 +292,10 @@ template <class T> LG_HD bool contains_leaf(const Tok<T> &l, V2<T> p) {
     T a = dot(q, V2<T>{l.p[2], l.p[3]});
     T b = dot(q, V2<T>{l.p[4], l.p[5]});
     return Real<T>::abs(a) < l.p[6] && Real<T>::abs(b) < l.p[7];
+  }
+  if (l.kind == TOK_ELLIPSE) {
+    V2<T> q = ellipse_frame(l.p, V2<T>{p.x - l.p[0], p.y - l.p[1]});
+    return dot(q, q) < (T)1;
   }
   return false; // mirrors never contain: src/light_garden/object.rs:243-244
 }

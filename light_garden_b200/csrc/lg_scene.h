@@ -20,7 +20,8 @@ namespace lg {
 
 struct HostTok {
   int32_t kind, op, a_start, b_start;
-  double p[8]; // world-space: CIRCLE cx cy r | RECT cx cy ux uy vx vy | SEGMENT ax ay bx by | BEZIER 8
+  double p[8]; // world-space: CIRCLE cx cy r | RECT cx cy ux uy vx vy | SEGMENT ax ay bx by | BEZIER 8 |
+               // ELLIPSE (kind 5) cx cy ux uy a b
 };
 struct HostObj {
   int32_t first, count;
@@ -100,6 +101,21 @@ inline bool lower_geo(const LgGeoNode *nodes, uint32_t n_nodes, int32_t ix, cons
     for (int k = 0; k < 4; ++k) xform(A, g.p[2 * k], g.p[2 * k + 1], t.p + 2 * k);
     out.push_back(t);
     return true;
+  case LG_GEO_ELLIPSE: { // object.rs:38-45: Ellipse{origin, a, b, rot}
+    t.kind = 5;
+    xform(A, g.p[0], g.p[1], t.p);
+    Affine W = compose_rot(A, g.rot);
+    t.p[2] = W.m11;
+    t.p[3] = W.m21;
+    t.p[4] = g.p[2];
+    t.p[5] = g.p[3];
+    if (!(g.p[2] > 0.0) || !(g.p[3] > 0.0)) {
+      err = "ellipse semi axes must be > 0";
+      return false;
+    }
+    out.push_back(t);
+    return true;
+  }
   case LG_GEO_LOGIC: {
     if (g.op < LG_OP_AND || g.op > LG_OP_ANDNOT) {
       err = "unknown LogicOp";
@@ -122,8 +138,8 @@ inline bool lower_geo(const LgGeoNode *nodes, uint32_t n_nodes, int32_t ix, cons
     return true;
   }
   default:
-    // ConvexPolygon / Ellipse / MCircle exist in collision2d's Geo
-    // (drawer.rs:57-98) but are outside the BASELINE configs: SURVEY.md §8f.
+    // ConvexPolygon / MCircle exist in collision2d's Geo (drawer.rs:57-84)
+    // but are outside the BASELINE configs: SURVEY.md §8f.
     err = "unsupported Geo kind";
     return false;
   }
@@ -159,7 +175,7 @@ inline int32_t lower_scene(const LgObject *objects, uint32_t n_obj, const LgGeoN
     o.can_contain = false;
     for (int k = 0; k < o.count; ++k) {
       const HostTok &t = hs.toks[o.first + k];
-      int np = t.kind == 0 ? 1 : t.kind == 1 ? 1 : t.kind == 2 ? 2 : t.kind == 3 ? 4 : 0;
+      int np = t.kind == 0 ? 1 : t.kind == 1 ? 1 : t.kind == 2 ? 2 : t.kind == 3 ? 4 : t.kind == 5 ? 1 : 0;
       for (int q = 0; q < np; ++q) bound = std::fmax(bound, std::fmax(std::fabs(t.p[2 * q]), std::fabs(t.p[2 * q + 1])));
       double ex = 0, ey = 0;
       if (t.kind == 0) {
@@ -167,6 +183,8 @@ inline int32_t lower_scene(const LgObject *objects, uint32_t n_obj, const LgGeoN
       } else if (t.kind == 1) {
         ex = std::fabs(t.p[2]) + std::fabs(t.p[4]);
         ey = std::fabs(t.p[3]) + std::fabs(t.p[5]);
+      } else if (t.kind == 5) {
+        ex = ey = std::fmax(t.p[4], t.p[5]);
       } else {
         continue;
       }
@@ -194,9 +212,10 @@ inline int32_t lower_scene(const LgObject *objects, uint32_t n_obj, const LgGeoN
     for (int k = 0; k < a.count; ++k) {
       const HostTok &t = hs.toks[a.first + k];
       if (t.kind == 4) continue;
-      if (t.kind == 0) {
-        bx.x0 = std::fmin(bx.x0, t.p[0] - t.p[2]), bx.x1 = std::fmax(bx.x1, t.p[0] + t.p[2]);
-        bx.y0 = std::fmin(bx.y0, t.p[1] - t.p[2]), bx.y1 = std::fmax(bx.y1, t.p[1] + t.p[2]);
+      if (t.kind == 0 || t.kind == 5) {
+        const double rr = t.kind == 0 ? t.p[2] : std::fmax(t.p[4], t.p[5]);
+        bx.x0 = std::fmin(bx.x0, t.p[0] - rr), bx.x1 = std::fmax(bx.x1, t.p[0] + rr);
+        bx.y0 = std::fmin(bx.y0, t.p[1] - rr), bx.y1 = std::fmax(bx.y1, t.p[1] + rr);
       } else if (t.kind == 1) {
         double ex = std::fabs(t.p[2]) + std::fabs(t.p[4]), ey = std::fabs(t.p[3]) + std::fabs(t.p[5]);
         bx.x0 = std::fmin(bx.x0, t.p[0] - ex), bx.x1 = std::fmax(bx.x1, t.p[0] + ex);
@@ -255,6 +274,12 @@ inline bool host_contains_leaf(const HostTok &t, double x, double y) {
     double a = std::fma(qx, t.p[2], qy * t.p[3]), b = std::fma(qx, t.p[4], qy * t.p[5]);
     double uu = std::fma(t.p[2], t.p[2], t.p[3] * t.p[3]), vv = std::fma(t.p[4], t.p[4], t.p[5] * t.p[5]);
     return std::fabs(a) < uu && std::fabs(b) < vv;
+  }
+  if (t.kind == 5) {
+    double qx = x - t.p[0], qy = y - t.p[1];
+    double lx = std::fma(qx, t.p[2], qy * t.p[3]) * (1.0 / t.p[4]);
+    double ly = std::fma(qx, -t.p[3], qy * t.p[2]) * (1.0 / t.p[5]);
+    return std::fma(lx, lx, ly * ly) < 1.0;
   }
   return false;
 }

@@ -231,6 +231,8 @@ __device__ __noinline__ void sweep_csg_object(const TraceArgs<T> &A, int obj, V2
       hit_rect(l.p, o, d, hl);
     else if (l.kind == TOK_SEGMENT)
       hit_segment(l.p, o, d, hl);
+    else if (l.kind == TOK_ELLIPSE)
+      hit_ellipse(l.p, o, d, hl);
     else
       hit_bezier(l.p, o, d, hl);
     for (int j = 0; j < hl.n; ++j) {
@@ -266,6 +268,8 @@ __device__ __noinline__ Best<T> narrow_phase(const TraceArgs<T> &A, Best<T> b, i
       hit_segment(k.p, o, d, hl);
     else if (k.kind == TOK_RECT)
       hit_rect(k.p, o, d, hl);
+    else if (k.kind == TOK_ELLIPSE)
+      hit_ellipse(k.p, o, d, hl);
     else
       hit_bezier(k.p, o, d, hl);
     for (int q = 0; q < hl.n; ++q) take(b, o, hl.h[q], obj, first);

@@ -8,7 +8,7 @@ tuples `( v, v )`, sequences `[ v, v ]`, enum variants `Name(..)`, `Some(..)`,
 """
 import re
 
-from .scene import (AND, AND_NOT, OR, Circle, CubicBezier, DirectionalLight, LineSegment, Logic, Material, Object,
+from .scene import (AND, AND_NOT, OR, Circle, CubicBezier, DirectionalLight, Ellipse, LineSegment, Logic, Material, Object,
                     PointLight, Rect, SpotLight)
 
 _TOKEN = re.compile(r"\s*(?:(//[^\n]*)|([A-Za-z_][A-Za-z_0-9]*)|([-+]?(?:\d+\.?\d*(?:[eE][-+]?\d+)?|\.\d+(?:[eE][-+]?\d+)?|inf|NaN))|(.))")
@@ -116,6 +116,8 @@ def _geo(v):
         return _logic(d)
     if name == "GeoCubicBezier":
         return CubicBezier(tuple(tuple(p) for p in d["points"]))
+    if name == "GeoEllipse":
+        return Ellipse(tuple(d["origin"]), d["a"], d["b"], tuple(d["rot"]))
     if name == "GeoLineSegment" and "a" in d and "b" in d:
         return LineSegment(tuple(d["a"]), tuple(d["b"]))
     raise ValueError(f"RON: unsupported Geo variant {name}")
@@ -140,6 +142,9 @@ def _object(d):
         return Object(Rect(tuple(body["origin"]), tuple(body["rotation"]), body["width"], body["height"]), material, "Rect", bool(d.get("moved", False)))
     if name == "Circle":
         return Object(Circle(tuple(body["origin"]), body["radius"]), material, "Circle", bool(d.get("moved", False)))
+    if name == "Ellipse":
+        return Object(Ellipse(tuple(body["origin"]), body["a"], body["b"], tuple(body["rot"])), material, "Ellipse",
+                      bool(d.get("moved", False)))
     if name == "Geo":
         return Object(_geo(_single(inner)), material, "Geo", bool(d.get("moved", False)))
     if name == "StraightMirror":

@@ -57,6 +57,15 @@ class Rect:
 
 
 @dataclass
+class Ellipse:
+    """collision2d Ellipse{origin, a, b, rot} (object.rs:38-45): x^2/a^2 + y^2/b^2 = 1 in the rotated local frame."""
+    origin: P2
+    a: float
+    b: float
+    rot: Tuple[float, float, float, float] = (1.0, 0.0, 0.0, 1.0)
+
+
+@dataclass
 class LineSegment:
     a: P2
     b: P2
@@ -119,6 +128,11 @@ class Object:
         # Lens::new, object.rs:393-410
         return Object(Logic(AND, Circle((distance * 0.5, 0.0), radius), Circle((-distance * 0.5, 0.0), radius),
                             tuple(origin), rot2_identity()), Material(), "Lens")
+
+    @staticmethod
+    def new_ellipse(origin, a, b):
+        # object.rs:38-45: rot = Rotation2::new(0.0)
+        return Object(Ellipse(tuple(origin), a, b, rot2_identity()), Material(), "Ellipse")
 
     @staticmethod
     def new_geo(geo):
@@ -216,6 +230,10 @@ def _push_geo(geo, nodes: list) -> int:
         n.kind = abi.LG_GEO_RECT
         n.p[0], n.p[1], n.p[2], n.p[3] = geo.origin[0], geo.origin[1], geo.width, geo.height
         n.rot[:] = geo.rotation
+    elif isinstance(geo, Ellipse):
+        n.kind = abi.LG_GEO_ELLIPSE
+        n.p[0], n.p[1], n.p[2], n.p[3] = geo.origin[0], geo.origin[1], geo.a, geo.b
+        n.rot[:] = geo.rot
     elif isinstance(geo, LineSegment):
         n.kind = abi.LG_GEO_SEGMENT
         n.p[0], n.p[1], n.p[2], n.p[3] = geo.a[0], geo.a[1], geo.b[0], geo.b[1]
@@ -262,6 +280,34 @@ def trace_params(max_bounce: int, cutoff_color: Sequence[float], canvas_bounds: 
 
 
 # ---- string mod (string_mod.rs) ---------------------------------------------------------------
+class Curve:
+    """string_mod.rs:182-188.  Circle | ComplexExp{c} | Hypotrochoid{r, s, d} | Lissajous{a, b, delta}."""
+
+    def __init__(self, kind, params=()):
+        self.kind, self.params = kind, tuple(float(p) for p in params)
+
+    def __eq__(self, other):
+        return isinstance(other, Curve) and (self.kind, self.params) == (other.kind, other.params)
+
+    def __hash__(self):
+        return hash((self.kind, self.params))
+
+    @staticmethod
+    def ComplexExp(c: complex):
+        return Curve(abi.LG_CURVE_COMPLEX_EXP, (c.real, c.imag))
+
+    @staticmethod
+    def Hypotrochoid(r: int, s: int, d: int):
+        return Curve(abi.LG_CURVE_HYPOTROCHOID, (int(r), int(s), int(d)))
+
+    @staticmethod
+    def Lissajous(a: int, b: int, delta: float):
+        return Curve(abi.LG_CURVE_LISSAJOUS, (int(a), int(b), delta))
+
+
+Curve.Circle = Curve(abi.LG_CURVE_CIRCLE)
+
+
 class StringModMode:
     Add, Mul, Pow, Base = abi.LG_SM_ADD, abi.LG_SM_MUL, abi.LG_SM_POW, abi.LG_SM_BASE
 
@@ -281,14 +327,16 @@ class StringMod:
     pow: int = 0
     color: Color = (1.0, 1.0, 1.0, 1.0)
     turns: int = 1
-    init_curve: int = abi.LG_CURVE_CIRCLE
+    init_curve: Curve = field(default_factory=lambda: Curve.Circle)
     mode: int = StringModMode.Mul
     modulo_colors: List[ModRemColor] = field(default_factory=list)
 
     def to_pod(self):
         s = abi.LgStringMod()
         s.modulo, s.num, s.turns = int(self.modulo), int(self.num), int(self.turns)
-        s.mode, s.curve = int(self.mode), int(self.init_curve)
+        s.mode, s.curve = int(self.mode), int(self.init_curve.kind)
+        for i, v in enumerate(self.init_curve.params):
+            s.curve_p[i] = v
         s.color[:] = [float(np.float32(c)) for c in self.color]
         rules = (abi.LgModRemColor * max(1, len(self.modulo_colors)))()
         for i, r in enumerate(self.modulo_colors):

@@ -53,7 +53,7 @@ template <class T> inline V2<T> along(V2<T> o, T t, V2<T> d) {
 // Lowered scene (ORACLE.md §2): every Geo tree becomes a postfix program over
 // world-space leaves.  Lowering is done in f64 and then cast to T.
 // ---------------------------------------------------------------------------
-enum TokKind : int32_t { TOK_CIRCLE = 0, TOK_RECT = 1, TOK_SEGMENT = 2, TOK_BEZIER = 3, TOK_OP = 4 };
+enum TokKind : int32_t { TOK_CIRCLE = 0, TOK_RECT = 1, TOK_SEGMENT = 2, TOK_BEZIER = 3, TOK_OP = 4, TOK_ELLIPSE = 5 };
 
 struct Token {
   int32_t kind;    // TokKind
@@ -131,6 +131,18 @@ inline bool lower_node(const std::vector<LgGeoNode> &nodes, int32_t ix, const Ma
   case LG_GEO_BEZIER: {
     tok.kind = TOK_BEZIER;
     for (int k = 0; k < 4; ++k) mat_apply(M, t, g.p[2 * k], g.p[2 * k + 1], tok.p + 2 * k);
+    out.push_back(tok);
+    return true;
+  }
+  case LG_GEO_ELLIPSE: { // centre, unit x axis of the ellipse in world space, semi axes
+    tok.kind = TOK_ELLIPSE;
+    mat_apply(M, t, g.p[0], g.p[1], tok.p);
+    Mat2 R{g.rot[0], g.rot[1], g.rot[2], g.rot[3]};
+    Mat2 W = mat_mul(M, R);
+    tok.p[2] = W.m11;
+    tok.p[3] = W.m21;
+    tok.p[4] = g.p[2];
+    tok.p[5] = g.p[3];
     out.push_back(tok);
     return true;
   }
@@ -243,6 +255,11 @@ template <class T> inline SceneT<T> cast_scene(const Scene &s) {
       break;
     case TOK_BEZIER:
       for (int k = 0; k < 8; ++k) l.p[k] = (T)t.p[k];
+      break;
+    case TOK_ELLIPSE: // cx cy ux uy a b 1/a 1/b
+      for (int k = 0; k < 6; ++k) l.p[k] = (T)t.p[k];
+      l.p[6] = (T)1 / l.p[4];
+      l.p[7] = (T)1 / l.p[5];
       break;
     default:
       break;
@@ -420,9 +437,42 @@ template <class T> inline void hit_bezier(const T *b, V2<T> o, V2<T> d, HitList<
   }
 }
 
+// §3.7 ellipse (centre c, unit axis u, semi axes a, b): the ray in the frame where the ellipse is the unit circle
+template <class T> inline V2<T> ellipse_local(const T *e, V2<T> w) { // world vector -> unit-circle frame
+  V2<T> u{e[2], e[3]}, up{-e[3], e[2]};
+  return {dot(w, u) * e[6], dot(w, up) * e[7]};
+}
+template <class T> inline V2<T> ellipse_normal(const T *e, V2<T> p) {
+  V2<T> u{e[2], e[3]}, up{-e[3], e[2]};
+  V2<T> l = ellipse_local(e, V2<T>{p.x - e[0], p.y - e[1]});
+  T gx = l.x * e[6], gy = l.y * e[7]; // gradient of x^2/a^2 + y^2/b^2 in the ellipse frame
+  return normalize(V2<T>{std::fma(gx, u.x, gy * up.x), std::fma(gx, u.y, gy * up.y)});
+}
+template <class T> inline void hit_ellipse(const T *e, V2<T> o, V2<T> d, HitList<T> &out) {
+  V2<T> lo = ellipse_local(e, V2<T>{o.x - e[0], o.y - e[1]});
+  V2<T> ld = ellipse_local(e, d);
+  T A = dot(ld, ld), B = dot(lo, ld), C = dot(lo, lo) - (T)1;
+  T disc = std::fma(B, B, -(A * C));
+  if (!(disc >= (T)0) || !(A > (T)0)) return;
+  T sq = std::sqrt(disc);
+  T t0 = (-B - sq) / A, t1 = (-B + sq) / A;
+  if (t0 > (T)T_MIN) {
+    V2<T> p = along(o, t0, d);
+    out.push({t0, p, ellipse_normal(e, p)});
+  }
+  if (t1 > (T)T_MIN) {
+    V2<T> p = along(o, t1, d);
+    out.push({t1, p, ellipse_normal(e, p)});
+  }
+}
+
 // §3.5 contains
 template <class T> inline bool contains_leaf(const LeafT<T> &l, V2<T> p) {
   switch (l.kind) {
+  case TOK_ELLIPSE: {
+    V2<T> q = ellipse_local(l.p, V2<T>{p.x - l.p[0], p.y - l.p[1]});
+    return dot(q, q) < (T)1;
+  }
   case TOK_CIRCLE: {
     V2<T> q{p.x - l.p[0], p.y - l.p[1]};
     return dot(q, q) < l.p[3];
@@ -479,6 +529,7 @@ template <class T> inline void intersect_object(const SceneT<T> &s, int obj, V2<
     case TOK_RECT: hit_rect(l.p, o, d, hl); break;
     case TOK_SEGMENT: hit_segment(l.p, o, d, hl); break;
     case TOK_BEZIER: hit_bezier(l.p, o, d, hl); break;
+    case TOK_ELLIPSE: hit_ellipse(l.p, o, d, hl); break;
     }
     for (int j = 0; j < hl.n; ++j) {
       bool keep = true;
@@ -762,11 +813,58 @@ inline uint64_t wrapping_pow(uint64_t base, uint32_t exp) { // Rust u64::pow in 
   }
   return acc;
 }
-inline void sm_point(const LgStringMod &sm, uint64_t n, double out[2]) { // string_mod.rs:45-55
+inline void sm_point(const LgStringMod &sm, uint64_t n, double out[2]) { // string_mod.rs:33-85
   const double TAU = 6.28318530717958647692;
-  double angle = (double)(sm.turns * n) * TAU / (double)sm.modulo;
-  out[0] = std::cos(angle);
-  out[1] = std::sin(angle);
+  const uint64_t tn = sm.turns * n; // u64 product, wraps
+  if (sm.curve == LG_CURVE_COMPLEX_EXP) {
+    // complex.powu((self.turns * n) as u32) -> num_traits::pow::pow (exponentiation by squaring), products
+    // (a+bi)(c+di) = (ac - bd) + (ad + bc)i in plain f64 (num-complex Mul)
+    uint32_t e = (uint32_t)tn;
+    double br = sm.curve_p[0], bi = sm.curve_p[1];
+    if (e == 0) {
+      out[0] = 1.0, out[1] = 0.0;
+      return;
+    }
+    auto mul = [](double ar, double ai, double cr, double ci, double &rr, double &ri) {
+      rr = ar * cr - ai * ci;
+      ri = ar * ci + ai * cr;
+    };
+    while ((e & 1u) == 0u) {
+      double r, i;
+      mul(br, bi, br, bi, r, i);
+      br = r, bi = i;
+      e >>= 1;
+    }
+    double ar = br, ai = bi;
+    while (e > 1u) {
+      e >>= 1;
+      double r, i;
+      mul(br, bi, br, bi, r, i);
+      br = r, bi = i;
+      if (e & 1u) {
+        mul(ar, ai, br, bi, r, i);
+        ar = r, ai = i;
+      }
+    }
+    out[0] = ar, out[1] = ai;
+    return;
+  }
+  double angle = (double)tn * TAU / (double)sm.modulo;
+  if (sm.curve == LG_CURVE_HYPOTROCHOID) { // string_mod.rs:56-71
+    double small_radius = (double)(uint64_t)sm.curve_p[0], big_radius = (double)(uint64_t)sm.curve_p[1];
+    double off_center = (double)(uint64_t)sm.curve_p[2];
+    double smr = big_radius - small_radius, ratio = smr + off_center;
+    double x = smr * std::cos(angle) + off_center * std::cos(angle * smr / small_radius);
+    double y = smr * std::sin(angle) - off_center * std::sin(angle * smr / small_radius);
+    out[0] = x / ratio, out[1] = y / ratio;
+  } else if (sm.curve == LG_CURVE_LISSAJOUS) { // string_mod.rs:73-83
+    double a = (double)(uint64_t)sm.curve_p[0], b = (double)(uint64_t)sm.curve_p[1];
+    out[0] = std::sin(a * angle + sm.curve_p[2]);
+    out[1] = std::sin(b * angle);
+  } else { // Circle, string_mod.rs:45-55
+    out[0] = std::cos(angle);
+    out[1] = std::sin(angle);
+  }
 }
 inline void sm_color(const LgStringMod &sm, const LgModRemColor *rules, uint32_t nr, uint64_t ix, float out[4]) {
   float c[4] = {0, 0, 0, 0}; // string_mod.rs:124-150

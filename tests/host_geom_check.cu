@@ -118,6 +118,32 @@ template <class T> static long run(int iters) {
       CHECK(lg::contains_leaf(k, q) == lgo::contains_leaf(l, lgo::V2<T>{q.x, q.y}), "rect contains");
       n += 1 + a.n;
     }
+    // ellipse
+    {
+      lg::Tok<T> k{};
+      k.kind = lg::TOK_ELLIPSE;
+      double ra = uni(0, 6.283185307179586);
+      k.p[0] = (T)uni(-1.5, 1.5), k.p[1] = (T)uni(-1, 1);
+      k.p[2] = (T)std::cos(ra), k.p[3] = (T)std::sin(ra);
+      k.p[4] = (T)uni(0.01, 0.8), k.p[5] = (T)uni(0.01, 0.8);
+      k.p[6] = (T)1 / k.p[4], k.p[7] = (T)1 / k.p[5];
+      lg::CandList<T> a;
+      a.n = 0;
+      lg::hit_ellipse(k.p, o, d, a);
+      lgo::HitList<T> b;
+      lgo::hit_ellipse(k.p, oo, od, b);
+      cmp_lists(a, b, "ellipse");
+      for (int i = 0; i < a.n && i < b.n; ++i) {
+        lg::V2<T> nn = lg::hit_normal(k, a.h[i].p, a.h[i].aux);
+        CHECK(same(nn.x, b.h[i].n.x) && same(nn.y, b.h[i].n.y), "ellipse normal");
+      }
+      lgo::LeafT<T> l{};
+      l.kind = lgo::TOK_ELLIPSE;
+      std::memcpy(l.p, k.p, sizeof k.p);
+      lg::V2<T> q{(T)(k.p[0] + uni(-0.8, 0.8)), (T)(k.p[1] + uni(-0.8, 0.8))};
+      CHECK(lg::contains_leaf(k, q) == lgo::contains_leaf(l, lgo::V2<T>{q.x, q.y}), "ellipse contains");
+      n += 1 + a.n;
+    }
     // bezier
     {
       lg::Tok<T> k{};
@@ -164,13 +190,18 @@ static int rand_geo(std::vector<LgGeoNode> &nodes, int depth) {
   LgGeoNode g{};
   g.child_a = g.child_b = -1;
   g.rot[0] = 1, g.rot[3] = 1;
-  int kind = depth >= 3 ? (int)(nextu() % 4) : (int)(nextu() % 5);
+  int kind = depth >= 3 ? (int)(nextu() % 5) : (int)(nextu() % 6);
+  if (depth >= 3 && kind == 4) kind = 5; // no deeper Logic nodes
   g.kind = kind;
   double ra = uni(0, 6.283185307179586);
   switch (kind) {
   case LG_GEO_CIRCLE: g.p[0] = uni(-1, 1), g.p[1] = uni(-1, 1), g.p[2] = uni(0.05, 0.5); break;
   case LG_GEO_RECT:
     g.p[0] = uni(-1, 1), g.p[1] = uni(-1, 1), g.p[2] = uni(0.05, 0.8), g.p[3] = uni(0.05, 0.8);
+    g.rot[0] = std::cos(ra), g.rot[1] = std::sin(ra), g.rot[2] = -std::sin(ra), g.rot[3] = std::cos(ra);
+    break;
+  case LG_GEO_ELLIPSE:
+    g.p[0] = uni(-1, 1), g.p[1] = uni(-1, 1), g.p[2] = uni(0.05, 0.6), g.p[3] = uni(0.05, 0.6);
     g.rot[0] = std::cos(ra), g.rot[1] = std::sin(ra), g.rot[2] = -std::sin(ra), g.rot[3] = std::cos(ra);
     break;
   case LG_GEO_SEGMENT: for (int k = 0; k < 4; ++k) g.p[k] = uni(-1, 1); break;
@@ -218,7 +249,7 @@ static long check_lowering(int n_scenes) {
       const lg::HostTok &a = hs.toks[i];
       const lgo::Token &b = os.tokens[i];
       bool ok = a.kind == b.kind && (a.kind != 4 || (a.op == b.op && a.a_start == b.a_start && a.b_start == b.b_start));
-      int np = a.kind == 0 ? 3 : a.kind == 1 ? 6 : a.kind == 2 ? 4 : a.kind == 3 ? 8 : 0;
+      int np = a.kind == 0 ? 3 : a.kind == 1 ? 6 : a.kind == 2 ? 4 : a.kind == 3 ? 8 : a.kind == 5 ? 6 : 0;
       for (int k = 0; k < np; ++k) ok = ok && std::memcmp(&a.p[k], &b.p[k], 8) == 0;
       if (!ok) { if (g_bad < 20) std::printf("MISMATCH lowering token %zu kind %d\n", i, a.kind); ++g_bad; }
       ++n;

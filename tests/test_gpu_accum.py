@@ -10,7 +10,7 @@ import numpy as np
 import pytest
 
 from light_garden_b200 import abi, scenes
-from light_garden_b200.scene import ModRemColor, StringMod, StringModMode
+from light_garden_b200.scene import Curve, ModRemColor, StringMod, StringModMode
 from util import have_cuda, primary_rays, small_specs
 
 pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not have_cuda(), reason="no CUDA device")]
@@ -128,6 +128,25 @@ def test_traced_segments_image(oracle, ctx, name, mode):
         assert (np.abs(got2 - exp) <= tol * np.maximum(1.0, np.abs(exp))).all()
     finally:
         ctx.call("lg_segment_capacity_set", 64 << 20)
+
+
+@pytest.mark.parametrize("curve", [Curve.ComplexExp(complex(0.9995, 0.01)), Curve.Hypotrochoid(3, 7, 2),
+                                   Curve.Lissajous(3, 2, 0.5)], ids=["complex_exp", "hypotrochoid", "lissajous"])
+def test_string_mod_other_curves(oracle, ctx, curve):
+    """the non-circle init curves of string_mod.rs:36-84."""
+    from light_garden_b200.tracer import Renderer
+    W = H = 256
+    k = 2.0 ** -8
+    sm = StringMod(modulo=1500, num=7, mode=StringModMode.Mul, color=(k, k, k, k), init_curve=curve)
+    r = Renderer(ctx, W, H)
+    st = r.render_string_mod(sm)
+    got = r.read_rgba32f()
+    exp = oracle.new_image(W, H)
+    n = oracle.accumulate_pairs(exp, oracle.string_mod(sm))
+    assert n > 20000
+    # end points pass through device sin/cos (or 10 complex squarings) vs libm: a handful of fragments may move
+    assert abs(int(st.pixel_updates) - int(n)) <= 8
+    assert len(np.nonzero((got != exp).any(axis=2))[0]) <= 32
 
 
 @pytest.mark.parametrize("mode", MODES)

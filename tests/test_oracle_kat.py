@@ -13,6 +13,7 @@ from light_garden_b200 import abi, scenes
 from light_garden_b200.scene import (AND, AND_NOT, OR, Circle, CubicBezier, DirectionalLight, LineSegment, Logic,
                                      Material, ModRemColor, Object, PointLight, Rect, SpotLight, StringMod,
                                      StringModMode, rot2, rot2_identity)
+from light_garden_b200.scene import Curve, Ellipse
 
 CANVAS = scenes.canvas(16.0 / 9.0)
 CUT = [0.001] * 4
@@ -507,3 +508,64 @@ def test_screenshot_conversion_known_values(oracle):
     exp_r = [0, 255, int(0.5 ** (1 / 2.2) * 255), 255, 0, int(0.25 ** (1 / 2.2) * 255)]   # saturates; NaN -> 0
     assert out[0, :, 2].tolist() == exp_r          # red lands in byte 2
     assert np.all(out[0, :, 1] == 255) and np.all(out[0, :, 0] == 0) and np.all(out[0, :, 3] == 0)
+
+
+def test_string_mod_curves(oracle):
+    """string_mod.rs:36-84: ComplexExp, Hypotrochoid and Lissajous point sets against direct formulas."""
+    m = 60
+    c = complex(0.995, 0.03)
+    ch = oracle.string_mod(StringMod(modulo=m, num=1, mode=StringModMode.Add, turns=2, init_curve=Curve.ComplexExp(c)))
+    for n in range(m):
+        z = c ** (2 * n)
+        np.testing.assert_allclose(ch["a"][n], (z.real, z.imag), rtol=1e-12, atol=1e-14)
+    r, s_, d = 3, 7, 2
+    ch = oracle.string_mod(StringMod(modulo=m, num=1, mode=StringModMode.Add, init_curve=Curve.Hypotrochoid(r, s_, d)))
+    for n in range(m):
+        ang = n * math.tau / m
+        smr = s_ - r
+        x = smr * math.cos(ang) + d * math.cos(ang * smr / r)
+        y = smr * math.sin(ang) - d * math.sin(ang * smr / r)
+        np.testing.assert_allclose(ch["a"][n], (x / (smr + d), y / (smr + d)), atol=1e-15)
+    ch = oracle.string_mod(StringMod(modulo=m, num=1, mode=StringModMode.Add, init_curve=Curve.Lissajous(3, 2, 0.5)))
+    for n in range(m):
+        ang = n * math.tau / m
+        np.testing.assert_allclose(ch["a"][n], (math.sin(3 * ang + 0.5), math.sin(2 * ang)), atol=1e-15)
+    assert np.array_equal(ch["b"][:-1], ch["a"][1:])          # Add 1: chord i -> i + 1
+
+
+def test_ray_ellipse(oracle):
+    """Ellipse{origin, a, b, rot} (object.rs:38-45): x^2/a^2 + y^2/b^2 = 1 in the rotated frame."""
+    sc = scene(oracle, [Object.new_ellipse((1.0, 0.5), 2.0, 1.0)])
+    h = sc.intersect(0, (-5, 0.5), (1, 0))
+    np.testing.assert_allclose(h[:, 0], [-1.0, 3.0], atol=1e-14)
+    np.testing.assert_allclose(h[:, 2:4], [[-1, 0], [1, 0]], atol=1e-14)
+    h = sc.intersect(0, (1.0, -5), (0, 1))
+    np.testing.assert_allclose(h[:, 1], [-0.5, 1.5], atol=1e-14)
+    # a generic point of the ellipse: (a cos t, b sin t); the normal is (cos t / a, sin t / b) normalised
+    t = 0.7
+    p = (1.0 + 2.0 * math.cos(t), 0.5 + 1.0 * math.sin(t))
+    h = sc.intersect(0, (1.0, 0.5), (p[0] - 1.0, p[1] - 0.5))
+    dirv = np.array([p[0] - 1.0, p[1] - 0.5])
+    dirv /= np.linalg.norm(dirv)
+    h = sc.intersect(0, (1.0, 0.5), dirv)
+    assert h.shape[0] == 1
+    np.testing.assert_allclose(h[0, :2], p, atol=1e-14)
+    nrm = np.array([math.cos(t) / 2.0, math.sin(t) / 1.0])
+    np.testing.assert_allclose(h[0, 2:4], nrm / np.linalg.norm(nrm), atol=1e-14)
+    assert sc.contains(0, (2.9, 0.5)) and not sc.contains(0, (3.1, 0.5)) and not sc.contains(0, (1.0, 1.6))
+    # rotated by 90 degrees the axes swap
+    rot = Object(Ellipse((0.0, 0.0), 2.0, 1.0, rot2(math.pi / 2)), Material(1.5), "Ellipse")
+    sc = scene(oracle, [rot])
+    h = sc.intersect(0, (-5, 0), (1, 0))
+    np.testing.assert_allclose(h[:, 0], [-1.0, 1.0], atol=1e-12)
+    h = sc.intersect(0, (0, -5), (0, 1))
+    np.testing.assert_allclose(h[:, 1], [-2.0, 2.0], atol=1e-12)
+    # a circle is the ellipse with a = b: same hit points as the circle primitive
+    e = scene(oracle, [Object.new_ellipse((0.3, -0.2), 0.7, 0.7)])
+    c = scene(oracle, [Object.new_circle((0.3, -0.2), 0.7)])
+    o, d = _rays(200, seed=9)
+    for i in range(len(o)):
+        he, hc = e.intersect(0, o[i], d[i]), c.intersect(0, o[i], d[i])
+        assert he.shape == hc.shape
+        if len(he):
+            np.testing.assert_allclose(he[:, :4], hc[:, :4], atol=1e-12)

@@ -14,9 +14,29 @@ def have_cuda():
         return False
 
 
+def ellipse_spec(total_rays=3000):
+    """Ellipses (object.rs:38-45), alone and inside CSG trees, plus a mirror: SURVEY.md §8f rank 2."""
+    import math
+    from light_garden_b200.scene import (AND_NOT, OR, Circle, Ellipse, Logic, Material, Object, PointLight, Rect,
+                                         SpotLight, rot2, rot2_identity)
+    objs = [
+        Object.new_ellipse((-0.9, 0.2), 0.5, 0.2).with_index(1.5),
+        Object(Ellipse((0.5, -0.3), 0.25, 0.6, rot2(0.6)), Material(1.33), "Ellipse"),
+        Object(Logic(AND_NOT, Ellipse((0.0, 0.0), 0.45, 0.3, rot2(0.2)), Circle((0.15, 0.0), 0.18), (0.9, 0.45), rot2(-0.4)),
+               Material(1.7), "Geo"),
+        Object(Logic(OR, Ellipse((0.0, 0.0), 0.3, 0.12, rot2_identity()), Rect((0.0, 0.0), rot2(0.9), 0.15, 0.5),
+                     (-0.2, -0.55), rot2(1.1)), Material(1.2), "Geo"),
+        Object.new_mirror((-1.6, -0.9), (-1.2, 0.9)),
+    ]
+    lights = [PointLight((0.05, 0.1), total_rays // 2, (0.012, 0.01, 0.008, 0.02)),
+              SpotLight((-1.5, 0.8), 1.2, (1.0, -0.5), total_rays - total_rays // 2, (0.006, 0.01, 0.014, 0.02))]
+    return scenes.SceneSpec("ellipses", objs, lights, 6, 480, 270)
+
+
 def small_specs():
     """CPU-oracle sized versions of the BASELINE configs (same shapes, fewer rays)."""
     return {
+        "ELL": ellipse_spec(),
         "C1": scenes.c1_default(total_rays=6000, width=480, height=270),
         "C2": scenes.c2_cavity(total_rays=1500, max_bounce=64, width=480, height=270),
         "C3": scenes.c3_refraction(total_rays=6000, grid=16, width=480, height=270),
