@@ -216,8 +216,12 @@ __device__ __forceinline__ void take(Best<T> &b, V2<T> o, const Cand<T> &c, int 
 
 // Ray::intersect(&Geo::GeoLogic): leaf hits in program order, each filtered by
 // the sibling subtrees on the way to the root (ORACLE.md §3.6)
+// (force-inlined, like narrow_phase below: with two levels of __noinline__ device functions the sm_100a build of
+// nvcc 12.9 produced a kernel that lost a live register across the nested call — compute-sanitizer: misaligned
+// shared-memory reads in the candidate loop right after CALL narrow_phase -> CALL sweep_csg_object.  The kernel
+// therefore contains no user-level calls; tools/gpu_round.sh runs the GPU suite under compute-sanitizer.)
 template <class T>
-__device__ __noinline__ void sweep_csg_object(const TraceArgs<T> &A, int obj, V2<T> o, V2<T> d, Best<T> &best) {
+__device__ __forceinline__ void sweep_csg_object(const TraceArgs<T> &A, int obj, V2<T> o, V2<T> d, Best<T> &best) {
   const int first = A.obj_first[obj], count = A.obj_count[obj];
   const Tok<T> *tok = A.toks + first;
   for (int k = 0; k < count; ++k) {
@@ -253,10 +257,11 @@ __device__ __noinline__ void sweep_csg_object(const TraceArgs<T> &A, int obj, V2
   }
 }
 
-// Narrow phase: the exact Ray::intersect of ORACLE.md §3 for one object.  Out of
-// line so that the broad-phase loop stays a handful of instructions per test.
+// Narrow phase: the exact Ray::intersect of ORACLE.md §3 for one object.  It runs in the candidate loop that
+// follows every 32-object chunk of the broad phase, so the broad-phase loop itself stays a handful of instructions
+// per test.
 template <class T>
-__device__ __noinline__ Best<T> narrow_phase(const TraceArgs<T> &A, Best<T> b, int obj, V2<T> o, V2<T> d) {
+__device__ __forceinline__ Best<T> narrow_phase(const TraceArgs<T> &A, Best<T> b, int obj, V2<T> o, V2<T> d) {
   const int first = A.obj_first[obj];
   if (A.obj_count[obj] == 1) {
     const Tok<T> &k = A.toks[first];

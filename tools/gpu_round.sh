@@ -22,7 +22,9 @@ for w in $what; do
       timeout 900 python tools/bench_configs.py --precision f64 > gpurun_out/configs_f64.jsonl 2>> gpurun_out/configs.err
       ;;
     sanitize)
-      timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 python __graft_entry__.py smoke > gpurun_out/sanitize_memcheck.log 2>&1
+      # the whole GPU suite under memcheck (found the nested-call miscompile of round 1), then racecheck on smoke
+      timeout 1500 compute-sanitizer --tool memcheck --error-exitcode 9 --print-limit 3 python -m pytest tests -m gpu -q -x \
+        -k "not full_size" > gpurun_out/sanitize_memcheck.log 2>&1
       echo "memcheck rc=$?" >> gpurun_out/sanitize_memcheck.log
       timeout 900 compute-sanitizer --tool racecheck --error-exitcode 9 python __graft_entry__.py smoke > gpurun_out/sanitize_racecheck.log 2>&1
       echo "racecheck rc=$?" >> gpurun_out/sanitize_racecheck.log
