@@ -156,6 +156,7 @@ struct lg_ctx {
   int accum_mode = 0; // 0 = auto, 1 = direct (one L2 reduction per fragment), 2 = tile-binned
   // auto mode: measured cost of each resolve on this context's recent work (ns per fragment, 0 = no sample yet)
   double ns_per_frag[3] = {0, 0, 0};
+  unsigned accum_samples[3] = {0, 0, 0};
   unsigned long long auto_calls = 0;
   DevBuf tile_count, tile_cursor, tile_offset, item_prefix, tile_totals, item_counter, tile_list, seg2, tile_hist;
 
@@ -533,8 +534,9 @@ bool use_tiled(lg_ctx *c, unsigned long long n) {
   if (c->accum_mode == 2) return true;
   if (n < kTiledMinSegments) return false;
   ++c->auto_calls;
-  if (c->ns_per_frag[2] == 0) return true;
-  if (c->ns_per_frag[1] == 0) return false;
+  // two samples of each first: the first call of a mode pays for its buffers (cudaMalloc) and module load
+  if (c->accum_samples[2] < 2) return true;
+  if (c->accum_samples[1] < 2) return false;
   const bool tiled_better = c->ns_per_frag[2] <= c->ns_per_frag[1];
   if (c->auto_calls % 64 == 0) return !tiled_better;
   return tiled_better;
@@ -544,8 +546,10 @@ bool use_tiled(lg_ctx *c, unsigned long long n) {
 void note_accum_cost(lg_ctx *c, bool tiled, float ms, unsigned long long frags, unsigned long long n) {
   if (frags == 0 || n < kTiledMinSegments) return;
   const double v = (double)ms * 1e6 / (double)frags;
-  double &slot = c->ns_per_frag[tiled ? 2 : 1];
-  slot = slot == 0 ? v : 0.5 * slot + 0.5 * v;
+  const int m = tiled ? 2 : 1;
+  double &slot = c->ns_per_frag[m];
+  slot = c->accum_samples[m] < 2 ? v : 0.5 * slot + 0.5 * v; // the warm second sample replaces the cold first
+  if (c->accum_samples[m] < 2) ++c->accum_samples[m];
 }
 
 // count -> scan -> fill -> raster over device segments of type Seg (LgSegment or Seg2)

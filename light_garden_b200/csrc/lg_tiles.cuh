@@ -197,16 +197,83 @@ __global__ void __launch_bounds__(1024) tile_scan_kernel(TileArgs T) {
   }
 }
 
-struct RasterScratch { // per warp
-  RasterSetup s[32];
-  float4 ca[32];
-  float4 dc[32];
+// Per-warp parking area of the raster kernel: 32 list entries reduced to what the blend loop reads.
+struct RasterScratch {
+  float4 geo[32];        // m0, 1/(m1 - m0), minor delta, minor start (RasterSetup)
+  float4 col[32];        // colour at a (single-colour segments: alpha already squared)
+  float4 dc[32];         // colour delta (two-colour segments only)
+  unsigned int rng[32];  // lanes of this tile the segment covers along its major axis: first | count << 8
 };
+
+// Blends parked entries [k0, k1), all of the same major axis, into the warp's private tile.  lane = major-axis step;
+// kMul = tile pitch along the minor axis (kTilePitch for x-major, 1 for y-major), `add` the lane's share of the
+// address, [nlo, nhi) the minor pixel range of the tile on the canvas, mc the lane's major pixel centre.
+// The arithmetic per fragment is raster_walk's (ORACLE.md 8.2-8.4).  Two entries are in flight: both pixels are
+// read before either is written; a lane that hits the same pixel in both carries the first sum into the second.
+template <bool kLerp, int kMul>
+__device__ __forceinline__ unsigned blend_run(float4 *tile, const RasterScratch &P, int k0, int k1, float mc, float nlo,
+                                              float nhi, int add, unsigned lane) {
+  unsigned n = 0;
+  int k = k0;
+  for (; k + 1 < k1; k += 2) {
+    const float4 ga = P.geo[k], gb = P.geo[k + 1];
+    const unsigned ra = P.rng[k], rb = P.rng[k + 1];
+    const float4 ca = P.col[k], cb = P.col[k + 1];
+    const float sa = (mc - ga.x) * ga.y, sb = (mc - gb.x) * gb.y;
+    const float fa = floorf(__fmaf_rn(sa, ga.z, ga.w)), fb = floorf(__fmaf_rn(sb, gb.z, gb.w));
+    const bool act_a = (lane - (ra & 255u)) < (ra >> 8) && fa >= nlo && fa < nhi;
+    const bool act_b = (lane - (rb & 255u)) < (rb >> 8) && fb >= nlo && fb < nhi;
+    const int off_a = (int)fa * kMul + add, off_b = (int)fb * kMul + add;
+    float a0 = ca.x, a1 = ca.y, a2 = ca.z, a3 = ca.w, b0 = cb.x, b1 = cb.y, b2 = cb.z, b3 = cb.w;
+    if (kLerp) {
+      const float4 da = P.dc[k], db = P.dc[k + 1];
+      a0 = __fmaf_rn(sa, da.x, ca.x), a1 = __fmaf_rn(sa, da.y, ca.y), a2 = __fmaf_rn(sa, da.z, ca.z);
+      a3 = __fmaf_rn(sa, da.w, ca.w), a3 *= a3;
+      b0 = __fmaf_rn(sb, db.x, cb.x), b1 = __fmaf_rn(sb, db.y, cb.y), b2 = __fmaf_rn(sb, db.z, cb.z);
+      b3 = __fmaf_rn(sb, db.w, cb.w), b3 *= b3;
+    }
+    float4 va, vb;
+    if (act_a) va = tile[off_a];
+    if (act_b) vb = tile[off_b];
+    if (act_a) {
+      va.x += a0, va.y += a1, va.z += a2, va.w += a3; // mod.rs:57-73
+      if (act_b && off_a == off_b) vb = va;
+      tile[off_a] = va;
+    }
+    if (act_b) {
+      vb.x += b0, vb.y += b1, vb.z += b2, vb.w += b3;
+      tile[off_b] = vb;
+    }
+    n += (act_a ? 1u : 0u) + (act_b ? 1u : 0u);
+  }
+  if (k < k1) {
+    const float4 ga = P.geo[k];
+    const unsigned ra = P.rng[k];
+    const float4 ca = P.col[k];
+    const float sa = (mc - ga.x) * ga.y;
+    const float fa = floorf(__fmaf_rn(sa, ga.z, ga.w));
+    if ((lane - (ra & 255u)) < (ra >> 8) && fa >= nlo && fa < nhi) {
+      const int off_a = (int)fa * kMul + add;
+      float a0 = ca.x, a1 = ca.y, a2 = ca.z, a3 = ca.w;
+      if (kLerp) {
+        const float4 da = P.dc[k];
+        a0 = __fmaf_rn(sa, da.x, ca.x), a1 = __fmaf_rn(sa, da.y, ca.y), a2 = __fmaf_rn(sa, da.z, ca.z);
+        a3 = __fmaf_rn(sa, da.w, ca.w), a3 *= a3;
+      }
+      float4 va = tile[off_a];
+      va.x += a0, va.y += a1, va.z += a2, va.w += a3;
+      tile[off_a] = va;
+      ++n;
+    }
+  }
+  return n;
+}
 
 template <class Seg> __global__ void __launch_bounds__(kRasterWarps * 32) tile_raster_kernel(TileArgs T, const Seg *seg) {
   extern __shared__ __align__(16) unsigned char tile_smem_raw[];
   const int warp_in_block = threadIdx.x >> 5;
   const unsigned lane = threadIdx.x & 31u;
+  const unsigned lt_mask = (1u << lane) - 1u;
   float4 *tile = reinterpret_cast<float4 *>(tile_smem_raw) + (size_t)warp_in_block * kTileFloat4;
   RasterScratch &P = reinterpret_cast<RasterScratch *>(reinterpret_cast<float4 *>(tile_smem_raw) +
                                                        (size_t)kRasterWarps * kTileFloat4)[warp_in_block];
@@ -230,90 +297,42 @@ template <class Seg> __global__ void __launch_bounds__(kRasterWarps * 32) tile_r
     const unsigned int first = chunk * kChunk, last = min(count, first + kChunk);
     const unsigned int *lst = T.list + T.tile_offset[t];
     const int tx = t % T.tiles_x, ty = t / T.tiles_x;
+    const int bx = tx << kTileShift, by = ty << kTileShift;
+    // loop constants of the two blend loops (x-major entries: lane = column, y-major: lane = row)
+    const float mcx = (float)(bx + (int)lane) + 0.5f, mcy = (float)(by + (int)lane) + 0.5f;
+    const float xlo = (float)bx, xhi = (float)min(T.A.W, bx + kTile), ylo = (float)by, yhi = (float)min(T.A.H, by + kTile);
+    const int addx = (int)lane - by * kTilePitch, addy = (int)lane * kTilePitch - bx;
     for (int k = lane; k < kTileFloat4; k += 32) tile[k] = make_float4(0.f, 0.f, 0.f, 0.f);
     __syncwarp();
     // the gather of the NEXT 32 list entries (index, then segment) is in flight while the current 32 are blended
     float4 g_ab = make_float4(0.f, 0.f, 0.f, 0.f), g_ca = g_ab, g_dc = g_ab;
     if (first + lane < last) SegIO<Seg>::load(seg, lst[first + lane], g_ab, g_ca, g_dc);
     for (unsigned int base = first; base < last; base += 32) {
-      if (base + lane < last) { // lane = one list entry: park its raster setup
-        P.s[lane] = raster_setup(T.A, g_ab.x, g_ab.y, g_ab.z, g_ab.w);
-        P.ca[lane] = g_ca;
-        if (kLerp) P.dc[lane] = g_dc;
+      // lane = one list entry: its raster setup, reduced to this tile, parked x-major entries first
+      const bool valid = base + lane < last;
+      const RasterSetup S = raster_setup(T.A, g_ab.x, g_ab.y, g_ab.z, g_ab.w);
+      const bool xm = S.xmajor != 0;
+      const unsigned vx = __ballot_sync(0xffffffffu, valid && xm), vy = __ballot_sync(0xffffffffu, valid && !xm);
+      const int nx = __popc(vx), m = nx + __popc(vy);
+      if (valid) {
+        const int pos = xm ? __popc(vx & lt_mask) : nx + __popc(vy & lt_mask);
+        const int tb = xm ? bx : by;
+        const int l0 = max(S.i0 - tb, 0), l1 = min(S.i1 - tb, kTile);
+        P.geo[pos] = make_float4(S.m0, S.inv, S.dn, S.n0);
+        P.col[pos] = make_float4(g_ca.x, g_ca.y, g_ca.z, kLerp ? g_ca.w : g_ca.w * g_ca.w);
+        if (kLerp) P.dc[pos] = g_dc;
+        P.rng[pos] = (unsigned)l0 | ((unsigned)max(l1 - l0, 0) << 8);
       }
       if (base + 32 + lane < last) SegIO<Seg>::load(seg, lst[base + 32 + lane], g_ab, g_ca, g_dc);
       __syncwarp();
-      const int m = (int)min(32u, last - base);
-      // Two parked segments are in flight at a time: their coordinate math is independent (ILP hides the
-      // shared-memory latency), the two read-modify-writes then happen in list order (a lane may hit the same
-      // pixel in both).  The next two are fetched from shared memory before the current two are blended.
-      RasterSetup Sa = P.s[0], Sb = P.s[m > 1 ? 1 : 0];
-      float4 ca_a = P.ca[0], ca_b = P.ca[m > 1 ? 1 : 0];
-      float4 dc_a = kLerp ? P.dc[0] : make_float4(0.f, 0.f, 0.f, 0.f);
-      float4 dc_b = kLerp ? P.dc[m > 1 ? 1 : 0] : dc_a;
-      for (int k = 0; k < m; k += 2) {
-        const bool has_b = k + 1 < m;
-        const int kn0 = k + 2 < m ? k + 2 : k, kn1 = k + 3 < m ? k + 3 : k;
-        const RasterSetup Na = P.s[kn0], Nb = P.s[kn1];
-        const float4 nca_a = P.ca[kn0], nca_b = P.ca[kn1];
-        const float4 ndc_a = kLerp ? P.dc[kn0] : dc_a, ndc_b = kLerp ? P.dc[kn1] : dc_a;
-        // this tile's stretch of each segment: one major-axis step per lane (arithmetic of raster_walk)
-        int off_a, off_b;
-        float s_a, s_b;
-        bool act_a, act_b;
-        {
-          const int i = ((Sa.xmajor ? tx : ty) << kTileShift) + (int)lane;
-          const float mc = (float)i + 0.5f;
-          s_a = (mc - Sa.m0) * Sa.inv;
-          const float fj = floorf(__fmaf_rn(s_a, Sa.dn, Sa.n0));
-          const int Nmin = Sa.xmajor ? T.A.H : T.A.W;
-          const int j = (int)fmaxf(fminf(fj, 1e9f), -1e9f);
-          act_a = i >= Sa.i0 && i < Sa.i1 && fj >= 0.f && fj < (float)Nmin && (j >> kTileShift) == (Sa.xmajor ? ty : tx);
-          const int jl = j & (kTile - 1);
-          off_a = Sa.xmajor ? jl * kTilePitch + (int)lane : (int)lane * kTilePitch + jl;
-        }
-        {
-          const int i = ((Sb.xmajor ? tx : ty) << kTileShift) + (int)lane;
-          const float mc = (float)i + 0.5f;
-          s_b = (mc - Sb.m0) * Sb.inv;
-          const float fj = floorf(__fmaf_rn(s_b, Sb.dn, Sb.n0));
-          const int Nmin = Sb.xmajor ? T.A.H : T.A.W;
-          const int j = (int)fmaxf(fminf(fj, 1e9f), -1e9f);
-          act_b = has_b && i >= Sb.i0 && i < Sb.i1 && fj >= 0.f && fj < (float)Nmin &&
-                  (j >> kTileShift) == (Sb.xmajor ? ty : tx);
-          const int jl = j & (kTile - 1);
-          off_b = Sb.xmajor ? jl * kTilePitch + (int)lane : (int)lane * kTilePitch + jl;
-        }
-        if (act_a) {
-          float c0 = ca_a.x, c1 = ca_a.y, c2 = ca_a.z, c3 = ca_a.w;
-          if (kLerp) {
-            c0 = __fmaf_rn(s_a, dc_a.x, ca_a.x), c1 = __fmaf_rn(s_a, dc_a.y, ca_a.y);
-            c2 = __fmaf_rn(s_a, dc_a.z, ca_a.z), c3 = __fmaf_rn(s_a, dc_a.w, ca_a.w);
-          }
-          float4 v = tile[off_a]; // private tile, distinct pixel per lane: plain read-modify-write
-          v.x += c0, v.y += c1, v.z += c2, v.w += c3 * c3; // mod.rs:57-73
-          tile[off_a] = v;
-          ++cnt;
-        }
-        if (act_b) {
-          float c0 = ca_b.x, c1 = ca_b.y, c2 = ca_b.z, c3 = ca_b.w;
-          if (kLerp) {
-            c0 = __fmaf_rn(s_b, dc_b.x, ca_b.x), c1 = __fmaf_rn(s_b, dc_b.y, ca_b.y);
-            c2 = __fmaf_rn(s_b, dc_b.z, ca_b.z), c3 = __fmaf_rn(s_b, dc_b.w, ca_b.w);
-          }
-          float4 v = tile[off_b];
-          v.x += c0, v.y += c1, v.z += c2, v.w += c3 * c3;
-          tile[off_b] = v;
-          ++cnt;
-        }
-        Sa = Na, Sb = Nb, ca_a = nca_a, ca_b = nca_b, dc_a = ndc_a, dc_b = ndc_b;
-      }
+      cnt += blend_run<kLerp, kTilePitch>(tile, P, 0, nx, mcx, ylo, yhi, addx, lane);
+      cnt += blend_run<kLerp, 1>(tile, P, nx, m, mcy, xlo, xhi, addy, lane);
       __syncwarp();
     }
     // flush: one vector reduction per touched pixel (lanes sweep a row: coalesced 512 B)
-    const int gx = (tx << kTileShift) + (int)lane;
+    const int gx = bx + (int)lane;
     for (int row = 0; row < kTile; ++row) {
-      const int gy = (ty << kTileShift) + row;
+      const int gy = by + row;
       const float4 v = tile[row * kTilePitch + lane];
       if (gx < T.A.W && gy < T.A.H && (v.x != 0.f || v.y != 0.f || v.z != 0.f || v.w != 0.f))
         red_add_v4(T.A.img + ((size_t)gy * T.A.W + gx) * 4, v.x, v.y, v.z, v.w);
