@@ -229,6 +229,13 @@ int32_t lg_segment_capacity_set(lg_ctx *ctx, uint64_t n_segments);
  * (one red.global.add.v4.f32 per fragment), 2 = tile-binned (fragments are summed in
  * shared-memory tiles first). Same image either way up to fp32 summation order. */
 int32_t lg_accumulate_mode_set(lg_ctx *ctx, int32_t mode);
+/* Tracer::enable_tile_map (tracer.rs:137-146): when enabled, the nearest-hit
+ * search of tracer.rs:395-411 walks a device-side uniform grid over the objects'
+ * bounding circles instead of testing every object (the reference's TileMap,
+ * tile_map.rs, is the same idea with angular slabs per tile). The segments are
+ * bit-identical to the all-objects loop; only the number of exact tests changes.
+ * Default 0: every object is tested (tracer.rs:412-424). */
+int32_t lg_tile_map_enable(lg_ctx *ctx, int32_t enable);
 /* Keep LgSegmentTag (and LgSegmentF64 on F64 contexts) per segment. */
 int32_t lg_tags_enable(lg_ctx *ctx, int32_t enable);
 

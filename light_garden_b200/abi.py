@@ -97,6 +97,7 @@ PROTOTYPES = {
     "lg_shard_set": [_ctx, C.c_uint32, C.c_uint32],
     "lg_segment_capacity_set": [_ctx, C.c_uint64],
     "lg_accumulate_mode_set": [_ctx, C.c_int32],
+    "lg_tile_map_enable": [_ctx, C.c_int32],
     "lg_tags_enable": [_ctx, C.c_int32],
     "lg_emit_rays": [_ctx, C.c_uint32, C.c_uint64, C.c_uint64, _p],
     "lg_trace": [_ctx, C.POINTER(LgTraceStats)],

@@ -14,6 +14,7 @@
 #include <cstring>
 #include <limits>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/light_garden_b200.h"
@@ -23,6 +24,7 @@
 #include "lg_reduce.cuh"
 #include <unistd.h>
 #include "lg_scene.h"
+#include "lg_tables.h"
 #include "lg_trace.cuh"
 
 static_assert(sizeof(LgGeoNode) == 112, "LgGeoNode ABI");
@@ -155,9 +157,22 @@ struct lg_ctx {
   // tile-binned accumulation (lg_tiles.cuh)
   int accum_mode = 0; // 0 = auto, 1 = direct (one L2 reduction per fragment), 2 = tile-binned
   // auto mode: measured cost of each resolve on this context's recent work (ns per fragment, 0 = no sample yet)
-  double ns_per_frag[3] = {0, 0, 0};
-  unsigned accum_samples[3] = {0, 0, 0};
-  unsigned long long auto_calls = 0;
+  // uniform grid (lg_tile_map_enable)
+  bool grid_on = false;
+  double grid_density = 1.0; // cells per object (LG_GRID_DENSITY)
+  int grid_slots = 1;        // ray slots per thread of the grid kernel (LG_GRID_SLOTS)
+  DevBuf grid_start, grid_obj;
+  double grid_x0 = 0, grid_y0 = 0, grid_x1 = 0, grid_y1 = 0, grid_cs = 1, grid_eta = 0;
+  int grid_nx = 0, grid_ny = 0;
+  // accumulate auto mode: measured cost of the two resolves per WORKLOAD (scene + lights + image for traced
+  // segments, chord pattern for string mod, segment-count class for host lines)
+  struct AutoStat {
+    double ns_per_frag[3] = {0, 0, 0};
+    unsigned samples[3] = {0, 0, 0};
+    unsigned long long calls = 0;
+  };
+  std::unordered_map<unsigned long long, AutoStat> auto_stats;
+  unsigned long long scene_hash = 0, lights_hash = 0;
   DevBuf tile_count, tile_cursor, tile_offset, item_prefix, tile_totals, item_counter, tile_list, seg2, tile_hist;
 
   // comm
@@ -220,41 +235,10 @@ template <class V> int upload(lg_ctx *c, DevBuf &b, const std::vector<V> &v) {
   return LG_OK;
 }
 
-// device tables in precision T (ORACLE.md §2.2: cast to T, then derive in T)
+// device tables in precision T (built by lg_tables.h, uploaded here)
 template <class T> int upload_scene(lg_ctx *c) {
   const HostScene &hs = c->hs;
-  std::vector<Tok<T>> toks(hs.toks.size());
-  for (size_t i = 0; i < hs.toks.size(); ++i) {
-    const HostTok &h = hs.toks[i];
-    Tok<T> t{};
-    t.kind = h.kind, t.op = h.op, t.a_start = h.a_start, t.b_start = h.b_start;
-    switch (h.kind) {
-    case 0:
-      t.p[0] = (T)h.p[0], t.p[1] = (T)h.p[1], t.p[2] = (T)h.p[2];
-      t.p[3] = t.p[2] * t.p[2];
-      break;
-    case 1:
-      for (int k = 0; k < 6; ++k) t.p[k] = (T)h.p[k];
-      t.p[6] = std::fma(t.p[2], t.p[2], t.p[3] * t.p[3]);
-      t.p[7] = std::fma(t.p[4], t.p[4], t.p[5] * t.p[5]);
-      break;
-    case 2:
-      t.p[0] = (T)h.p[0], t.p[1] = (T)h.p[1];
-      t.p[2] = (T)h.p[2] - t.p[0];
-      t.p[3] = (T)h.p[3] - t.p[1];
-      break;
-    case 3:
-      for (int k = 0; k < 8; ++k) t.p[k] = (T)h.p[k];
-      break;
-    case 5:
-      for (int k = 0; k < 6; ++k) t.p[k] = (T)h.p[k];
-      t.p[6] = (T)1 / t.p[4];
-      t.p[7] = (T)1 / t.p[5];
-      break;
-    default: break;
-    }
-    toks[i] = t;
-  }
+  const std::vector<Tok<T>> toks = device_tokens<T>(hs);
   std::vector<int> obj_first, obj_count;
   std::vector<T> obj_n;
   for (size_t i = 0; i < hs.objs.size(); ++i) {
@@ -284,78 +268,28 @@ template <class T> int upload_scene(lg_ctx *c) {
   cv[6] = cv[2] * cv[2];
   cv[7] = cv[5] * cv[5];
   for (int k = 0; k < 8; ++k) c->canvas[k] = (double)cv[k];
-  // broad phase: one bounding circle per object, in f64 (every hit point of an object lies on one
-  // of its leaves, so the union of the leaves' bounding circles bounds all of them)
-  c->bound_c.assign(3 * hs.objs.size(), 0.0);
-  for (size_t i = 0; i < hs.objs.size(); ++i) {
-    const HostObj &o = hs.objs[i];
-    double x0 = 1e300, y0 = 1e300, x1 = -1e300, y1 = -1e300;
-    auto leaf_circle = [&](const HostTok &t, double &cx, double &cy, double &rr) {
-      if (t.kind == 0) {
-        cx = t.p[0], cy = t.p[1], rr = std::fabs(t.p[2]);
-      } else if (t.kind == 5) {
-        cx = t.p[0], cy = t.p[1], rr = std::fmax(t.p[4], t.p[5]);
-      } else if (t.kind == 1) {
-        cx = t.p[0], cy = t.p[1], rr = std::hypot(std::hypot(t.p[2], t.p[3]), std::hypot(t.p[4], t.p[5]));
-      } else {
-        const int np = t.kind == 2 ? 2 : 4;
-        cx = cy = 0;
-        for (int q = 0; q < np; ++q) cx += t.p[2 * q] / np, cy += t.p[2 * q + 1] / np;
-        rr = 0;
-        for (int q = 0; q < np; ++q) rr = std::fmax(rr, std::hypot(t.p[2 * q] - cx, t.p[2 * q + 1] - cy));
-      }
-    };
-    for (int k = 0; k < o.count; ++k) {
-      const HostTok &t = hs.toks[o.first + k];
-      if (t.kind == 4) continue;
-      double cx, cy, rr;
-      leaf_circle(t, cx, cy, rr);
-      x0 = std::fmin(x0, cx - rr), x1 = std::fmax(x1, cx + rr), y0 = std::fmin(y0, cy - rr), y1 = std::fmax(y1, cy + rr);
-    }
-    const double mx = 0.5 * (x0 + x1), my = 0.5 * (y0 + y1);
-    double rad = 0;
-    for (int k = 0; k < o.count; ++k) {
-      const HostTok &t = hs.toks[o.first + k];
-      if (t.kind == 4) continue;
-      double cx, cy, rr;
-      leaf_circle(t, cx, cy, rr);
-      rad = std::fmax(rad, std::hypot(cx - mx, cy - my) + rr);
-    }
-    c->bound_c[3 * i] = mx, c->bound_c[3 * i + 1] = my, c->bound_c[3 * i + 2] = rad;
-  }
+  c->bound_c = object_circles(hs);
   c->coord_bound = 0; // forces the broad-phase table to be rebuilt at the next launch
   LG_CUDA(c, cudaStreamSynchronize(c->stream)); // host vectors die here
   return LG_OK;
 }
 
-// Broad-phase table for coordinate bound B (scene, canvas, lights, explicit ray origins): the margin
-// delta = 64 eps B covers every rounding difference between the 3-FFMA line test and the exact tests.
+// Broad-phase table and uniform grid for coordinate bound B (scene, canvas, lights, explicit ray origins)
 template <class T> int upload_bounds(lg_ctx *c, double B) {
   const size_t n = c->bound_c.size() / 3;
-  const int n_pad = (int)((n + 31) / 32 * 32);
-  const double eps = std::numeric_limits<T>::epsilon();
-  const double delta = 64.0 * eps * B;
-  std::vector<T> tab(4 * (size_t)n_pad);
-  T *bx = tab.data(), *by = bx + n_pad, *br2 = by + n_pad, *brb = br2 + n_pad;
-  for (int i = 0; i < n_pad; ++i) {
-    if ((size_t)i < n) {
-      bx[i] = (T)c->bound_c[3 * i];
-      by[i] = (T)c->bound_c[3 * i + 1];
-      const double rb = (c->bound_c[3 * i + 2] * (1.0 + 1e-6) + delta) * (1.0 + 4 * eps);
-      brb[i] = std::nextafter((T)rb, std::numeric_limits<T>::max());
-      br2[i] = std::nextafter((T)((double)brb[i] * (double)brb[i] * (1.0 + 4 * eps)), std::numeric_limits<T>::max());
-    } else {
-      bx[i] = by[i] = (T)0;
-      br2[i] = (T)-1; // never a candidate
-      brb[i] = (T)0;
-    }
-  }
-  c->n_pad = n_pad;
-  c->bounds_bytes = (unsigned)(tab.size() * sizeof(T));
+  const BoundsTable<T> bt = build_bounds<T>(c->bound_c.data(), n, B);
+  const HostGrid g = build_scene_grid<T>(bt, n, c->grid_density);
+  c->grid_x0 = g.x0, c->grid_y0 = g.y0, c->grid_x1 = g.x1, c->grid_y1 = g.y1, c->grid_cs = g.cs;
+  c->grid_nx = g.nx, c->grid_ny = g.ny, c->grid_eta = bt.delta;
+  int rc;
+  if ((rc = upload(c, c->grid_start, g.start))) return rc;
+  if ((rc = upload(c, c->grid_obj, g.obj))) return rc;
+  if (g.obj.empty() && (rc = ensure(c, c->grid_obj, 4))) return rc;
+  c->n_pad = bt.n_pad;
+  c->bounds_bytes = (unsigned)(bt.tab.size() * sizeof(T));
   c->coord_bound = B;
-  c->delta = delta;
-  int rc = upload(c, c->bounds, tab);
-  if (rc) return rc;
+  c->delta = bt.delta;
+  if ((rc = upload(c, c->bounds, bt.tab))) return rc;
   LG_CUDA(c, cudaStreamSynchronize(c->stream));
   return LG_OK;
 }
@@ -425,22 +359,30 @@ template <class T> void fill_args(lg_ctx *c, TraceArgs<T> &A) {
   A.seg_cap = c->seg_cap;
   A.ctr = (TraceCounters *)c->ctr.p;
   A.stack = (uint4 *)c->stack.p;
+  A.grid_x0 = (T)c->grid_x0, A.grid_y0 = (T)c->grid_y0, A.grid_x1 = (T)c->grid_x1, A.grid_y1 = (T)c->grid_y1;
+  A.grid_cs = (T)c->grid_cs, A.grid_ics = (T)(1.0 / c->grid_cs), A.grid_eta = (T)c->grid_eta;
+  A.grid_nx = c->grid_nx, A.grid_ny = c->grid_ny;
+  A.grid_start = (const unsigned *)c->grid_start.p, A.grid_obj = (const unsigned *)c->grid_obj.p;
 }
 
 template <class T> struct KernelOf;
 template <> struct KernelOf<float> {
   static const void *get(int slots, bool smem) { return trace_kernel_f32(slots, smem); }
+  static const void *grid(int slots) { return trace_kernel_grid_f32(slots); }
   static int clamp(int slots) { return (slots == 1 || slots == 4) ? slots : 2; }
 };
 template <> struct KernelOf<double> {
   static const void *get(int slots, bool smem) { return trace_kernel_f64(slots, smem); }
+  static const void *grid(int slots) { return trace_kernel_grid_f64(slots); }
   static int clamp(int slots) { return slots == 2 ? 2 : 1; }
 };
 
 template <class T> int launch_trace(lg_ctx *c, TraceArgs<T> &A) {
-  const int R = KernelOf<T>::clamp(c->slots);
-  const bool use_smem = (size_t)A.bounds_bytes + 1024 <= c->smem_optin;
-  const void *kern = KernelOf<T>::get(R, use_smem);
+  const bool grid_mode = c->grid_on && c->n_obj > 0;
+  int R = KernelOf<T>::clamp(c->slots);
+  if (grid_mode) R = (sizeof(T) == 4 && c->grid_slots == 2) ? 2 : 1; // divergent cell walks: one ray per thread by default
+  const bool use_smem = !grid_mode && (size_t)A.bounds_bytes + 1024 <= c->smem_optin;
+  const void *kern = grid_mode ? KernelOf<T>::grid(R) : KernelOf<T>::get(R, use_smem);
   const size_t smem = use_smem ? A.bounds_bytes : 0;
   if (smem > 48 * 1024) LG_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
@@ -525,31 +467,54 @@ bool tiled_possible(lg_ctx *c, unsigned long long n) {
   return n_tiles * 4 + 1024 <= c->smem_optin; // the per-CTA histogram must fit in shared memory
 }
 
+// 64-bit content hash (workload signatures of the auto mode; never used to skip work)
+unsigned long long hash_bytes(const void *p, size_t n, unsigned long long h = 0x9E3779B97F4A7C15ull) {
+  const unsigned char *b = (const unsigned char *)p;
+  size_t i = 0;
+  for (; i + 8 <= n; i += 8) {
+    unsigned long long v;
+    std::memcpy(&v, b + i, 8);
+    h = (h ^ v) * 0xFF51AFD7ED558CCDull;
+    h ^= h >> 32;
+  }
+  for (; i < n; ++i) h = (h ^ b[i]) * 0x100000001B3ull;
+  return h;
+}
+unsigned long long mix_sig(unsigned long long a, unsigned long long b) { return hash_bytes(&b, 8, a); }
+unsigned long long traced_signature(lg_ctx *c) {
+  unsigned long long h = mix_sig(c->scene_hash, c->lights_hash);
+  h = mix_sig(h, ((unsigned long long)c->W << 32) | (unsigned)c->H);
+  return mix_sig(h, ((unsigned long long)c->rank << 32) | c->world);
+}
+
 // Which resolve to use.  Forced modes aside, small inputs go direct; large ones use whichever of the two has been
-// cheaper per fragment on this context so far (both are sampled first, the loser is re-probed every 64th call):
-// long coalescing segments favour the direct kernel, short or scattered ones the tile bins.
-bool use_tiled(lg_ctx *c, unsigned long long n) {
+// cheaper per fragment on this workload (signature `sig`) so far: each is sampled twice first (the first call of a
+// mode pays for its buffers), the loser is re-probed every 64th call.  Long coalescing segments favour the direct
+// kernel, short or scattered ones the tile bins.
+bool use_tiled(lg_ctx *c, unsigned long long n, unsigned long long sig) {
   if (!tiled_possible(c, n)) return false;
   if (c->accum_mode == 1) return false;
   if (c->accum_mode == 2) return true;
   if (n < kTiledMinSegments) return false;
-  ++c->auto_calls;
-  // two samples of each first: the first call of a mode pays for its buffers (cudaMalloc) and module load
-  if (c->accum_samples[2] < 2) return true;
-  if (c->accum_samples[1] < 2) return false;
-  const bool tiled_better = c->ns_per_frag[2] <= c->ns_per_frag[1];
-  if (c->auto_calls % 64 == 0) return !tiled_better;
+  if (c->auto_stats.size() > 256) c->auto_stats.clear();
+  lg_ctx::AutoStat &a = c->auto_stats[sig];
+  ++a.calls;
+  if (a.samples[2] < 2) return true;
+  if (a.samples[1] < 2) return false;
+  const bool tiled_better = a.ns_per_frag[2] <= a.ns_per_frag[1];
+  if (a.calls % 64 == 0) return !tiled_better;
   return tiled_better;
 }
 
 // feed the auto mode: elapsed time of one resolve over `frags` fragments
-void note_accum_cost(lg_ctx *c, bool tiled, float ms, unsigned long long frags, unsigned long long n) {
+void note_accum_cost(lg_ctx *c, bool tiled, float ms, unsigned long long frags, unsigned long long n,
+                     unsigned long long sig) {
   if (frags == 0 || n < kTiledMinSegments) return;
   const double v = (double)ms * 1e6 / (double)frags;
+  lg_ctx::AutoStat &a = c->auto_stats[sig];
   const int m = tiled ? 2 : 1;
-  double &slot = c->ns_per_frag[m];
-  slot = c->accum_samples[m] < 2 ? v : 0.5 * slot + 0.5 * v; // the warm second sample replaces the cold first
-  if (c->accum_samples[m] < 2) ++c->accum_samples[m];
+  a.ns_per_frag[m] = a.samples[m] < 2 ? v : 0.5 * a.ns_per_frag[m] + 0.5 * v; // the warm second sample replaces the cold first
+  if (a.samples[m] < 2) ++a.samples[m];
 }
 
 // count -> scan -> fill -> raster over device segments of type Seg (LgSegment or Seg2)
@@ -614,7 +579,8 @@ int read_pixel_counter(lg_ctx *c, uint64_t *out);
 int accumulate_device_segments(lg_ctx *c, unsigned long long n, float *ms, unsigned *launches) {
   if (n == 0) return LG_OK;
   c->img16_valid = false;
-  const bool tiled = use_tiled(c, n);
+  const unsigned long long sig = traced_signature(c);
+  const bool tiled = use_tiled(c, n, sig);
   uint64_t before = 0, after = 0;
   int rc;
   if (c->accum_mode == 0 && n >= kTiledMinSegments && (rc = read_pixel_counter(c, &before))) return rc;
@@ -634,7 +600,7 @@ int accumulate_device_segments(lg_ctx *c, unsigned long long n, float *ms, unsig
   if (ms) *ms += t;
   if (c->accum_mode == 0 && n >= kTiledMinSegments) {
     if ((rc = read_pixel_counter(c, &after))) return rc;
-    note_accum_cost(c, tiled, t, after - before, n);
+    note_accum_cost(c, tiled, t, after - before, n, sig);
   }
   return LG_OK;
 }
@@ -706,6 +672,14 @@ int32_t lg_create(int32_t device, int32_t precision, lg_ctx **out) {
     int v = atoi(e);
     if (v >= 0 && v <= 2) c->accum_mode = v;
   }
+  if (const char *e = getenv("LG_GRID_DENSITY")) {
+    double v = atof(e);
+    if (v > 0.01 && v < 100.0) c->grid_density = v;
+  }
+  if (const char *e = getenv("LG_GRID_SLOTS")) {
+    int v = atoi(e);
+    if (v == 1 || v == 2) c->grid_slots = v;
+  }
   if (const char *e = getenv("LG_TRACE_SLOTS")) {
     int v = atoi(e);
     if (v == 1 || v == 2 || v == 4) c->slots = v;
@@ -749,6 +723,8 @@ int32_t lg_scene_set(lg_ctx *c, const LgObject *objects, uint32_t n_objects, con
   rc = c->precision == LG_PRECISION_F64 ? upload_scene<double>(c) : upload_scene<float>(c);
   if (rc) return rc;
   c->have_scene = true;
+  c->scene_hash = hash_bytes(params, sizeof(LgTraceParams), hash_bytes(nodes, (size_t)n_nodes * sizeof(LgGeoNode),
+                                                                        hash_bytes(objects, (size_t)n_objects * sizeof(LgObject))));
   if (!c->lights.empty()) { // start media depend on the scene
     rebuild_dev_lights(c);
     if ((rc = upload(c, c->d_lights, c->dev_lights))) return rc;
@@ -765,6 +741,7 @@ int32_t lg_lights_set(lg_ctx *c, const LgLight *lights, uint32_t n) {
   LG_CUDA(c, cudaSetDevice(c->device));
   c->lights.assign(lights, lights + n);
   c->have_lights = true;
+  c->lights_hash = hash_bytes(lights, (size_t)n * sizeof(LgLight));
   rebuild_dev_lights(c);
   int rc = upload(c, c->d_lights, c->dev_lights);
   if (rc) return rc;
@@ -798,6 +775,12 @@ int32_t lg_accumulate_mode_set(lg_ctx *c, int32_t mode) {
   if (!c) return LG_ERR_INVALID;
   if (mode < 0 || mode > 2) return fail(c, LG_ERR_INVALID, "accumulate mode");
   c->accum_mode = mode;
+  return LG_OK;
+}
+
+int32_t lg_tile_map_enable(lg_ctx *c, int32_t enable) {
+  if (!c) return LG_ERR_INVALID;
+  c->grid_on = enable != 0;
   return LG_OK;
 }
 
@@ -955,7 +938,9 @@ int32_t lg_accumulate_segments(lg_ctx *c, const LgVertexPair *pairs, uint64_t n,
   // reuse the ray staging buffer for the upload (update_vertex_buffer makes a NEW buffer per frame)
   if ((rc = ensure(c, c->rays, n * sizeof(LgVertexPair)))) return rc;
   LG_CUDA(c, cudaMemcpyAsync(c->rays.p, pairs, n * sizeof(LgVertexPair), cudaMemcpyHostToDevice, c->stream));
-  const bool tiled = use_tiled(c, n);
+  // host lines: workloads are told apart by image and segment-count class only
+  const unsigned long long sig = mix_sig(mix_sig(2, ((unsigned long long)c->W << 32) | (unsigned)c->H), 63 - __builtin_clzll(n | 1));
+  const bool tiled = use_tiled(c, n, sig);
   uint64_t frag0 = 0;
   if ((rc = read_pixel_counter(c, &frag0))) return rc;
   LG_CUDA(c, cudaEventRecord(c->ev0, c->stream));
@@ -977,7 +962,7 @@ int32_t lg_accumulate_segments(lg_ctx *c, const LgVertexPair *pairs, uint64_t n,
   LG_CUDA(c, cudaEventElapsedTime(&t, c->ev0, c->ev1));
   uint64_t frag1 = 0;
   if ((rc = read_pixel_counter(c, &frag1))) return rc;
-  if (c->accum_mode == 0) note_accum_cost(c, tiled, t, frag1 - frag0, n);
+  if (c->accum_mode == 0) note_accum_cost(c, tiled, t, frag1 - frag0, n, sig);
   if (stats) {
     stats->accumulate_ms += t;
     stats->accumulate_launches += nl;
@@ -1009,7 +994,9 @@ int32_t lg_string_mod(lg_ctx *c, const LgStringMod *sm, const LgModRemColor *rul
   S.rules = (const LgModRemColor *)c->rays.p;
   S.n_rules = n_rules;
   S.first = first, S.count = count;
-  const bool tiled = count && use_tiled(c, count);
+  unsigned long long sig = hash_bytes(sm, sizeof(LgStringMod), 3);
+  sig = mix_sig(mix_sig(sig, ((unsigned long long)c->W << 32) | (unsigned)c->H), mix_sig(first, count));
+  const bool tiled = count && use_tiled(c, count, sig);
   uint64_t frag0 = 0;
   if ((rc = read_pixel_counter(c, &frag0))) return rc;
   LG_CUDA(c, cudaEventRecord(c->ev0, c->stream));
@@ -1032,7 +1019,7 @@ int32_t lg_string_mod(lg_ctx *c, const LgStringMod *sm, const LgModRemColor *rul
   LG_CUDA(c, cudaEventElapsedTime(&t, c->ev0, c->ev1));
   uint64_t frag1 = 0;
   if ((rc = read_pixel_counter(c, &frag1))) return rc;
-  if (c->accum_mode == 0 && count) note_accum_cost(c, tiled, t, frag1 - frag0, count);
+  if (c->accum_mode == 0 && count) note_accum_cost(c, tiled, t, frag1 - frag0, count, sig);
   if (stats) {
     stats->accumulate_ms += t;
     stats->accumulate_launches += nl;

@@ -306,4 +306,69 @@ inline double host_start_medium(const HostScene &hs, double x, double y) {
   return n;
 }
 
+// ---- uniform grid over the objects' bounding circles (stands in for tile_map.rs) ----------
+// Cell (ix, iy) is [x0 + ix cs, x0 + (ix + 1) cs] x [y0 + iy cs, y0 + (iy + 1) cs]; it lists every object whose
+// circle (cx, cy, r) comes within `reach` of it.  x0, y0, cs, x1, y1 are representable in the device precision, so
+// the device reproduces the cell boundaries with one fma.
+struct HostGrid {
+  double x0 = 0, y0 = 0, x1 = 0, y1 = 0, cs = 1;
+  int nx = 1, ny = 1;
+  std::vector<unsigned> start, obj; // CSR
+};
+inline double grid_round(double v, bool f32) { return f32 ? (double)(float)v : v; }
+// circ = n x (cx, cy, r); `reach` is added to every radius; `pad` (> reach) is the empty rim around the box;
+// `density` = target number of cells per object
+inline HostGrid build_grid(const double *circ, size_t n, double reach, double pad, bool f32, double density = 1.0) {
+  HostGrid g;
+  if (n == 0) {
+    g.start.assign(2, 0u);
+    g.x1 = g.y1 = 1;
+    return g;
+  }
+  double lox = 1e300, loy = 1e300, hix = -1e300, hiy = -1e300;
+  for (size_t i = 0; i < n; ++i) {
+    const double r = circ[3 * i + 2] + reach;
+    lox = std::min(lox, circ[3 * i] - r), hix = std::max(hix, circ[3 * i] + r);
+    loy = std::min(loy, circ[3 * i + 1] - r), hiy = std::max(hiy, circ[3 * i + 1] + r);
+  }
+  const double w = hix - lox, h = hiy - loy;
+  double cs = std::sqrt(std::max(w * h, 1e-300) / (std::max(density, 1e-3) * (double)n));
+  cs = std::max(cs, std::max(w, h) / 1024.0); // at most 1024 cells a side
+  if (!(cs > 0)) cs = 1.0;
+  for (int attempt = 0;; ++attempt) {
+    pad = std::max(pad, 1e-3 * cs);
+    g.cs = grid_round(cs, f32);
+    g.x0 = grid_round(lox - 2 * pad, f32), g.y0 = grid_round(loy - 2 * pad, f32);
+    g.nx = std::max(1, (int)std::ceil((hix + 2 * pad - g.x0) / g.cs));
+    g.ny = std::max(1, (int)std::ceil((hiy + 2 * pad - g.y0) / g.cs));
+    g.x1 = grid_round(std::fma((double)g.nx, g.cs, g.x0), f32), g.y1 = grid_round(std::fma((double)g.ny, g.cs, g.y0), f32);
+    const size_t cells = (size_t)g.nx * g.ny;
+    std::vector<unsigned> count(cells + 1, 0u);
+    auto for_cells = [&](size_t i, auto f) {
+      const double cx = circ[3 * i], cy = circ[3 * i + 1], r = circ[3 * i + 2] + reach;
+      const int ia = std::max(0, (int)std::floor((cx - r - g.x0) / g.cs) - 1), ib = std::min(g.nx - 1, (int)std::floor((cx + r - g.x0) / g.cs) + 1);
+      const int ja = std::max(0, (int)std::floor((cy - r - g.y0) / g.cs) - 1), jb = std::min(g.ny - 1, (int)std::floor((cy + r - g.y0) / g.cs) + 1);
+      for (int j = ja; j <= jb; ++j)
+        for (int i2 = ia; i2 <= ib; ++i2) {
+          const double bx0 = g.x0 + i2 * g.cs, bx1 = g.x0 + (i2 + 1) * g.cs, by0 = g.y0 + j * g.cs, by1 = g.y0 + (j + 1) * g.cs;
+          const double dx = std::max(std::max(bx0 - cx, cx - bx1), 0.0), dy = std::max(std::max(by0 - cy, cy - by1), 0.0);
+          if (dx * dx + dy * dy <= r * r) f((size_t)j * g.nx + i2);
+        }
+    };
+    for (size_t i = 0; i < n; ++i) for_cells(i, [&](size_t c) { ++count[c + 1]; });
+    size_t total = 0;
+    for (size_t c = 1; c <= cells; ++c) total += count[c];
+    if (total > 32 * n + 4096 && attempt < 12) { // large objects in a fine grid: coarsen
+      cs *= 2;
+      continue;
+    }
+    for (size_t c = 1; c <= cells; ++c) count[c] += count[c - 1];
+    g.start = count;
+    g.obj.assign(total, 0u);
+    std::vector<unsigned> cur(count.begin(), count.end() - 1);
+    for (size_t i = 0; i < n; ++i) for_cells(i, [&](size_t c) { g.obj[cur[c]++] = (unsigned)i; }); // ascending object index
+    return g;
+  }
+}
+
 } // namespace lg

@@ -30,6 +30,7 @@
 #pragma once
 #include "../../include/light_garden_b200.h"
 #include "lg_geom.cuh"
+#include "lg_nearest.cuh"
 
 namespace lg {
 
@@ -59,16 +60,13 @@ struct TraceCounters {
   unsigned int stack_overflow;   // a split did not fit the slot's stack
 };
 
-template <class T> struct TraceArgs {
+template <class T> struct TraceArgs : SceneArgs<T> { // + toks, obj_first/count, delta, grid (lg_nearest.cuh)
   // broad-phase table, contiguous SoA of n_pad entries each: centre x, centre y,
   // (radius + margin)^2, radius + margin.  n_pad is a multiple of 32; padding
   // entries have a negative squared radius and can never become candidates.
   const T *bounds;
   unsigned int bounds_bytes;
   int n_pad;
-  T delta; // rounding margin of the broad phase (64 eps x coordinate bound)
-  const Tok<T> *toks;
-  const int *obj_first, *obj_count;
   const T *obj_n; // refractive index, NaN = no material
   const int *ovl_start, *ovl_list;
   T canvas[8];
@@ -191,99 +189,6 @@ static __global__ void emit_rays_kernel(DevLight l, unsigned long long first, un
   dst[i] = r;
 }
 
-// ---- best-hit bookkeeping (tracer.rs:412-424) -------------------------------------
-template <class T> struct Best {
-  T d2;
-  T px, py, aux;
-  int obj, tok;
-};
-
-template <class T>
-__device__ __forceinline__ void take(Best<T> &b, V2<T> o, const Cand<T> &c, int obj, int tok) {
-  T dx = c.p.x - o.x, dy = c.p.y - o.y;
-  T d2 = dx * dx + dy * dy; // nalgebra distance_squared, no fused multiply-add
-  // strict `<`; the sweep visits objects grouped by type, so equal distances
-  // are resolved towards the lower object index, as the in-order loop would
-  if (d2 < b.d2 || (d2 == b.d2 && obj < b.obj)) {
-    b.d2 = d2;
-    b.px = c.p.x;
-    b.py = c.p.y;
-    b.aux = c.aux;
-    b.obj = obj;
-    b.tok = tok;
-  }
-}
-
-// Ray::intersect(&Geo::GeoLogic): leaf hits in program order, each filtered by
-// the sibling subtrees on the way to the root (ORACLE.md §3.6)
-// (force-inlined, like narrow_phase below: with two levels of __noinline__ device functions the sm_100a build of
-// nvcc 12.9 produced a kernel that lost a live register across the nested call — compute-sanitizer: misaligned
-// shared-memory reads in the candidate loop right after CALL narrow_phase -> CALL sweep_csg_object.  The kernel
-// therefore contains no user-level calls; tools/gpu_round.sh runs the GPU suite under compute-sanitizer.)
-template <class T>
-__device__ __forceinline__ void sweep_csg_object(const TraceArgs<T> &A, int obj, V2<T> o, V2<T> d, Best<T> &best) {
-  const int first = A.obj_first[obj], count = A.obj_count[obj];
-  const Tok<T> *tok = A.toks + first;
-  for (int k = 0; k < count; ++k) {
-    const Tok<T> &l = tok[k];
-    if (l.kind == TOK_OP) continue;
-    CandList<T> hl;
-    hl.n = 0;
-    if (l.kind == TOK_CIRCLE)
-      hit_circle(l.p, o, d, hl);
-    else if (l.kind == TOK_RECT)
-      hit_rect(l.p, o, d, hl);
-    else if (l.kind == TOK_SEGMENT)
-      hit_segment(l.p, o, d, hl);
-    else if (l.kind == TOK_ELLIPSE)
-      hit_ellipse(l.p, o, d, hl);
-    else
-      hit_bezier(l.p, o, d, hl);
-    for (int j = 0; j < hl.n; ++j) {
-      bool keep = true;
-      for (int i = k + 1; i < count && keep; ++i) {
-        const Tok<T> &q = tok[i];
-        if (q.kind != TOK_OP || q.a_start > k) continue;
-        if (k < q.b_start) {
-          bool inb = contains_range(tok, q.b_start, i - 1, hl.h[j].p);
-          keep = (q.op == OP_AND) ? inb : !inb;
-        } else {
-          bool ina = contains_range(tok, q.a_start, q.b_start - 1, hl.h[j].p);
-          keep = (q.op == OP_OR) ? !ina : ina;
-        }
-      }
-      if (keep) take(best, o, hl.h[j], obj, first + k);
-    }
-  }
-}
-
-// Narrow phase: the exact Ray::intersect of ORACLE.md §3 for one object.  It runs in the candidate loop that
-// follows every 32-object chunk of the broad phase, so the broad-phase loop itself stays a handful of instructions
-// per test.
-template <class T>
-__device__ __forceinline__ Best<T> narrow_phase(const TraceArgs<T> &A, Best<T> b, int obj, V2<T> o, V2<T> d) {
-  const int first = A.obj_first[obj];
-  if (A.obj_count[obj] == 1) {
-    const Tok<T> &k = A.toks[first];
-    CandList<T> hl;
-    hl.n = 0;
-    if (k.kind == TOK_CIRCLE)
-      hit_circle(k.p, o, d, hl);
-    else if (k.kind == TOK_SEGMENT)
-      hit_segment(k.p, o, d, hl);
-    else if (k.kind == TOK_RECT)
-      hit_rect(k.p, o, d, hl);
-    else if (k.kind == TOK_ELLIPSE)
-      hit_ellipse(k.p, o, d, hl);
-    else
-      hit_bezier(k.p, o, d, hl);
-    for (int q = 0; q < hl.n; ++q) take(b, o, hl.h[q], obj, first);
-  } else {
-    sweep_csg_object(A, obj, o, d, b);
-  }
-  return b;
-}
-
 template <class T> struct SignBits;
 template <> struct SignBits<float> {
   static __device__ __forceinline__ unsigned get(float v) { return __float_as_uint(v); }
@@ -361,7 +266,7 @@ __device__ __forceinline__ bool culled(float r, float g, float b, float a, const
 }
 
 // ---- K2 ---------------------------------------------------------------------------
-template <class T, int R, bool kSmem>
+template <class T, int R, bool kSmem, bool kGrid = false>
 __global__ void __launch_bounds__(kTraceBlock, (R >= 4 || sizeof(T) == 8) ? 2 : 3)
     trace_kernel(const __grid_constant__ TraceArgs<T> A) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -503,7 +408,12 @@ __global__ void __launch_bounds__(kTraceBlock, (R >= 4 || sizeof(T) == 8) ? 2 : 
         nkd[r] = (T)0;
       }
     }
-    for (int c0 = 0; c0 < A.n_pad; c0 += 32) {
+    if (kGrid) {
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+        if (alive[r]) best[r] = grid_nearest(A, best[r], o[r], d[r]);
+    }
+    for (int c0 = 0; !kGrid && c0 < A.n_pad; c0 += 32) {
       // broad phase over 32 objects: bit (31 - i) of m[r] = "object c0 + i cannot be hit"
       unsigned m[R];
 #pragma unroll
@@ -516,23 +426,42 @@ __global__ void __launch_bounds__(kTraceBlock, (R >= 4 || sizeof(T) == 8) ? 2 : 
 #pragma unroll
         for (int r = 0; r < R; ++r) m[r] = Broad<T>::test4(x4, y4, r4, sdx[r], sdy[r], nk[r], m[r]);
       }
-      // narrow phase: survivors in ascending object order, so the strict `<` of
-      // tracer.rs:417 resolves equal distances exactly like the in-order loop
+      // narrow phase: survivors of a slot in ascending object order (take() resolves equal distances towards the
+      // lower object index, like the strict `<` of the in-order loop, tracer.rs:417).  The exact test is
+      // instantiated ONCE for all slots: a lane picks its next surviving candidate from whichever slot has one, so
+      // lanes busy with different slots run the test together and the kernel carries one copy of the code.
+      unsigned cand[R];
 #pragma unroll
-      for (int r = 0; r < R; ++r) {
-        unsigned cand = ~m[r];
-        while (cand) {
-          const int bit = 31 - __clz(cand);
-          cand ^= 1u << bit;
-          const int j = c0 + 31 - bit;
-          // all hits of object j have t in [tca - rb, tca + rb]: skip it when that lies
-          // behind the origin or beyond the nearest hit found so far
-          const T tca = Real<T>::fma(bx[j], sdx[r], Real<T>::fma(by[j], sdy[r], nkd[r]));
-          const T rb = brb[j];
-          if (tca < -rb || tca - rb > tb[r]) continue;
-          const T before = best[r].d2;
-          best[r] = narrow_phase(A, best[r], j, o[r], d[r]);
-          if (best[r].d2 != before) tb[r] = Real<T>::sqrt(best[r].d2) * (T)1.000001 + A.delta;
+      for (int r = 0; r < R; ++r) cand[r] = ~m[r];
+      while (true) {
+        int s = -1, j = 0;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          while (s < 0 && cand[r]) {
+            const int bit = 31 - __clz(cand[r]);
+            cand[r] ^= 1u << bit;
+            const int jj = c0 + 31 - bit;
+            // all hits of object jj have t in [tca - rb, tca + rb]: skip it when that lies
+            // behind the origin or beyond the nearest hit found so far
+            const T tca = Real<T>::fma(bx[jj], sdx[r], Real<T>::fma(by[jj], sdy[r], nkd[r]));
+            const T rb = brb[jj];
+            if (tca < -rb || tca - rb > tb[r]) continue;
+            s = r, j = jj;
+          }
+        }
+        if (s < 0) break;
+        V2<T> os = o[0], ds = d[0];
+        Best<T> bs = best[0];
+#pragma unroll
+        for (int r = 1; r < R; ++r)
+          if (s == r) os = o[r], ds = d[r], bs = best[r];
+        const T before = bs.d2;
+        bs = narrow_phase(A, bs, j, os, ds);
+        if (bs.d2 != before) {
+          const T nt = Real<T>::sqrt(bs.d2) * (T)1.000001 + A.delta;
+#pragma unroll
+          for (int r = 0; r < R; ++r)
+            if (s == r) best[r] = bs, tb[r] = nt;
         }
       }
     }
@@ -672,5 +601,7 @@ __global__ void __launch_bounds__(kTraceBlock, (R >= 4 || sizeof(T) == 8) ? 2 : 
 // lg_trace_f32.cu / lg_trace_f64.cu, so they compile in parallel).
 const void *trace_kernel_f32(int slots, bool smem);
 const void *trace_kernel_f64(int slots, bool smem);
+const void *trace_kernel_grid_f32(int slots);
+const void *trace_kernel_grid_f64(int slots);
 
 } // namespace lg

@@ -175,6 +175,12 @@ public:
   const std::vector<Object> &object_iterator() const { return objects_; }
   const std::vector<Light> &light_iterator() const { return lights_; }
   void resize(const Rect &bounds) { canvas_bounds = bounds; }
+  // Tracer::enable_tile_map / tile_map_enabled (tracer.rs:126-146)
+  void enable_tile_map(bool enable) {
+    check(lg_tile_map_enable(ctx_, enable ? 1 : 0));
+    tile_map_enabled_ = enable;
+  }
+  bool tile_map_enabled() const { return tile_map_enabled_; }
 
   // Tracer::trace_all -> Vec<(P2, Color)>: two vertices per segment, in the reference's order
   // (light -> ray -> generation -> queue order), followed by the curved mirrors' control lines (tracer.rs:342-346).
@@ -260,6 +266,7 @@ private:
     return (int32_t)ix;
   }
   lg_ctx *ctx_ = nullptr;
+  bool tile_map_enabled_ = false;
   std::vector<Object> objects_;
   std::vector<Light> lights_;
 };

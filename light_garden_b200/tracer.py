@@ -152,6 +152,15 @@ class Tracer:
         self.clear()
         self.objects, self.lights = objects, lights
 
+    def enable_tile_map(self, enable: bool):
+        """Tracer::enable_tile_map (tracer.rs:137-146): nearest-hit search through the device grid (same segments)."""
+        self._tile_map_enabled = bool(enable)
+        self.ctx.call("lg_tile_map_enable", 1 if enable else 0)
+
+    def tile_map_enabled(self) -> bool:
+        """Tracer::tile_map_enabled (tracer.rs:126-129)."""
+        return getattr(self, "_tile_map_enabled", False)
+
     # -- device state -----------------------------------------------------------------------------
     def set_shard(self, rank: int, world: int):
         self._rank, self._world = rank, world

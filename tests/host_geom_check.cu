@@ -12,6 +12,8 @@
 
 #include "../light_garden_b200/csrc/lg_geom.cuh"
 #include "../light_garden_b200/csrc/lg_scene.h"
+#include "../light_garden_b200/csrc/lg_nearest.cuh"
+#include "../light_garden_b200/csrc/lg_tables.h"
 #include "../oracle/lg_oracle.hpp"
 
 static uint64_t s_state = 0x4C47BEEFull;
@@ -290,10 +292,110 @@ static long check_lowering(int n_scenes) {
   return n;
 }
 
+// The uniform-grid walk (lg_nearest.cuh grid_nearest, tables from lg_tables.h) must return the all-objects loop's
+// nearest hit bit for bit: object, token, distance, point.  Scenes: random sizes, and a jittered lattice whose pitch
+// equals the cell size so that rays graze cell corners; rays: random, axis-parallel, from outside the box, and aimed
+// at cell corners.
+template <class T> static long check_grid_scene(const std::vector<LgObject> &objs, const std::vector<LgGeoNode> &nodes, int n_rays,
+                                                double density) {
+  LgTraceParams prm{};
+  prm.max_bounce = 5;
+  prm.canvas_tlbr[0] = 1, prm.canvas_tlbr[1] = -1.7, prm.canvas_tlbr[2] = -1, prm.canvas_tlbr[3] = 1.7;
+  lg::HostScene hs;
+  std::string err;
+  if (lg::lower_scene(objs.data(), (uint32_t)objs.size(), nodes.data(), (uint32_t)nodes.size(), prm, hs, err)) return 0;
+  const std::vector<lg::Tok<T>> toks = lg::device_tokens<T>(hs);
+  std::vector<int> first, count;
+  for (const lg::HostObj &o : hs.objs) first.push_back(o.first), count.push_back(o.count);
+  const std::vector<double> circ = lg::object_circles(hs);
+  const size_t n = hs.objs.size();
+  const double B = std::fmax(hs.bound, 4.0);
+  const lg::BoundsTable<T> bt = lg::build_bounds<T>(circ.data(), n, B);
+  const lg::HostGrid g = lg::build_scene_grid<T>(bt, n, density);
+  lg::SceneArgs<T> A{};
+  A.toks = toks.data(), A.obj_first = first.data(), A.obj_count = count.data(), A.delta = (T)bt.delta;
+  A.grid_x0 = (T)g.x0, A.grid_y0 = (T)g.y0, A.grid_x1 = (T)g.x1, A.grid_y1 = (T)g.y1;
+  A.grid_cs = (T)g.cs, A.grid_ics = (T)(1.0 / g.cs), A.grid_eta = (T)bt.delta;
+  A.grid_nx = g.nx, A.grid_ny = g.ny, A.grid_start = g.start.data(), A.grid_obj = g.obj.data();
+  long done = 0;
+  for (int q = 0; q < n_rays; ++q) {
+    lg::V2<T> o{(T)uni(-2.2, 2.2), (T)uni(-1.4, 1.4)};
+    double ang = uni(0, 6.283185307179586);
+    lg::V2<T> d{(T)std::cos(ang), (T)std::sin(ang)};
+    const int mode = q % 8;
+    if (mode == 1) d = {(T)1, (T)0};
+    if (mode == 2) d = {(T)0, (T)-1};
+    if (mode == 3 || mode == 4) { // through a cell corner (exactly, or an ulp-scale distance away)
+      const double cx = g.x0 + (double)(nextu() % (unsigned)(g.nx + 1)) * g.cs, cy = g.y0 + (double)(nextu() % (unsigned)(g.ny + 1)) * g.cs;
+      const double tt = uni(0.01, 1.5), wob = mode == 4 ? uni(-1e-6, 1e-6) : 0.0;
+      o = {(T)(cx - tt * std::cos(ang) + wob), (T)(cy - tt * std::sin(ang))};
+    }
+    if (mode == 5 && n) { // starts on an object's bounding circle
+      const size_t i = nextu() % n;
+      o = {(T)(circ[3 * i] + circ[3 * i + 2] * std::cos(ang)), (T)(circ[3 * i + 1] + circ[3 * i + 2] * std::sin(ang))};
+    }
+    lg::Best<T> b0;
+    b0.d2 = lg::Real<T>::max_value(), b0.obj = -1, b0.tok = -1, b0.px = b0.py = b0.aux = (T)0;
+    const lg::Best<T> a = lg::all_objects_nearest(A, (int)n, b0, o, d), b = lg::grid_nearest(A, b0, o, d);
+    if (a.obj != b.obj || a.tok != b.tok || !same(a.d2, b.d2) || !same(a.px, b.px) || !same(a.py, b.py) || !same(a.aux, b.aux)) {
+      if (g_bad < 20)
+        std::printf("MISMATCH grid walk (%s): all-objects obj %d d2 %.9g, grid obj %d d2 %.9g, ray (%.9g %.9g)+(%.9g %.9g), grid %dx%d\n",
+                    sizeof(T) == 4 ? "f32" : "f64", a.obj, (double)a.d2, b.obj, (double)b.d2, (double)o.x, (double)o.y, (double)d.x,
+                    (double)d.y, g.nx, g.ny);
+      ++g_bad;
+    }
+    ++done;
+  }
+  return done;
+}
+
+static long check_grid(int n_scenes) {
+  long n = 0;
+  for (int sidx = 0; sidx < n_scenes; ++sidx) {
+    std::vector<LgGeoNode> nodes;
+    std::vector<LgObject> objs;
+    const bool lattice = sidx % 2 == 0;
+    const int side = 4 + (int)(nextu() % 20);
+    const int nobj = lattice ? side * side : 1 + (int)(nextu() % 60);
+    for (int i = 0; i < nobj; ++i) {
+      LgObject o{};
+      if (lattice) {
+        LgGeoNode g{};
+        g.child_a = g.child_b = -1;
+        g.rot[0] = 1, g.rot[3] = 1;
+        const double pitch = 3.0 / side, x = -1.5 + (i % side + 0.5 + uni(-0.3, 0.3)) * pitch, y = -1.0 + (i / side + 0.5 + uni(-0.3, 0.3)) * (2.0 / side);
+        const int kind = (int)(nextu() % 3);
+        if (kind == 0) {
+          g.kind = LG_GEO_CIRCLE, g.p[0] = x, g.p[1] = y, g.p[2] = uni(0.1, 0.45) * pitch;
+        } else if (kind == 1) {
+          const double ra = uni(0, 6.283185307179586);
+          g.kind = LG_GEO_RECT, g.p[0] = x, g.p[1] = y, g.p[2] = uni(0.1, 0.4) * pitch, g.p[3] = uni(0.1, 0.4) * pitch;
+          g.rot[0] = std::cos(ra), g.rot[1] = std::sin(ra), g.rot[2] = -std::sin(ra), g.rot[3] = std::cos(ra);
+        } else {
+          const double ra = uni(0, 6.283185307179586), l = uni(0.1, 0.6) * pitch;
+          g.kind = LG_GEO_SEGMENT, g.p[0] = x - l * std::cos(ra), g.p[1] = y - l * std::sin(ra), g.p[2] = x + l * std::cos(ra), g.p[3] = y + l * std::sin(ra);
+        }
+        nodes.push_back(g);
+        o.root = (int)nodes.size() - 1;
+      } else {
+        o.root = rand_geo(nodes, 0);
+      }
+      o.has_material = (int)(nextu() % 2);
+      o.refractive_index = uni(1.05, 2.4);
+      objs.push_back(o);
+    }
+    const double density = sidx % 3 == 0 ? 1.0 : (sidx % 3 == 1 ? 4.0 : 0.25);
+    n += check_grid_scene<float>(objs, nodes, 2000, density);
+    n += check_grid_scene<double>(objs, nodes, 2000, density);
+  }
+  return n;
+}
+
 int main(int argc, char **argv) {
   int iters = argc > 1 ? std::atoi(argv[1]) : 200000;
   long n = run<float>(iters) + run<double>(iters);
   n += check_lowering(iters / 500 + 10);
+  n += check_grid(iters / 2500 + 4);
   if (g_bad) {
     std::printf("FAILED %ld mismatches\n", g_bad);
     return 1;

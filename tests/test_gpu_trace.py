@@ -234,6 +234,73 @@ def test_table_larger_than_shared_memory(oracle, ctx32):
     assert_same_segments(got, exp)
 
 
+@pytest.mark.parametrize("name", list(SPECS))
+def test_tile_map_walk_gives_the_all_objects_result(oracle, ctx32, ctx64, name):
+    """SURVEY.md 8f rank 1: with Tracer::enable_tile_map the nearest-hit search walks the device-side uniform grid
+    instead of testing every object; segments, tags and colours must stay bit-identical to the oracle's
+    all-objects loop, in both precisions."""
+    spec = SPECS[name]
+    osc = oracle.OracleScene.from_spec(spec)
+    rays = primary_rays(oracle, spec, osc)
+    for ctx, prec in ((ctx32, abi.LG_PRECISION_F32), (ctx64, abi.LG_PRECISION_F64)):
+        t = make_tracer(spec, ctx)
+        assert not t.tile_map_enabled()
+        t.enable_tile_map(True)
+        try:
+            got = t.trace(rays)
+            exp = osc.trace_rays(rays, prec)
+            assert_same_segments(got, exp, f64=prec == abi.LG_PRECISION_F64)
+            assert t.last_stats.ray_steps == exp.ray_steps
+        finally:
+            t.enable_tile_map(False)
+
+
+@pytest.mark.parametrize("density,slots", [("0.25", "1"), ("4", "2")])
+def test_tile_map_cell_size_and_slots_do_not_matter(oracle, density, slots):
+    from light_garden_b200.tracer import Context
+    spec = SPECS["C5"]
+    osc = oracle.OracleScene.from_spec(spec)
+    rays = primary_rays(oracle, spec, osc)
+    os.environ["LG_GRID_DENSITY"], os.environ["LG_GRID_SLOTS"] = density, slots
+    try:
+        c = Context(0, abi.LG_PRECISION_F32)
+    finally:
+        del os.environ["LG_GRID_DENSITY"], os.environ["LG_GRID_SLOTS"]
+    try:
+        t = make_tracer(spec, c)
+        t.enable_tile_map(True)
+        assert_same_segments(t.trace(rays), osc.trace_rays(rays, abi.LG_PRECISION_F32))
+    finally:
+        c.close()
+
+
+def test_tile_map_with_twenty_thousand_objects(oracle, ctx32):
+    """The scene of test_table_larger_than_shared_memory through the grid, device emission, end to end."""
+    from light_garden_b200.tracer import Tracer
+    rng = scenes.SplitMix64(0x4C47B16)
+    t = Tracer(scenes.canvas(16 / 9), ctx=ctx32)
+    for k in range(20000):
+        cx, cy = rng.uniform(-1.7, 1.7), rng.uniform(-0.95, 0.95)
+        r = rng.uniform(0.002, 0.004)
+        if k % 3 == 0:
+            t.push_object(Object.new_mirror((cx - r, cy - r), (cx + r, cy + r)))
+        elif k % 3 == 1:
+            t.push_object(Object.new_circle((cx, cy), r).with_index(rng.uniform(1.1, 1.8)))
+        else:
+            t.push_object(Object.new_rect((cx, cy), 2 * r, 1.5 * r).with_index(rng.uniform(1.1, 1.8)))
+    t.push_light(PointLight((0.01, 0.02), 20000, (0.01, 0.008, 0.006, 0.02)))
+    seg_all, tag_all, _ = t.trace_all(control_lines=False, return_tags=True)
+    steps = t.last_stats.ray_steps
+    t.enable_tile_map(True)
+    try:
+        seg_grid, tag_grid, _ = t.trace_all(control_lines=False, return_tags=True)
+    finally:
+        t.enable_tile_map(False)
+    assert t.last_stats.ray_steps == steps and len(seg_all) > 40000
+    assert np.array_equal(tag_all, tag_grid)
+    assert seg_all.tobytes() == seg_grid.tobytes()
+
+
 def test_errors_are_reported_not_hidden(ctx32):
     from light_garden_b200._lib import LightGardenError
     from light_garden_b200.tracer import Context, Tracer
