@@ -5,7 +5,9 @@ import os
 
 from . import abi
 
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_lib", "liblight_garden_b200.so")
+# LG_LIB_PATH: an alternate build of the same library (kernel tuning experiments); still no fallback
+LIB_PATH = os.environ.get("LG_LIB_PATH") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "_lib",
+                                                         "liblight_garden_b200.so")
 _lib = None
 
 

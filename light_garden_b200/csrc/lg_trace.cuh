@@ -32,6 +32,10 @@
 #include "lg_geom.cuh"
 #include "lg_nearest.cuh"
 
+#ifndef LG_TRACE_GROUP
+#define LG_TRACE_GROUP 4
+#endif
+
 namespace lg {
 
 constexpr int kTraceBlock = 256;
@@ -304,6 +308,7 @@ __global__ void __launch_bounds__(kTraceBlock, (R >= 4 || sizeof(T) == 8) ? 2 : 
   const T *br2 = by + A.n_pad;
   const T *brb = br2 + A.n_pad;
   typedef typename Vec4<T>::type T4;
+  constexpr int kGroup = LG_TRACE_GROUP; // 32-object chunks per candidate pass
 
   const unsigned lane = threadIdx.x & 31u;
   const unsigned lt_mask = (1u << lane) - 1u;
@@ -413,40 +418,49 @@ __global__ void __launch_bounds__(kTraceBlock, (R >= 4 || sizeof(T) == 8) ? 2 : 
       for (int r = 0; r < R; ++r)
         if (alive[r]) best[r] = grid_nearest(A, best[r], o[r], d[r]);
     }
-    for (int c0 = 0; !kGrid && c0 < A.n_pad; c0 += 32) {
-      // broad phase over 32 objects: bit (31 - i) of m[r] = "object c0 + i cannot be hit"
-      unsigned m[R];
+    for (int c0 = 0; !kGrid && c0 < A.n_pad; c0 += 32 * kGroup) {
+      // broad phase over kGroup chunks of 32 objects: bit (31 - i) of m[r][g] = "object c0 + 32 g + i cannot be
+      // hit".  Candidates are handled once per group, not per chunk: a lane then has a few of them at a time, so
+      // the lanes of a warp spend fewer of the candidate loop's iterations idle.
+      unsigned m[R][kGroup];
 #pragma unroll
-      for (int r = 0; r < R; ++r) m[r] = 0u;
+      for (int g = 0; g < kGroup; ++g) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) m[r][g] = 0xffffffffu;
+        if (c0 + 32 * g < A.n_pad) {
+#pragma unroll
+          for (int r = 0; r < R; ++r) m[r][g] = 0u;
 #pragma unroll 4
-      for (int q = 0; q < 32; q += 4) {
-        const T4 x4 = *reinterpret_cast<const T4 *>(bx + c0 + q);
-        const T4 y4 = *reinterpret_cast<const T4 *>(by + c0 + q);
-        const T4 r4 = *reinterpret_cast<const T4 *>(br2 + c0 + q);
+          for (int q = 0; q < 32; q += 4) {
+            const T4 x4 = *reinterpret_cast<const T4 *>(bx + c0 + 32 * g + q);
+            const T4 y4 = *reinterpret_cast<const T4 *>(by + c0 + 32 * g + q);
+            const T4 r4 = *reinterpret_cast<const T4 *>(br2 + c0 + 32 * g + q);
 #pragma unroll
-        for (int r = 0; r < R; ++r) m[r] = Broad<T>::test4(x4, y4, r4, sdx[r], sdy[r], nk[r], m[r]);
+            for (int r = 0; r < R; ++r) m[r][g] = Broad<T>::test4(x4, y4, r4, sdx[r], sdy[r], nk[r], m[r][g]);
+          }
+        }
       }
       // narrow phase: survivors of a slot in ascending object order (take() resolves equal distances towards the
       // lower object index, like the strict `<` of the in-order loop, tracer.rs:417).  The exact test is
       // instantiated ONCE for all slots: a lane picks its next surviving candidate from whichever slot has one, so
       // lanes busy with different slots run the test together and the kernel carries one copy of the code.
-      unsigned cand[R];
-#pragma unroll
-      for (int r = 0; r < R; ++r) cand[r] = ~m[r];
       while (true) {
         int s = -1, j = 0;
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-          while (s < 0 && cand[r]) {
-            const int bit = 31 - __clz(cand[r]);
-            cand[r] ^= 1u << bit;
-            const int jj = c0 + 31 - bit;
-            // all hits of object jj have t in [tca - rb, tca + rb]: skip it when that lies
-            // behind the origin or beyond the nearest hit found so far
-            const T tca = Real<T>::fma(bx[jj], sdx[r], Real<T>::fma(by[jj], sdy[r], nkd[r]));
-            const T rb = brb[jj];
-            if (tca < -rb || tca - rb > tb[r]) continue;
-            s = r, j = jj;
+#pragma unroll
+          for (int g = 0; g < kGroup; ++g) {
+            while (s < 0 && m[r][g] != 0xffffffffu) {
+              const int bit = 31 - __clz(~m[r][g]);
+              m[r][g] |= 1u << bit;
+              const int jj = c0 + 32 * g + 31 - bit;
+              // all hits of object jj have t in [tca - rb, tca + rb]: skip it when that lies
+              // behind the origin or beyond the nearest hit found so far
+              const T tca = Real<T>::fma(bx[jj], sdx[r], Real<T>::fma(by[jj], sdy[r], nkd[r]));
+              const T rb = brb[jj];
+              if (tca < -rb || tca - rb > tb[r]) continue;
+              s = r, j = jj;
+            }
           }
         }
         if (s < 0) break;

@@ -20,6 +20,8 @@ def main():
     ap.add_argument("--precision", default="f32")
     ap.add_argument("--repeat", type=int, default=4)
     ap.add_argument("--scale", type=float, default=1.0, help="scale ray / chord counts (smoke runs)")
+    ap.add_argument("--only", default="C1,C2,C3,C4", help="comma-separated subset of the configs")
+    ap.add_argument("--tile-map", action="store_true", help="Tracer::enable_tile_map(true): nearest hit through the device grid")
     args = ap.parse_args()
     from light_garden_b200 import abi, scenes
     from light_garden_b200.tracer import Context, Renderer, Tracer
@@ -30,8 +32,11 @@ def main():
         ("C2", scenes.c2_cavity(total_rays=int(4_000_000 * k), max_bounce=64, width=1920, height=1080)),
         ("C3", scenes.c3_refraction(total_rays=int(16_000_000 * k), width=1920, height=1080)),
     ]
+    only = set(args.only.split(","))
+    specs = [(n, sp) for n, sp in specs if n in only]
     ctx = Context(0, prec)
     ctx.call("lg_segment_capacity_set", 512 << 20)
+    ctx.call("lg_tile_map_enable", 1 if args.tile_map else 0)
     for name, spec in specs:
         t = spec.apply(Tracer(spec.canvas_bounds, ctx=ctx))
         r = Renderer(ctx, spec.width, spec.height)
@@ -47,7 +52,7 @@ def main():
                 best = (dt, st.as_dict())
         dt, st = best
         print(json.dumps({
-            "config": name, "scene": spec.name, "precision": args.precision, "objects": len(spec.objects),
+            "config": name, "tile_map": args.tile_map, "scene": spec.name, "precision": args.precision, "objects": len(spec.objects),
             "primary_rays": st["primary_rays"], "max_bounce": spec.max_bounce, "image": [spec.width, spec.height],
             "wall_ms": dt * 1e3, "trace_ms": st["trace_ms"], "accumulate_ms": st["accumulate_ms"],
             "rays_per_s": st["primary_rays"] / dt, "ray_steps": st["ray_steps"], "segments": st["segments"],
@@ -57,7 +62,7 @@ def main():
             "pixel_updates_per_s_in_kernel": st["pixel_updates"] / max(1e-9, st["accumulate_ms"] * 1e-3),
             "launches": st["trace_launches"] + st["accumulate_launches"]}), flush=True)
     # C4: string mod, pure accumulation
-    for num in (2, 7919):
+    for num in ((2, 7919) if "C4" in only else ()):
         sm = scenes.c4_string_mod(modulo=int(10_000_000 * k), num=num)
         r = Renderer(ctx, 4096, 4096)
         best = None
