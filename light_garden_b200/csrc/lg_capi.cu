@@ -158,6 +158,7 @@ struct lg_ctx {
   int accum_mode = 0; // 0 = auto, 1 = direct (one L2 reduction per fragment), 2 = tile-binned
   // auto mode: measured cost of each resolve on this context's recent work (ns per fragment, 0 = no sample yet)
   // uniform grid (lg_tile_map_enable)
+  int trace_merged = -1; // -1 = by scene size
   bool grid_on = false;
   double grid_density = 1.0; // cells per object (LG_GRID_DENSITY)
   int grid_slots = 1;        // ray slots per thread of the grid kernel (LG_GRID_SLOTS)
@@ -383,6 +384,9 @@ template <class T> int launch_trace(lg_ctx *c, TraceArgs<T> &A) {
   if (grid_mode) R = (sizeof(T) == 4 && c->grid_slots == 2) ? 2 : 1; // divergent cell walks: one ray per thread by default
   const bool use_smem = !grid_mode && (size_t)A.bounds_bytes + 1024 <= c->smem_optin;
   const void *kern = grid_mode ? KernelOf<T>::grid(R) : KernelOf<T>::get(R, use_smem);
+  // large scenes: per-slot narrow phase (see trace_kernel); LG_TRACE_MERGED=0/1 forces one or the other
+  const bool per_slot = c->trace_merged < 0 ? c->n_obj >= 512 : c->trace_merged == 0;
+  if (!grid_mode && sizeof(T) == 4 && R == 2 && per_slot) kern = trace_kernel_f32_per_slot(use_smem);
   const size_t smem = use_smem ? A.bounds_bytes : 0;
   if (smem > 48 * 1024) LG_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
@@ -672,6 +676,7 @@ int32_t lg_create(int32_t device, int32_t precision, lg_ctx **out) {
     int v = atoi(e);
     if (v >= 0 && v <= 2) c->accum_mode = v;
   }
+  if (const char *e = getenv("LG_TRACE_MERGED")) c->trace_merged = atoi(e) ? 1 : 0;
   if (const char *e = getenv("LG_GRID_DENSITY")) {
     double v = atof(e);
     if (v > 0.01 && v < 100.0) c->grid_density = v;

@@ -32,9 +32,6 @@
 #include "lg_geom.cuh"
 #include "lg_nearest.cuh"
 
-#ifndef LG_TRACE_GROUP
-#define LG_TRACE_GROUP 4
-#endif
 
 namespace lg {
 
@@ -270,7 +267,10 @@ __device__ __forceinline__ bool culled(float r, float g, float b, float a, const
 }
 
 // ---- K2 ---------------------------------------------------------------------------
-template <class T, int R, bool kSmem, bool kGrid = false>
+// kMerged: one narrow-phase instance shared by the R slots (small scenes: the exact tests dominate, lanes busy with
+// different slots run them together, C2 43 vs 78 ms) or one instance per slot (large scenes: the broad phase and the
+// candidate filter dominate and the simpler per-slot loops win, C5 114 vs 123 ms).  Same results either way.
+template <class T, int R, bool kSmem, bool kGrid = false, bool kMerged = true>
 __global__ void __launch_bounds__(kTraceBlock, (R >= 4 || sizeof(T) == 8) ? 2 : 3)
     trace_kernel(const __grid_constant__ TraceArgs<T> A) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -308,7 +308,6 @@ __global__ void __launch_bounds__(kTraceBlock, (R >= 4 || sizeof(T) == 8) ? 2 : 
   const T *br2 = by + A.n_pad;
   const T *brb = br2 + A.n_pad;
   typedef typename Vec4<T>::type T4;
-  constexpr int kGroup = LG_TRACE_GROUP; // 32-object chunks per candidate pass
 
   const unsigned lane = threadIdx.x & 31u;
   const unsigned lt_mask = (1u << lane) - 1u;
@@ -418,65 +417,80 @@ __global__ void __launch_bounds__(kTraceBlock, (R >= 4 || sizeof(T) == 8) ? 2 : 
       for (int r = 0; r < R; ++r)
         if (alive[r]) best[r] = grid_nearest(A, best[r], o[r], d[r]);
     }
-    for (int c0 = 0; !kGrid && c0 < A.n_pad; c0 += 32 * kGroup) {
-      // broad phase over kGroup chunks of 32 objects: bit (31 - i) of m[r][g] = "object c0 + 32 g + i cannot be
-      // hit".  Candidates are handled once per group, not per chunk: a lane then has a few of them at a time, so
-      // the lanes of a warp spend fewer of the candidate loop's iterations idle.
-      unsigned m[R][kGroup];
+    for (int c0 = 0; !kGrid && c0 < A.n_pad; c0 += 32) {
+      // broad phase over 32 objects: bit (31 - i) of m[r] = "object c0 + i cannot be hit"
+      unsigned m[R];
 #pragma unroll
-      for (int g = 0; g < kGroup; ++g) {
-#pragma unroll
-        for (int r = 0; r < R; ++r) m[r][g] = 0xffffffffu;
-        if (c0 + 32 * g < A.n_pad) {
-#pragma unroll
-          for (int r = 0; r < R; ++r) m[r][g] = 0u;
+      for (int r = 0; r < R; ++r) m[r] = 0u;
 #pragma unroll 4
-          for (int q = 0; q < 32; q += 4) {
-            const T4 x4 = *reinterpret_cast<const T4 *>(bx + c0 + 32 * g + q);
-            const T4 y4 = *reinterpret_cast<const T4 *>(by + c0 + 32 * g + q);
-            const T4 r4 = *reinterpret_cast<const T4 *>(br2 + c0 + 32 * g + q);
+      for (int q = 0; q < 32; q += 4) {
+        const T4 x4 = *reinterpret_cast<const T4 *>(bx + c0 + q);
+        const T4 y4 = *reinterpret_cast<const T4 *>(by + c0 + q);
+        const T4 r4 = *reinterpret_cast<const T4 *>(br2 + c0 + q);
 #pragma unroll
-            for (int r = 0; r < R; ++r) m[r][g] = Broad<T>::test4(x4, y4, r4, sdx[r], sdy[r], nk[r], m[r][g]);
-          }
-        }
+        for (int r = 0; r < R; ++r) m[r] = Broad<T>::test4(x4, y4, r4, sdx[r], sdy[r], nk[r], m[r]);
       }
-      // narrow phase: survivors of a slot in ascending object order (take() resolves equal distances towards the
-      // lower object index, like the strict `<` of the in-order loop, tracer.rs:417).  The exact test is
-      // instantiated ONCE for all slots: a lane picks its next surviving candidate from whichever slot has one, so
-      // lanes busy with different slots run the test together and the kernel carries one copy of the code.
+      if (kMerged) {
+      // narrow phase, ONE instance for all slots: a lane walks the survivors of its slots one after the other
+      // (ascending object order within a slot; take() resolves equal distances towards the lower object index, like
+      // the strict `<` of the in-order loop, tracer.rs:417), so lanes busy with different slots run the exact
+      // test together and the kernel carries one copy of its code.
+      int s = 0;
+      unsigned cand = ~m[0];
       while (true) {
-        int s = -1, j = 0;
+        if (cand == 0u) {
+          if (++s >= R) break;
 #pragma unroll
-        for (int r = 0; r < R; ++r) {
-#pragma unroll
-          for (int g = 0; g < kGroup; ++g) {
-            while (s < 0 && m[r][g] != 0xffffffffu) {
-              const int bit = 31 - __clz(~m[r][g]);
-              m[r][g] |= 1u << bit;
-              const int jj = c0 + 32 * g + 31 - bit;
-              // all hits of object jj have t in [tca - rb, tca + rb]: skip it when that lies
-              // behind the origin or beyond the nearest hit found so far
-              const T tca = Real<T>::fma(bx[jj], sdx[r], Real<T>::fma(by[jj], sdy[r], nkd[r]));
-              const T rb = brb[jj];
-              if (tca < -rb || tca - rb > tb[r]) continue;
-              s = r, j = jj;
-            }
-          }
+          for (int r = 1; r < R; ++r)
+            if (s == r) cand = ~m[r];
+          continue;
         }
-        if (s < 0) break;
-        V2<T> os = o[0], ds = d[0];
+        const int bit = 31 - __clz(cand);
+        cand ^= 1u << bit;
+        const int j = c0 + 31 - bit;
+        T sx = sdx[0], sy = sdy[0], sk = nkd[0], st = tb[0];
+#pragma unroll
+        for (int r = 1; r < R; ++r)
+          if (s == r) sx = sdx[r], sy = sdy[r], sk = nkd[r], st = tb[r];
+        // all hits of object j have t in [tca - rb, tca + rb]: skip it when that lies
+        // behind the origin or beyond the nearest hit found so far
+        const T tca = Real<T>::fma(bx[j], sx, Real<T>::fma(by[j], sy, sk));
+        const T rb = brb[j];
+        if (tca < -rb || tca - rb > st) continue;
+        V2<T> os = o[0];
         Best<T> bs = best[0];
 #pragma unroll
         for (int r = 1; r < R; ++r)
-          if (s == r) os = o[r], ds = d[r], bs = best[r];
+          if (s == r) os = o[r], bs = best[r];
         const T before = bs.d2;
-        bs = narrow_phase(A, bs, j, os, ds);
+        bs = narrow_phase(A, bs, j, os, V2<T>{sx, sy});
         if (bs.d2 != before) {
           const T nt = Real<T>::sqrt(bs.d2) * (T)1.000001 + A.delta;
 #pragma unroll
           for (int r = 0; r < R; ++r)
             if (s == r) best[r] = bs, tb[r] = nt;
         }
+      }
+      } else {
+      // narrow phase: survivors in ascending object order, so the strict `<` of
+      // tracer.rs:417 resolves equal distances exactly like the in-order loop
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        unsigned cand = ~m[r];
+        while (cand) {
+          const int bit = 31 - __clz(cand);
+          cand ^= 1u << bit;
+          const int j = c0 + 31 - bit;
+          // all hits of object j have t in [tca - rb, tca + rb]: skip it when that lies
+          // behind the origin or beyond the nearest hit found so far
+          const T tca = Real<T>::fma(bx[j], sdx[r], Real<T>::fma(by[j], sdy[r], nkd[r]));
+          const T rb = brb[j];
+          if (tca < -rb || tca - rb > tb[r]) continue;
+          const T before = best[r].d2;
+          best[r] = narrow_phase(A, best[r], j, o[r], d[r]);
+          if (best[r].d2 != before) tb[r] = Real<T>::sqrt(best[r].d2) * (T)1.000001 + A.delta;
+        }
+      }
       }
     }
 
@@ -615,6 +629,7 @@ __global__ void __launch_bounds__(kTraceBlock, (R >= 4 || sizeof(T) == 8) ? 2 : 
 // lg_trace_f32.cu / lg_trace_f64.cu, so they compile in parallel).
 const void *trace_kernel_f32(int slots, bool smem);
 const void *trace_kernel_f64(int slots, bool smem);
+const void *trace_kernel_f32_per_slot(bool smem);
 const void *trace_kernel_grid_f32(int slots);
 const void *trace_kernel_grid_f64(int slots);
 

@@ -68,19 +68,20 @@ def test_trace_f32_bit_exact(oracle, ctx32, name):
     assert t.last_stats.ray_steps == exp.ray_steps
 
 
-@pytest.mark.parametrize("slots", ["1", "2", "4"])
-def test_slot_counts_give_identical_results(oracle, slots):
-    """R ray slots per thread is a scheduling choice: results must not depend on it."""
+@pytest.mark.parametrize("slots,merged", [("1", "1"), ("2", "1"), ("2", "0"), ("4", "1")])
+def test_slot_counts_give_identical_results(oracle, slots, merged):
+    """R ray slots per thread, and whether they share one narrow-phase instance (small scenes) or have one each
+    (large scenes), are scheduling choices: results must not depend on them."""
     from light_garden_b200.tracer import Context
     spec = SPECS["C3"]
     osc = oracle.OracleScene.from_spec(spec)
     rays = primary_rays(oracle, spec, osc)
     for prec in (abi.LG_PRECISION_F32, abi.LG_PRECISION_F64):
-        os.environ["LG_TRACE_SLOTS"] = slots
+        os.environ["LG_TRACE_SLOTS"], os.environ["LG_TRACE_MERGED"] = slots, merged
         try:
             c = Context(0, prec)
         finally:
-            del os.environ["LG_TRACE_SLOTS"]
+            del os.environ["LG_TRACE_SLOTS"], os.environ["LG_TRACE_MERGED"]
         try:
             got = make_tracer(spec, c).trace(rays)
             assert_same_segments(got, osc.trace_rays(rays, prec), f64=prec == abi.LG_PRECISION_F64)
