@@ -44,9 +44,14 @@ for w in $what; do
       LG_TRACE_SLOTS=2 timeout 300 python bench.py --precision f64 --rays-per-gpu 4000000 --steps 2 --no-cpu-baseline > gpurun_out/bench_f64_slots2.log 2>&1
       ;;
     prof)
-      timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv \
+      # launch list: the accumulate resolve is pinned to the one the un-profiled bench settles on (tile bins) -- under
+      # ncu every launch is serialised, which distorts the auto mode's own timing of its two candidates
+      LG_ACCUM_MODE=2 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv \
         --log-file gpurun_out/launches.csv python bench.py --rays-per-gpu 4000000 --steps 2 --warmup 3 --no-cpu-baseline \
         > gpurun_out/bench_under_ncu.log 2>&1
+      timeout 600 ncu --set full --clock-control none --import-source on -k regex:trace_kernel -s 12 -c 1 \
+        -f -o gpurun_out/prof_trace_grid python bench.py --rays-per-gpu 2000000 --steps 1 --warmup 3 --no-cpu-baseline \
+        > gpurun_out/prof_trace_grid.log 2>&1
       timeout 600 ncu --set full --clock-control none --import-source on -k regex:trace_kernel -s 1 -c 1 \
         -f -o gpurun_out/prof_trace python bench.py --rays-per-gpu 2000000 --steps 1 --warmup 3 --no-cpu-baseline \
         > gpurun_out/prof_trace.log 2>&1
