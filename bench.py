@@ -4,7 +4,7 @@
 Workload (BASELINE.json configs[4], the one the north-star target is quoted on): the synthetic 4096-object scene
 (2048 circles, 1024 straight mirrors, 1024 rects on a jittered 64x64 lattice), 32 M primary rays PER GPU
 (N point lights x 32 M rays, rank r of N traces the r-th N-th of every light: weak scaling; N = 8 is exactly
-C5 = 256 M rays), max_bounce 5, brute-force ray x object tests, 3840x2160 accumulation, NCCL image reduce.
+C5 = 256 M rays), max_bounce 5, brute-force ray x object tests, 3840x2160 accumulation, image reduce over NVLink peer memory.
 
 One step = one frame of the reference (framework.rs:200-234): clear, trace every ray of the shard, accumulate
 every segment, sum the partial images onto rank 0.
@@ -155,7 +155,7 @@ def run_reference(args):
 def workload_config(n):
     return {"workload": "C5: synthetic 4096-object scene (2048 circles, 1024 mirrors, 1024 rects), "
                         f"{RAYS_PER_GPU} primary rays per GPU x {n} GPU(s), max_bounce 5, brute force, "
-                        f"{WIDTH}x{HEIGHT} RGBA accumulation, NCCL image reduce",
+                        f"{WIDTH}x{HEIGHT} RGBA accumulation, image reduce over NVLink peer memory (NCCL for the handle exchange and barriers)",
             "objects": 4096, "rays_per_gpu": RAYS_PER_GPU, "max_bounce": 5, "width": WIDTH, "height": HEIGHT,
             "parallelism": f"ray-shard x{n}",
             "l2": "inputs larger than L2: GB-scale segment stream and a 132.7 MB image per step"}
@@ -363,14 +363,20 @@ def main():
                                  f"({'FP64' if args.precision == 'f64' else 'FP32'} pipe; MEASURED_PEAKS.json has none). "
                                  "frac can exceed 1: the kernel decides most tests with a conservative 3-FMA bounding-"
                                  "circle line test (6 executed flop) and runs the full ORACLE.md test only on survivors; "
-                                 "`executed` counts that broad phase alone. ncu: FMA pipe 46 %, issue slots 86 % busy "
-                                 "(profiles/). The contract's hbm/tensor bounds do not apply: the table lives in shared "
+                                 "`executed` counts that broad phase alone. ncu (profiles/r01d_trace_full.txt): FMA pipe "
+                                 "cycles 54 %, issue slots 71 % busy. The contract's hbm/tensor bounds do not apply: the table lives in shared "
                                  "memory and the kernel writes 32 B per segment"},
-            "roofline_accumulate": {"bound": "hbm", "kernel": "lg::accumulate_segments_kernel", "achieved": acc_gbs,
+            "roofline_accumulate": {"bound": "hbm",
+                                    "kernel": "lg::tile_count/fill/raster_kernel (tile-binned resolve)"
+                                    if agg["accumulate_launches"] > 2 * args.steps * world
+                                    else "lg::accumulate_segments_kernel (direct resolve)", "achieved": acc_gbs,
                                     "peak": hbm_peak, "unit": "GB/s", "frac": acc_gbs / hbm_peak, "traffic": None,
                                     "peak_source": hbm_src,
                                     "red_v4_peak_gred_per_s": {"coalesced": red_coal.value, "random": red_rand.value},
-                                    "note": "algorithmic bytes = 32 B per segment read + 16 B per blended fragment"},
+                                    "note": "algorithmic bytes = 32 B per segment read + 16 B per blended fragment, over the "
+                                            "whole accumulate phase of a step; the tile-binned resolve is bound by "
+                                            "shared-memory bandwidth (74 % of the wavefront peak, "
+                                            "profiles/r01d_tile_raster_full.txt), the direct one by L2 reductions"},
         }
     # CPU baseline: rank 0, N = 1 only, bounded sample
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
