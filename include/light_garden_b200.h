@@ -67,8 +67,16 @@ enum {
   LG_GEO_SEGMENT = 2, /* Geo::GeoLineSegment  p = {ax, ay, bx, by}            */
   LG_GEO_BEZIER = 3,  /* Geo::GeoCubicBezier  p = {x0,y0,x1,y1,x2,y2,x3,y3}   */
   LG_GEO_LOGIC = 4,   /* Geo::GeoLogic        p = {ox, oy}, rot, op, a, b     */
-  LG_GEO_ELLIPSE = 5  /* Geo::GeoEllipse      p = {ox, oy, a, b}, rot         */
+  LG_GEO_ELLIPSE = 5, /* Geo::GeoEllipse      p = {ox, oy, a, b}, rot         */
+  /* Geo::GeoConvexPolygon (object.rs:34-36, ConvexPolygon::new_convex_hull): p = {ox, oy}, rot,
+   * op = number of hull vertices (3..32), child_a = first LG_GEO_POINTS node. The vertices are in
+   * the polygon's local frame (world = origin + rot * local), already in hull order. */
+  LG_GEO_POLYGON = 6,
+  /* continuation node of a polygon: up to 4 vertices p = {x0,y0,..,x3,y3} (op = how many, 1..4),
+   * child_a = next LG_GEO_POINTS node or -1 */
+  LG_GEO_POINTS = 7
 };
+#define LG_POLYGON_MAX_VERTICES 32
 /* collision2d LogicOp (src/light_garden/mod.rs:368-372) */
 enum { LG_OP_AND = 0, LG_OP_OR = 1, LG_OP_ANDNOT = 2 };
 

@@ -4,10 +4,10 @@ The package is a thin host layer over light_garden_b200/_lib/liblight_garden_b20
 (C ABI: include/light_garden_b200.h).  There is no CPU or PyTorch fallback.
 """
 from . import abi
-from .scene import (AND, AND_NOT, OR, Circle, CubicBezier, Curve, DirectionalLight, Ellipse, LineSegment, Logic, Material, ModRemColor,
+from .scene import (AND, AND_NOT, OR, Circle, ConvexPolygon, CubicBezier, Curve, DirectionalLight, Ellipse, LineSegment, Logic, Material, ModRemColor,
                     Object, PointLight, Rect, SpotLight, StringMod, StringModMode, rot2, rot2_identity)
 
-__all__ = ["abi", "AND", "AND_NOT", "OR", "Circle", "CubicBezier", "Curve", "DirectionalLight", "Ellipse", "LineSegment", "Logic",
+__all__ = ["abi", "AND", "AND_NOT", "OR", "Circle", "ConvexPolygon", "CubicBezier", "Curve", "DirectionalLight", "Ellipse", "LineSegment", "Logic",
            "Material", "ModRemColor", "Object", "PointLight", "Rect", "SpotLight", "StringMod", "StringModMode",
            "rot2", "rot2_identity", "Context", "Tracer", "Renderer"]
 

@@ -19,6 +19,7 @@ ERROR_NAMES = {
 
 LG_PRECISION_F32, LG_PRECISION_F64 = 0, 1
 LG_GEO_CIRCLE, LG_GEO_RECT, LG_GEO_SEGMENT, LG_GEO_BEZIER, LG_GEO_LOGIC, LG_GEO_ELLIPSE = 0, 1, 2, 3, 4, 5
+LG_GEO_POLYGON, LG_GEO_POINTS, LG_POLYGON_MAX_VERTICES = 6, 7, 32
 LG_OP_AND, LG_OP_OR, LG_OP_ANDNOT = 0, 1, 2
 LG_LIGHT_POINT, LG_LIGHT_DIRECTIONAL, LG_LIGHT_SPOT = 0, 1, 2
 LG_SM_ADD, LG_SM_MUL, LG_SM_POW, LG_SM_BASE = 0, 1, 2, 3

@@ -21,7 +21,7 @@ namespace lg {
 constexpr double kTMin = 1e-5;    // ORACLE.md §1: accept a hit iff t > T_MIN
 constexpr double kParEps = 1e-12; // ORACLE.md §1: |cross(d,e)| <= PAR_EPS is parallel
 
-enum : int32_t { TOK_CIRCLE = 0, TOK_RECT = 1, TOK_SEGMENT = 2, TOK_BEZIER = 3, TOK_OP = 4, TOK_ELLIPSE = 5 };
+enum : int32_t { TOK_CIRCLE = 0, TOK_RECT = 1, TOK_SEGMENT = 2, TOK_BEZIER = 3, TOK_OP = 4, TOK_ELLIPSE = 5, TOK_POLY = 6, TOK_POINTS = 7 };
 enum : int32_t { OP_AND = 0, OP_OR = 1, OP_ANDNOT = 2 };
 
 // ---- real-type wrappers ----------------------------------------------------
@@ -81,6 +81,7 @@ template <class T> struct Tok {
   // CIRCLE : cx cy r r2          SEGMENT: ax ay ex ey
   // RECT   : cx cy ux uy vx vy uu vv     BEZIER : x0 y0 .. x3 y3
   // ELLIPSE: cx cy ux uy a b 1/a 1/b  (u = unit x axis of the ellipse in world space)
+  // POLY   : op = vertex count k; the next ceil(k / 4) tokens are POINTS: x0 y0 .. x3 y3 (world space, hull order)
 };
 
 // A candidate hit: ray parameter, point, and what is needed to rebuild the
@@ -266,6 +267,40 @@ template <class T> LG_HD void hit_ellipse(const T *e, V2<T> o, V2<T> d, CandList
   if (t1 > (T)kTMin) out.h[out.n++] = {t1, ray_at(o, t1, d), (T)1};
 }
 
+// ---- ORACLE.md §3.8 convex polygon: the edges v_i -> v_(i+1) as segments, in hull order ------------
+// (the vertices live in the POINTS tokens that follow the POLY token)
+template <class T> LG_HD V2<T> poly_vertex(const Tok<T> &k, int i) {
+  const Tok<T> &q = (&k)[1 + (i >> 2)];
+  return {q.p[2 * (i & 3)], q.p[2 * (i & 3) + 1]};
+}
+template <class T> LG_HD void hit_poly(const Tok<T> &k, V2<T> o, V2<T> d, CandList<T> &out) {
+  const int n = k.op;
+  V2<T> a = poly_vertex(k, 0);
+  for (int i = 0; i < n; ++i) {
+    const V2<T> b = poly_vertex(k, i + 1 < n ? i + 1 : 0);
+    Cand<T> h;
+    if (out.n < 4 && hit_edge(a, V2<T>{b.x - a.x, b.y - a.y}, o, d, (T)i, h)) out.h[out.n++] = h;
+    a = b;
+  }
+}
+template <class T> LG_HD V2<T> poly_normal(const Tok<T> &k, int i) {
+  const int n = k.op;
+  const V2<T> a = poly_vertex(k, i), b = poly_vertex(k, i + 1 < n ? i + 1 : 0);
+  return unit(V2<T>{-(b.y - a.y), b.x - a.x});
+}
+template <class T> LG_HD bool poly_contains(const Tok<T> &k, V2<T> p) {
+  const int n = k.op;
+  int pos = 0, neg = 0;
+  V2<T> a = poly_vertex(k, 0);
+  for (int i = 0; i < n; ++i) {
+    const V2<T> b = poly_vertex(k, i + 1 < n ? i + 1 : 0);
+    const T c = cross(V2<T>{b.x - a.x, b.y - a.y}, V2<T>{p.x - a.x, p.y - a.y});
+    pos += c > (T)0 ? 1 : 0, neg += c < (T)0 ? 1 : 0;
+    a = b;
+  }
+  return pos == n || neg == n; // strictly on the same side of every edge, whichever way the hull is wound
+}
+
 // unit normal of the hit (token, point, aux); orientation is fixed later
 template <class T> LG_HD V2<T> hit_normal(const Tok<T> &k, V2<T> p, T aux) {
   switch (k.kind) {
@@ -277,6 +312,7 @@ template <class T> LG_HD V2<T> hit_normal(const Tok<T> &k, V2<T> p, T aux) {
     return unit(V2<T>{-e.y, e.x});
   }
   case TOK_ELLIPSE: return ellipse_normal(k.p, p);
+  case TOK_POLY: return poly_normal(k, (int)aux);
   default: return bezier_normal(k.p, aux);
   }
 }
@@ -297,6 +333,7 @@ template <class T> LG_HD bool contains_leaf(const Tok<T> &l, V2<T> p) {
     V2<T> q = ellipse_frame(l.p, V2<T>{p.x - l.p[0], p.y - l.p[1]});
     return dot(q, q) < (T)1;
   }
+  if (l.kind == TOK_POLY) return poly_contains(l, p);
   return false; // mirrors never contain: src/light_garden/object.rs:243-244
 }
 // postfix evaluation of tokens [s, e] with a bit stack
@@ -309,7 +346,7 @@ template <class T> LG_HD bool contains_range(const Tok<T> *tok, int s, int e, V2
       st >>= 2;
       bool r = l.op == OP_AND ? (a && b) : l.op == OP_OR ? (a || b) : (a && !b);
       st = (st << 1) | (r ? 1ull : 0ull);
-    } else {
+    } else if (l.kind != TOK_POINTS) {
       st = (st << 1) | (contains_leaf(l, p) ? 1ull : 0ull);
     }
   }

@@ -60,7 +60,7 @@ LG_HD void sweep_csg_object(const SceneArgs<T> &A, int obj, V2<T> o, V2<T> d, Be
   const Tok<T> *tok = A.toks + first;
   for (int k = 0; k < count; ++k) {
     const Tok<T> &l = tok[k];
-    if (l.kind == TOK_OP) continue;
+    if (l.kind == TOK_OP || l.kind == TOK_POINTS) continue;
     CandList<T> hl;
     hl.n = 0;
     if (l.kind == TOK_CIRCLE)
@@ -71,6 +71,8 @@ LG_HD void sweep_csg_object(const SceneArgs<T> &A, int obj, V2<T> o, V2<T> d, Be
       hit_segment(l.p, o, d, hl);
     else if (l.kind == TOK_ELLIPSE)
       hit_ellipse(l.p, o, d, hl);
+    else if (l.kind == TOK_POLY)
+      hit_poly(l, o, d, hl);
     else
       hit_bezier(l.p, o, d, hl);
     for (int j = 0; j < hl.n; ++j) {

@@ -21,7 +21,8 @@ namespace lg {
 struct HostTok {
   int32_t kind, op, a_start, b_start;
   double p[8]; // world-space: CIRCLE cx cy r | RECT cx cy ux uy vx vy | SEGMENT ax ay bx by | BEZIER 8 |
-               // ELLIPSE (kind 5) cx cy ux uy a b
+               // ELLIPSE (kind 5) cx cy ux uy a b | POLYGON (kind 6) op = vertex count, followed by
+               // POINTS tokens (kind 7) with op = 1..4 world-space vertices x0 y0 .. x3 y3 each
 };
 struct HostObj {
   int32_t first, count;
@@ -137,9 +138,51 @@ inline bool lower_geo(const LgGeoNode *nodes, uint32_t n_nodes, int32_t ix, cons
     out.push_back(t);
     return true;
   }
+  case LG_GEO_POLYGON: { // object.rs:34-36: ConvexPolygon::new_convex_hull(points); vertices arrive in hull order
+    const int k = g.op;
+    if (k < 3 || k > LG_POLYGON_MAX_VERTICES) {
+      err = "convex polygon needs 3..32 vertices";
+      return false;
+    }
+    const Affine W = [&] {
+      Affine w = compose_rot(A, g.rot);
+      double tw[2];
+      xform(A, g.p[0], g.p[1], tw);
+      w.tx = tw[0], w.ty = tw[1];
+      return w;
+    }();
+    t.kind = 6;
+    t.op = k;
+    out.push_back(t);
+    // kind 7 tokens carry the world-space vertices, four each
+    int got = 0;
+    int32_t pn = g.child_a;
+    HostTok dt{};
+    dt.kind = 7, dt.a_start = dt.b_start = -1;
+    for (int guard = 0; got < k && guard < LG_POLYGON_MAX_VERTICES; ++guard) {
+      if (pn < 0 || (uint32_t)pn >= n_nodes || nodes[pn].kind != LG_GEO_POINTS || nodes[pn].op < 1 || nodes[pn].op > 4) {
+        err = "convex polygon: bad vertex list";
+        return false;
+      }
+      for (int q = 0; q < nodes[pn].op && got < k; ++q, ++got) {
+        xform(W, nodes[pn].p[2 * q], nodes[pn].p[2 * q + 1], dt.p + 2 * (got & 3));
+        if ((got & 3) == 3 || got == k - 1) {
+          dt.op = (got & 3) + 1;
+          out.push_back(dt);
+          dt = HostTok{};
+          dt.kind = 7, dt.a_start = dt.b_start = -1;
+        }
+      }
+      pn = nodes[pn].child_a;
+    }
+    if (got != k) {
+      err = "convex polygon: vertex list shorter than its count";
+      return false;
+    }
+    return true;
+  }
   default:
-    // ConvexPolygon / MCircle exist in collision2d's Geo (drawer.rs:57-84)
-    // but are outside the BASELINE configs: SURVEY.md §8f.
+    // MCircle exists in collision2d's Geo (drawer.rs:57-78) but no Object constructor makes one: SURVEY.md §8f.
     err = "unsupported Geo kind";
     return false;
   }
@@ -175,8 +218,16 @@ inline int32_t lower_scene(const LgObject *objects, uint32_t n_obj, const LgGeoN
     o.can_contain = false;
     for (int k = 0; k < o.count; ++k) {
       const HostTok &t = hs.toks[o.first + k];
-      int np = t.kind == 0 ? 1 : t.kind == 1 ? 1 : t.kind == 2 ? 2 : t.kind == 3 ? 4 : t.kind == 5 ? 1 : 0;
+      int np = t.kind == 0 ? 1 : t.kind == 1 ? 1 : t.kind == 2 ? 2 : t.kind == 3 ? 4 : t.kind == 5 ? 1 : t.kind == 7 ? t.op : 0;
       for (int q = 0; q < np; ++q) bound = std::fmax(bound, std::fmax(std::fabs(t.p[2 * q]), std::fabs(t.p[2 * q + 1])));
+      if (t.kind == 7) { // vertices of a convex polygon: it contains points
+        o.can_contain = true;
+        for (int q = 0; q < np; ++q) {
+          o.aabb[0] = std::fmin(o.aabb[0], t.p[2 * q]), o.aabb[2] = std::fmax(o.aabb[2], t.p[2 * q]);
+          o.aabb[1] = std::fmin(o.aabb[1], t.p[2 * q + 1]), o.aabb[3] = std::fmax(o.aabb[3], t.p[2 * q + 1]);
+        }
+        continue;
+      }
       double ex = 0, ey = 0;
       if (t.kind == 0) {
         ex = ey = std::fabs(t.p[2]);
@@ -211,7 +262,7 @@ inline int32_t lower_scene(const LgObject *objects, uint32_t n_obj, const LgGeoN
     Box bx{1e300, 1e300, -1e300, -1e300};
     for (int k = 0; k < a.count; ++k) {
       const HostTok &t = hs.toks[a.first + k];
-      if (t.kind == 4) continue;
+      if (t.kind == 4 || t.kind == 6) continue;
       if (t.kind == 0 || t.kind == 5) {
         const double rr = t.kind == 0 ? t.p[2] : std::fmax(t.p[4], t.p[5]);
         bx.x0 = std::fmin(bx.x0, t.p[0] - rr), bx.x1 = std::fmax(bx.x1, t.p[0] + rr);
@@ -221,7 +272,7 @@ inline int32_t lower_scene(const LgObject *objects, uint32_t n_obj, const LgGeoN
         bx.x0 = std::fmin(bx.x0, t.p[0] - ex), bx.x1 = std::fmax(bx.x1, t.p[0] + ex);
         bx.y0 = std::fmin(bx.y0, t.p[1] - ey), bx.y1 = std::fmax(bx.y1, t.p[1] + ey);
       } else {
-        int np = t.kind == 2 ? 2 : 4;
+        int np = t.kind == 2 ? 2 : t.kind == 7 ? t.op : 4;
         for (int q = 0; q < np; ++q) {
           bx.x0 = std::fmin(bx.x0, t.p[2 * q]), bx.x1 = std::fmax(bx.x1, t.p[2 * q]);
           bx.y0 = std::fmin(bx.y0, t.p[2 * q + 1]), bx.y1 = std::fmax(bx.y1, t.p[2 * q + 1]);
@@ -281,6 +332,18 @@ inline bool host_contains_leaf(const HostTok &t, double x, double y) {
     double ly = std::fma(qx, -t.p[3], qy * t.p[2]) * (1.0 / t.p[5]);
     return std::fma(lx, lx, ly * ly) < 1.0;
   }
+  if (t.kind == 6) { // convex polygon: strictly on the same side of every edge (ORACLE.md §3.8)
+    const int k = t.op;
+    int pos = 0, neg = 0;
+    for (int i = 0; i < k; ++i) {
+      const int j = i + 1 < k ? i + 1 : 0;
+      const double ax = (&t)[1 + (i >> 2)].p[2 * (i & 3)], ay = (&t)[1 + (i >> 2)].p[2 * (i & 3) + 1];
+      const double bx = (&t)[1 + (j >> 2)].p[2 * (j & 3)], by = (&t)[1 + (j >> 2)].p[2 * (j & 3) + 1];
+      const double ex = bx - ax, ey = by - ay, c = std::fma(ex, y - ay, -(ey * (x - ax)));
+      pos += c > 0.0, neg += c < 0.0;
+    }
+    return pos == k || neg == k;
+  }
   return false;
 }
 inline bool host_contains(const HostScene &hs, int obj, double x, double y) {
@@ -293,7 +356,7 @@ inline bool host_contains(const HostScene &hs, int obj, double x, double y) {
       st >>= 2;
       bool r = t.op == LG_OP_AND ? (a && b) : t.op == LG_OP_OR ? (a || b) : (a && !b);
       st = (st << 1) | (r ? 1 : 0);
-    } else {
+    } else if (t.kind != 7) {
       st = (st << 1) | (host_contains_leaf(t, x, y) ? 1 : 0);
     }
   }

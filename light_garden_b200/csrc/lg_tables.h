@@ -41,6 +41,9 @@ template <class T> std::vector<Tok<T>> device_tokens(const HostScene &hs) {
       t.p[6] = (T)1 / t.p[4];
       t.p[7] = (T)1 / t.p[5];
       break;
+    case 7: // polygon vertices
+      for (int k = 0; k < 8; ++k) t.p[k] = (T)h.p[k];
+      break;
     default: break;
     }
     toks[i] = t;
@@ -59,8 +62,8 @@ inline std::vector<double> object_circles(const HostScene &hs) {
       cx = t.p[0], cy = t.p[1], rr = std::fmax(t.p[4], t.p[5]);
     } else if (t.kind == 1) {
       cx = t.p[0], cy = t.p[1], rr = std::hypot(std::hypot(t.p[2], t.p[3]), std::hypot(t.p[4], t.p[5]));
-    } else { // segment / Bezier: the control polygon
-      const int np = t.kind == 2 ? 2 : 4;
+    } else { // segment / Bezier: the control polygon; kind 7: up to four vertices of a convex polygon
+      const int np = t.kind == 2 ? 2 : t.kind == 7 ? t.op : 4;
       cx = cy = 0;
       for (int q = 0; q < np; ++q) cx += t.p[2 * q] / np, cy += t.p[2 * q + 1] / np;
       rr = 0;
@@ -72,7 +75,7 @@ inline std::vector<double> object_circles(const HostScene &hs) {
     double x0 = 1e300, y0 = 1e300, x1 = -1e300, y1 = -1e300;
     for (int k = 0; k < o.count; ++k) {
       const HostTok &t = hs.toks[o.first + k];
-      if (t.kind == 4) continue;
+      if (t.kind == 4 || t.kind == 6) continue;
       double cx, cy, rr;
       leaf_circle(t, cx, cy, rr);
       x0 = std::fmin(x0, cx - rr), x1 = std::fmax(x1, cx + rr), y0 = std::fmin(y0, cy - rr), y1 = std::fmax(y1, cy + rr);
@@ -81,7 +84,7 @@ inline std::vector<double> object_circles(const HostScene &hs) {
     double rad = 0;
     for (int k = 0; k < o.count; ++k) {
       const HostTok &t = hs.toks[o.first + k];
-      if (t.kind == 4) continue;
+      if (t.kind == 4 || t.kind == 6) continue;
       double cx, cy, rr;
       leaf_circle(t, cx, cy, rr);
       rad = std::fmax(rad, std::hypot(cx - mx, cy - my) + rr);

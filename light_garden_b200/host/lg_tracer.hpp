@@ -47,6 +47,7 @@ struct Geo {
   Rot2 rot = rot2_identity();
   LogicOp op = LogicOp::And;
   std::shared_ptr<Geo> a, b;
+  std::vector<P2> points; // ConvexPolygon: hull vertices, local frame
 
   static Geo circle(P2 origin, double radius) {
     Geo g;
@@ -71,6 +72,40 @@ struct Geo {
     Geo g;
     g.kind = LG_GEO_BEZIER;
     for (int k = 0; k < 4; ++k) g.p[2 * k] = pts[k].x, g.p[2 * k + 1] = pts[k].y;
+    return g;
+  }
+  static Geo ellipse(P2 origin, double a, double b, Rot2 rotation = rot2_identity()) { // object.rs:38-45
+    Geo g;
+    g.kind = LG_GEO_ELLIPSE;
+    g.p = {origin.x, origin.y, a, b};
+    g.rot = rotation;
+    return g;
+  }
+  // ConvexPolygon::new_convex_hull (object.rs:34-36): Andrew's monotone chain, counter-clockwise from the lowest
+  // (x, then y) point, collinear points dropped (ORACLE.md §3.8)
+  static Geo convex_polygon(std::vector<P2> pts, P2 origin = {}, Rot2 rotation = rot2_identity()) {
+    std::sort(pts.begin(), pts.end(), [](P2 a, P2 b) { return a.x < b.x || (a.x == b.x && a.y < b.y); });
+    pts.erase(std::unique(pts.begin(), pts.end(), [](P2 a, P2 b) { return a.x == b.x && a.y == b.y; }), pts.end());
+    auto turn = [](P2 o, P2 a, P2 b) { return (a.x - o.x) * (b.y - o.y) - (a.y - o.y) * (b.x - o.x); };
+    std::vector<P2> lower, upper;
+    for (const P2 &q : pts) {
+      while (lower.size() >= 2 && turn(lower[lower.size() - 2], lower.back(), q) <= 0.0) lower.pop_back();
+      lower.push_back(q);
+    }
+    for (auto it = pts.rbegin(); it != pts.rend(); ++it) {
+      while (upper.size() >= 2 && turn(upper[upper.size() - 2], upper.back(), *it) <= 0.0) upper.pop_back();
+      upper.push_back(*it);
+    }
+    Geo g;
+    g.kind = LG_GEO_POLYGON;
+    g.p = {origin.x, origin.y};
+    g.rot = rotation;
+    if (!lower.empty()) lower.pop_back();
+    if (!upper.empty()) upper.pop_back();
+    g.points = lower;
+    g.points.insert(g.points.end(), upper.begin(), upper.end());
+    if (g.points.size() < 3 || g.points.size() > LG_POLYGON_MAX_VERTICES)
+      throw Error(LG_ERR_INVALID, "convex polygon needs 3..32 hull vertices");
     return g;
   }
   static Geo logic(LogicOp op, Geo a, Geo b, P2 origin, Rot2 rotation) { // Logic::new
@@ -115,6 +150,8 @@ struct Object {
                        origin, rot2_identity()),
             Material{}};
   }
+  static Object new_ellipse(P2 origin, double a, double b) { return {Geo::ellipse(origin, a, b), Material{}}; }
+  static Object new_convex_polygon(const std::vector<P2> &points) { return {Geo::convex_polygon(points), Material{}}; }
   static Object new_geo(Geo g) { return {std::move(g), Material{}}; }
   std::optional<Material> get_material() const { return material_opt; }
 };
@@ -254,6 +291,24 @@ private:
     n.child_a = n.child_b = -1;
     std::copy(g.p.begin(), g.p.end(), n.p);
     std::copy(g.rot.begin(), g.rot.end(), n.rot);
+    if (g.kind == LG_GEO_POLYGON) { // header node + continuation nodes of four vertices each
+      n.op = (int32_t)g.points.size();
+      const size_t ix = nodes.size();
+      nodes.push_back(n);
+      size_t prev = ix;
+      for (size_t v = 0; v < g.points.size(); v += 4) {
+        LgGeoNode c{};
+        c.kind = LG_GEO_POINTS;
+        c.child_a = c.child_b = -1;
+        c.rot[0] = c.rot[3] = 1.0;
+        c.op = (int32_t)std::min<size_t>(4, g.points.size() - v);
+        for (int q = 0; q < c.op; ++q) c.p[2 * q] = g.points[v + q].x, c.p[2 * q + 1] = g.points[v + q].y;
+        nodes[prev].child_a = (int32_t)nodes.size();
+        prev = nodes.size();
+        nodes.push_back(c);
+      }
+      return (int32_t)ix;
+    }
     if (g.kind != LG_GEO_LOGIC) {
       nodes.push_back(n);
       return (int32_t)nodes.size() - 1;

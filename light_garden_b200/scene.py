@@ -65,6 +65,44 @@ class Ellipse:
     rot: Tuple[float, float, float, float] = (1.0, 0.0, 0.0, 1.0)
 
 
+def convex_hull(points: Sequence[P2]):
+    """ConvexPolygon::new_convex_hull (object.rs:34-36).  collision2d's own hull routine is not available offline;
+    ORACLE.md §3.8 fixes it as Andrew's monotone chain: counter-clockwise, starting at the lowest (x, then y) point,
+    collinear points dropped."""
+    pts = sorted(set((float(p[0]), float(p[1])) for p in points))
+    if len(pts) < 3:
+        raise ValueError("a convex polygon needs three points that are not collinear")
+
+    def turn(o, a, b):
+        return (a[0] - o[0]) * (b[1] - o[1]) - (a[1] - o[1]) * (b[0] - o[0])
+
+    lower, upper = [], []
+    for p in pts:
+        while len(lower) >= 2 and turn(lower[-2], lower[-1], p) <= 0.0:
+            lower.pop()
+        lower.append(p)
+    for p in reversed(pts):
+        while len(upper) >= 2 and turn(upper[-2], upper[-1], p) <= 0.0:
+            upper.pop()
+        upper.append(p)
+    hull = lower[:-1] + upper[:-1]
+    if len(hull) < 3:
+        raise ValueError("a convex polygon needs three points that are not collinear")
+    return hull
+
+
+@dataclass
+class ConvexPolygon:
+    """collision2d ConvexPolygon: hull vertices in the local frame (world = origin + rot * local)."""
+    points: Tuple[P2, ...]
+    origin: P2 = (0.0, 0.0)
+    rotation: Tuple[float, float, float, float] = (1.0, 0.0, 0.0, 1.0)
+
+    @staticmethod
+    def new_convex_hull(points):
+        return ConvexPolygon(tuple(convex_hull(points)))
+
+
 @dataclass
 class LineSegment:
     a: P2
@@ -133,6 +171,11 @@ class Object:
     def new_ellipse(origin, a, b):
         # object.rs:38-45: rot = Rotation2::new(0.0)
         return Object(Ellipse(tuple(origin), a, b, rot2_identity()), Material(), "Ellipse")
+
+    @staticmethod
+    def new_convex_polygon(points):
+        # object.rs:34-36
+        return Object(ConvexPolygon.new_convex_hull(points), Material(), "ConvexPolygon")
 
     @staticmethod
     def new_geo(geo):
@@ -241,6 +284,29 @@ def _push_geo(geo, nodes: list) -> int:
         n.kind = abi.LG_GEO_BEZIER
         for k, pt in enumerate(geo.points):
             n.p[2 * k], n.p[2 * k + 1] = pt[0], pt[1]
+    elif isinstance(geo, ConvexPolygon):
+        k = len(geo.points)
+        if not 3 <= k <= abi.LG_POLYGON_MAX_VERTICES:
+            raise ValueError(f"convex polygon with {k} vertices (3..{abi.LG_POLYGON_MAX_VERTICES} supported)")
+        n.kind = abi.LG_GEO_POLYGON
+        n.op = k
+        n.p[0], n.p[1] = geo.origin
+        n.rot[:] = geo.rotation
+        ix = len(nodes)
+        nodes.append(n)
+        prev = n
+        for v in range(0, k, 4):   # continuation nodes, four vertices each
+            c = abi.LgGeoNode()
+            c.kind, c.child_a, c.child_b = abi.LG_GEO_POINTS, -1, -1
+            c.rot[:] = rot2_identity()
+            chunk = geo.points[v:v + 4]
+            c.op = len(chunk)
+            for q, pt in enumerate(chunk):
+                c.p[2 * q], c.p[2 * q + 1] = pt[0], pt[1]
+            prev.child_a = len(nodes)
+            nodes.append(c)
+            prev = c
+        return ix
     elif isinstance(geo, Logic):
         n.kind = abi.LG_GEO_LOGIC
         n.op = geo.op

@@ -17,6 +17,7 @@
 // compared bit-for-bit.  Compile with -ffp-contract=off.
 #pragma once
 #include <cmath>
+#include <algorithm>
 #include <cstdint>
 #include <cstring>
 #include <limits>
@@ -53,7 +54,11 @@ template <class T> inline V2<T> along(V2<T> o, T t, V2<T> d) {
 // Lowered scene (ORACLE.md §2): every Geo tree becomes a postfix program over
 // world-space leaves.  Lowering is done in f64 and then cast to T.
 // ---------------------------------------------------------------------------
-enum TokKind : int32_t { TOK_CIRCLE = 0, TOK_RECT = 1, TOK_SEGMENT = 2, TOK_BEZIER = 3, TOK_OP = 4, TOK_ELLIPSE = 5 };
+enum TokKind : int32_t {
+  TOK_CIRCLE = 0, TOK_RECT = 1, TOK_SEGMENT = 2, TOK_BEZIER = 3, TOK_OP = 4, TOK_ELLIPSE = 5,
+  TOK_POLY = 6,  // convex polygon header: op = number of vertices; its vertices follow in TOK_VERTS tokens
+  TOK_VERTS = 7  // up to four world-space vertices (op = how many)
+};
 
 struct Token {
   int32_t kind;    // TokKind
@@ -144,6 +149,38 @@ inline bool lower_node(const std::vector<LgGeoNode> &nodes, int32_t ix, const Ma
     tok.p[4] = g.p[2];
     tok.p[5] = g.p[3];
     out.push_back(tok);
+    return true;
+  }
+  case LG_GEO_POLYGON: { // ORACLE.md §3.8: vertices given in hull order, local frame (origin, rot)
+    const int nv = g.op;
+    if (nv < 3 || nv > LG_POLYGON_MAX_VERTICES) return false;
+    Mat2 R{g.rot[0], g.rot[1], g.rot[2], g.rot[3]};
+    Mat2 W = mat_mul(M, R);
+    double tw[2];
+    mat_apply(M, t, g.p[0], g.p[1], tw);
+    std::vector<double> xy; // world-space vertices, flattened
+    for (int32_t pn = g.child_a; (int)xy.size() < 2 * nv;) {
+      if (pn < 0 || (size_t)pn >= nodes.size()) return false;
+      const LgGeoNode &pts = nodes[pn];
+      if (pts.kind != LG_GEO_POINTS || pts.op < 1 || pts.op > 4) return false;
+      for (int q = 0; q < pts.op && (int)xy.size() < 2 * nv; ++q) {
+        double w[2];
+        mat_apply(W, tw, pts.p[2 * q], pts.p[2 * q + 1], w);
+        xy.push_back(w[0]);
+        xy.push_back(w[1]);
+      }
+      pn = pts.child_a;
+    }
+    tok.kind = TOK_POLY;
+    tok.op = nv;
+    out.push_back(tok);
+    for (int v = 0; v < nv; v += 4) {
+      Token vt{};
+      vt.kind = TOK_VERTS;
+      vt.op = std::min(4, nv - v);
+      for (int q = 0; q < vt.op; ++q) vt.p[2 * q] = xy[2 * (v + q)], vt.p[2 * q + 1] = xy[2 * (v + q) + 1];
+      out.push_back(vt);
+    }
     return true;
   }
   case LG_GEO_LOGIC: {
@@ -260,6 +297,9 @@ template <class T> inline SceneT<T> cast_scene(const Scene &s) {
       for (int k = 0; k < 6; ++k) l.p[k] = (T)t.p[k];
       l.p[6] = (T)1 / l.p[4];
       l.p[7] = (T)1 / l.p[5];
+      break;
+    case TOK_VERTS:
+      for (int k = 0; k < 8; ++k) l.p[k] = (T)t.p[k];
       break;
     default:
       break;
@@ -466,9 +506,38 @@ template <class T> inline void hit_ellipse(const T *e, V2<T> o, V2<T> d, HitList
   }
 }
 
+// §3.8 convex polygon: vertex i of the polygon whose header token is `hdr` (vertices sit in the tokens after it)
+template <class T> inline V2<T> polygon_vertex(const LeafT<T> *hdr, int i) {
+  const LeafT<T> &blk = hdr[1 + i / 4];
+  return {blk.p[2 * (i % 4)], blk.p[2 * (i % 4) + 1]};
+}
+// the edges v_i -> v_(i+1) as §3.2 segments, in hull order, closing edge last
+template <class T> inline void hit_polygon(const LeafT<T> *hdr, V2<T> o, V2<T> d, HitList<T> &out) {
+  const int nv = hdr->op;
+  for (int i = 0; i < nv; ++i) {
+    V2<T> a = polygon_vertex(hdr, i), b = polygon_vertex(hdr, (i + 1) % nv);
+    Hit<T> h;
+    if (hit_segment_ae(a, sub(b, a), o, d, h)) out.push(h);
+  }
+}
+// inside = strictly on one side of all edges (either winding)
+template <class T> inline bool polygon_contains(const LeafT<T> *hdr, V2<T> p) {
+  const int nv = hdr->op;
+  bool all_left = true, all_right = true;
+  for (int i = 0; i < nv; ++i) {
+    V2<T> a = polygon_vertex(hdr, i), b = polygon_vertex(hdr, (i + 1) % nv);
+    T side = cross(sub(b, a), sub(p, a));
+    all_left = all_left && side > (T)0;
+    all_right = all_right && side < (T)0;
+  }
+  return all_left || all_right;
+}
+
 // §3.5 contains
 template <class T> inline bool contains_leaf(const LeafT<T> &l, V2<T> p) {
   switch (l.kind) {
+  case TOK_POLY:
+    return polygon_contains(&l, p);
   case TOK_ELLIPSE: {
     V2<T> q = ellipse_local(l.p, V2<T>{p.x - l.p[0], p.y - l.p[1]});
     return dot(q, q) < (T)1;
@@ -498,6 +567,8 @@ template <class T> inline bool contains_range(const LeafT<T> *tok, int s, int e,
       st >>= 2;
       bool r = l.op == LG_OP_AND ? (a && b) : l.op == LG_OP_OR ? (a || b) : (a && !b);
       st = (st << 1) | (r ? 1 : 0);
+    } else if (l.kind == TOK_VERTS) {
+      continue; // data of the polygon before it
     } else {
       st = (st << 1) | (contains_leaf(l, p) ? 1 : 0);
     }
@@ -522,9 +593,10 @@ template <class T> inline void intersect_object(const SceneT<T> &s, int obj, V2<
   out.n = 0;
   for (int k = 0; k < ob.count; ++k) {
     const LeafT<T> &l = tok[k];
-    if (l.kind == TOK_OP) continue;
+    if (l.kind == TOK_OP || l.kind == TOK_VERTS) continue;
     HitList<T> hl;
     switch (l.kind) {
+    case TOK_POLY: hit_polygon(&l, o, d, hl); break;
     case TOK_CIRCLE: hit_circle(l.p, o, d, hl); break;
     case TOK_RECT: hit_rect(l.p, o, d, hl); break;
     case TOK_SEGMENT: hit_segment(l.p, o, d, hl); break;

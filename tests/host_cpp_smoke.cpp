@@ -28,6 +28,15 @@ int main() {
     std::printf("vertices %zu segments %llu ray_steps %llu\n", lines.size(), (unsigned long long)t.last_stats.segments,
                 (unsigned long long)t.last_stats.ray_steps);
     std::printf("checksum %.9e %.9e %.9e\n", sx, sy, sc);
+    // the remaining Object constructors (object.rs:34-45): a prism and an ellipse in front of a point light
+    lg::Tracer extra(lg::Rect::from_tlbr(1., -aspect, -1., aspect));
+    extra.push_object(lg::Object::new_convex_polygon({{-0.5, -0.3}, {0.5, -0.3}, {0.0, 0.5}, {0.0, 0.0}}));
+    extra.push_object(lg::Object::new_ellipse({0.9, 0.1}, 0.3, 0.15));
+    extra.push_light(lg::Light::point({-1.2, 0.0}, 2000, {0.01f, 0.01f, 0.01f, 0.02f}));
+    extra.enable_tile_map(true);
+    const size_t with_grid = extra.trace_all().size();
+    extra.enable_tile_map(false);
+    std::printf("polygon+ellipse vertices %zu (tile map) %zu (all objects)\n", with_grid, extra.trace_all().size());
     // error behaviour: the reference panics on a bad scene, here the error crosses the boundary as a status
     lg::Tracer bad(lg::Rect::from_tlbr(1, -1, -1, 1));
     lg::Object neg = lg::Object::new_circle({0, 0}, 0.5);

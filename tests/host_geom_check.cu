@@ -3,6 +3,7 @@
 // __host__ __device__ functions) against the oracle (oracle/lg_oracle.hpp) on
 // random inputs and demands bit-identical results.  CPU only; built and run by
 // tests/test_geom_host.py.  Prints "OK <n>" or "MISMATCH ..." lines.
+#include <algorithm>
 #include <cstdio>
 #include <cstring>
 #include <cstdint>
@@ -194,9 +195,35 @@ static int rand_geo(std::vector<LgGeoNode> &nodes, int depth) {
   g.rot[0] = 1, g.rot[3] = 1;
   int kind = depth >= 3 ? (int)(nextu() % 5) : (int)(nextu() % 6);
   if (depth >= 3 && kind == 4) kind = 5; // no deeper Logic nodes
+  if (nextu() % 6 == 0) kind = LG_GEO_POLYGON;
   g.kind = kind;
   double ra = uni(0, 6.283185307179586);
   switch (kind) {
+  case LG_GEO_POLYGON: { // vertices on an ellipse at sorted random angles: convex, either winding
+    const int k = 3 + (int)(nextu() % 10);
+    std::vector<double> ang(k);
+    for (double &a : ang) a = uni(0, 6.283185307179586);
+    std::sort(ang.begin(), ang.end());
+    if (nextu() % 2) std::reverse(ang.begin(), ang.end());
+    const double ax = uni(0.05, 0.5), ay = uni(0.05, 0.5);
+    g.op = k;
+    g.p[0] = uni(-1, 1), g.p[1] = uni(-1, 1);
+    g.rot[0] = std::cos(ra), g.rot[1] = std::sin(ra), g.rot[2] = -std::sin(ra), g.rot[3] = std::cos(ra);
+    const int ix = (int)nodes.size();
+    nodes.push_back(g);
+    int prev = ix;
+    for (int v = 0; v < k; v += 4) {
+      LgGeoNode c{};
+      c.kind = LG_GEO_POINTS, c.child_a = c.child_b = -1;
+      c.rot[0] = 1, c.rot[3] = 1;
+      c.op = std::min(4, k - v);
+      for (int q = 0; q < c.op; ++q) c.p[2 * q] = ax * std::cos(ang[v + q]), c.p[2 * q + 1] = ay * std::sin(ang[v + q]);
+      nodes[prev].child_a = (int)nodes.size();
+      prev = (int)nodes.size();
+      nodes.push_back(c);
+    }
+    return ix;
+  }
   case LG_GEO_CIRCLE: g.p[0] = uni(-1, 1), g.p[1] = uni(-1, 1), g.p[2] = uni(0.05, 0.5); break;
   case LG_GEO_RECT:
     g.p[0] = uni(-1, 1), g.p[1] = uni(-1, 1), g.p[2] = uni(0.05, 0.8), g.p[3] = uni(0.05, 0.8);
@@ -251,7 +278,8 @@ static long check_lowering(int n_scenes) {
       const lg::HostTok &a = hs.toks[i];
       const lgo::Token &b = os.tokens[i];
       bool ok = a.kind == b.kind && (a.kind != 4 || (a.op == b.op && a.a_start == b.a_start && a.b_start == b.b_start));
-      int np = a.kind == 0 ? 3 : a.kind == 1 ? 6 : a.kind == 2 ? 4 : a.kind == 3 ? 8 : a.kind == 5 ? 6 : 0;
+      if (a.kind == 6 || a.kind == 7) ok = ok && a.op == b.op;
+      int np = a.kind == 0 ? 3 : a.kind == 1 ? 6 : a.kind == 2 ? 4 : a.kind == 3 ? 8 : a.kind == 5 ? 6 : a.kind == 7 ? 2 * a.op : 0;
       for (int k = 0; k < np; ++k) ok = ok && std::memcmp(&a.p[k], &b.p[k], 8) == 0;
       if (!ok) { if (g_bad < 20) std::printf("MISMATCH lowering token %zu kind %d\n", i, a.kind); ++g_bad; }
       ++n;
@@ -317,6 +345,10 @@ template <class T> static long check_grid_scene(const std::vector<LgObject> &obj
   A.grid_x0 = (T)g.x0, A.grid_y0 = (T)g.y0, A.grid_x1 = (T)g.x1, A.grid_y1 = (T)g.y1;
   A.grid_cs = (T)g.cs, A.grid_ics = (T)(1.0 / g.cs), A.grid_eta = (T)bt.delta;
   A.grid_nx = g.nx, A.grid_ny = g.ny, A.grid_start = g.start.data(), A.grid_obj = g.obj.data();
+  // the oracle's view of the same scene: Ray::intersect per object, strict `<` on the squared distance in object
+  // order (tracer.rs:412-424) -- the product's all-objects loop must agree bit for bit
+  const lgo::Scene osc = lgo::make_scene(objs.data(), (uint32_t)objs.size(), nodes.data(), (uint32_t)nodes.size(), &prm);
+  const lgo::SceneT<T> ost = lgo::cast_scene<T>(osc);
   long done = 0;
   for (int q = 0; q < n_rays; ++q) {
     lg::V2<T> o{(T)uni(-2.2, 2.2), (T)uni(-1.4, 1.4)};
@@ -343,6 +375,26 @@ template <class T> static long check_grid_scene(const std::vector<LgObject> &obj
                     sizeof(T) == 4 ? "f32" : "f64", a.obj, (double)a.d2, b.obj, (double)b.d2, (double)o.x, (double)o.y, (double)d.x,
                     (double)d.y, g.nx, g.ny);
       ++g_bad;
+    }
+    if (q % 4 == 0 && osc.ok) {
+      T best = lg::Real<T>::max_value();
+      int bobj = -1;
+      lgo::V2<T> bp{0, 0};
+      for (int j = 0; j < (int)n; ++j) {
+        lgo::ObjHits<T> oh;
+        lgo::intersect_object(ost, j, lgo::V2<T>{o.x, o.y}, lgo::V2<T>{d.x, d.y}, oh);
+        for (int h = 0; h < oh.n; ++h) {
+          const T dx = oh.h[h].p.x - o.x, dy = oh.h[h].p.y - o.y, d2 = dx * dx + dy * dy;
+          if (d2 < best) best = d2, bobj = j, bp = oh.h[h].p;
+        }
+      }
+      if (bobj != a.obj || (bobj >= 0 && (!same(best, a.d2) || !same(bp.x, a.px) || !same(bp.y, a.py)))) {
+        if (g_bad < 20)
+          std::printf("MISMATCH nearest hit vs oracle (%s): oracle obj %d d2 %.9g, product obj %d d2 %.9g\n",
+                      sizeof(T) == 4 ? "f32" : "f64", bobj, (double)best, a.obj, (double)a.d2);
+        ++g_bad;
+      }
+      ++done;
     }
     ++done;
   }

@@ -37,6 +37,8 @@ def test_cpp_host_mirror_matches_python_host(tmp_path, product_lib):
     assert r.returncode == 0, r.stdout + r.stderr
     m = re.search(r"vertices (\d+) segments (\d+) ray_steps (\d+)", r.stdout)
     cs = [float(x) for x in re.search(r"checksum (\S+) (\S+) (\S+)", r.stdout).groups()]
+    pe = re.search(r"polygon\+ellipse vertices (\d+) \(tile map\) (\d+) \(all objects\)", r.stdout)
+    assert pe and int(pe.group(1)) == int(pe.group(2)) > 4000
     assert "error -4" in r.stdout                      # LG_ERR_UNSUPPORTED crossed the boundary as a status
     spec = scenes.c1_default(total_rays=6000, width=480, height=270)
     t = spec.apply(Tracer(spec.canvas_bounds))

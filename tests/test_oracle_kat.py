@@ -569,3 +569,80 @@ def test_ray_ellipse(oracle):
         assert he.shape == hc.shape
         if len(he):
             np.testing.assert_allclose(he[:, :4], hc[:, :4], atol=1e-12)
+
+
+def test_convex_hull_and_polygon(oracle):
+    """ConvexPolygon::new_convex_hull (object.rs:34-36) and ORACLE.md §3.8: edges in hull order as §3.2 segments,
+    contains = strictly inside every edge."""
+    from light_garden_b200.scene import ConvexPolygon, convex_hull
+    # hull: interior and collinear points dropped, counter-clockwise from the lowest (x, y) point
+    pts = [(1, 1), (0, 0), (2, 0), (1, 0), (2, 2), (0, 2), (1, 0.5), (0, 1)]
+    assert convex_hull(pts) == [(0.0, 0.0), (2.0, 0.0), (2.0, 2.0), (0.0, 2.0)]
+    with pytest.raises(ValueError):
+        convex_hull([(0, 0), (1, 1), (2, 2)])
+    sq = Object.new_convex_polygon(pts)
+    assert sq.material_opt is not None and sq.kind == "ConvexPolygon"
+    sc = scene(oracle, [sq])
+    # hits are listed in edge order: bottom (0), right (1), top (2), left (3)
+    h = sc.intersect(0, (-3, 0.5), (1, 0))
+    np.testing.assert_allclose(h[:, :2], [[2.0, 0.5], [0.0, 0.5]], atol=1e-15)
+    np.testing.assert_allclose(np.abs(h[:, 2:4]), [[1, 0], [1, 0]], atol=1e-15)
+    h = sc.intersect(0, (0.5, -3), (0, 1))
+    np.testing.assert_allclose(h[:, :2], [[0.5, 0.0], [0.5, 2.0]], atol=1e-15)
+    assert sc.intersect(0, (-3, 2.5), (1, 0)).shape[0] == 0
+    assert sc.contains(0, (1.0, 1.0)) and sc.contains(0, (1.99, 0.01))
+    assert not sc.contains(0, (2.0, 1.0)) and not sc.contains(0, (1.0, -0.01))   # the boundary is outside
+    # the same square as a Rect: identical hit points and containment on random rays
+    rc = scene(oracle, [Object.new_rect((1.0, 1.0), 2.0, 2.0)])
+    o, d = _rays(300, seed=5)
+    for i in range(len(o)):
+        hp, hr = sc.intersect(0, o[i] * 2, d[i]), rc.intersect(0, o[i] * 2, d[i])
+        assert hp.shape == hr.shape
+        if len(hp):
+            key = lambda a: a[np.lexsort((a[:, 1], a[:, 0]))]
+            np.testing.assert_allclose(key(hp)[:, :2], key(hr)[:, :2], atol=1e-12)
+        assert sc.contains(0, o[i]) == rc.contains(0, o[i])
+    # clockwise input order, own frame: a triangle rotated by 90 degrees about its origin (1, 0)
+    tri = Object(ConvexPolygon(((0.0, 0.0), (0.0, 1.0), (2.0, 0.0)), (1.0, 0.0), rot2(math.pi / 2)), Material(1.5))
+    sc = scene(oracle, [tri])          # world vertices (1, 0), (0, 0), (1, 2)
+    assert sc.contains(0, (0.8, 0.3)) and not sc.contains(0, (0.2, 1.0)) and not sc.contains(0, (1.1, 0.5))
+    h = sc.intersect(0, (-1, 0.5), (1, 0))
+    np.testing.assert_allclose(sorted(h[:, 0]), [0.25, 1.0], atol=1e-12)
+    # 32 vertices approximate a circle: hit distances within the sagitta of the polygon
+    ring = [(math.cos(2 * math.pi * k / 32), math.sin(2 * math.pi * k / 32)) for k in range(32)]
+    sc = scene(oracle, [Object.new_convex_polygon(ring)])
+    for ang in np.linspace(0.05, 6.2, 23):
+        h = sc.intersect(0, (0, 0), (math.cos(ang), math.sin(ang)))
+        assert h.shape[0] == 1 and math.cos(math.pi / 32) - 1e-12 <= h[0, 4] <= 1.0 + 1e-12
+    with pytest.raises(ValueError):
+        scene(oracle, [Object.new_convex_polygon([(math.cos(k), math.sin(k)) for k in range(40)])])
+
+
+def test_prism_deviates_a_ray_by_the_textbook_angle(oracle):
+    """An equilateral n = 1.5 prism at minimum deviation: delta = 2 asin(n sin(A / 2)) - A with A = 60 degrees."""
+    A, n = math.radians(60.0), 1.5
+    s = 1.0
+    prism = Object.new_convex_polygon([(-s / 2, 0.0), (s / 2, 0.0), (0.0, s * math.sin(A))]).with_index(n)
+    sc = scene(oracle, [prism])
+    # minimum deviation: the ray inside runs parallel to the base; outside angle of incidence i = asin(n sin(A/2))
+    i = math.asin(n * math.sin(A / 2))
+    # left face goes from (-0.5, 0) to (0, 0.866): outward normal points up-left at 150 degrees
+    nl = (math.cos(math.radians(150)), math.sin(math.radians(150)))
+    hit = (-0.25, 0.5 * s * math.sin(A))                      # midpoint of the left face
+    # incoming direction = -normal rotated by i (towards the base side)
+    a = math.atan2(-nl[1], -nl[0]) + i
+    d_in = (math.cos(a), math.sin(a))
+    o = (hit[0] - 0.5 * d_in[0], hit[1] - 0.5 * d_in[1])
+    res = sc.trace_rays(ray(o, d_in, color=(1, 1, 1, 1)), abi.LG_PRECISION_F64)
+    seg, tag = res.seg, res.tags
+    # follow the refracted path: generation 1 segment that is inside (path bit 1), then generation 2 leaving
+    inside = [k for k in range(len(seg)) if tag["generation"][k] == 1 and tag["path"][k] == 1]
+    assert len(inside) == 1
+    k = inside[0]
+    v = np.array(seg["b"][k], dtype=np.float64) - np.array(seg["a"][k], dtype=np.float64)
+    assert abs(v[1]) < 1e-6 * abs(v[0]) and v[0] > 0               # parallel to the base
+    out = [k for k in range(len(seg)) if tag["generation"][k] == 2 and tag["path"][k] == 3]
+    assert len(out) == 1
+    w = np.array(seg["b"][out[0]], dtype=np.float64) - np.array(seg["a"][out[0]], dtype=np.float64)
+    dev = math.atan2(d_in[1], d_in[0]) - math.atan2(w[1], w[0])
+    assert abs(dev - (2 * i - A)) < 1e-6

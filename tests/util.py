@@ -33,10 +33,33 @@ def ellipse_spec(total_rays=3000):
     return scenes.SceneSpec("ellipses", objs, lights, 6, 480, 270)
 
 
+def polygon_spec(total_rays=3000):
+    """Convex polygons (object.rs:34-36): refractive, as a mirror-less prism, inside CSG trees, rotated frames, and
+    the 32-vertex maximum: SURVEY.md §8f rank 2."""
+    import math
+    from light_garden_b200.scene import (AND, AND_NOT, Circle, ConvexPolygon, Logic, Material, Object, PointLight,
+                                         SpotLight, rot2)
+    ring = [(0.3 * math.cos(2 * math.pi * k / 32), 0.22 * math.sin(2 * math.pi * k / 32)) for k in range(32)]
+    objs = [
+        Object.new_convex_polygon([(-1.2, -0.5), (-0.6, -0.55), (-0.9, 0.1), (-0.9, -0.3)]).with_index(1.5),  # prism
+        Object.new_convex_polygon([(0.2, 0.2), (0.8, 0.25), (0.95, 0.6), (0.5, 0.85), (0.15, 0.6)]).with_index(1.33),
+        Object(ConvexPolygon(tuple(ring), (0.6, -0.45), rot2(0.5)), Material(1.7), "ConvexPolygon"),
+        Object(Logic(AND_NOT, ConvexPolygon(((-0.3, -0.2), (0.3, -0.2), (0.3, 0.2), (-0.3, 0.2))), Circle((0.1, 0.0), 0.15),
+                     (-0.4, 0.55), rot2(-0.3)), Material(1.2), "Geo"),
+        Object(Logic(AND, ConvexPolygon(((0.0, -0.25), (0.25, 0.2), (-0.25, 0.2))), Circle((0.0, 0.0), 0.2),
+                     (-1.3, 0.5), rot2(1.0)), Material(2.0), "Geo"),
+        Object.new_mirror((1.4, -0.9), (1.6, 0.9)),
+    ]
+    lights = [PointLight((0.0, -0.1), total_rays // 2, (0.012, 0.01, 0.008, 0.02)),
+              SpotLight((-1.6, -0.8), 1.0, (1.0, 0.6), total_rays - total_rays // 2, (0.006, 0.01, 0.014, 0.02))]
+    return scenes.SceneSpec("polygons", objs, lights, 6, 480, 270)
+
+
 def small_specs():
     """CPU-oracle sized versions of the BASELINE configs (same shapes, fewer rays)."""
     return {
         "ELL": ellipse_spec(),
+        "POLY": polygon_spec(),
         "C1": scenes.c1_default(total_rays=6000, width=480, height=270),
         "C2": scenes.c2_cavity(total_rays=1500, max_bounce=64, width=480, height=270),
         "C3": scenes.c3_refraction(total_rays=6000, grid=16, width=480, height=270),
