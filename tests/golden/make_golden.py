@@ -3,7 +3,7 @@ be built or run offline (oracle/ORACLE.md, "PARITY UNPINNED") — they freeze th
 samples of the BASELINE configs so that (a) the oracle cannot drift silently and (b) the GPU box, which has no
 /root/reference and may have a different libm, checks the device against committed bits.
 
-    python tests/golden/make_golden.py
+    python tests/golden/make_golden.py [name ...]      (default: all; existing files are rewritten with the same bits)
 """
 import os
 import sys
@@ -19,7 +19,13 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 def golden_specs():
     from light_garden_b200 import scenes
+    from util import ellipse_spec, polygon_spec
+    ell, poly = ellipse_spec(total_rays=300), polygon_spec(total_rays=300)
+    ell.width = poly.width = 240
+    ell.height = poly.height = 135
     return {
+        "ell": ell,     # SURVEY.md 8f rank 2 geometry: ellipses and convex polygons, alone and in CSG trees
+        "poly": poly,
         "c1": scenes.c1_default(total_rays=360, width=240, height=135),
         "c2": scenes.c2_cavity(total_rays=48, max_bounce=64, width=240, height=135),
         "c3": scenes.c3_refraction(total_rays=400, grid=16, width=240, height=135),
@@ -31,7 +37,10 @@ def main():
     import lg_oracle as oracle
     from light_garden_b200 import abi
     from util import primary_rays
+    only = set(sys.argv[1:])
     for name, spec in golden_specs().items():
+        if only and name not in only:
+            continue
         osc = oracle.OracleScene.from_spec(spec)
         rays = primary_rays(oracle, spec, osc)
         out = {"rays": rays}

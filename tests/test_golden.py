@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(HERE, "golden"))
 from make_golden import golden_specs  # noqa: E402
 
-NAMES = ["c1", "c2", "c3", "c5"]
+NAMES = ["c1", "c2", "c3", "c5", "ell", "poly"]
 
 
 def load(name):
