@@ -1,0 +1,114 @@
+"""BASELINE.json's configurations at FULL size on one GPU, checked through size-independent properties (the oracle
+needs minutes for these sizes; tests/test_gpu_trace.py and test_gpu_accum.py compare small versions bit for bit):
+
+  * counters are exact integers and do not depend on how the work is done (all-objects loop vs device grid, one shard
+    vs two interleaved shards);
+  * scaling every light colour and the cutoff by two (exact in fp32) doubles the image: linearity of the whole path;
+  * a closed cavity of mirrors keeps every ray for all of its bounces.
+
+Images are compared within a tolerance because fp32 sums depend on the order in which segments reach a pixel.
+"""
+import copy
+
+import numpy as np
+import pytest
+
+from light_garden_b200 import abi, scenes
+from util import have_cuda
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not have_cuda(), reason="no CUDA device")]
+
+# relative to the brightest pixel: fp32 accumulation of up to ~1e5 fragments per pixel in different orders
+IMG_TOL = 2e-4
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from light_garden_b200.tracer import Context
+    c = Context(0, abi.LG_PRECISION_F32)
+    c.call("lg_segment_capacity_set", 256 << 20)
+    yield c
+    c.close()
+
+
+def render(ctx, spec, tile_map=False, shard=(0, 1), clear_alpha=1.0):
+    from light_garden_b200.tracer import Renderer, Tracer
+    t = spec.apply(Tracer(spec.canvas_bounds, ctx=ctx))
+    t.enable_tile_map(tile_map)
+    t.set_shard(*shard)
+    r = Renderer(ctx, spec.width, spec.height)
+    r.clear(clear_alpha)
+    try:
+        st = r.render(t)
+        return st, r.read_rgba32f()
+    finally:
+        t.enable_tile_map(False)
+        t.set_shard(0, 1)
+
+
+def close(a, b, tol=IMG_TOL):
+    scale = float(max(np.abs(a).max(), np.abs(b).max()))
+    return float(np.abs(a.astype(np.float64) - b).max()) <= tol * scale
+
+
+def test_c5_full_size_properties(ctx):
+    """C5 / 8 = the bench workload: 4096 objects, 32 M rays of one light, 3840 x 2160."""
+    spec = scenes.c5_large(n_lights=1, rays_per_light=32_000_000)
+    st, img = render(ctx, spec)
+    assert st.primary_rays == 32_000_000
+    assert st.object_tests == st.ray_steps * 4096
+    assert 5.0 < st.segments / st.primary_rays < 7.0 and st.segments <= st.ray_steps
+    assert st.pixel_updates > 40 * st.segments
+    # every fragment adds its colour: the image sums are a checksum of all segment colours x coverage
+    assert np.isfinite(img).all() and (img[..., :3] >= 0).all() and (img[..., 3] >= 1).all()
+
+    # the device grid finds the same nearest hits: identical counters, same image
+    st_g, img_g = render(ctx, spec, tile_map=True)
+    assert (st_g.ray_steps, st_g.segments, st_g.pixel_updates) == (st.ray_steps, st.segments, st.pixel_updates)
+    assert close(img, img_g)
+
+    # two interleaved shards partition the rays: counters add up, partial images (only shard 0 owns the clear
+    # alpha) sum to the frame -- what lg_image_reduce does across GPUs
+    st0, img0 = render(ctx, spec, shard=(0, 2), clear_alpha=1.0)
+    st1, img1 = render(ctx, spec, shard=(1, 2), clear_alpha=0.0)
+    assert st0.primary_rays == st1.primary_rays == 16_000_000
+    for f in ("ray_steps", "segments", "pixel_updates"):
+        assert getattr(st0, f) + getattr(st1, f) == getattr(st, f), f
+    assert abs(st0.ray_steps - st1.ray_steps) < 0.01 * st.ray_steps           # interleaving balances the shards
+    assert close(img, img0.astype(np.float64) + img1)
+
+    # linearity: colours and cutoff x 2 (exact in fp32, the same rays are culled) -> the same tree, twice the light
+    spec2 = copy.deepcopy(spec)
+    for l in spec2.lights:
+        l.color = tuple(2.0 * c for c in l.color)
+    spec2.cutoff_color = [2.0 * c for c in spec.cutoff_color]
+    st2, img2 = render(ctx, spec2)
+    assert (st2.ray_steps, st2.segments, st2.pixel_updates) == (st.ray_steps, st.segments, st.pixel_updates)
+    assert close(2.0 * img[..., :3].astype(np.float64), img2[..., :3])
+    assert close(4.0 * (img[..., 3].astype(np.float64) - 1.0), img2[..., 3].astype(np.float64) - 1.0)  # alpha adds a^2
+
+
+def test_c2_full_size_cavity_keeps_its_rays(ctx):
+    """C2: 4 M rays x 64 bounces in a closed cavity of straight and curved mirrors, no refraction: one segment per
+    ray step, 64 steps per ray except for the few rays that leave through a corner."""
+    spec = scenes.c2_cavity(total_rays=4_000_000, max_bounce=64, width=1920, height=1080)
+    st, img = render(ctx, spec)
+    assert st.segments == st.ray_steps
+    assert 0.999 * 64 * 4_000_000 <= st.segments <= 64 * 4_000_000
+    assert np.isfinite(img).all()
+    st_g, img_g = render(ctx, spec, tile_map=True)
+    assert (st_g.ray_steps, st_g.segments, st_g.pixel_updates) == (st.ray_steps, st.segments, st.pixel_updates)
+    assert close(img, img_g)
+
+
+def test_c3_full_size_grid_and_determinism(ctx):
+    """C3: 256 CSG / refractive objects, 16 M rays of four lights: counters are reproducible run to run and do not
+    depend on the nearest-hit search."""
+    spec = scenes.c3_refraction(total_rays=16_000_000, width=1920, height=1080)
+    st, img = render(ctx, spec)
+    st_b, img_b = render(ctx, spec)
+    st_g, img_g = render(ctx, spec, tile_map=True)
+    for other in (st_b, st_g):
+        assert (other.ray_steps, other.segments, other.pixel_updates) == (st.ray_steps, st.segments, st.pixel_updates)
+    assert st.primary_rays == 16_000_000 and st.segments > st.primary_rays
+    assert close(img, img_b) and close(img, img_g)
