@@ -338,7 +338,10 @@ def main():
             "phase_ms_per_step": {"trace": agg["trace_ms"] / args.steps, "accumulate": agg["accumulate_ms"] / args.steps,
                                   "image_reduce": agg["reduce_ms"] / args.steps},
             "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": ms_e2e / args.steps},
+                    "ms_per_step": ms_e2e / args.steps,
+                    "phase_ms_per_step": {"trace": agg_e2e["trace_ms"] / args.steps,
+                                          "accumulate": agg_e2e["accumulate_ms"] / args.steps,
+                                          "image_reduce": agg_e2e["reduce_ms"] / args.steps}},
             "gpu_launches": int(agg["launches"]),
             "clocks": clocks,
             "tile_map_enabled": {

@@ -6,7 +6,12 @@ needs minutes for these sizes; tests/test_gpu_trace.py and test_gpu_accum.py com
   * scaling every light colour and the cutoff by two (exact in fp32) doubles the image: linearity of the whole path;
   * a closed cavity of mirrors keeps every ray for all of its bounces.
 
-Images are compared within a tolerance because fp32 sums depend on the order in which segments reach a pixel.
+Images are compared within a tolerance because fp32 sums depend on the order in which segments reach a pixel.  The
+comparisons pin the tile-binned resolve (what the auto mode settles on for these workloads): it adds a tile's partial
+sums to the image, so the pixels a light sits in -- 1e7 fragments, values near 1e5 -- keep their accuracy; the direct
+resolve adds every 0.01-sized fragment to that running sum with one fp32 `red.add`, which rounds each of them to the
+sum's ulp (0.008 at 1e5) and is only compared loosely (last test).  The reference's own fp16 target stops growing at
+32, so neither path is asked to reproduce its hot pixels.
 """
 import copy
 
@@ -18,8 +23,10 @@ from util import have_cuda
 
 pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not have_cuda(), reason="no CUDA device")]
 
-# relative to the brightest pixel: fp32 accumulation of up to ~1e5 fragments per pixel in different orders
-IMG_TOL = 2e-4
+# fp32 accumulation of up to ~1e7 fragments per pixel (the pixel a light sits in) in different orders: the rounding
+# of the running sum random-walks to ~1e-4 of that pixel; the image as a whole agrees far better
+IMG_TOL = 1e-3      # max-abs difference, relative to the brightest pixel
+IMG_L2_TOL = 2e-5   # relative L2 difference (PSNR > 94 dB against the image's RMS)
 
 
 @pytest.fixture(scope="module")
@@ -31,8 +38,12 @@ def ctx():
     c.close()
 
 
-def render(ctx, spec, tile_map=False, shard=(0, 1), clear_alpha=1.0):
+DIRECT, TILED = 1, 2
+
+
+def render(ctx, spec, tile_map=False, shard=(0, 1), clear_alpha=1.0, mode=TILED):
     from light_garden_b200.tracer import Renderer, Tracer
+    ctx.call("lg_accumulate_mode_set", mode)
     t = spec.apply(Tracer(spec.canvas_bounds, ctx=ctx))
     t.enable_tile_map(tile_map)
     t.set_shard(*shard)
@@ -46,9 +57,18 @@ def render(ctx, spec, tile_map=False, shard=(0, 1), clear_alpha=1.0):
         t.set_shard(0, 1)
 
 
-def close(a, b, tol=IMG_TOL):
-    scale = float(max(np.abs(a).max(), np.abs(b).max()))
-    return float(np.abs(a.astype(np.float64) - b).max()) <= tol * scale
+def close(a, b, tol=IMG_TOL, l2_tol=IMG_L2_TOL):
+    """max-abs difference relative to the brightest pixel, and relative L2 difference of the whole image."""
+    a64, b64 = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    scale = float(max(np.abs(a64).max(), np.abs(b64).max()))
+    d = a64 - b64
+    max_abs = float(np.abs(d).max())
+    l2 = float(np.sqrt((d * d).sum() / max((a64 * a64).sum(), 1e-300)))
+    ok = max_abs <= tol * scale and l2 <= l2_tol
+    if not ok:
+        print(f"image mismatch: max-abs {max_abs:.6g} = {max_abs / scale:.3g} of the brightest pixel {scale:.6g} "
+              f"(tolerance {tol:g}), relative L2 {l2:.3g} (tolerance {l2_tol:g})")
+    return ok
 
 
 def test_c5_full_size_properties(ctx):
@@ -112,3 +132,18 @@ def test_c3_full_size_grid_and_determinism(ctx):
         assert (other.ray_steps, other.segments, other.pixel_updates) == (st.ray_steps, st.segments, st.pixel_updates)
     assert st.primary_rays == 16_000_000 and st.segments > st.primary_rays
     assert close(img, img_b) and close(img, img_g)
+
+
+def test_direct_and_tiled_resolves_agree_at_full_size(ctx):
+    """Same fragments through both resolves (C3 size): identical counters; the images agree closely everywhere except
+    in the hottest pixels, where the direct resolve's per-fragment fp32 adds lose low-order bits (module docstring)."""
+    spec = scenes.c3_refraction(total_rays=16_000_000, width=1920, height=1080)
+    st_t, img_t = render(ctx, spec, mode=TILED)
+    st_d, img_d = render(ctx, spec, mode=DIRECT)
+    assert (st_d.ray_steps, st_d.segments, st_d.pixel_updates) == (st_t.ray_steps, st_t.segments, st_t.pixel_updates)
+    assert close(img_t, img_d, tol=5e-2, l2_tol=3e-2)
+    # away from the lights (pixels below 1 % of the brightest) the two agree to fp32 accumulation noise
+    rgb_t, rgb_d = img_t[..., :3].astype(np.float64), img_d[..., :3].astype(np.float64)
+    cool = rgb_t.max(axis=2) < 0.01 * rgb_t.max()
+    assert cool.mean() > 0.9
+    assert np.abs(rgb_t[cool] - rgb_d[cool]).max() <= 2e-3 * rgb_t[cool].max()
