@@ -356,7 +356,11 @@ def main():
                         "headline because the north star's metric counts the all-objects loop"},
             "roofline": {"bound": "fp32", "kernel": "lg::trace_kernel", "achieved": achieved_tflops,
                          "peak": fma.value, "unit": "TFLOP/s", "frac": achieved_tflops / fma.value if fma.value else None,
-                         "traffic": None,
+                         # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this kernel
+                         # (profiles/r01d_trace_full.txt: 5.5 MB + 378.9 MB for 2 M rays = 192 B per ray, the 32-byte
+                         # segments: 5.9 per ray = 189 B algorithmic), scaled to the rays of one launch
+                         "traffic": 192.2 * rays_per_gpu if args.precision == "f32" else None,
+                         "traffic_unit": "bytes per launch (ncu capture at 2 M rays, scaled by rays per launch)",
                          "executed": {"flop_per_test_broad_phase": 6.0,
                                       "tflops": tests * 6.0 / tr_launches / (tr_ms_per_launch * 1e-3) / 1e12,
                                       "frac": tests * 6.0 / tr_launches / (tr_ms_per_launch * 1e-3) / 1e12 / fma.value
