@@ -282,6 +282,18 @@ int32_t lg_accumulate_segments(lg_ctx *ctx, const LgVertexPair *pairs,
 int32_t lg_string_mod(lg_ctx *ctx, const LgStringMod *sm,
                       const LgModRemColor *rules, uint32_t n_rules,
                       uint64_t first, uint64_t count, LgTraceStats *stats);
+/* StringMod::draw with `nested: Some(inner)` (string_mod.rs:87-101,152-158): the chords of
+ * `outer` are intersected pairwise in the reference's order (diff = 1..L-1, ixa = 0..L-1,
+ * partner (ixa + diff) % L; ORACLE.md 7.2 defines the segment intersection), the crossing
+ * points become the point set of `inner`, whose chords are then drawn with its own colours. */
+int32_t lg_string_mod_nested(lg_ctx *ctx, const LgStringMod *outer, const LgStringMod *inner,
+                             const LgModRemColor *inner_rules, uint32_t n_inner_rules,
+                             LgTraceStats *stats);
+/* The outer chords (f64 end points) and the crossing points (x, y pairs) of the last
+ * lg_string_mod_nested call; either destination may be NULL. */
+int32_t lg_string_mod_nested_read(lg_ctx *ctx, LgVertexPair *outer_chords, uint64_t chord_cap,
+                                  double *crossings_xy, uint64_t crossing_cap,
+                                  uint64_t *n_chords, uint64_t *n_crossings);
 /* trace_all + render fused: rays are traced in waves through the bounded
  * segment buffer and each wave is accumulated before the next is traced. */
 int32_t lg_render(lg_ctx *ctx, LgTraceStats *stats);

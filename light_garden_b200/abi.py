@@ -111,6 +111,9 @@ PROTOTYPES = {
     "lg_accumulate_segments": [_ctx, _p, C.c_uint64, C.POINTER(LgTraceStats)],
     "lg_string_mod": [_ctx, C.POINTER(LgStringMod), _p, C.c_uint32, C.c_uint64, C.c_uint64,
                       C.POINTER(LgTraceStats)],
+    "lg_string_mod_nested": [_ctx, C.POINTER(LgStringMod), C.POINTER(LgStringMod), _p, C.c_uint32,
+                             C.POINTER(LgTraceStats)],
+    "lg_string_mod_nested_read": [_ctx, _p, C.c_uint64, _p, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)],
     "lg_render": [_ctx, C.POINTER(LgTraceStats)],
     "lg_image_read": [_ctx, C.c_int32, _p, C.c_size_t],
     "lg_comm_unique_id": [_p],

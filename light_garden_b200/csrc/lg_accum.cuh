@@ -221,8 +221,16 @@ __device__ __forceinline__ unsigned long long sm_target(const LgStringMod &sm, u
   default: return wrapping_pow(sm.num, (unsigned int)i) % m;
   }
 }
-// StringMod::init_points (string_mod.rs:33-85), f64 like the reference, then `as f32` (sub_render_pass.rs:192)
+// StringMod::init_points (string_mod.rs:33-85) in f64 like the reference
+__device__ __forceinline__ void sm_point64(const LgStringMod &sm, unsigned long long n, double &x, double &y);
+// ... then `as f32` (sub_render_pass.rs:192)
 __device__ __forceinline__ void sm_point(const LgStringMod &sm, unsigned long long n, float &x, float &y) {
+  double px, py;
+  sm_point64(sm, n, px, py);
+  x = (float)px;
+  y = (float)py;
+}
+__device__ __forceinline__ void sm_point64(const LgStringMod &sm, unsigned long long n, double &x, double &y) {
   const double TAU = 6.28318530717958647692;
   const unsigned long long tn = sm.turns * n; // u64 product, wraps
   double px, py;
@@ -270,8 +278,8 @@ __device__ __forceinline__ void sm_point(const LgStringMod &sm, unsigned long lo
       px = c, py = s;
     }
   }
-  x = (float)px;
-  y = (float)py;
+  x = px;
+  y = py;
 }
 __device__ __forceinline__ void sm_color(const StringModArgs &S, unsigned long long ix, float out[4]) {
   float c0 = 0.f, c1 = 0.f, c2 = 0.f, c3 = 0.f; // string_mod.rs:124-150

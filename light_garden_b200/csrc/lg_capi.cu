@@ -21,6 +21,7 @@
 #include "lg_accum.cuh"
 #include "lg_bench.cuh"
 #include "lg_tiles.cuh"
+#include "lg_nested.cuh"
 #include "lg_reduce.cuh"
 #include <unistd.h>
 #include "lg_scene.h"
@@ -163,6 +164,9 @@ struct lg_ctx {
   double grid_density = 1.0; // cells per object (LG_GRID_DENSITY)
   int grid_slots = 1;        // ray slots per thread of the grid kernel (LG_GRID_SLOTS)
   DevBuf grid_start, grid_obj;
+  // nested string mod: outer chords, per-block crossing counts, crossing points, inner chords
+  DevBuf nest_lines, nest_counts, nest_points, nest_pairs;
+  unsigned long long nest_lines_n = 0, nest_points_n = 0;
   double grid_x0 = 0, grid_y0 = 0, grid_x1 = 0, grid_y1 = 0, grid_cs = 1, grid_eta = 0;
   int grid_nx = 0, grid_ny = 0;
   // accumulate auto mode: measured cost of the two resolves per WORKLOAD (scene + lights + image for traced
@@ -703,7 +707,8 @@ int32_t lg_destroy(lg_ctx *c) {
                     &c->tags,      &c->seg64,    &c->ctr,      &c->stack,   &c->rays,     &c->img,     &c->img16,
                     &c->pixctr,    &c->tile_count, &c->tile_cursor, &c->tile_offset, &c->item_prefix,
                     &c->tile_totals, &c->item_counter, &c->tile_list, &c->seg2,       &c->tile_hist,
-                    &c->sync_buf,  &c->peer_xchg,  &c->img8};
+                    &c->sync_buf,  &c->peer_xchg,  &c->img8,       &c->grid_start,  &c->grid_obj,
+                    &c->nest_lines, &c->nest_counts, &c->nest_points, &c->nest_pairs};
   for (DevBuf *b : bufs) release(*b);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
@@ -933,18 +938,11 @@ int32_t lg_accumulate_traced(lg_ctx *c, LgTraceStats *stats) {
   return LG_OK;
 }
 
-int32_t lg_accumulate_segments(lg_ctx *c, const LgVertexPair *pairs, uint64_t n, LgTraceStats *stats) {
-  int rc = need_image(c);
-  if (rc) return rc;
-  if (n && !pairs) return fail(c, LG_ERR_INVALID, "null pairs");
-  if (n == 0) return LG_OK;
-  c->img16_valid = false;
-  LG_CUDA(c, cudaSetDevice(c->device));
-  // reuse the ray staging buffer for the upload (update_vertex_buffer makes a NEW buffer per frame)
-  if ((rc = ensure(c, c->rays, n * sizeof(LgVertexPair)))) return rc;
-  LG_CUDA(c, cudaMemcpyAsync(c->rays.p, pairs, n * sizeof(LgVertexPair), cudaMemcpyHostToDevice, c->stream));
-  // host lines: workloads are told apart by image and segment-count class only
-  const unsigned long long sig = mix_sig(mix_sig(2, ((unsigned long long)c->W << 32) | (unsigned)c->H), 63 - __builtin_clzll(n | 1));
+} // extern "C"
+namespace {
+// update_vertex_buffer + render for `n` vertex pairs that already live on the device
+int accumulate_device_pairs(lg_ctx *c, const LgVertexPair *d_pairs, uint64_t n, unsigned long long sig, LgTraceStats *stats) {
+  int rc;
   const bool tiled = use_tiled(c, n, sig);
   uint64_t frag0 = 0;
   if ((rc = read_pixel_counter(c, &frag0))) return rc;
@@ -952,12 +950,12 @@ int32_t lg_accumulate_segments(lg_ctx *c, const LgVertexPair *pairs, uint64_t n,
   unsigned nl = 0;
   if (tiled) {
     if ((rc = ensure(c, c->seg2, n * sizeof(Seg2)))) return rc;
-    pairs_to_seg2_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>((const LgVertexPair *)c->rays.p, (Seg2 *)c->seg2.p, n);
+    pairs_to_seg2_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(d_pairs, (Seg2 *)c->seg2.p, n);
     LG_CUDA(c, cudaGetLastError());
     c->launches++, nl++;
     if ((rc = accumulate_tiled<Seg2>(c, (const Seg2 *)c->seg2.p, n, &nl))) return rc;
   } else {
-    accumulate_pairs_kernel<<<accum_grid(c), kAccumBlock, 0, c->stream>>>(accum_args(c), (const LgVertexPair *)c->rays.p, n);
+    accumulate_pairs_kernel<<<accum_grid(c), kAccumBlock, 0, c->stream>>>(accum_args(c), d_pairs, n);
     LG_CUDA(c, cudaGetLastError());
     c->launches++, nl++;
   }
@@ -974,6 +972,101 @@ int32_t lg_accumulate_segments(lg_ctx *c, const LgVertexPair *pairs, uint64_t n,
     stats->segments += n;
     stats->pixel_updates = frag1;
   }
+  return LG_OK;
+}
+} // namespace
+extern "C" {
+
+int32_t lg_accumulate_segments(lg_ctx *c, const LgVertexPair *pairs, uint64_t n, LgTraceStats *stats) {
+  int rc = need_image(c);
+  if (rc) return rc;
+  if (n && !pairs) return fail(c, LG_ERR_INVALID, "null pairs");
+  if (n == 0) return LG_OK;
+  c->img16_valid = false;
+  LG_CUDA(c, cudaSetDevice(c->device));
+  // reuse the ray staging buffer for the upload (update_vertex_buffer makes a NEW buffer per frame)
+  if ((rc = ensure(c, c->rays, n * sizeof(LgVertexPair)))) return rc;
+  LG_CUDA(c, cudaMemcpyAsync(c->rays.p, pairs, n * sizeof(LgVertexPair), cudaMemcpyHostToDevice, c->stream));
+  // host lines: workloads are told apart by image and segment-count class only
+  const unsigned long long sig = mix_sig(mix_sig(2, ((unsigned long long)c->W << 32) | (unsigned)c->H), 63 - __builtin_clzll(n | 1));
+  return accumulate_device_pairs(c, (const LgVertexPair *)c->rays.p, n, sig, stats);
+}
+
+// StringMod::draw with `nested: Some(inner)` (string_mod.rs:87-101,152-158)
+int32_t lg_string_mod_nested(lg_ctx *c, const LgStringMod *outer, const LgStringMod *inner, const LgModRemColor *inner_rules,
+                             uint32_t n_inner_rules, LgTraceStats *stats) {
+  int rc = need_image(c);
+  if (rc) return rc;
+  if (!outer || !inner || (n_inner_rules && !inner_rules)) return fail(c, LG_ERR_INVALID, "null string mod");
+  for (const LgStringMod *sm : {outer, inner}) {
+    if (sm->curve < LG_CURVE_CIRCLE || sm->curve > LG_CURVE_LISSAJOUS) return fail(c, LG_ERR_INVALID, "Curve");
+    if (sm->mode < LG_SM_ADD || sm->mode > LG_SM_BASE) return fail(c, LG_ERR_INVALID, "StringModMode");
+  }
+  c->nest_lines_n = c->nest_points_n = 0;
+  const unsigned long long L = outer->modulo;
+  if (L > (1ull << 20)) return fail(c, LG_ERR_UNSUPPORTED, "nested string mod: more than 2^20 outer chords (L^2 crossing tests)");
+  if (L < 2 || inner->modulo == 0) return LG_OK; // no crossings, or draw_init_points of nothing (string_mod.rs:106-108)
+  c->img16_valid = false;
+  LG_CUDA(c, cudaSetDevice(c->device));
+  // 1. the outer pattern's chords, f64 (their colours play no role)
+  StringModArgs S;
+  S.sm = *outer, S.rules = nullptr, S.n_rules = 0, S.first = 0, S.count = L;
+  if ((rc = ensure(c, c->nest_lines, L * sizeof(LgVertexPair)))) return rc;
+  string_mod_pairs_kernel<<<(unsigned)((L + 255) / 256), 256, 0, c->stream>>>(S, (LgVertexPair *)c->nest_lines.p);
+  LG_CUDA(c, cudaGetLastError());
+  c->nest_lines_n = L;
+  // 2. crossings in the reference's order: count per block, scan, ordered write
+  const unsigned long long n_cand = L * (L - 1ull);
+  const unsigned long long per_block = (unsigned long long)kNestBlock * kNestPer;
+  const unsigned long long n_blocks = (n_cand + per_block - 1) / per_block;
+  if (n_blocks > 0x7fffffffull) return fail(c, LG_ERR_UNSUPPORTED, "nested string mod: too many crossing candidates");
+  if ((rc = ensure(c, c->nest_counts, (n_blocks + 1) * 8))) return rc;
+  unsigned long long *counts = (unsigned long long *)c->nest_counts.p;
+  nested_count_kernel<<<(unsigned)n_blocks, kNestBlock, 0, c->stream>>>((const LgVertexPair *)c->nest_lines.p, L, n_cand, counts);
+  LG_CUDA(c, cudaGetLastError());
+  nested_scan_kernel<<<1, 1024, 0, c->stream>>>(counts, n_blocks, counts + n_blocks);
+  LG_CUDA(c, cudaGetLastError());
+  unsigned long long P = 0;
+  LG_CUDA(c, cudaMemcpyAsync(&P, counts + n_blocks, 8, cudaMemcpyDeviceToHost, c->stream));
+  LG_CUDA(c, cudaStreamSynchronize(c->stream));
+  c->launches += 3;
+  if (stats) stats->accumulate_launches += 3;
+  if (P == 0) return LG_OK;
+  if ((rc = ensure(c, c->nest_points, P * sizeof(double2)))) return rc;
+  nested_write_kernel<<<(unsigned)n_blocks, kNestBlock, 0, c->stream>>>((const LgVertexPair *)c->nest_lines.p, L, n_cand, counts,
+                                                                        (double2 *)c->nest_points.p);
+  LG_CUDA(c, cudaGetLastError());
+  c->nest_points_n = P;
+  // 3. the inner pattern's chords between those points, then the line pass
+  std::vector<LgModRemColor> rv(inner_rules, inner_rules + n_inner_rules);
+  if ((rc = upload(c, c->rays, rv))) return rc;
+  LG_CUDA(c, cudaStreamSynchronize(c->stream)); // rv dies at the end of this call; the kernel below reads the copy
+  StringModArgs I;
+  I.sm = *inner, I.rules = (const LgModRemColor *)c->rays.p, I.n_rules = n_inner_rules, I.first = 0, I.count = inner->modulo;
+  if ((rc = ensure(c, c->nest_pairs, inner->modulo * sizeof(LgVertexPair)))) return rc;
+  nested_pairs_kernel<<<(unsigned)((inner->modulo + 255) / 256), 256, 0, c->stream>>>(I, (const double2 *)c->nest_points.p, P,
+                                                                                      (LgVertexPair *)c->nest_pairs.p);
+  LG_CUDA(c, cudaGetLastError());
+  c->launches += 2;
+  if (stats) stats->accumulate_launches += 2;
+  unsigned long long sig = hash_bytes(inner, sizeof(LgStringMod), hash_bytes(outer, sizeof(LgStringMod), 4));
+  sig = mix_sig(sig, ((unsigned long long)c->W << 32) | (unsigned)c->H);
+  return accumulate_device_pairs(c, (const LgVertexPair *)c->nest_pairs.p, inner->modulo, sig, stats);
+}
+
+// The outer chords and the crossing points of the last lg_string_mod_nested call (tests, inspection)
+int32_t lg_string_mod_nested_read(lg_ctx *c, LgVertexPair *outer_chords, uint64_t chord_cap, double *crossings_xy,
+                                  uint64_t crossing_cap, uint64_t *n_chords, uint64_t *n_crossings) {
+  if (!c) return LG_ERR_INVALID;
+  LG_CUDA(c, cudaSetDevice(c->device));
+  if (n_chords) *n_chords = c->nest_lines_n;
+  if (n_crossings) *n_crossings = c->nest_points_n;
+  const uint64_t nl = std::min<uint64_t>(chord_cap, c->nest_lines_n), np = std::min<uint64_t>(crossing_cap, c->nest_points_n);
+  if (outer_chords && nl)
+    LG_CUDA(c, cudaMemcpyAsync(outer_chords, c->nest_lines.p, nl * sizeof(LgVertexPair), cudaMemcpyDeviceToHost, c->stream));
+  if (crossings_xy && np)
+    LG_CUDA(c, cudaMemcpyAsync(crossings_xy, c->nest_points.p, np * 16, cudaMemcpyDeviceToHost, c->stream));
+  LG_CUDA(c, cudaStreamSynchronize(c->stream));
   return LG_OK;
 }
 

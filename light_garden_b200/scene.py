@@ -396,6 +396,8 @@ class StringMod:
     init_curve: Curve = field(default_factory=lambda: Curve.Circle)
     mode: int = StringModMode.Mul
     modulo_colors: List[ModRemColor] = field(default_factory=list)
+    modulo_color_index: int = 0
+    nested: Optional["StringMod"] = None   # string_mod.rs:14: drawn between the crossings of this pattern's chords
 
     def to_pod(self):
         s = abi.LgStringMod()

@@ -264,9 +264,25 @@ class Renderer:
         """LightGarden::draw in Mode::StringMod (mod.rs:681-689) + the line pass."""
         pod, rules, n = sm.to_pod()
         st = abi.LgTraceStats()
-        self.ctx.call("lg_string_mod", C.byref(pod), C.cast(rules, C.c_void_p), n, first, count, C.byref(st))
+        if sm.nested is not None:   # StringMod::draw, string_mod.rs:152-158
+            if first or count:
+                raise ValueError("a nested string mod is drawn as a whole")
+            ipod, irules, ni = sm.nested.to_pod()
+            self.ctx.call("lg_string_mod_nested", C.byref(pod), C.byref(ipod), C.cast(irules, C.c_void_p), ni, C.byref(st))
+        else:
+            self.ctx.call("lg_string_mod", C.byref(pod), C.cast(rules, C.c_void_p), n, first, count, C.byref(st))
         self.last_stats = st
         return st
+
+    def nested_crossings(self):
+        """The outer chords (abi.VERTEX_PAIR_DTYPE) and crossing points (n x 2 f64) of the last nested string mod."""
+        nl, npts = C.c_uint64(), C.c_uint64()
+        self.ctx.call("lg_string_mod_nested_read", None, 0, None, 0, C.byref(nl), C.byref(npts))
+        lines = np.zeros(nl.value, dtype=abi.VERTEX_PAIR_DTYPE)
+        pts = np.zeros((npts.value, 2), dtype=np.float64)
+        self.ctx.call("lg_string_mod_nested_read", abi.array_ptr(lines) if nl.value else None, nl.value,
+                      abi.array_ptr(pts) if npts.value else None, npts.value, C.byref(nl), C.byref(npts))
+        return lines, pts
 
     def render(self, tracer: Tracer):
         """Renderer::render's trace + line pass fused (waves through the bounded segment buffer)."""

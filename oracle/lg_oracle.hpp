@@ -970,6 +970,40 @@ inline void sm_chord(const LgStringMod &sm, const LgModRemColor *rules, uint32_t
   sm_color(sm, rules, nr, ix, vp.color_b);
 }
 
+// §7.2 nested string mod (string_mod.rs:87-101,152-158).  LineSegment::intersect(&LineSegment) of collision2d is
+// taken as: both parameters in [0, 1] (end points included), none for parallel segments.
+inline bool segment_segment(const LgVertexPair &p, const LgVertexPair &q, double out[2]) {
+  V2<double> a1{p.a[0], p.a[1]}, e1{p.b[0] - p.a[0], p.b[1] - p.a[1]};
+  V2<double> a2{q.a[0], q.a[1]}, e2{q.b[0] - q.a[0], q.b[1] - q.a[1]};
+  double denom = cross(e1, e2);
+  if (!(std::fabs(denom) > PAR_EPS)) return false;
+  V2<double> w = sub(a2, a1);
+  double t = cross(w, e2) / denom, u = cross(w, e1) / denom;
+  if (!(t >= 0.0 && t <= 1.0 && u >= 0.0 && u <= 1.0)) return false;
+  V2<double> x = along(a1, t, e1);
+  out[0] = x.x, out[1] = x.y;
+  return true;
+}
+// StringMod::line_crossings_as_points over the chords `lines` (their order is the reference's loop nest)
+inline std::vector<double> line_crossings(const LgVertexPair *lines, uint64_t n) {
+  std::vector<double> pts;
+  for (uint64_t diff = 1; diff < n; ++diff)
+    for (uint64_t ixa = 0; ixa < n; ++ixa) {
+      double x[2];
+      if (segment_segment(lines[ixa], lines[(ixa + diff) % n], x)) pts.push_back(x[0]), pts.push_back(x[1]);
+    }
+  return pts;
+}
+// inner.draw_init_points(points): chord iix joins points[iix % P] and points[f(iix) % P]
+inline void nested_chord(const LgStringMod &inner, const LgModRemColor *rules, uint32_t nr, const double *pts, uint64_t P,
+                         uint64_t iix, LgVertexPair &vp) {
+  uint64_t ix = sm_target(inner, iix);
+  vp.a[0] = pts[2 * (iix % P)], vp.a[1] = pts[2 * (iix % P) + 1];
+  vp.b[0] = pts[2 * (ix % P)], vp.b[1] = pts[2 * (ix % P) + 1];
+  sm_color(inner, rules, nr, iix, vp.color_a);
+  sm_color(inner, rules, nr, ix, vp.color_b);
+}
+
 // ---------------------------------------------------------------------------
 // §8 accumulate — sub_render_pass.rs:188-212 + shader.wgsl + blend mod.rs:57-73
 // Non-AA 1-px LineList coverage, colour lerp, rgb += src.rgb, a += src.a².

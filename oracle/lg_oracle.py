@@ -63,6 +63,9 @@ def lib():
         L.lgo_result_copy.argtypes = [vp, vp, vp, vp]
         L.lgo_result_free.argtypes = [vp]
         L.lgo_string_mod.argtypes = [C.POINTER(abi.LgStringMod), vp, C.c_uint32, C.c_uint64, C.c_uint64, vp]
+        L.lgo_line_crossings.argtypes = [vp, C.c_uint64, vp, C.c_uint64]
+        L.lgo_line_crossings.restype = C.c_uint64
+        L.lgo_nested_chords.argtypes = [C.POINTER(abi.LgStringMod), vp, C.c_uint32, vp, C.c_uint64, vp]
         L.lgo_image_clear.argtypes = [vp, C.c_int32, C.c_int32, C.c_float]
         L.lgo_accumulate_segments.restype = C.c_uint64
         L.lgo_accumulate_segments.argtypes = [vp, C.c_int32, C.c_int32, vp, C.c_uint64, C.c_int32]
@@ -180,6 +183,34 @@ def string_mod(sm, first=0, count=None):
     out = np.zeros(count, dtype=abi.VERTEX_PAIR_DTYPE)
     lib().lgo_string_mod(C.byref(pod), C.cast(rules, C.c_void_p), n, first, count, abi.array_ptr(out))
     return out
+
+
+def line_crossings(lines):
+    """StringMod::line_crossings_as_points (string_mod.rs:87-101) over chords given as vertex pairs -> n x 2 f64."""
+    lines = np.ascontiguousarray(lines, dtype=abi.VERTEX_PAIR_DTYPE)
+    n = lib().lgo_line_crossings(abi.array_ptr(lines), len(lines), None, 0)
+    out = np.zeros((n, 2), dtype=np.float64)
+    if n:
+        lib().lgo_line_crossings(abi.array_ptr(lines), len(lines), abi.array_ptr(out), n)
+    return out
+
+
+def nested_chords(inner, points):
+    """inner.draw_init_points(points) (string_mod.rs:103-122) -> vertex pairs."""
+    pod, rules, n = inner.to_pod()
+    points = np.ascontiguousarray(points, dtype=np.float64)
+    out = np.zeros(inner.modulo if len(points) else 0, dtype=abi.VERTEX_PAIR_DTYPE)
+    if len(points):
+        lib().lgo_nested_chords(C.byref(pod), C.cast(rules, C.c_void_p), n, abi.array_ptr(points), len(points),
+                                abi.array_ptr(out))
+    return out
+
+
+def string_mod_draw(sm):
+    """StringMod::draw (string_mod.rs:152-158), nested or not -> vertex pairs."""
+    if sm.nested is None:
+        return string_mod(sm)
+    return nested_chords(sm.nested, line_crossings(string_mod(sm)))
 
 
 def new_image(width, height, clear_alpha=1.0):

@@ -232,6 +232,21 @@ void lgo_string_mod(const LgStringMod *sm, const LgModRemColor *rules, uint32_t 
   for (int64_t i = 0; i < (int64_t)count; ++i) sm_chord(*sm, rules, n_rules, first + i, dst[i]);
 }
 
+// StringMod::line_crossings_as_points (string_mod.rs:87-101) over given chords: returns the number of crossing
+// points and copies up to `cap` of them (x, y pairs)
+uint64_t lgo_line_crossings(const LgVertexPair *lines, uint64_t n, double *xy, uint64_t cap) {
+  std::vector<double> pts = line_crossings(lines, n);
+  const uint64_t np = pts.size() / 2;
+  if (xy) std::memcpy(xy, pts.data(), std::min(np, cap) * 16);
+  return np;
+}
+// inner.draw_init_points(points) (string_mod.rs:103-122): inner.modulo chords between the given points
+void lgo_nested_chords(const LgStringMod *inner, const LgModRemColor *rules, uint32_t n_rules, const double *xy,
+                       uint64_t n_points, LgVertexPair *dst) {
+  if (n_points == 0) return;
+  for (uint64_t i = 0; i < inner->modulo; ++i) nested_chord(*inner, rules, n_rules, xy, n_points, i, dst[i]);
+}
+
 } // extern "C"
 
 // SubRenderPass::update_vertex_buffer + render into an fp32 RGBA image

@@ -185,6 +185,44 @@ def test_string_mod_matches_oracle(oracle, ctx, mode):
     assert r.render_string_mod(StringMod(modulo=0)).segments == 0
 
 
+@pytest.mark.parametrize("mode", MODES)
+def test_nested_string_mod(oracle, ctx, mode):
+    """StringMod with nested = Some(inner) (string_mod.rs:87-101,152-158).  The crossing
+    points of the device's own outer chords must equal the oracle's on the same chords bit for bit, in the
+    reference's order; the inner pattern drawn between them must match the oracle's line pass."""
+    from light_garden_b200.tracer import Renderer
+    ctx.call("lg_accumulate_mode_set", mode)
+    W = H = 256
+    k = 2.0 ** -8
+    inner = StringMod(modulo=5000, num=3, mode=StringModMode.Mul, color=(k, k, k, k),
+                      modulo_colors=[ModRemColor(3, 0, (k, 0, 0, k)), ModRemColor(5, 1, (0, k, 0, k))])
+    for outer in (StringMod(modulo=120, num=2, mode=StringModMode.Mul, nested=inner),
+                  StringMod(modulo=257, num=100, mode=StringModMode.Add, nested=inner,
+                            init_curve=Curve.Lissajous(3, 2, 0.5))):
+        r = Renderer(ctx, W, H)
+        st = r.render_string_mod(outer)
+        got = r.read_rgba32f()
+        lines, pts = r.nested_crossings()
+        # the outer chords themselves: device sin/cos vs libm, a few ulps of f64
+        ref_lines = oracle.string_mod(StringMod(modulo=outer.modulo, num=outer.num, mode=outer.mode, init_curve=outer.init_curve))
+        assert len(lines) == outer.modulo
+        np.testing.assert_allclose(lines["a"], ref_lines["a"], atol=1e-15)
+        np.testing.assert_allclose(lines["b"], ref_lines["b"], atol=1e-15)
+        # crossings of THOSE chords: same points, same order, same bits
+        exp_pts = oracle.line_crossings(lines)
+        assert len(exp_pts) > 1000
+        assert pts.shape == exp_pts.shape and pts.tobytes() == exp_pts.tobytes()
+        # the inner chords between them through the line pass
+        exp = oracle.new_image(W, H)
+        n = oracle.accumulate_pairs(exp, oracle.nested_chords(inner, pts))
+        assert st.segments == inner.modulo and int(st.pixel_updates) == int(n) > 100000
+        assert (np.abs(got - exp) <= 1e-6 * np.maximum(1.0, np.abs(exp))).all()
+    # an outer pattern without crossings draws nothing
+    r = Renderer(ctx, W, H)
+    assert r.render_string_mod(StringMod(modulo=1, nested=inner)).segments == 0
+    assert np.array_equal(r.read_rgba32f(), oracle.new_image(W, H))
+
+
 def test_finalize_rgba16f(oracle, ctx):
     """K5: the Rgba16Float image is the fp32 image rounded to nearest even, bit for bit."""
     from light_garden_b200.tracer import Renderer

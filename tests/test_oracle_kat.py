@@ -646,3 +646,50 @@ def test_prism_deviates_a_ray_by_the_textbook_angle(oracle):
     w = np.array(seg["b"][out[0]], dtype=np.float64) - np.array(seg["a"][out[0]], dtype=np.float64)
     dev = math.atan2(d_in[1], d_in[0]) - math.atan2(w[1], w[0])
     assert abs(dev - (2 * i - A)) < 1e-6
+
+
+def test_nested_string_mod_crossings(oracle):
+    """StringMod with nested = Some(inner) (string_mod.rs:87-101,152-158): crossings of the outer chords in the
+    reference's loop order (diff = 1..L-1, ixa = 0..L-1), then the inner pattern's chords between those points."""
+    # a pentagram (5 points, i -> i + 2): its 5 inner crossings lie on the circle of radius 1 / phi^2
+    outer = StringMod(modulo=5, num=2, mode=StringModMode.Add)
+    lines = oracle.string_mod(outer)
+    pts = oracle.line_crossings(lines)
+    rad = np.hypot(pts[:, 0], pts[:, 1])
+    inner_r = 1.0 / ((1 + math.sqrt(5)) / 2) ** 2
+    assert (np.abs(rad - inner_r) < 1e-12).sum() == 10       # every unordered pair is visited twice (diff and L - diff)
+    assert ((np.abs(rad - inner_r) < 1e-12) | (np.abs(rad - 1.0) < 1e-12)).all()   # the rest are shared end points
+    # order and values against a plain numpy restatement of the loop nest on random segments
+    rng = np.random.default_rng(11)
+    L = 40
+    segs = np.zeros(L, dtype=abi.VERTEX_PAIR_DTYPE)
+    segs["a"], segs["b"] = rng.uniform(-1, 1, (L, 2)), rng.uniform(-1, 1, (L, 2))
+    exp = []
+    for diff in range(1, L):
+        for i in range(L):
+            j = (i + diff) % L
+            a1, e1 = segs["a"][i], segs["b"][i] - segs["a"][i]
+            a2, e2 = segs["a"][j], segs["b"][j] - segs["a"][j]
+            den = e1[0] * e2[1] - e1[1] * e2[0]
+            w = a2 - a1
+            t, u = (w[0] * e2[1] - w[1] * e2[0]) / den, (w[0] * e1[1] - w[1] * e1[0]) / den
+            if 0 <= t <= 1 and 0 <= u <= 1:
+                exp.append(a1 + t * e1)
+    got = oracle.line_crossings(segs)
+    assert len(got) == len(exp) > 100
+    np.testing.assert_allclose(got, np.array(exp), atol=1e-13)
+    # the inner pattern indexes the crossing points modulo their number and colours by its own rules
+    k = 2.0 ** -6
+    inner = StringMod(modulo=7, num=3, mode=StringModMode.Mul, color=(k, k, k, k), modulo_colors=[ModRemColor(2, 0, (k, 0, 0, k))])
+    outer.nested = inner
+    ch = oracle.string_mod_draw(outer)
+    assert len(ch) == 7
+    P = len(pts)
+    for i in range(7):
+        j = (i * 3) % 7
+        np.testing.assert_array_equal(ch["a"][i], pts[i % P])
+        np.testing.assert_array_equal(ch["b"][i], pts[j % P])
+        np.testing.assert_array_equal(ch["color_a"][i], (k, 0, 0, k) if i % 2 == 0 else (k, k, k, k))
+        np.testing.assert_array_equal(ch["color_b"][i], (k, 0, 0, k) if j % 2 == 0 else (k, k, k, k))
+    # no crossings -> nothing is drawn (string_mod.rs:106-108)
+    assert len(oracle.string_mod_draw(StringMod(modulo=1, nested=inner))) == 0
