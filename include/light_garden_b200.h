@@ -191,6 +191,24 @@ typedef struct LgStringMod {
   double curve_p[4];
 } LgStringMod; /* 80 bytes */
 
+/* ---- blend state (wgpu::BlendState as the GUI edits it, src/gui/settings.rs:59-105;
+ *      default src/light_garden/mod.rs:57-73) --------------------------------- */
+enum { /* wgpu::BlendFactor (discriminants of wgpu-types = the order of gui/settings.rs:59-73) */
+  LG_BF_ZERO = 0, LG_BF_ONE, LG_BF_SRC, LG_BF_ONE_MINUS_SRC, LG_BF_SRC_ALPHA, LG_BF_ONE_MINUS_SRC_ALPHA,
+  LG_BF_DST, LG_BF_ONE_MINUS_DST, LG_BF_DST_ALPHA, LG_BF_ONE_MINUS_DST_ALPHA, LG_BF_SRC_ALPHA_SATURATED,
+  LG_BF_CONSTANT, LG_BF_ONE_MINUS_CONSTANT
+};
+enum { /* wgpu::BlendOperation (discriminants of wgpu-types; the GUI lists them at gui/settings.rs:99-105) */
+  LG_BO_ADD = 0, LG_BO_SUBTRACT, LG_BO_REVERSE_SUBTRACT, LG_BO_MIN, LG_BO_MAX
+};
+typedef struct LgBlendComponent {
+  int32_t src_factor, dst_factor, operation;
+} LgBlendComponent;
+typedef struct LgBlendState {
+  LgBlendComponent color, alpha;
+  float constant[4]; /* wgpu blend constant (the app never sets it: transparent black) */
+} LgBlendState;      /* 40 bytes */
+
 /* ---- accumulation target -------------------------------------------------- */
 /* LG_BGRA8_GAMMA is the reference's screenshot conversion (src/renderer.rs:313-328):
  * every Rgba16Float channel -> (f.powf(1/2.2) * 255) as u8, stored [b, g, r, a]. */
@@ -272,6 +290,14 @@ int32_t lg_image_configure(lg_ctx *ctx, uint32_t width, uint32_t height);
 /* LoadOp::Clear(BLACK) (renderer.rs:174-177): rgb = 0, alpha =
  * clear_alpha (1 on the rank that owns the clear, 0 on the others). */
 int32_t lg_image_clear(lg_ctx *ctx, float clear_alpha);
+/* LightGarden.color_state_descriptor.blend (mod.rs:57-73, edited by gui/settings.rs:59-127); NULL
+ * restores the default (rgb: One/One/Add, alpha: SrcAlpha/One/Add). Supported are the states whose
+ * result does not depend on the order of the fragments, which is what a parallel line pass can
+ * reproduce: Add or ReverseSubtract with dst_factor One and a source-only src_factor (Zero, One,
+ * Src, OneMinusSrc, SrcAlpha, OneMinusSrcAlpha, Constant, OneMinusConstant), and Min / Max (wgpu
+ * ignores their factors). Anything else is LG_ERR_UNSUPPORTED, here and never silently later.
+ * Non-default states use the direct resolve; Min / Max images cannot be summed by lg_image_reduce. */
+int32_t lg_blend_set(lg_ctx *ctx, const LgBlendState *state);
 /* SubRenderPass::render for the device segment buffer. */
 int32_t lg_accumulate_traced(lg_ctx *ctx, LgTraceStats *stats);
 /* update_vertex_buffer + render for host lines. */

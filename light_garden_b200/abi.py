@@ -20,6 +20,11 @@ ERROR_NAMES = {
 LG_PRECISION_F32, LG_PRECISION_F64 = 0, 1
 LG_GEO_CIRCLE, LG_GEO_RECT, LG_GEO_SEGMENT, LG_GEO_BEZIER, LG_GEO_LOGIC, LG_GEO_ELLIPSE = 0, 1, 2, 3, 4, 5
 LG_GEO_POLYGON, LG_GEO_POINTS, LG_POLYGON_MAX_VERTICES = 6, 7, 32
+# wgpu::BlendFactor / BlendOperation (gui/settings.rs:59-105)
+(LG_BF_ZERO, LG_BF_ONE, LG_BF_SRC, LG_BF_ONE_MINUS_SRC, LG_BF_SRC_ALPHA, LG_BF_ONE_MINUS_SRC_ALPHA, LG_BF_DST,
+ LG_BF_ONE_MINUS_DST, LG_BF_DST_ALPHA, LG_BF_ONE_MINUS_DST_ALPHA, LG_BF_SRC_ALPHA_SATURATED, LG_BF_CONSTANT,
+ LG_BF_ONE_MINUS_CONSTANT) = range(13)
+LG_BO_ADD, LG_BO_SUBTRACT, LG_BO_REVERSE_SUBTRACT, LG_BO_MIN, LG_BO_MAX = range(5)
 LG_OP_AND, LG_OP_OR, LG_OP_ANDNOT = 0, 1, 2
 LG_LIGHT_POINT, LG_LIGHT_DIRECTIONAL, LG_LIGHT_SPOT = 0, 1, 2
 LG_SM_ADD, LG_SM_MUL, LG_SM_POW, LG_SM_BASE = 0, 1, 2, 3
@@ -65,6 +70,14 @@ class LgModRemColor(C.Structure):
     _fields_ = [("modulo", C.c_uint64), ("rem", C.c_uint64), ("color", C.c_float * 4)]
 
 
+class LgBlendComponent(C.Structure):
+    _fields_ = [("src_factor", C.c_int32), ("dst_factor", C.c_int32), ("operation", C.c_int32)]
+
+
+class LgBlendState(C.Structure):
+    _fields_ = [("color", LgBlendComponent), ("alpha", LgBlendComponent), ("constant", C.c_float * 4)]
+
+
 # bulk data travels as numpy structured arrays with the same layout
 RAY_DTYPE = np.dtype([("origin", "<f8", 2), ("direction", "<f8", 2), ("color", "<f4", 4),
                       ("refractive_index", "<f8")], align=True)
@@ -82,6 +95,7 @@ SIZES = {
     "LgVertexPair": (VERTEX_PAIR_DTYPE.itemsize, 64), "LgSegmentTag": (SEGMENT_TAG_DTYPE.itemsize, 24),
     "LgSegmentF64": (SEGMENT_F64_DTYPE.itemsize, 32), "LgModRemColor": (C.sizeof(LgModRemColor), 32),
     "LgStringMod": (C.sizeof(LgStringMod), 80), "LgTraceStats": (C.sizeof(LgTraceStats), 56),
+    "LgBlendState": (C.sizeof(LgBlendState), 40),
 }
 
 _ctx = C.c_void_p
@@ -99,6 +113,7 @@ PROTOTYPES = {
     "lg_segment_capacity_set": [_ctx, C.c_uint64],
     "lg_accumulate_mode_set": [_ctx, C.c_int32],
     "lg_tile_map_enable": [_ctx, C.c_int32],
+    "lg_blend_set": [_ctx, C.POINTER(LgBlendState)],
     "lg_tags_enable": [_ctx, C.c_int32],
     "lg_emit_rays": [_ctx, C.c_uint32, C.c_uint64, C.c_uint64, _p],
     "lg_trace": [_ctx, C.POINTER(LgTraceStats)],

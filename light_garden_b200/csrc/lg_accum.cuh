@@ -26,15 +26,60 @@ namespace lg {
 
 constexpr int kAccumBlock = 256;
 
+// non-default blend states (lg_blend_set): per component a source factor and how the product meets the image
+struct BlendCfg {
+  int color_factor, alpha_factor; // LG_BF_* (source-only factors)
+  int color_op, alpha_op;         // LG_BO_ADD, LG_BO_REVERSE_SUBTRACT, LG_BO_MIN, LG_BO_MAX
+  float constant[4];
+};
+
 struct AccumArgs {
   float *img; // RGBA fp32, row-major, y down
   int W, H;
   float m00, m11, hw, hh; // projection + viewport (ORACLE.md §8.1)
   unsigned long long *pixel_updates;
+  BlendCfg blend;         // read by the <kBlend = true> kernels only
 };
 
 __device__ __forceinline__ void red_add_v4(float *p, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+// ---- generic blend (ORACLE.md §8.6): source factor, then Add / ReverseSubtract / Min / Max against the image ----
+__device__ __forceinline__ float blend_factor(int f, float c, float alpha, float constant) {
+  switch (f) {
+  case LG_BF_ZERO: return 0.f;
+  case LG_BF_ONE: return 1.f;
+  case LG_BF_SRC: return c;
+  case LG_BF_ONE_MINUS_SRC: return 1.f - c;
+  case LG_BF_SRC_ALPHA: return alpha;
+  case LG_BF_ONE_MINUS_SRC_ALPHA: return 1.f - alpha;
+  case LG_BF_CONSTANT: return constant;
+  default: return 1.f - constant; // LG_BF_ONE_MINUS_CONSTANT
+  }
+}
+// float min / max on a word that always holds a float: order-preserving integer views of the two sign classes
+__device__ __forceinline__ void atomic_max_f32(float *p, float v) {
+  if (v != v) return;
+  if (v >= 0.f) atomicMax(reinterpret_cast<int *>(p), __float_as_int(v));
+  else atomicMin(reinterpret_cast<unsigned int *>(p), __float_as_uint(v));
+}
+__device__ __forceinline__ void atomic_min_f32(float *p, float v) {
+  if (v != v) return;
+  if (v >= 0.f) atomicMin(reinterpret_cast<int *>(p), __float_as_int(v));
+  else atomicMax(reinterpret_cast<unsigned int *>(p), __float_as_uint(v));
+}
+__device__ __forceinline__ void blend_channel(float *p, int op, float src, float factor) {
+  if (op == LG_BO_MIN) atomic_min_f32(p, src);          // wgpu: Min / Max ignore the factors
+  else if (op == LG_BO_MAX) atomic_max_f32(p, src);
+  else if (op == LG_BO_ADD) atomicAdd(p, src * factor); // dst * One + src * factor
+  else atomicAdd(p, -(src * factor));                   // ReverseSubtract: dst * One - src * factor
+}
+__device__ __forceinline__ void blend_fragment(const BlendCfg &B, float *px, float c0, float c1, float c2, float c3) {
+  blend_channel(px + 0, B.color_op, c0, blend_factor(B.color_factor, c0, c3, B.constant[0]));
+  blend_channel(px + 1, B.color_op, c1, blend_factor(B.color_factor, c1, c3, B.constant[1]));
+  blend_channel(px + 2, B.color_op, c2, blend_factor(B.color_factor, c2, c3, B.constant[2]));
+  blend_channel(px + 3, B.alpha_op, c3, blend_factor(B.alpha_factor, c3, c3, B.constant[3]));
 }
 
 // Per-segment raster setup (ORACLE.md §8.1-8.2), computed by ONE lane for its own segment and
@@ -78,7 +123,7 @@ __device__ __forceinline__ RasterSetup raster_setup(const AccumArgs &A, float ax
 }
 
 // One warp rasterises one parked segment; returns this lane's number of blended fragments.
-template <bool kLerp>
+template <bool kLerp, bool kBlend = false>
 __device__ __forceinline__ unsigned raster_walk(const AccumArgs &A, const RasterSetup &S, const float4 ca,
                                                 const float4 dc, unsigned lane) {
   const int Nmin = S.xmajor ? A.H : A.W;
@@ -97,7 +142,8 @@ __device__ __forceinline__ unsigned raster_walk(const AccumArgs &A, const Raster
       c2 = __fmaf_rn(s, dc.z, ca.z), c3 = __fmaf_rn(s, dc.w, ca.w);
     }
     // blend: rgb = src*1 + dst*1 ; a = src.a*src.a + dst.a   (mod.rs:57-73)
-    red_add_v4(A.img + ((size_t)py * A.W + px) * 4, c0, c1, c2, c3 * c3);
+    if (kBlend) blend_fragment(A.blend, A.img + ((size_t)py * A.W + px) * 4, c0, c1, c2, c3);
+    else red_add_v4(A.img + ((size_t)py * A.W + px) * 4, c0, c1, c2, c3 * c3);
     ++n;
   }
   return n;
@@ -117,7 +163,7 @@ __device__ __forceinline__ void flush_count(const AccumArgs &A, unsigned long lo
 
 // walk the m parked segments of this warp; the next segment's parameters are fetched from shared
 // memory while the current one is being rasterised (hides the LDS latency between short segments)
-template <bool kLerp>
+template <bool kLerp, bool kBlend = false>
 __device__ __forceinline__ unsigned long long walk_parked(const AccumArgs &A, const WarpScratch &W, int m,
                                                           unsigned lane) {
   unsigned long long cnt = 0;
@@ -130,13 +176,14 @@ __device__ __forceinline__ unsigned long long walk_parked(const AccumArgs &A, co
     const RasterSetup Sn = W.s[kn];
     const float4 can = W.ca[kn];
     const float4 dcn = kLerp ? W.dc[kn] : dc;
-    if (S.i0 < S.i1) cnt += raster_walk<kLerp>(A, S, ca, dc, lane); // warp-uniform condition
+    if (S.i0 < S.i1) cnt += raster_walk<kLerp, kBlend>(A, S, ca, dc, lane); // warp-uniform condition
     S = Sn, ca = can, dc = dcn;
   }
   return cnt;
 }
 
 // K4 over the compact device segments written by the trace kernel
+template <bool kBlend>
 __global__ void __launch_bounds__(kAccumBlock) accumulate_segments_kernel(AccumArgs A, const LgSegment *seg,
                                                                            unsigned long long n) {
   __shared__ WarpScratch scratch[kWarpsPerBlock];
@@ -164,13 +211,14 @@ __global__ void __launch_bounds__(kAccumBlock) accumulate_segments_kernel(AccumA
     }
     __syncwarp();
     const int m = (int)((n - base) < 32ull ? (n - base) : 32ull);
-    cnt += walk_parked<false>(A, W, m, lane);
+    cnt += walk_parked<false, kBlend>(A, W, m, lane);
     __syncwarp();
   }
   flush_count(A, cnt, lane);
 }
 
 // K4 over host supplied vertex pairs (two colours, f64 positions cast `as f32`)
+template <bool kBlend>
 __global__ void __launch_bounds__(kAccumBlock) accumulate_pairs_kernel(AccumArgs A, const LgVertexPair *vp,
                                                                         unsigned long long n) {
   __shared__ WarpScratch scratch[kWarpsPerBlock];
@@ -189,7 +237,7 @@ __global__ void __launch_bounds__(kAccumBlock) accumulate_pairs_kernel(AccumArgs
     }
     __syncwarp();
     const int m = (int)((n - base) < 32ull ? (n - base) : 32ull);
-    cnt += walk_parked<true>(A, W, m, lane);
+    cnt += walk_parked<true, kBlend>(A, W, m, lane);
     __syncwarp();
   }
   flush_count(A, cnt, lane);
@@ -299,6 +347,7 @@ __device__ __forceinline__ void sm_color(const StringModArgs &S, unsigned long l
   }
 }
 
+template <bool kBlend>
 __global__ void __launch_bounds__(kAccumBlock) string_mod_kernel(AccumArgs A, StringModArgs S) {
   __shared__ WarpScratch scratch[kWarpsPerBlock];
   WarpScratch &W = scratch[threadIdx.x >> 5];
@@ -321,7 +370,7 @@ __global__ void __launch_bounds__(kAccumBlock) string_mod_kernel(AccumArgs A, St
     }
     __syncwarp();
     const int m = (int)((S.count - base) < 32ull ? (S.count - base) : 32ull);
-    cnt += walk_parked<true>(A, W, m, lane);
+    cnt += walk_parked<true, kBlend>(A, W, m, lane);
     __syncwarp();
   }
   flush_count(A, cnt, lane);

@@ -159,6 +159,9 @@ struct lg_ctx {
   int accum_mode = 0; // 0 = auto, 1 = direct (one L2 reduction per fragment), 2 = tile-binned
   // auto mode: measured cost of each resolve on this context's recent work (ns per fragment, 0 = no sample yet)
   // uniform grid (lg_tile_map_enable)
+  bool blend_generic = false; // lg_blend_set: a non-default (order-independent) blend state
+  bool blend_linear = true;   // the image is a sum of fragment terms (Add / ReverseSubtract): partial images can be summed
+  BlendCfg blend{};
   int trace_merged = -1; // -1 = by scene size
   bool grid_on = false;
   double grid_density = 1.0; // cells per object (LG_GRID_DENSITY)
@@ -463,6 +466,7 @@ AccumArgs accum_args(lg_ctx *c) {
   A.hw = (float)c->W * 0.5f;
   A.hh = (float)c->H * 0.5f;
   A.pixel_updates = (unsigned long long *)c->pixctr.p;
+  A.blend = c->blend;
   return A;
 }
 int accum_grid(lg_ctx *c) { return c->sm_count * 8; }
@@ -501,6 +505,7 @@ unsigned long long traced_signature(lg_ctx *c) {
 // kernel, short or scattered ones the tile bins.
 bool use_tiled(lg_ctx *c, unsigned long long n, unsigned long long sig) {
   if (!tiled_possible(c, n)) return false;
+  if (c->blend_generic) return false; // non-default blend states go through the direct kernels (lg_blend_set)
   if (c->accum_mode == 1) return false;
   if (c->accum_mode == 2) return true;
   if (n < kTiledMinSegments) return false;
@@ -596,7 +601,10 @@ int accumulate_device_segments(lg_ctx *c, unsigned long long n, float *ms, unsig
   if (tiled) {
     if ((rc = accumulate_tiled<LgSegment>(c, (const LgSegment *)c->seg.p, n, launches))) return rc;
   } else {
-    accumulate_segments_kernel<<<accum_grid(c), kAccumBlock, 0, c->stream>>>(accum_args(c), (const LgSegment *)c->seg.p, n);
+    if (c->blend_generic)
+      accumulate_segments_kernel<true><<<accum_grid(c), kAccumBlock, 0, c->stream>>>(accum_args(c), (const LgSegment *)c->seg.p, n);
+    else
+      accumulate_segments_kernel<false><<<accum_grid(c), kAccumBlock, 0, c->stream>>>(accum_args(c), (const LgSegment *)c->seg.p, n);
     LG_CUDA(c, cudaGetLastError());
     c->launches++;
     if (launches) (*launches)++;
@@ -784,7 +792,42 @@ int32_t lg_segment_capacity_set(lg_ctx *c, uint64_t n) {
 int32_t lg_accumulate_mode_set(lg_ctx *c, int32_t mode) {
   if (!c) return LG_ERR_INVALID;
   if (mode < 0 || mode > 2) return fail(c, LG_ERR_INVALID, "accumulate mode");
+  if (mode == 2 && c->blend_generic) return fail(c, LG_ERR_UNSUPPORTED, "the tile-binned resolve implements the default blend state only");
   c->accum_mode = mode;
+  return LG_OK;
+}
+
+int32_t lg_blend_set(lg_ctx *c, const LgBlendState *st) {
+  if (!c) return LG_ERR_INVALID;
+  LgBlendState def{};
+  def.color = {LG_BF_ONE, LG_BF_ONE, LG_BO_ADD};       // mod.rs:65-69
+  def.alpha = {LG_BF_SRC_ALPHA, LG_BF_ONE, LG_BO_ADD}; // mod.rs:60-64
+  const LgBlendState s = st ? *st : def;
+  auto source_only = [](int f) {
+    return f == LG_BF_ZERO || f == LG_BF_ONE || f == LG_BF_SRC || f == LG_BF_ONE_MINUS_SRC || f == LG_BF_SRC_ALPHA ||
+           f == LG_BF_ONE_MINUS_SRC_ALPHA || f == LG_BF_CONSTANT || f == LG_BF_ONE_MINUS_CONSTANT;
+  };
+  bool linear = true;
+  for (const LgBlendComponent *k : {&s.color, &s.alpha}) {
+    if (k->operation < LG_BO_ADD || k->operation > LG_BO_MAX || k->src_factor < LG_BF_ZERO ||
+        k->src_factor > LG_BF_ONE_MINUS_CONSTANT || k->dst_factor < LG_BF_ZERO || k->dst_factor > LG_BF_ONE_MINUS_CONSTANT)
+      return fail(c, LG_ERR_INVALID, "blend state: unknown factor or operation");
+    if (k->operation == LG_BO_MIN || k->operation == LG_BO_MAX) {
+      linear = false; // wgpu ignores the factors of Min / Max
+    } else if (k->operation == LG_BO_SUBTRACT) {
+      return fail(c, LG_ERR_UNSUPPORTED, "blend Subtract (src - dst) depends on the fragment order");
+    } else if (k->dst_factor != LG_BF_ONE || !source_only(k->src_factor)) {
+      return fail(c, LG_ERR_UNSUPPORTED,
+                  "blend Add / ReverseSubtract is order-independent only with dst_factor One and a source-only src_factor");
+    }
+  }
+  if (c->accum_mode == 2 && std::memcmp(&s, &def, sizeof s) != 0)
+    return fail(c, LG_ERR_UNSUPPORTED, "non-default blend states use the direct resolve (lg_accumulate_mode_set 0 or 1)");
+  c->blend_generic = std::memcmp(&s, &def, sizeof s) != 0;
+  c->blend_linear = linear;
+  c->blend.color_factor = s.color.src_factor, c->blend.alpha_factor = s.alpha.src_factor;
+  c->blend.color_op = s.color.operation, c->blend.alpha_op = s.alpha.operation;
+  std::memcpy(c->blend.constant, s.constant, 16);
   return LG_OK;
 }
 
@@ -955,7 +998,10 @@ int accumulate_device_pairs(lg_ctx *c, const LgVertexPair *d_pairs, uint64_t n, 
     c->launches++, nl++;
     if ((rc = accumulate_tiled<Seg2>(c, (const Seg2 *)c->seg2.p, n, &nl))) return rc;
   } else {
-    accumulate_pairs_kernel<<<accum_grid(c), kAccumBlock, 0, c->stream>>>(accum_args(c), d_pairs, n);
+    if (c->blend_generic)
+      accumulate_pairs_kernel<true><<<accum_grid(c), kAccumBlock, 0, c->stream>>>(accum_args(c), d_pairs, n);
+    else
+      accumulate_pairs_kernel<false><<<accum_grid(c), kAccumBlock, 0, c->stream>>>(accum_args(c), d_pairs, n);
     LG_CUDA(c, cudaGetLastError());
     c->launches++, nl++;
   }
@@ -1107,7 +1153,10 @@ int32_t lg_string_mod(lg_ctx *c, const LgStringMod *sm, const LgModRemColor *rul
     c->launches++, nl++;
     if ((rc = accumulate_tiled<Seg2>(c, (const Seg2 *)c->seg2.p, count, &nl))) return rc;
   } else if (count) {
-    string_mod_kernel<<<accum_grid(c), kAccumBlock, 0, c->stream>>>(accum_args(c), S);
+    if (c->blend_generic)
+      string_mod_kernel<true><<<accum_grid(c), kAccumBlock, 0, c->stream>>>(accum_args(c), S);
+    else
+      string_mod_kernel<false><<<accum_grid(c), kAccumBlock, 0, c->stream>>>(accum_args(c), S);
     LG_CUDA(c, cudaGetLastError());
     c->launches++, nl++;
   }
@@ -1370,6 +1419,7 @@ int32_t lg_image_reduce(lg_ctx *c, int32_t root, float *reduce_ms) {
   if (reduce_ms) *reduce_ms = 0.f;
   if (c->comm_world <= 1 || !c->comm) return LG_OK; // one partial image: nothing to sum
   if (root < 0 || root >= c->comm_world) return fail(c, LG_ERR_INVALID, "root");
+  if (!c->blend_linear) return fail(c, LG_ERR_UNSUPPORTED, "Min / Max blend states: partial images cannot be summed");
   LG_CUDA(c, cudaSetDevice(c->device));
   LG_CUDA(c, cudaEventRecord(c->ev0, c->stream));
   bool fused = c->reduce_mode != 1 && c->comm_world <= kMaxPeers;

@@ -293,6 +293,20 @@ class Renderer:
         self.last_stats = st
         return st
 
+    def set_blend(self, color=None, alpha=None, constant=(0.0, 0.0, 0.0, 0.0)):
+        """LightGarden.color_state_descriptor.blend (mod.rs:57-73, gui/settings.rs:59-127): each component is
+        (src_factor, dst_factor, operation) in abi.LG_BF_* / abi.LG_BO_*; None restores the default state."""
+        if color is None and alpha is None:
+            self.ctx.call("lg_blend_set", None)
+            return
+        st = abi.LgBlendState()
+        c = color if color is not None else (abi.LG_BF_ONE, abi.LG_BF_ONE, abi.LG_BO_ADD)
+        a = alpha if alpha is not None else (abi.LG_BF_SRC_ALPHA, abi.LG_BF_ONE, abi.LG_BO_ADD)
+        st.color.src_factor, st.color.dst_factor, st.color.operation = c
+        st.alpha.src_factor, st.alpha.dst_factor, st.alpha.operation = a
+        st.constant[:] = [float(v) for v in constant]
+        self.ctx.call("lg_blend_set", C.byref(st))
+
     def read_rgba32f(self):
         out = np.zeros((self.height, self.width, 4), dtype=np.float32)
         self.ctx.call("lg_image_read", abi.LG_RGBA32F, abi.array_ptr(out), 0)

@@ -63,6 +63,8 @@ def lib():
         L.lgo_result_copy.argtypes = [vp, vp, vp, vp]
         L.lgo_result_free.argtypes = [vp]
         L.lgo_string_mod.argtypes = [C.POINTER(abi.LgStringMod), vp, C.c_uint32, C.c_uint64, C.c_uint64, vp]
+        L.lgo_accumulate_pairs_blend.argtypes = [vp, C.c_int32, C.c_int32, vp, C.c_uint64, C.POINTER(abi.LgBlendState)]
+        L.lgo_accumulate_pairs_blend.restype = C.c_uint64
         L.lgo_line_crossings.argtypes = [vp, C.c_uint64, vp, C.c_uint64]
         L.lgo_line_crossings.restype = C.c_uint64
         L.lgo_nested_chords.argtypes = [C.POINTER(abi.LgStringMod), vp, C.c_uint32, vp, C.c_uint64, vp]
@@ -183,6 +185,17 @@ def string_mod(sm, first=0, count=None):
     out = np.zeros(count, dtype=abi.VERTEX_PAIR_DTYPE)
     lib().lgo_string_mod(C.byref(pod), C.cast(rules, C.c_void_p), n, first, count, abi.array_ptr(out))
     return out
+
+
+def accumulate_pairs_blend(img, pairs, color, alpha, constant=(0.0, 0.0, 0.0, 0.0)):
+    """The line pass under a blend state: color / alpha = (src_factor, dst_factor, operation) in abi.LG_BF_* / LG_BO_*."""
+    pairs = np.ascontiguousarray(pairs, dtype=abi.VERTEX_PAIR_DTYPE)
+    st = abi.LgBlendState()
+    st.color.src_factor, st.color.dst_factor, st.color.operation = color
+    st.alpha.src_factor, st.alpha.dst_factor, st.alpha.operation = alpha
+    st.constant[:] = [float(v) for v in constant]
+    h, w = img.shape[:2]
+    return lib().lgo_accumulate_pairs_blend(abi.array_ptr(img), w, h, abi.array_ptr(pairs), len(pairs), C.byref(st))
 
 
 def line_crossings(lines):

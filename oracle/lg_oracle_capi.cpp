@@ -311,6 +311,43 @@ uint64_t lgo_accumulate_segments_f64(double *img, int32_t W, int32_t H, const Lg
   return total;
 }
 
+// §8.6 the line pass under a user-selected blend state (gui/settings.rs:59-127), fragment by fragment in list order
+static float blend_src_factor(int f, float c, float alpha, float constant) {
+  switch (f) {
+  case LG_BF_ZERO: return 0.f;
+  case LG_BF_ONE: return 1.f;
+  case LG_BF_SRC: return c;
+  case LG_BF_ONE_MINUS_SRC: return 1.f - c;
+  case LG_BF_SRC_ALPHA: return alpha;
+  case LG_BF_ONE_MINUS_SRC_ALPHA: return 1.f - alpha;
+  case LG_BF_CONSTANT: return constant;
+  default: return 1.f - constant;
+  }
+}
+static void blend_one(float &dst, const LgBlendComponent &k, float src, float alpha, float constant) {
+  switch (k.operation) {
+  case LG_BO_MIN: dst = src < dst ? src : dst; break; // wgpu: factors ignored
+  case LG_BO_MAX: dst = src > dst ? src : dst; break;
+  case LG_BO_ADD: dst = dst + src * blend_src_factor(k.src_factor, src, alpha, constant); break;
+  default: dst = dst - src * blend_src_factor(k.src_factor, src, alpha, constant); break; // ReverseSubtract, dst One
+  }
+}
+uint64_t lgo_accumulate_pairs_blend(float *img, int32_t W, int32_t H, const LgVertexPair *vp, uint64_t n,
+                                    const LgBlendState *st) {
+  Proj pr = make_proj(W, H);
+  uint64_t total = 0;
+  for (uint64_t i = 0; i < n; ++i) {
+    const LgVertexPair &s = vp[i];
+    float a[2] = {(float)s.a[0], (float)s.a[1]}, b[2] = {(float)s.b[0], (float)s.b[1]};
+    total += raster_segment(pr, a, b, s.color_a, s.color_b, 0, H, [&](int px, int py, const float c[4]) {
+      float *p = img + ((size_t)py * W + px) * 4;
+      for (int k = 0; k < 3; ++k) blend_one(p[k], st->color, c[k], c[3], st->constant[k]);
+      blend_one(p[3], st->alpha, c[3], c[3], st->constant[3]);
+    });
+  }
+  return total;
+}
+
 uint64_t lgo_accumulate_pairs(float *img, int32_t W, int32_t H, const LgVertexPair *vp, uint64_t n,
                               int32_t threads) {
   return accumulate_t(img, W, H, n, threads, [&](uint64_t i, float a[2], float b[2], float ca[4], float cb[4]) {

@@ -223,6 +223,76 @@ def test_nested_string_mod(oracle, ctx, mode):
     assert np.array_equal(r.read_rgba32f(), oracle.new_image(W, H))
 
 
+BLENDS = {
+    "max": ((abi.LG_BF_ONE, abi.LG_BF_ONE, abi.LG_BO_MAX), (abi.LG_BF_ONE, abi.LG_BF_ONE, abi.LG_BO_MAX)),
+    "min_alpha": ((abi.LG_BF_ONE, abi.LG_BF_ONE, abi.LG_BO_ADD), (abi.LG_BF_ONE, abi.LG_BF_ONE, abi.LG_BO_MIN)),
+    "src_alpha": ((abi.LG_BF_SRC_ALPHA, abi.LG_BF_ONE, abi.LG_BO_ADD), (abi.LG_BF_ONE, abi.LG_BF_ONE, abi.LG_BO_ADD)),
+    "rev_sub_constant": ((abi.LG_BF_CONSTANT, abi.LG_BF_ONE, abi.LG_BO_REVERSE_SUBTRACT),
+                         (abi.LG_BF_ONE_MINUS_SRC_ALPHA, abi.LG_BF_ONE, abi.LG_BO_ADD)),
+}
+
+
+@pytest.mark.parametrize("name", list(BLENDS))
+def test_blend_states_match_oracle(oracle, ctx, name):
+    """the order-independent blend states of gui/settings.rs:59-127 (lg_blend_set).  Power-of-two
+    colours make every Add exact, Min / Max are exact anyway: the image must equal the oracle's bit for bit."""
+    from light_garden_b200.tracer import Renderer
+    color, alpha = BLENDS[name]
+    const = (0.5, 0.25, 2.0, 1.0)
+    ctx.call("lg_accumulate_mode_set", 0)
+    r = Renderer(ctx, 320, 200)
+    p = random_pairs(4000, seed=33, pow2=True)
+    try:
+        r.set_blend(color, alpha, const)
+        st = r.render_lines(p)
+        got = r.read_rgba32f()
+        exp = oracle.new_image(320, 200)
+        n = oracle.accumulate_pairs_blend(exp, p, color, alpha, const)
+        assert int(st.pixel_updates) == int(n) > 50000
+        assert np.array_equal(got, exp)
+        # string mod chords and traced segments go through the same blend
+        k = 2.0 ** -6
+        sm = StringMod(modulo=700, num=3, mode=StringModMode.Mul, color=(k, 2 * k, 4 * k, 8 * k))
+        r.clear()
+        r.render_string_mod(sm)
+        exp = oracle.new_image(320, 200)
+        oracle.accumulate_pairs_blend(exp, oracle.string_mod(sm), color, alpha, const)
+        diff = np.nonzero((r.read_rgba32f() != exp).any(axis=2))
+        assert len(diff[0]) <= 16          # chord end points: device sincos vs libm
+    finally:
+        r.set_blend()
+    # back on the default state the dedicated kernels run again
+    r.clear()
+    r.render_lines(p)
+    exp = oracle.new_image(320, 200)
+    oracle.accumulate_pairs(exp, p)
+    assert np.array_equal(r.read_rgba32f(), exp)
+
+
+def test_blend_states_that_depend_on_the_fragment_order_are_refused(ctx):
+    from light_garden_b200._lib import LightGardenError
+    from light_garden_b200.tracer import Renderer
+    r = Renderer(ctx, 64, 64)
+    ONE, ADD = abi.LG_BF_ONE, abi.LG_BO_ADD
+    for color in ((ONE, abi.LG_BF_ZERO, ADD),                         # dst factor != One: later fragments erase earlier ones
+                  (abi.LG_BF_DST, ONE, ADD),                          # source factor reads the image
+                  (ONE, ONE, abi.LG_BO_SUBTRACT),                     # src - dst
+                  (abi.LG_BF_SRC_ALPHA_SATURATED, ONE, ADD)):
+        with pytest.raises(LightGardenError) as e:
+            r.set_blend(color, None)
+        assert e.value.code == abi.LG_ERR_UNSUPPORTED
+    with pytest.raises(LightGardenError):
+        r.set_blend((99, ONE, ADD), None)
+    # the tile-binned resolve implements the default state only
+    r.set_blend((ONE, ONE, abi.LG_BO_MAX), None)
+    try:
+        with pytest.raises(LightGardenError):
+            ctx.call("lg_accumulate_mode_set", 2)
+    finally:
+        r.set_blend()
+        ctx.call("lg_accumulate_mode_set", 0)
+
+
 def test_finalize_rgba16f(oracle, ctx):
     """K5: the Rgba16Float image is the fp32 image rounded to nearest even, bit for bit."""
     from light_garden_b200.tracer import Renderer

@@ -693,3 +693,41 @@ def test_nested_string_mod_crossings(oracle):
         np.testing.assert_array_equal(ch["color_b"][i], (k, 0, 0, k) if j % 2 == 0 else (k, k, k, k))
     # no crossings -> nothing is drawn (string_mod.rs:106-108)
     assert len(oracle.string_mod_draw(StringMod(modulo=1, nested=inner))) == 0
+
+
+def test_blend_states(oracle):
+    """gui/settings.rs:59-127: the blend equation per component, op(src * src_factor, dst * dst_factor), on two
+    crossing lines whose values are known in every pixel."""
+    W = H = 16
+    c1, c2 = (0.5, 0.25, 0.125, 0.5), (0.25, 0.5, 1.0, 0.25)
+    horiz = _pair(_world(0.0, 8.5, W, H), _world(16.0, 8.5, W, H), c1)     # row 8
+    vert = _pair(_world(8.5, 0.0, W, H), _world(8.5, 16.0, W, H), c2)      # column 8
+    pairs = np.concatenate([horiz, vert])
+    ONE, ADD = abi.LG_BF_ONE, abi.LG_BO_ADD
+
+    def run(color, alpha, constant=(0, 0, 0, 0)):
+        img = oracle.new_image(W, H)
+        assert oracle.accumulate_pairs_blend(img, pairs, color, alpha, constant) == 32
+        return img
+
+    # the default state through the generic path equals the dedicated one
+    img = run((ONE, ONE, ADD), (abi.LG_BF_SRC_ALPHA, ONE, ADD))
+    ref = oracle.new_image(W, H)
+    oracle.accumulate_pairs(ref, pairs)
+    assert np.array_equal(img, ref)
+    np.testing.assert_array_equal(img[8, 8], (0.75, 0.75, 1.125, 1 + 0.25 + 0.0625))
+    # Max: the brighter of the two lines where they cross; the clear alpha 1 stays
+    img = run((ONE, ONE, abi.LG_BO_MAX), (ONE, ONE, abi.LG_BO_MAX))
+    np.testing.assert_array_equal(img[8, 8], (0.5, 0.5, 1.0, 1.0))
+    np.testing.assert_array_equal(img[8, 3], (0.5, 0.25, 0.125, 1.0))
+    # Min against the cleared image: black stays black, alpha drops to the smallest source alpha
+    img = run((ONE, ONE, abi.LG_BO_MIN), (ONE, ONE, abi.LG_BO_MIN))
+    np.testing.assert_array_equal(img[8, 8], (0, 0, 0, 0.25))
+    np.testing.assert_array_equal(img[0, 0], (0, 0, 0, 1))
+    # Add with SrcAlpha on the colour and a constant on alpha
+    img = run((abi.LG_BF_SRC_ALPHA, ONE, ADD), (abi.LG_BF_CONSTANT, ONE, ADD), constant=(0, 0, 0, 2.0))
+    np.testing.assert_array_equal(img[8, 8], (0.5 * 0.5 + 0.25 * 0.25, 0.25 * 0.5 + 0.5 * 0.25, 0.125 * 0.5 + 1.0 * 0.25,
+                                             1 + 0.5 * 2 + 0.25 * 2))
+    # ReverseSubtract: the lines darken the image; OneMinusSrc as the factor
+    img = run((abi.LG_BF_ONE_MINUS_SRC, ONE, abi.LG_BO_REVERSE_SUBTRACT), (abi.LG_BF_ZERO, ONE, ADD))
+    np.testing.assert_array_equal(img[8, 3], (-(0.5 * 0.5), -(0.25 * 0.75), -(0.125 * 0.875), 1.0))
