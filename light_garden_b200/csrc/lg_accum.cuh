@@ -39,7 +39,6 @@ struct AccumArgs {
   float m00, m11, hw, hh; // projection + viewport (ORACLE.md §8.1)
   unsigned long long *pixel_updates;
   BlendCfg blend;         // read by the <kBlend = true> kernels only
-  int axis_filter;        // 0 = every segment; 1 = x-major segments only; 2 = y-major only (hybrid resolve)
 };
 
 __device__ __forceinline__ void red_add_v4(float *p, float a, float b, float c, float d) {
@@ -103,7 +102,6 @@ __device__ __forceinline__ RasterSetup raster_setup(const AccumArgs &A, float ax
   const float dx = x1 - x0, dy = y1 - y0;
   if (!(fabsf(dx) < 1e30f) || !(fabsf(dy) < 1e30f)) return S;
   const bool xmajor = fabsf(dx) >= fabsf(dy);
-  if (A.axis_filter != 0 && A.axis_filter != (xmajor ? 1 : 2)) return S; // the other resolve draws this one
   const float m0 = xmajor ? x0 : y0, m1 = xmajor ? x1 : y1;
   const float n0 = xmajor ? y0 : x0, n1 = xmajor ? y1 : x1;
   const float dm = m1 - m0;

@@ -117,10 +117,6 @@ struct lg_ctx {
   int device = 0;
   int precision = LG_PRECISION_F32;
   cudaStream_t stream = nullptr;
-  cudaStream_t stream2 = nullptr;            // the direct half of the hybrid resolve
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-  int hybrid_ctas = 4;        // CTAs per SM of the direct half (LG_HYBRID_CTAS): leaves room for the tile raster
-  int hybrid_direct_axis = 1; // which major axis the direct half draws (LG_HYBRID_AXIS)
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   std::string err;
   int sm_count = 0;
@@ -471,7 +467,6 @@ AccumArgs accum_args(lg_ctx *c) {
   A.hh = (float)c->H * 0.5f;
   A.pixel_updates = (unsigned long long *)c->pixctr.p;
   A.blend = c->blend;
-  A.axis_filter = 0;
   return A;
 }
 int accum_grid(lg_ctx *c) { return c->sm_count * 8; }
@@ -512,7 +507,7 @@ bool use_tiled(lg_ctx *c, unsigned long long n, unsigned long long sig) {
   if (!tiled_possible(c, n)) return false;
   if (c->blend_generic) return false; // non-default blend states go through the direct kernels (lg_blend_set)
   if (c->accum_mode == 1) return false;
-  if (c->accum_mode >= 2) return true; // 3 = hybrid for traced segments, tile bins for everything else
+  if (c->accum_mode == 2) return true;
   if (n < kTiledMinSegments) return false;
   if (c->auto_stats.size() > 256) c->auto_stats.clear();
   lg_ctx::AutoStat &a = c->auto_stats[sig];
@@ -536,11 +531,9 @@ void note_accum_cost(lg_ctx *c, bool tiled, float ms, unsigned long long frags, 
 }
 
 // count -> scan -> fill -> raster over device segments of type Seg (LgSegment or Seg2)
-template <class Seg>
-int accumulate_tiled(lg_ctx *c, const Seg *d_seg, unsigned long long n, unsigned *launches, int axis_filter = 0) {
+template <class Seg> int accumulate_tiled(lg_ctx *c, const Seg *d_seg, unsigned long long n, unsigned *launches) {
   TileArgs T;
   T.A = accum_args(c);
-  T.A.axis_filter = axis_filter;
   T.tiles_x = (c->W + kTile - 1) / kTile, T.tiles_y = (c->H + kTile - 1) / kTile;
   T.n_tiles = T.tiles_x * T.tiles_y;
   int rc;
@@ -605,22 +598,7 @@ int accumulate_device_segments(lg_ctx *c, unsigned long long n, float *ms, unsig
   int rc;
   if (c->accum_mode == 0 && n >= kTiledMinSegments && (rc = read_pixel_counter(c, &before))) return rc;
   LG_CUDA(c, cudaEventRecord(c->ev0, c->stream));
-  if (c->accum_mode == 3 && !c->blend_generic && tiled_possible(c, n)) {
-    // hybrid resolve: the x-major segments (consecutive pixels of a row: two fragments per 32-byte sector, the
-    // case the L2 reduction units like best) go through the direct kernel on a second stream while the y-major
-    // ones go through the tile bins -- one is bound by L2 reductions, the other by shared memory, so they overlap
-    LG_CUDA(c, cudaEventRecord(c->ev_fork, c->stream));
-    LG_CUDA(c, cudaStreamWaitEvent(c->stream2, c->ev_fork, 0));
-    AccumArgs D = accum_args(c);
-    D.axis_filter = c->hybrid_direct_axis;
-    accumulate_segments_kernel<false><<<c->sm_count * c->hybrid_ctas, kAccumBlock, 0, c->stream2>>>(D, (const LgSegment *)c->seg.p, n);
-    LG_CUDA(c, cudaGetLastError());
-    LG_CUDA(c, cudaEventRecord(c->ev_join, c->stream2));
-    c->launches++;
-    if (launches) (*launches)++;
-    if ((rc = accumulate_tiled<LgSegment>(c, (const LgSegment *)c->seg.p, n, launches, 3 - c->hybrid_direct_axis))) return rc;
-    LG_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_join, 0));
-  } else if (tiled) {
+  if (tiled) {
     if ((rc = accumulate_tiled<LgSegment>(c, (const LgSegment *)c->seg.p, n, launches))) return rc;
   } else {
     if (c->blend_generic)
@@ -698,9 +676,6 @@ int32_t lg_create(int32_t device, int32_t precision, lg_ctx **out) {
   cudaDeviceProp prop;
   if (cudaSetDevice(device) != cudaSuccess || cudaGetDeviceProperties(&prop, device) != cudaSuccess ||
       cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
-      cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking) != cudaSuccess ||
-      cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
-      cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreate(&c->ev0) != cudaSuccess || cudaEventCreate(&c->ev1) != cudaSuccess) {
     cudaGetLastError();
     delete c;
@@ -711,15 +686,7 @@ int32_t lg_create(int32_t device, int32_t precision, lg_ctx **out) {
   c->slots = precision == LG_PRECISION_F64 ? 1 : 2;
   if (const char *e = getenv("LG_ACCUM_MODE")) {
     int v = atoi(e);
-    if (v >= 0 && v <= 3) c->accum_mode = v;
-  }
-  if (const char *e = getenv("LG_HYBRID_CTAS")) {
-    int v = atoi(e);
-    if (v >= 1 && v <= 8) c->hybrid_ctas = v;
-  }
-  if (const char *e = getenv("LG_HYBRID_AXIS")) {
-    int v = atoi(e);
-    if (v == 1 || v == 2) c->hybrid_direct_axis = v;
+    if (v >= 0 && v <= 2) c->accum_mode = v;
   }
   if (const char *e = getenv("LG_TRACE_MERGED")) c->trace_merged = atoi(e) ? 1 : 0;
   if (const char *e = getenv("LG_GRID_DENSITY")) {
@@ -753,9 +720,6 @@ int32_t lg_destroy(lg_ctx *c) {
   for (DevBuf *b : bufs) release(*b);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
-  if (c->ev_fork) cudaEventDestroy(c->ev_fork);
-  if (c->ev_join) cudaEventDestroy(c->ev_join);
-  if (c->stream2) cudaStreamDestroy(c->stream2);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
   return LG_OK;
@@ -827,8 +791,8 @@ int32_t lg_segment_capacity_set(lg_ctx *c, uint64_t n) {
 
 int32_t lg_accumulate_mode_set(lg_ctx *c, int32_t mode) {
   if (!c) return LG_ERR_INVALID;
-  if (mode < 0 || mode > 3) return fail(c, LG_ERR_INVALID, "accumulate mode");
-  if (mode >= 2 && c->blend_generic) return fail(c, LG_ERR_UNSUPPORTED, "the tile-binned resolve implements the default blend state only");
+  if (mode < 0 || mode > 2) return fail(c, LG_ERR_INVALID, "accumulate mode");
+  if (mode == 2 && c->blend_generic) return fail(c, LG_ERR_UNSUPPORTED, "the tile-binned resolve implements the default blend state only");
   c->accum_mode = mode;
   return LG_OK;
 }
@@ -857,7 +821,7 @@ int32_t lg_blend_set(lg_ctx *c, const LgBlendState *st) {
                   "blend Add / ReverseSubtract is order-independent only with dst_factor One and a source-only src_factor");
     }
   }
-  if (c->accum_mode >= 2 && std::memcmp(&s, &def, sizeof s) != 0)
+  if (c->accum_mode == 2 && std::memcmp(&s, &def, sizeof s) != 0)
     return fail(c, LG_ERR_UNSUPPORTED, "non-default blend states use the direct resolve (lg_accumulate_mode_set 0 or 1)");
   c->blend_generic = std::memcmp(&s, &def, sizeof s) != 0;
   c->blend_linear = linear;

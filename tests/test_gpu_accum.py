@@ -25,8 +25,7 @@ def ctx():
 
 
 DIRECT, TILED = 1, 2   # lg_accumulate_mode_set: one L2 reduction per fragment / shared-memory tile bins
-HYBRID = 3   # traced segments: x-major ones direct, y-major ones through the tile bins, concurrently
-MODES = [pytest.param(DIRECT, id="direct"), pytest.param(TILED, id="tiled"), pytest.param(HYBRID, id="hybrid")]
+MODES = [pytest.param(DIRECT, id="direct"), pytest.param(TILED, id="tiled")]
 
 
 @pytest.fixture(autouse=True)
