@@ -475,8 +475,8 @@ constexpr unsigned long long kTiledMinSegments = 1ull << 17; // below this the d
 
 bool tiled_possible(lg_ctx *c, unsigned long long n) {
   if (n == 0 || n >= (1ull << 32)) return false; // the tile lists hold 32-bit segment indices
-  const size_t n_tiles = (size_t)((c->W + kTile - 1) / kTile) * ((c->H + kTile - 1) / kTile);
-  return n_tiles * 4 + 1024 <= c->smem_optin; // the per-CTA histogram must fit in shared memory
+  const size_t n_lists = 2 * (size_t)((c->W + kTile - 1) / kTile) * ((c->H + kTile - 1) / kTile);
+  return n_lists * 4 + 1024 <= c->smem_optin; // the per-CTA histogram must fit in shared memory
 }
 
 // 64-bit content hash (workload signatures of the auto mode; never used to skip work)
@@ -535,7 +535,7 @@ template <class Seg> int accumulate_tiled(lg_ctx *c, const Seg *d_seg, unsigned 
   TileArgs T;
   T.A = accum_args(c);
   T.tiles_x = (c->W + kTile - 1) / kTile, T.tiles_y = (c->H + kTile - 1) / kTile;
-  T.n_tiles = T.tiles_x * T.tiles_y;
+  T.n_tiles = 2 * T.tiles_x * T.tiles_y; // two lists per tile: x-major and y-major segments
   int rc;
   if ((rc = ensure(c, c->tile_count, (size_t)T.n_tiles * 4))) return rc;
   if ((rc = ensure(c, c->tile_cursor, (size_t)T.n_tiles * 4))) return rc;

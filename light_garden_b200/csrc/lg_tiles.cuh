@@ -7,15 +7,19 @@
 //
 //   1. tile_count : lane = segment; walk the 32x32-pixel tiles the segment's fragments fall into and count them in
 //                   a per-CTA SHARED-MEMORY histogram (hot tiles next to a light take millions of hits: global
-//                   atomics on one address would serialise), written out as hist[cta][tile]
+//                   atomics on one address would serialise), written out as hist[cta][list].  Every tile has TWO
+//                   lists, one for x-major and one for y-major segments (list = 2 tile + axis)
 //   2. tile_rowscan + tile_scan: exclusive scans -> every CTA's write position in every tile's list; work items =
 //                   (tile, chunk of <= kChunk list entries)
 //   3. tile_fill  : same walk by the same CTA over the same segments, positions from a shared-memory cursor
-//   4. tile_raster: persistent warps; a warp owns a PRIVATE 32x32 RGBA fp32 tile in shared memory (33-pixel pitch:
-//                   conflict-free for x-major and y-major lines), adds every fragment of its work item with plain
-//                   LDS.128 / FADD / STS.128 — lanes are distinct major-axis steps of one segment, so there are no
-//                   collisions and no shared-memory atomics (those are CAS spin loops for float) — and finally
-//                   flushes the touched pixels with one red.global.add.v4.f32 each.
+//   4. tile_raster: persistent warps; a warp owns a PRIVATE 32x32 RGBA fp32 tile in shared memory, stored
+//                   major-axis-fastest for the list it is working on (row-major for an x-major list, transposed for a
+//                   y-major one): lane = major-axis step, so the 8 lanes of a quarter warp always hit 8 different
+//                   16-byte bank groups whatever the slope — conflict-free LDS.128 / FADD / STS.128 (a 33-pixel pitch
+//                   serving both axes at once cost 2.06 wavefronts per ideal one, ncu r01d).  Lanes are distinct
+//                   major-axis steps of one segment, so there are no collisions and no shared-memory atomics (those
+//                   are CAS spin loops for float).  Finally the touched pixels are flushed with one
+//                   red.global.add.v4.f32 each.
 //
 // Fragment coordinates use exactly the arithmetic of raster_walk(); a fragment lands in the tile that contains its
 // pixel, every (segment, tile) pair that can own a fragment is listed (the walk brackets the minor coordinate of a
@@ -27,7 +31,7 @@ namespace lg {
 
 constexpr int kTile = 32;          // tile edge in pixels
 constexpr int kTileShift = 5;
-constexpr int kTilePitch = 33;     // float4 per tile row in shared memory
+constexpr int kTilePitch = 32;     // float4 per major-axis line of the tile in shared memory
 constexpr int kChunk = 2048;       // list entries per work item
 constexpr int kRasterWarps = 4;    // warps per CTA of tile_raster_kernel
 constexpr int kTileFloat4 = kTile * kTilePitch;
@@ -40,7 +44,8 @@ struct Seg2 {
 
 struct TileArgs {
   AccumArgs A;
-  int tiles_x, tiles_y, n_tiles;
+  int tiles_x, tiles_y;
+  int n_tiles; // number of LISTS = 2 x tiles (x-major and y-major segments of a tile are binned apart)
   unsigned int *tile_count;   // [n_tiles]
   unsigned int *tile_cursor;  // [n_tiles]
   unsigned long long *tile_offset; // [n_tiles + 1]
@@ -118,7 +123,8 @@ template <class Seg> __global__ void __launch_bounds__(256) tile_count_kernel(Ti
   for (unsigned long long i = lo + threadIdx.x; i < hi; i += blockDim.x) {
     const float4 ab = SegIO<Seg>::load_ab(seg, i);
     const RasterSetup S = raster_setup(T.A, ab.x, ab.y, ab.z, ab.w);
-    for_each_tile(S, T.A.W, T.A.H, T.tiles_x, [&](int tile) { atomicAdd(&s_hist[tile], 1u); });
+    const int axis = S.xmajor ? 0 : 1;
+    for_each_tile(S, T.A.W, T.A.H, T.tiles_x, [&](int tile) { atomicAdd(&s_hist[2 * tile + axis], 1u); });
   }
   __syncthreads();
   unsigned int *out = T.hist + (size_t)blockIdx.x * T.n_tiles;
@@ -149,9 +155,10 @@ template <class Seg> __global__ void __launch_bounds__(256) tile_fill_kernel(Til
   for (unsigned long long i = lo + threadIdx.x; i < hi; i += blockDim.x) {
     const float4 ab = SegIO<Seg>::load_ab(seg, i);
     const RasterSetup S = raster_setup(T.A, ab.x, ab.y, ab.z, ab.w);
+    const int axis = S.xmajor ? 0 : 1;
     for_each_tile(S, T.A.W, T.A.H, T.tiles_x, [&](int tile) {
-      const unsigned int pos = atomicAdd(&s_cur[tile], 1u);
-      T.list[T.tile_offset[tile] + pos] = (unsigned int)i;
+      const unsigned int pos = atomicAdd(&s_cur[2 * tile + axis], 1u);
+      T.list[T.tile_offset[2 * tile + axis] + pos] = (unsigned int)i;
     });
   }
 }
@@ -205,9 +212,9 @@ struct RasterScratch {
   unsigned int rng[32];  // lanes of this tile the segment covers along its major axis: first | count << 8
 };
 
-// Blends parked entries [k0, k1), all of the same major axis, into the warp's private tile.  lane = major-axis step;
-// kMul = tile pitch along the minor axis (kTilePitch for x-major, 1 for y-major), `add` the lane's share of the
-// address, [nlo, nhi) the minor pixel range of the tile on the canvas, mc the lane's major pixel centre.
+// Blends parked entries [k0, k1) into the warp's private tile.  lane = major-axis step; the tile is stored
+// major-axis-fastest, so a fragment at minor offset j sits at j * kMul + lane (kMul = kTilePitch); `add` is the lane's
+// share of that address, [nlo, nhi) the minor pixel range of the tile on the canvas, mc the lane's major pixel centre.
 // The arithmetic per fragment is raster_walk's (ORACLE.md 8.2-8.4).  Two entries are in flight: both pixels are
 // read before either is written; a lane that hits the same pixel in both carries the first sum into the second.
 template <bool kLerp, int kMul>
@@ -273,7 +280,6 @@ template <class Seg> __global__ void __launch_bounds__(kRasterWarps * 32) tile_r
   extern __shared__ __align__(16) unsigned char tile_smem_raw[];
   const int warp_in_block = threadIdx.x >> 5;
   const unsigned lane = threadIdx.x & 31u;
-  const unsigned lt_mask = (1u << lane) - 1u;
   float4 *tile = reinterpret_cast<float4 *>(tile_smem_raw) + (size_t)warp_in_block * kTileFloat4;
   RasterScratch &P = reinterpret_cast<RasterScratch *>(reinterpret_cast<float4 *>(tile_smem_raw) +
                                                        (size_t)kRasterWarps * kTileFloat4)[warp_in_block];
@@ -285,55 +291,52 @@ template <class Seg> __global__ void __launch_bounds__(kRasterWarps * 32) tile_r
     if (lane == 0) item = atomicAdd(T.item_counter, 1u);
     item = __shfl_sync(0xffffffffu, item, 0);
     if (item >= n_items) break;
-    // item -> (tile, chunk): last tile whose item prefix is <= item
+    // item -> (list, chunk): last list whose item prefix is <= item
     int lo = 0, hi = T.n_tiles;
     while (hi - lo > 1) {
       const int mid = (lo + hi) >> 1;
       if (T.item_prefix[mid] <= item) lo = mid; else hi = mid;
     }
-    const int t = lo;
-    const unsigned int chunk = item - T.item_prefix[t];
-    const unsigned int count = T.tile_count[t];
+    const int list = lo, t = list >> 1;
+    const bool xmajor = (list & 1) == 0;
+    const unsigned int chunk = item - T.item_prefix[list];
+    const unsigned int count = T.tile_count[list];
     const unsigned int first = chunk * kChunk, last = min(count, first + kChunk);
-    const unsigned int *lst = T.list + T.tile_offset[t];
+    const unsigned int *lst = T.list + T.tile_offset[list];
     const int tx = t % T.tiles_x, ty = t / T.tiles_x;
     const int bx = tx << kTileShift, by = ty << kTileShift;
-    // loop constants of the two blend loops (x-major entries: lane = column, y-major: lane = row)
-    const float mcx = (float)(bx + (int)lane) + 0.5f, mcy = (float)(by + (int)lane) + 0.5f;
-    const float xlo = (float)bx, xhi = (float)min(T.A.W, bx + kTile), ylo = (float)by, yhi = (float)min(T.A.H, by + kTile);
-    const int addx = (int)lane - by * kTilePitch, addy = (int)lane * kTilePitch - bx;
+    // loop constants of the blend loop: lane = column for an x-major list (tile stored row-major), lane = row for a
+    // y-major one (tile stored transposed)
+    const int bmaj = xmajor ? bx : by, bmin = xmajor ? by : bx;
+    const float mc = (float)(bmaj + (int)lane) + 0.5f;
+    const float nlo = (float)bmin, nhi = (float)min(xmajor ? T.A.H : T.A.W, bmin + kTile);
+    const int add = (int)lane - bmin * kTilePitch;
     for (int k = lane; k < kTileFloat4; k += 32) tile[k] = make_float4(0.f, 0.f, 0.f, 0.f);
     __syncwarp();
     // the gather of the NEXT 32 list entries (index, then segment) is in flight while the current 32 are blended
     float4 g_ab = make_float4(0.f, 0.f, 0.f, 0.f), g_ca = g_ab, g_dc = g_ab;
     if (first + lane < last) SegIO<Seg>::load(seg, lst[first + lane], g_ab, g_ca, g_dc);
     for (unsigned int base = first; base < last; base += 32) {
-      // lane = one list entry: its raster setup, reduced to this tile, parked x-major entries first
-      const bool valid = base + lane < last;
-      const RasterSetup S = raster_setup(T.A, g_ab.x, g_ab.y, g_ab.z, g_ab.w);
-      const bool xm = S.xmajor != 0;
-      const unsigned vx = __ballot_sync(0xffffffffu, valid && xm), vy = __ballot_sync(0xffffffffu, valid && !xm);
-      const int nx = __popc(vx), m = nx + __popc(vy);
-      if (valid) {
-        const int pos = xm ? __popc(vx & lt_mask) : nx + __popc(vy & lt_mask);
-        const int tb = xm ? bx : by;
-        const int l0 = max(S.i0 - tb, 0), l1 = min(S.i1 - tb, kTile);
-        P.geo[pos] = make_float4(S.m0, S.inv, S.dn, S.n0);
-        P.col[pos] = make_float4(g_ca.x, g_ca.y, g_ca.z, kLerp ? g_ca.w : g_ca.w * g_ca.w);
-        if (kLerp) P.dc[pos] = g_dc;
-        P.rng[pos] = (unsigned)l0 | ((unsigned)max(l1 - l0, 0) << 8);
+      // lane = one list entry: its raster setup, reduced to this tile, parked for the blend loop
+      if (base + lane < last) {
+        const RasterSetup S = raster_setup(T.A, g_ab.x, g_ab.y, g_ab.z, g_ab.w);
+        const int l0 = max(S.i0 - bmaj, 0), l1 = min(S.i1 - bmaj, kTile);
+        P.geo[lane] = make_float4(S.m0, S.inv, S.dn, S.n0);
+        P.col[lane] = make_float4(g_ca.x, g_ca.y, g_ca.z, kLerp ? g_ca.w : g_ca.w * g_ca.w);
+        if (kLerp) P.dc[lane] = g_dc;
+        P.rng[lane] = (unsigned)l0 | ((unsigned)max(l1 - l0, 0) << 8);
       }
       if (base + 32 + lane < last) SegIO<Seg>::load(seg, lst[base + 32 + lane], g_ab, g_ca, g_dc);
       __syncwarp();
-      cnt += blend_run<kLerp, kTilePitch>(tile, P, 0, nx, mcx, ylo, yhi, addx, lane);
-      cnt += blend_run<kLerp, 1>(tile, P, nx, m, mcy, xlo, xhi, addy, lane);
+      cnt += blend_run<kLerp, kTilePitch>(tile, P, 0, (int)min(32u, last - base), mc, nlo, nhi, add, lane);
       __syncwarp();
     }
-    // flush: one vector reduction per touched pixel (lanes sweep a row: coalesced 512 B)
+    // flush: one vector reduction per touched pixel, lanes sweep an image row (coalesced 512 B).  A transposed
+    // tile is read down its columns here: bank conflicts, but 1024 pixels against thousands of entries per item
     const int gx = bx + (int)lane;
     for (int row = 0; row < kTile; ++row) {
       const int gy = by + row;
-      const float4 v = tile[row * kTilePitch + lane];
+      const float4 v = xmajor ? tile[row * kTilePitch + lane] : tile[lane * kTilePitch + row];
       if (gx < T.A.W && gy < T.A.H && (v.x != 0.f || v.y != 0.f || v.z != 0.f || v.w != 0.f))
         red_add_v4(T.A.img + ((size_t)gy * T.A.W + gx) * 4, v.x, v.y, v.z, v.w);
     }
