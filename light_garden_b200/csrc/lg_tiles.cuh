@@ -218,22 +218,27 @@ struct RasterScratch {
 // The arithmetic per fragment is raster_walk's (ORACLE.md 8.2-8.4).  Two entries are in flight: both pixels are
 // read before either is written; a lane that hits the same pixel in both carries the first sum into the second.
 template <bool kLerp, int kMul>
-__device__ __forceinline__ unsigned blend_run(float4 *tile, const RasterScratch &P, int k0, int k1, float mc, float nlo,
-                                              float nhi, int add, unsigned lane) {
+__device__ __forceinline__ unsigned blend_run(float4 *tile, const RasterScratch &P, int m, float mc, float nlo, float nhi,
+                                              int add, unsigned lane) {
+  // entries [0, m) two at a time; when m is odd the caller has parked an empty entry (lane range 0) at index m.
+  // The records of the NEXT two entries are fetched before the current two touch the tile: the compiler cannot
+  // move those loads across the tile's stores by itself (same shared-memory array).
   unsigned n = 0;
-  int k = k0;
-  for (; k + 1 < k1; k += 2) {
-    const float4 ga = P.geo[k], gb = P.geo[k + 1];
-    const unsigned ra = P.rng[k], rb = P.rng[k + 1];
-    const float4 ca = P.col[k], cb = P.col[k + 1];
+  float4 ga = P.geo[0], gb = P.geo[1], ca = P.col[0], cb = P.col[1];
+  float4 da = kLerp ? P.dc[0] : make_float4(0.f, 0.f, 0.f, 0.f), db = kLerp ? P.dc[1] : da;
+  uint2 r = *reinterpret_cast<const uint2 *>(&P.rng[0]);
+  for (int k = 0; k < m; k += 2) {
+    const int kn = k + 2 < m ? k + 2 : k;
+    const float4 nga = P.geo[kn], ngb = P.geo[kn + 1], nca = P.col[kn], ncb = P.col[kn + 1];
+    const float4 nda = kLerp ? P.dc[kn] : da, ndb = kLerp ? P.dc[kn + 1] : da;
+    const uint2 nr = *reinterpret_cast<const uint2 *>(&P.rng[kn]);
     const float sa = (mc - ga.x) * ga.y, sb = (mc - gb.x) * gb.y;
     const float fa = floorf(__fmaf_rn(sa, ga.z, ga.w)), fb = floorf(__fmaf_rn(sb, gb.z, gb.w));
-    const bool act_a = (lane - (ra & 255u)) < (ra >> 8) && fa >= nlo && fa < nhi;
-    const bool act_b = (lane - (rb & 255u)) < (rb >> 8) && fb >= nlo && fb < nhi;
+    const bool act_a = (lane - (r.x & 255u)) < (r.x >> 8) && fa >= nlo && fa < nhi;
+    const bool act_b = (lane - (r.y & 255u)) < (r.y >> 8) && fb >= nlo && fb < nhi;
     const int off_a = (int)fa * kMul + add, off_b = (int)fb * kMul + add;
     float a0 = ca.x, a1 = ca.y, a2 = ca.z, a3 = ca.w, b0 = cb.x, b1 = cb.y, b2 = cb.z, b3 = cb.w;
     if (kLerp) {
-      const float4 da = P.dc[k], db = P.dc[k + 1];
       a0 = __fmaf_rn(sa, da.x, ca.x), a1 = __fmaf_rn(sa, da.y, ca.y), a2 = __fmaf_rn(sa, da.z, ca.z);
       a3 = __fmaf_rn(sa, da.w, ca.w), a3 *= a3;
       b0 = __fmaf_rn(sb, db.x, cb.x), b1 = __fmaf_rn(sb, db.y, cb.y), b2 = __fmaf_rn(sb, db.z, cb.z);
@@ -252,26 +257,7 @@ __device__ __forceinline__ unsigned blend_run(float4 *tile, const RasterScratch 
       tile[off_b] = vb;
     }
     n += (act_a ? 1u : 0u) + (act_b ? 1u : 0u);
-  }
-  if (k < k1) {
-    const float4 ga = P.geo[k];
-    const unsigned ra = P.rng[k];
-    const float4 ca = P.col[k];
-    const float sa = (mc - ga.x) * ga.y;
-    const float fa = floorf(__fmaf_rn(sa, ga.z, ga.w));
-    if ((lane - (ra & 255u)) < (ra >> 8) && fa >= nlo && fa < nhi) {
-      const int off_a = (int)fa * kMul + add;
-      float a0 = ca.x, a1 = ca.y, a2 = ca.z, a3 = ca.w;
-      if (kLerp) {
-        const float4 da = P.dc[k];
-        a0 = __fmaf_rn(sa, da.x, ca.x), a1 = __fmaf_rn(sa, da.y, ca.y), a2 = __fmaf_rn(sa, da.z, ca.z);
-        a3 = __fmaf_rn(sa, da.w, ca.w), a3 *= a3;
-      }
-      float4 va = tile[off_a];
-      va.x += a0, va.y += a1, va.z += a2, va.w += a3;
-      tile[off_a] = va;
-      ++n;
-    }
+    ga = nga, gb = ngb, ca = nca, cb = ncb, da = nda, db = ndb, r = nr;
   }
   return n;
 }
@@ -313,22 +299,31 @@ template <class Seg> __global__ void __launch_bounds__(kRasterWarps * 32) tile_r
     const int add = (int)lane - bmin * kTilePitch;
     for (int k = lane; k < kTileFloat4; k += 32) tile[k] = make_float4(0.f, 0.f, 0.f, 0.f);
     __syncwarp();
-    // the gather of the NEXT 32 list entries (index, then segment) is in flight while the current 32 are blended
+    // gather pipeline, two batches deep: while batch b is blended, the SEGMENTS of batch b + 1 (their list indices
+    // arrived during the previous batch) and the INDICES of batch b + 2 are in flight
     float4 g_ab = make_float4(0.f, 0.f, 0.f, 0.f), g_ca = g_ab, g_dc = g_ab;
     if (first + lane < last) SegIO<Seg>::load(seg, lst[first + lane], g_ab, g_ca, g_dc);
+    unsigned int idx_next = first + 32 + lane < last ? lst[first + 32 + lane] : 0u;
     for (unsigned int base = first; base < last; base += 32) {
       // lane = one list entry: its raster setup, reduced to this tile, parked for the blend loop
-      if (base + lane < last) {
+      const int m = (int)min(32u, last - base);
+      if ((int)lane < m) {
         const RasterSetup S = raster_setup(T.A, g_ab.x, g_ab.y, g_ab.z, g_ab.w);
         const int l0 = max(S.i0 - bmaj, 0), l1 = min(S.i1 - bmaj, kTile);
         P.geo[lane] = make_float4(S.m0, S.inv, S.dn, S.n0);
         P.col[lane] = make_float4(g_ca.x, g_ca.y, g_ca.z, kLerp ? g_ca.w : g_ca.w * g_ca.w);
         if (kLerp) P.dc[lane] = g_dc;
         P.rng[lane] = (unsigned)l0 | ((unsigned)max(l1 - l0, 0) << 8);
+      } else if ((int)lane == m) { // the empty partner of an odd last entry
+        P.geo[lane] = make_float4(0.f, 0.f, 0.f, 0.f);
+        P.col[lane] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (kLerp) P.dc[lane] = make_float4(0.f, 0.f, 0.f, 0.f);
+        P.rng[lane] = 0u;
       }
-      if (base + 32 + lane < last) SegIO<Seg>::load(seg, lst[base + 32 + lane], g_ab, g_ca, g_dc);
+      if (base + 32 + lane < last) SegIO<Seg>::load(seg, idx_next, g_ab, g_ca, g_dc);
+      idx_next = base + 64 + lane < last ? lst[base + 64 + lane] : 0u;
       __syncwarp();
-      cnt += blend_run<kLerp, kTilePitch>(tile, P, 0, (int)min(32u, last - base), mc, nlo, nhi, add, lane);
+      cnt += blend_run<kLerp, kTilePitch>(tile, P, m, mc, nlo, nhi, add, lane);
       __syncwarp();
     }
     // flush: one vector reduction per touched pixel, lanes sweep an image row (coalesced 512 B).  A transposed
