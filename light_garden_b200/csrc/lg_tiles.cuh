@@ -212,52 +212,69 @@ struct RasterScratch {
   unsigned int rng[32];  // lanes of this tile the segment covers along its major axis: first | count << 8
 };
 
-// Blends parked entries [k0, k1) into the warp's private tile.  lane = major-axis step; the tile is stored
-// major-axis-fastest, so a fragment at minor offset j sits at j * kMul + lane (kMul = kTilePitch); `add` is the lane's
-// share of that address, [nlo, nhi) the minor pixel range of the tile on the canvas, mc the lane's major pixel centre.
+// Blends parked entries into the warp's private tile.  lane = major-axis step; the tile is stored
+// major-axis-fastest, so a fragment at minor offset j sits at j * kTilePitch + lane; [nlo, nhi) is the minor pixel
+// range of the tile on the canvas, mc the lane's major pixel centre.
 // The arithmetic per fragment is raster_walk's (ORACLE.md 8.2-8.4).  Two entries are in flight: both pixels are
 // read before either is written; a lane that hits the same pixel in both carries the first sum into the second.
-template <bool kLerp, int kMul>
-__device__ __forceinline__ unsigned blend_run(float4 *tile, const RasterScratch &P, int m, float mc, float nlo, float nhi,
-                                              int add, unsigned lane) {
+// the records of two parked entries, as the blend loop holds them in registers
+struct PairRecs {
+  float4 ga, gb, ca, cb, da, db;
+  uint2 r;
+};
+template <bool kLerp> __device__ __forceinline__ void load_recs(const RasterScratch &P, int k, PairRecs &q) {
+  q.ga = P.geo[k], q.gb = P.geo[k + 1], q.ca = P.col[k], q.cb = P.col[k + 1];
+  if (kLerp) q.da = P.dc[k], q.db = P.dc[k + 1];
+  q.r = *reinterpret_cast<const uint2 *>(&P.rng[k]);
+}
+// two entries against the tile; lane_base = this lane's byte address of minor offset 0, row_bytes = bytes per minor step
+template <bool kLerp>
+__device__ __forceinline__ unsigned blend_two(unsigned char *lane_base, int row_bytes, const PairRecs &q, float mc, float nlo,
+                                              float nhi, unsigned lane) {
+  const float sa = (mc - q.ga.x) * q.ga.y, sb = (mc - q.gb.x) * q.gb.y;
+  const float fa = floorf(__fmaf_rn(sa, q.ga.z, q.ga.w)), fb = floorf(__fmaf_rn(sb, q.gb.z, q.gb.w));
+  const bool act_a = (lane - (q.r.x & 255u)) < (q.r.x >> 8) && fa >= nlo && fa < nhi;
+  const bool act_b = (lane - (q.r.y & 255u)) < (q.r.y >> 8) && fb >= nlo && fb < nhi;
+  float4 *pa = reinterpret_cast<float4 *>(lane_base + (int)fa * row_bytes);
+  float4 *pb = reinterpret_cast<float4 *>(lane_base + (int)fb * row_bytes);
+  float a0 = q.ca.x, a1 = q.ca.y, a2 = q.ca.z, a3 = q.ca.w, b0 = q.cb.x, b1 = q.cb.y, b2 = q.cb.z, b3 = q.cb.w;
+  if (kLerp) {
+    a0 = __fmaf_rn(sa, q.da.x, q.ca.x), a1 = __fmaf_rn(sa, q.da.y, q.ca.y), a2 = __fmaf_rn(sa, q.da.z, q.ca.z);
+    a3 = __fmaf_rn(sa, q.da.w, q.ca.w), a3 *= a3;
+    b0 = __fmaf_rn(sb, q.db.x, q.cb.x), b1 = __fmaf_rn(sb, q.db.y, q.cb.y), b2 = __fmaf_rn(sb, q.db.z, q.cb.z);
+    b3 = __fmaf_rn(sb, q.db.w, q.cb.w), b3 *= b3;
+  }
+  float4 va, vb;
+  if (act_a) va = *pa;
+  if (act_b) vb = *pb;
+  if (act_a) {
+    va.x += a0, va.y += a1, va.z += a2, va.w += a3; // mod.rs:57-73
+    if (act_b && pa == pb) vb = va;
+    *pa = va;
+  }
+  if (act_b) {
+    vb.x += b0, vb.y += b1, vb.z += b2, vb.w += b3;
+    *pb = vb;
+  }
+  return (act_a ? 1u : 0u) + (act_b ? 1u : 0u);
+}
+template <bool kLerp>
+__device__ __forceinline__ unsigned blend_run(unsigned char *lane_base, int row_bytes, const RasterScratch &P, int m, float mc,
+                                              float nlo, float nhi, unsigned lane) {
   // entries [0, m) two at a time; when m is odd the caller has parked an empty entry (lane range 0) at index m.
-  // The records of the NEXT two entries are fetched before the current two touch the tile: the compiler cannot
-  // move those loads across the tile's stores by itself (same shared-memory array).
+  // The records of the NEXT two entries are fetched before the current two touch the tile (the compiler cannot
+  // move those loads across the tile's stores by itself: same shared-memory array); the two register sets swap
+  // roles every half iteration, so nothing is copied.
   unsigned n = 0;
-  float4 ga = P.geo[0], gb = P.geo[1], ca = P.col[0], cb = P.col[1];
-  float4 da = kLerp ? P.dc[0] : make_float4(0.f, 0.f, 0.f, 0.f), db = kLerp ? P.dc[1] : da;
-  uint2 r = *reinterpret_cast<const uint2 *>(&P.rng[0]);
-  for (int k = 0; k < m; k += 2) {
-    const int kn = k + 2 < m ? k + 2 : k;
-    const float4 nga = P.geo[kn], ngb = P.geo[kn + 1], nca = P.col[kn], ncb = P.col[kn + 1];
-    const float4 nda = kLerp ? P.dc[kn] : da, ndb = kLerp ? P.dc[kn + 1] : da;
-    const uint2 nr = *reinterpret_cast<const uint2 *>(&P.rng[kn]);
-    const float sa = (mc - ga.x) * ga.y, sb = (mc - gb.x) * gb.y;
-    const float fa = floorf(__fmaf_rn(sa, ga.z, ga.w)), fb = floorf(__fmaf_rn(sb, gb.z, gb.w));
-    const bool act_a = (lane - (r.x & 255u)) < (r.x >> 8) && fa >= nlo && fa < nhi;
-    const bool act_b = (lane - (r.y & 255u)) < (r.y >> 8) && fb >= nlo && fb < nhi;
-    const int off_a = (int)fa * kMul + add, off_b = (int)fb * kMul + add;
-    float a0 = ca.x, a1 = ca.y, a2 = ca.z, a3 = ca.w, b0 = cb.x, b1 = cb.y, b2 = cb.z, b3 = cb.w;
-    if (kLerp) {
-      a0 = __fmaf_rn(sa, da.x, ca.x), a1 = __fmaf_rn(sa, da.y, ca.y), a2 = __fmaf_rn(sa, da.z, ca.z);
-      a3 = __fmaf_rn(sa, da.w, ca.w), a3 *= a3;
-      b0 = __fmaf_rn(sb, db.x, cb.x), b1 = __fmaf_rn(sb, db.y, cb.y), b2 = __fmaf_rn(sb, db.z, cb.z);
-      b3 = __fmaf_rn(sb, db.w, cb.w), b3 *= b3;
-    }
-    float4 va, vb;
-    if (act_a) va = tile[off_a];
-    if (act_b) vb = tile[off_b];
-    if (act_a) {
-      va.x += a0, va.y += a1, va.z += a2, va.w += a3; // mod.rs:57-73
-      if (act_b && off_a == off_b) vb = va;
-      tile[off_a] = va;
-    }
-    if (act_b) {
-      vb.x += b0, vb.y += b1, vb.z += b2, vb.w += b3;
-      tile[off_b] = vb;
-    }
-    n += (act_a ? 1u : 0u) + (act_b ? 1u : 0u);
-    ga = nga, gb = ngb, ca = nca, cb = ncb, da = nda, db = ndb, r = nr;
+  PairRecs A, B;
+  A.da = A.db = B.da = B.db = make_float4(0.f, 0.f, 0.f, 0.f);
+  load_recs<kLerp>(P, 0, A);
+  for (int k = 0; k < m; k += 4) {
+    load_recs<kLerp>(P, k + 2 < m ? k + 2 : k, B);
+    n += blend_two<kLerp>(lane_base, row_bytes, A, mc, nlo, nhi, lane);
+    if (k + 2 >= m) break;
+    load_recs<kLerp>(P, k + 4 < m ? k + 4 : k, A);
+    n += blend_two<kLerp>(lane_base, row_bytes, B, mc, nlo, nhi, lane);
   }
   return n;
 }
@@ -296,7 +313,8 @@ template <class Seg> __global__ void __launch_bounds__(kRasterWarps * 32) tile_r
     const int bmaj = xmajor ? bx : by, bmin = xmajor ? by : bx;
     const float mc = (float)(bmaj + (int)lane) + 0.5f;
     const float nlo = (float)bmin, nhi = (float)min(xmajor ? T.A.H : T.A.W, bmin + kTile);
-    const int add = (int)lane - bmin * kTilePitch;
+    // byte address of this lane's pixel at minor offset 0 of the canvas (the tile starts at minor offset bmin)
+    unsigned char *lane_base = reinterpret_cast<unsigned char *>(tile) + ((int)lane - bmin * kTilePitch) * (int)sizeof(float4);
     for (int k = lane; k < kTileFloat4; k += 32) tile[k] = make_float4(0.f, 0.f, 0.f, 0.f);
     __syncwarp();
     // gather pipeline, two batches deep: while batch b is blended, the SEGMENTS of batch b + 1 (their list indices
@@ -323,7 +341,7 @@ template <class Seg> __global__ void __launch_bounds__(kRasterWarps * 32) tile_r
       if (base + 32 + lane < last) SegIO<Seg>::load(seg, idx_next, g_ab, g_ca, g_dc);
       idx_next = base + 64 + lane < last ? lst[base + 64 + lane] : 0u;
       __syncwarp();
-      cnt += blend_run<kLerp, kTilePitch>(tile, P, m, mc, nlo, nhi, add, lane);
+      cnt += blend_run<kLerp>(lane_base, kTilePitch * (int)sizeof(float4), P, m, mc, nlo, nhi, lane);
       __syncwarp();
     }
     // flush: one vector reduction per touched pixel, lanes sweep an image row (coalesced 512 B).  A transposed
