@@ -32,6 +32,10 @@
 #include "lg_geom.cuh"
 #include "lg_nearest.cuh"
 
+#ifndef LG_MERGED_CTAS
+#define LG_MERGED_CTAS 3 // CTAs per SM the shared-narrow-phase f32 kernel is compiled for
+#endif
+
 
 namespace lg {
 
@@ -271,7 +275,7 @@ __device__ __forceinline__ bool culled(float r, float g, float b, float a, const
 // different slots run them together, C2 43 vs 78 ms) or one instance per slot (large scenes: the broad phase and the
 // candidate filter dominate and the simpler per-slot loops win, C5 114 vs 123 ms).  Same results either way.
 template <class T, int R, bool kSmem, bool kGrid = false, bool kMerged = true>
-__global__ void __launch_bounds__(kTraceBlock, (R >= 4 || sizeof(T) == 8) ? 2 : 3)
+__global__ void __launch_bounds__(kTraceBlock, (R >= 4 || sizeof(T) == 8) ? 2 : ((kMerged && !kGrid && R == 2) ? LG_MERGED_CTAS : 3))
     trace_kernel(const __grid_constant__ TraceArgs<T> A) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ __align__(8) unsigned long long mbar;
@@ -435,35 +439,34 @@ __global__ void __launch_bounds__(kTraceBlock, (R >= 4 || sizeof(T) == 8) ? 2 : 
       // (ascending object order within a slot; take() resolves equal distances towards the lower object index, like
       // the strict `<` of the in-order loop, tracer.rs:417), so lanes busy with different slots run the exact
       // test together and the kernel carries one copy of its code.
-      int s = 0;
-      unsigned cand = ~m[0];
+      unsigned cand[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) cand[r] = ~m[r];
       while (true) {
-        if (cand == 0u) {
-          if (++s >= R) break;
+        // the lane's next candidate that survives the range filter, from whichever slot has one
+        int s = -1, j = 0;
 #pragma unroll
-          for (int r = 1; r < R; ++r)
-            if (s == r) cand = ~m[r];
-          continue;
+        for (int r = 0; r < R; ++r) {
+          while (s < 0 && cand[r]) {
+            const int bit = 31 - __clz(cand[r]);
+            cand[r] ^= 1u << bit;
+            const int jj = c0 + 31 - bit;
+            // all hits of object jj have t in [tca - rb, tca + rb]: skip it when that lies
+            // behind the origin or beyond the nearest hit found so far
+            const T tca = Real<T>::fma(bx[jj], sdx[r], Real<T>::fma(by[jj], sdy[r], nkd[r]));
+            const T rb = brb[jj];
+            if (tca < -rb || tca - rb > tb[r]) continue;
+            s = r, j = jj;
+          }
         }
-        const int bit = 31 - __clz(cand);
-        cand ^= 1u << bit;
-        const int j = c0 + 31 - bit;
-        T sx = sdx[0], sy = sdy[0], sk = nkd[0], st = tb[0];
-#pragma unroll
-        for (int r = 1; r < R; ++r)
-          if (s == r) sx = sdx[r], sy = sdy[r], sk = nkd[r], st = tb[r];
-        // all hits of object j have t in [tca - rb, tca + rb]: skip it when that lies
-        // behind the origin or beyond the nearest hit found so far
-        const T tca = Real<T>::fma(bx[j], sx, Real<T>::fma(by[j], sy, sk));
-        const T rb = brb[j];
-        if (tca < -rb || tca - rb > st) continue;
-        V2<T> os = o[0];
+        if (s < 0) break;
+        V2<T> os = o[0], ds = d[0];
         Best<T> bs = best[0];
 #pragma unroll
         for (int r = 1; r < R; ++r)
-          if (s == r) os = o[r], bs = best[r];
+          if (s == r) os = o[r], ds = d[r], bs = best[r];
         const T before = bs.d2;
-        bs = narrow_phase(A, bs, j, os, V2<T>{sx, sy});
+        bs = narrow_phase(A, bs, j, os, ds);
         if (bs.d2 != before) {
           const T nt = Real<T>::sqrt(bs.d2) * (T)1.000001 + A.delta;
 #pragma unroll
