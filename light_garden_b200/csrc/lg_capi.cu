@@ -547,10 +547,6 @@ template <class Seg> int accumulate_tiled(lg_ctx *c, const Seg *d_seg, unsigned 
   T.tile_offset = (unsigned long long *)c->tile_offset.p, T.item_prefix = (unsigned *)c->item_prefix.p;
   T.totals = (unsigned long long *)c->tile_totals.p, T.item_counter = (unsigned *)c->item_counter.p;
   T.list = nullptr;
-  const int grid = c->sm_count * 4; // CTAs of the count and fill passes (same split of the segments in both)
-  T.n_ctas = grid;
-  if ((rc = ensure(c, c->tile_hist, (size_t)grid * T.n_tiles * 4))) return rc;
-  T.hist = (unsigned *)c->tile_hist.p;
   const size_t hist_smem = (size_t)T.n_tiles * 4;
   auto count_k = tile_count_kernel<Seg>;
   auto fill_k = tile_fill_kernel<Seg>;
@@ -558,6 +554,16 @@ template <class Seg> int accumulate_tiled(lg_ctx *c, const Seg *d_seg, unsigned 
     LG_CUDA(c, cudaFuncSetAttribute(count_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_smem));
     LG_CUDA(c, cudaFuncSetAttribute(fill_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_smem));
   }
+  // CTAs of the count and fill passes (the same split of the segments in both): one resident wave -- the histogram
+  // in shared memory decides how many fit on an SM -- and no more than the segments can keep busy
+  int hist_per_sm = 0;
+  LG_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&hist_per_sm, fill_k, 256, hist_smem));
+  if (hist_per_sm < 1) return fail(c, LG_ERR_CUDA, "tile histogram does not fit in shared memory");
+  int grid = c->sm_count * std::min(hist_per_sm, 4);
+  grid = (int)std::max<unsigned long long>(1ull, std::min<unsigned long long>((unsigned long long)grid, (n + 1023ull) / 1024ull));
+  T.n_ctas = grid;
+  if ((rc = ensure(c, c->tile_hist, (size_t)grid * T.n_tiles * 4))) return rc;
+  T.hist = (unsigned *)c->tile_hist.p;
   count_k<<<grid, 256, hist_smem, c->stream>>>(T, d_seg, n);
   LG_CUDA(c, cudaGetLastError());
   tile_rowscan_kernel<<<(T.n_tiles + 255) / 256, 256, 0, c->stream>>>(T);
