@@ -114,7 +114,7 @@ __device__ __forceinline__ void cta_range(unsigned long long n, unsigned b, unsi
   hi = lo + per < n ? lo + per : n;
 }
 
-template <class Seg> __global__ void __launch_bounds__(256) tile_count_kernel(TileArgs T, const Seg *seg, unsigned long long n) {
+template <class Seg> __global__ void __launch_bounds__(1024) tile_count_kernel(TileArgs T, const Seg *seg, unsigned long long n) {
   extern __shared__ unsigned int s_hist[];
   for (int t = threadIdx.x; t < T.n_tiles; t += blockDim.x) s_hist[t] = 0u;
   __syncthreads();
@@ -145,7 +145,7 @@ __global__ void __launch_bounds__(256) tile_rowscan_kernel(TileArgs T) {
   T.tile_count[t] = run;
 }
 
-template <class Seg> __global__ void __launch_bounds__(256) tile_fill_kernel(TileArgs T, const Seg *seg, unsigned long long n) {
+template <class Seg> __global__ void __launch_bounds__(1024) tile_fill_kernel(TileArgs T, const Seg *seg, unsigned long long n) {
   extern __shared__ unsigned int s_cur[]; // this CTA's next slot in every tile's list, relative to the tile's offset
   const unsigned int *mine = T.hist + (size_t)blockIdx.x * T.n_tiles;
   for (int t = threadIdx.x; t < T.n_tiles; t += blockDim.x) s_cur[t] = mine[t];
