@@ -227,83 +227,54 @@ template <bool kLerp> __device__ __forceinline__ void load_recs(const RasterScra
   if (kLerp) q.da = P.dc[k], q.db = P.dc[k + 1];
   q.r = *reinterpret_cast<const uint2 *>(&P.rng[k]);
 }
-// one entry's fragment on this lane: whether there is one, its pixel in the tile, its blend terms
-struct Frag {
-  bool act;
-  float4 *p;
-  float c0, c1, c2, c3; // rgb += c0..c2, alpha += c3 (already squared)
-};
+// two entries against the tile; lane_base = this lane's byte address of minor offset 0, row_bytes = bytes per minor step
 template <bool kLerp>
-__device__ __forceinline__ Frag make_frag(unsigned char *lane_base, int row_bytes, float4 g, float4 c, float4 dc, unsigned rng,
-                                          float mc, float nlo, float nhi, unsigned lane) {
-  Frag f;
-  const float s = (mc - g.x) * g.y;
-  const float fj = floorf(__fmaf_rn(s, g.z, g.w));
-  f.act = (lane - (rng & 255u)) < (rng >> 8) && fj >= nlo && fj < nhi;
-  f.p = reinterpret_cast<float4 *>(lane_base + (int)fj * row_bytes);
-  f.c0 = c.x, f.c1 = c.y, f.c2 = c.z, f.c3 = c.w;
+__device__ __forceinline__ unsigned blend_two(unsigned char *lane_base, int row_bytes, const PairRecs &q, float mc, float nlo,
+                                              float nhi, unsigned lane) {
+  const float sa = (mc - q.ga.x) * q.ga.y, sb = (mc - q.gb.x) * q.gb.y;
+  const float fa = floorf(__fmaf_rn(sa, q.ga.z, q.ga.w)), fb = floorf(__fmaf_rn(sb, q.gb.z, q.gb.w));
+  const bool act_a = (lane - (q.r.x & 255u)) < (q.r.x >> 8) && fa >= nlo && fa < nhi;
+  const bool act_b = (lane - (q.r.y & 255u)) < (q.r.y >> 8) && fb >= nlo && fb < nhi;
+  float4 *pa = reinterpret_cast<float4 *>(lane_base + (int)fa * row_bytes);
+  float4 *pb = reinterpret_cast<float4 *>(lane_base + (int)fb * row_bytes);
+  float a0 = q.ca.x, a1 = q.ca.y, a2 = q.ca.z, a3 = q.ca.w, b0 = q.cb.x, b1 = q.cb.y, b2 = q.cb.z, b3 = q.cb.w;
   if (kLerp) {
-    f.c0 = __fmaf_rn(s, dc.x, c.x), f.c1 = __fmaf_rn(s, dc.y, c.y), f.c2 = __fmaf_rn(s, dc.z, c.z);
-    f.c3 = __fmaf_rn(s, dc.w, c.w), f.c3 *= f.c3;
+    a0 = __fmaf_rn(sa, q.da.x, q.ca.x), a1 = __fmaf_rn(sa, q.da.y, q.ca.y), a2 = __fmaf_rn(sa, q.da.z, q.ca.z);
+    a3 = __fmaf_rn(sa, q.da.w, q.ca.w), a3 *= a3;
+    b0 = __fmaf_rn(sb, q.db.x, q.cb.x), b1 = __fmaf_rn(sb, q.db.y, q.cb.y), b2 = __fmaf_rn(sb, q.db.z, q.cb.z);
+    b3 = __fmaf_rn(sb, q.db.w, q.cb.w), b3 *= b3;
   }
-  return f;
-}
-__device__ __forceinline__ void blend_one(const Frag &f) {
-  if (f.act) {
-    float4 v = *f.p;
-    v.x += f.c0, v.y += f.c1, v.z += f.c2, v.w += f.c3; // mod.rs:57-73
-    *f.p = v;
+  float4 va, vb;
+  if (act_a) va = *pa;
+  if (act_b) vb = *pb;
+  if (act_a) {
+    va.x += a0, va.y += a1, va.z += a2, va.w += a3; // mod.rs:57-73
+    if (act_b && pa == pb) vb = va;
+    *pa = va;
   }
-}
-// Four entries against the tile (Q0 = entries k, k + 1; Q1 = k + 2, k + 3).  When no lane of the warp hits the same
-// pixel in two of them -- the usual case away from a light -- the four pixels are read, updated and written as four
-// independent chains; otherwise the warp falls back to four read-modify-writes in list order.
-template <bool kLerp>
-__device__ __forceinline__ unsigned blend_four(unsigned char *lane_base, int row_bytes, const PairRecs &Q0, const PairRecs &Q1,
-                                               float mc, float nlo, float nhi, unsigned lane) {
-  const Frag a = make_frag<kLerp>(lane_base, row_bytes, Q0.ga, Q0.ca, Q0.da, Q0.r.x, mc, nlo, nhi, lane);
-  const Frag b = make_frag<kLerp>(lane_base, row_bytes, Q0.gb, Q0.cb, Q0.db, Q0.r.y, mc, nlo, nhi, lane);
-  const Frag c = make_frag<kLerp>(lane_base, row_bytes, Q1.ga, Q1.ca, Q1.da, Q1.r.x, mc, nlo, nhi, lane);
-  const Frag d = make_frag<kLerp>(lane_base, row_bytes, Q1.gb, Q1.cb, Q1.db, Q1.r.y, mc, nlo, nhi, lane);
-  const bool clash = (a.act && ((b.act && a.p == b.p) || (c.act && a.p == c.p) || (d.act && a.p == d.p))) ||
-                     (b.act && ((c.act && b.p == c.p) || (d.act && b.p == d.p))) || (c.act && d.act && c.p == d.p);
-  if (__any_sync(0xffffffffu, clash)) {
-    blend_one(a), blend_one(b), blend_one(c), blend_one(d);
-  } else {
-    float4 va, vb, vc, vd;
-    if (a.act) va = *a.p;
-    if (b.act) vb = *b.p;
-    if (c.act) vc = *c.p;
-    if (d.act) vd = *d.p;
-    if (a.act) va.x += a.c0, va.y += a.c1, va.z += a.c2, va.w += a.c3, *a.p = va;
-    if (b.act) vb.x += b.c0, vb.y += b.c1, vb.z += b.c2, vb.w += b.c3, *b.p = vb;
-    if (c.act) vc.x += c.c0, vc.y += c.c1, vc.z += c.c2, vc.w += c.c3, *c.p = vc;
-    if (d.act) vd.x += d.c0, vd.y += d.c1, vd.z += d.c2, vd.w += d.c3, *d.p = vd;
+  if (act_b) {
+    vb.x += b0, vb.y += b1, vb.z += b2, vb.w += b3;
+    *pb = vb;
   }
-  return (a.act ? 1u : 0u) + (b.act ? 1u : 0u) + (c.act ? 1u : 0u) + (d.act ? 1u : 0u);
+  return (act_a ? 1u : 0u) + (act_b ? 1u : 0u);
 }
 template <bool kLerp>
 __device__ __forceinline__ unsigned blend_run(unsigned char *lane_base, int row_bytes, const RasterScratch &P, int m, float mc,
                                               float nlo, float nhi, unsigned lane) {
-  // entries [0, m) four at a time; the caller has parked empty entries (lane range 0) up to the next multiple of 4.
-  // The records of the NEXT four entries are fetched before the current four touch the tile (the compiler cannot
+  // entries [0, m) two at a time; when m is odd the caller has parked an empty entry (lane range 0) at index m.
+  // The records of the NEXT two entries are fetched before the current two touch the tile (the compiler cannot
   // move those loads across the tile's stores by itself: same shared-memory array); the two register sets swap
   // roles every half iteration, so nothing is copied.
   unsigned n = 0;
-  PairRecs A0, A1, B0, B1;
-  A0.da = A0.db = A1.da = A1.db = B0.da = B0.db = B1.da = B1.db = make_float4(0.f, 0.f, 0.f, 0.f);
-  load_recs<kLerp>(P, 0, A0);
-  load_recs<kLerp>(P, 2, A1);
-  for (int k = 0; k < m; k += 8) {
-    const int kb = k + 4 < m ? k + 4 : k;
-    load_recs<kLerp>(P, kb, B0);
-    load_recs<kLerp>(P, kb + 2, B1);
-    n += blend_four<kLerp>(lane_base, row_bytes, A0, A1, mc, nlo, nhi, lane);
-    if (k + 4 >= m) break;
-    const int ka = k + 8 < m ? k + 8 : k;
-    load_recs<kLerp>(P, ka, A0);
-    load_recs<kLerp>(P, ka + 2, A1);
-    n += blend_four<kLerp>(lane_base, row_bytes, B0, B1, mc, nlo, nhi, lane);
+  PairRecs A, B;
+  A.da = A.db = B.da = B.db = make_float4(0.f, 0.f, 0.f, 0.f);
+  load_recs<kLerp>(P, 0, A);
+  for (int k = 0; k < m; k += 4) {
+    load_recs<kLerp>(P, k + 2 < m ? k + 2 : k, B);
+    n += blend_two<kLerp>(lane_base, row_bytes, A, mc, nlo, nhi, lane);
+    if (k + 2 >= m) break;
+    load_recs<kLerp>(P, k + 4 < m ? k + 4 : k, A);
+    n += blend_two<kLerp>(lane_base, row_bytes, B, mc, nlo, nhi, lane);
   }
   return n;
 }
@@ -361,7 +332,7 @@ template <class Seg> __global__ void __launch_bounds__(kRasterWarps * 32) tile_r
         P.col[lane] = make_float4(g_ca.x, g_ca.y, g_ca.z, kLerp ? g_ca.w : g_ca.w * g_ca.w);
         if (kLerp) P.dc[lane] = g_dc;
         P.rng[lane] = (unsigned)l0 | ((unsigned)max(l1 - l0, 0) << 8);
-      } else if ((int)lane < ((m + 3) & ~3)) { // empty entries up to the next multiple of four
+      } else if ((int)lane == m) { // the empty partner of an odd last entry
         P.geo[lane] = make_float4(0.f, 0.f, 0.f, 0.f);
         P.col[lane] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (kLerp) P.dc[lane] = make_float4(0.f, 0.f, 0.f, 0.f);
