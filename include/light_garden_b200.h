@@ -211,8 +211,14 @@ typedef struct LgBlendState {
 
 /* ---- accumulation target -------------------------------------------------- */
 /* LG_BGRA8_GAMMA is the reference's screenshot conversion (src/renderer.rs:313-328):
- * every Rgba16Float channel -> (f.powf(1/2.2) * 255) as u8, stored [b, g, r, a]. */
-enum { LG_RGBA32F = 0, LG_RGBA16F = 1, LG_BGRA8_GAMMA = 2 };
+ * every Rgba16Float channel -> (f.powf(1/2.2) * 255) as u8, stored [b, g, r, a].
+ * LG_BGRA8_SRGB is the 8-bit target of the path with `render_to_texture` off
+ * (the app's default, src/light_garden/mod.rs:86): the pipeline then draws
+ * into the surface format (src/sub_render_pass.rs:59-63) and the screenshot
+ * into Bgra8UnormSrgb (src/renderer.rs:207-209).  Every channel saturates at
+ * 1; colour is stored sRGB-encoded, alpha linear, both rounded to nearest
+ * (ORACLE.md 8.7: the order-free limit of the ROP's saturating blend). */
+enum { LG_RGBA32F = 0, LG_RGBA16F = 1, LG_BGRA8_GAMMA = 2, LG_BGRA8_SRGB = 3 };
 
 typedef struct LgTraceStats {
   uint64_t primary_rays;    /* rays this context traced (its shard)          */
@@ -324,8 +330,9 @@ int32_t lg_string_mod_nested_read(lg_ctx *ctx, LgVertexPair *outer_chords, uint6
  * segment buffer and each wave is accumulated before the next is traced. */
 int32_t lg_render(lg_ctx *ctx, LgTraceStats *stats);
 /* Image out: LG_RGBA32F (16 B/px), LG_RGBA16F (8 B/px, round to nearest even,
- * what the ROP would have stored) or LG_BGRA8_GAMMA (4 B/px, the screenshot
- * path). pitch in bytes, 0 = tight (wgpu's readback pads rows to 256 bytes,
+ * what the ROP would have stored), LG_BGRA8_GAMMA (4 B/px, the screenshot
+ * path) or LG_BGRA8_SRGB (4 B/px, the 8-bit surface target). pitch in
+ * bytes, 0 = tight (wgpu's readback pads rows to 256 bytes,
  * renderer.rs:250-255: pass that pitch to get the same layout). */
 int32_t lg_image_read(lg_ctx *ctx, int32_t format, void *dst, size_t pitch);
 

@@ -29,7 +29,7 @@ LG_OP_AND, LG_OP_OR, LG_OP_ANDNOT = 0, 1, 2
 LG_LIGHT_POINT, LG_LIGHT_DIRECTIONAL, LG_LIGHT_SPOT = 0, 1, 2
 LG_SM_ADD, LG_SM_MUL, LG_SM_POW, LG_SM_BASE = 0, 1, 2, 3
 LG_CURVE_CIRCLE, LG_CURVE_COMPLEX_EXP, LG_CURVE_HYPOTROCHOID, LG_CURVE_LISSAJOUS = 0, 1, 2, 3
-LG_RGBA32F, LG_RGBA16F, LG_BGRA8_GAMMA = 0, 1, 2
+LG_RGBA32F, LG_RGBA16F, LG_BGRA8_GAMMA, LG_BGRA8_SRGB = 0, 1, 2, 3
 
 
 class LgGeoNode(C.Structure):

@@ -1265,6 +1265,17 @@ int32_t lg_image_read(lg_ctx *c, int32_t format, void *dst, size_t pitch) {
     LG_CUDA(c, cudaGetLastError());
     c->launches++;
     LG_CUDA(c, cudaMemcpy2DAsync(dst, pitch, c->img8.p, row, row, c->H, cudaMemcpyDeviceToHost, c->stream));
+  } else if (format == LG_BGRA8_SRGB) {
+    const size_t row = (size_t)c->W * 4;
+    if (pitch == 0) pitch = row;
+    if (pitch < row) return fail(c, LG_ERR_INVALID, "pitch");
+    if ((rc = ensure(c, c->img8, npx * 4))) return rc;
+    static const SrgbThresholds thresholds = srgb_thresholds();
+    surface_bgra8_srgb_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>((const float4 *)c->img.p, (uchar4 *)c->img8.p, npx,
+                                                                      thresholds);
+    LG_CUDA(c, cudaGetLastError());
+    c->launches++;
+    LG_CUDA(c, cudaMemcpy2DAsync(dst, pitch, c->img8.p, row, row, c->H, cudaMemcpyDeviceToHost, c->stream));
   } else {
     return fail(c, LG_ERR_INVALID, "format");
   }

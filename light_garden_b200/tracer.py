@@ -320,6 +320,14 @@ class Renderer:
         self.ctx.call("lg_image_read", abi.LG_BGRA8_GAMMA, abi.array_ptr(out), row)
         return out[:, : self.width * 4].reshape(self.height, self.width, 4)
 
+    def read_surface_bgra8(self, pitch: int = 0):
+        """The frame as the 8-bit surface target holds it when `render_to_texture` is off (sub_render_pass.rs:59-63;
+        the screenshot's Bgra8UnormSrgb, renderer.rs:207-209): saturated, colour sRGB-encoded, [b, g, r, a]."""
+        row = pitch if pitch else self.width * 4
+        out = np.zeros((self.height, row), dtype=np.uint8)
+        self.ctx.call("lg_image_read", abi.LG_BGRA8_SRGB, abi.array_ptr(out), row)
+        return out[:, : self.width * 4].reshape(self.height, self.width, 4)
+
     def read_rgba16f(self, out=None):
         if out is None:
             out = np.zeros((self.height, self.width, 4), dtype=np.float16)

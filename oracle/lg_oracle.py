@@ -77,6 +77,7 @@ def lib():
         L.lgo_accumulate_pairs.argtypes = [vp, C.c_int32, C.c_int32, vp, C.c_uint64, C.c_int32]
         L.lgo_image_to_f16.argtypes = [vp, C.c_uint64, vp]
         L.lgo_image_to_bgra8.argtypes = [vp, C.c_uint64, vp]
+        L.lgo_image_to_bgra8_srgb.argtypes = [vp, C.c_uint64, vp]
         L.lgo_num_threads.restype = C.c_int32
         _lib = L
     return _lib
@@ -262,6 +263,15 @@ def to_bgra8(img):
     img = np.ascontiguousarray(img, dtype=np.float32)
     out = np.zeros(img.shape[:2] + (4,), dtype=np.uint8)
     lib().lgo_image_to_bgra8(abi.array_ptr(img), img.shape[0] * img.shape[1], abi.array_ptr(out))
+    return out
+
+
+def to_bgra8_srgb(img):
+    """The 8-bit surface target (render_to_texture off, sub_render_pass.rs:59-63; Bgra8UnormSrgb,
+    renderer.rs:207-209): saturate, sRGB-encode the colour, round to nearest (ORACLE.md 8.7)."""
+    img = np.ascontiguousarray(img, dtype=np.float32)
+    out = np.zeros(img.shape[:2] + (4,), dtype=np.uint8)
+    lib().lgo_image_to_bgra8_srgb(abi.array_ptr(img), img.shape[0] * img.shape[1], abi.array_ptr(out))
     return out
 
 

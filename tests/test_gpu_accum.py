@@ -330,6 +330,25 @@ def test_screenshot_bgra8(oracle, ctx):
     assert np.array_equal(padded, got)
 
 
+def test_surface_bgra8_srgb(oracle, ctx):
+    """the 8-bit surface target of the path with render_to_texture off
+    (sub_render_pass.rs:59-63; Bgra8UnormSrgb, renderer.rs:207-209), ORACLE.md 8.7 -- bit for bit, padded rows too."""
+    from light_garden_b200.tracer import Renderer
+    W, H = 100, 40
+    r = Renderer(ctx, W, H)
+    p = random_pairs(3000, seed=22, pow2=False)
+    p["color_a"] *= 6        # part of the frame saturates, most of it does not
+    p["color_b"] *= 6
+    r.render_lines(p)
+    f32 = r.read_rgba32f()
+    got = r.read_surface_bgra8()
+    assert np.array_equal(got, oracle.to_bgra8_srgb(f32))
+    assert got[..., 3].min() == 255 and 0 < (got[..., :3] == 255).mean() < 0.9 and (got[..., :3] == 0).any()
+    assert np.array_equal(r.read_surface_bgra8(pitch=512), got)
+    r.clear(0.0)
+    assert not r.read_surface_bgra8().any()
+
+
 def test_clear_value_and_partial_alpha(ctx):
     from light_garden_b200.tracer import Renderer
     r = Renderer(ctx, 40, 30)

@@ -510,6 +510,32 @@ def test_screenshot_conversion_known_values(oracle):
     assert np.all(out[0, :, 1] == 255) and np.all(out[0, :, 0] == 0) and np.all(out[0, :, 3] == 0)
 
 
+def test_surface_srgb_conversion_known_values(oracle):
+    """ORACLE.md 8.7 (sub_render_pass.rs:59-63, renderer.rs:207-209): saturate, sRGB-encode, round to nearest;
+    alpha linear; pixel order [b, g, r, a].  Checked against the closed-form sRGB encoding."""
+    img = np.zeros((1, 8, 4), dtype=np.float32)
+    img[0, :, 0] = [0.0, 1.0, 0.5, 7.0, -1.0, 0.0031308, 0.21404114, np.nan]
+    img[0, :, 1] = 1.0
+    img[0, :, 3] = [0.0, 1.0, 0.5, 3.0, -2.0, 0.25, 0.001, np.nan]
+    out = oracle.to_bgra8_srgb(img)
+    #        0    1    .5: 1.055*.5^(1/2.4)-.055 = .7354 -> 187.5.. -> 188; >1 saturates; <0 -> 0; 12.92*.0031308*255 = 10.3
+    assert out[0, :, 2].tolist() == [0, 255, 188, 255, 0, 10, 128, 0]          # red lands in byte 2
+    assert np.all(out[0, :, 1] == 255) and np.all(out[0, :, 0] == 0)
+    assert out[0, :, 3].tolist() == [0, 255, 128, 255, 0, 64, 0, 0]            # alpha: linear, floor(a*255 + .5)
+    rng = np.random.default_rng(3)
+    x = np.concatenate([rng.uniform(0, 1.2, 20000), rng.uniform(0, 0.01, 4000)]).astype(np.float32)
+    im = np.zeros((1, x.size, 4), dtype=np.float32)
+    im[0, :, 0] = im[0, :, 1] = im[0, :, 2] = x
+    got = oracle.to_bgra8_srgb(im)[0, :, 0].astype(np.int64)
+    c = np.clip(x.astype(np.float64), 0, 1)
+    enc = np.where(c <= 0.0031308, 12.92 * c, 1.055 * c ** (1 / 2.4) - 0.055)
+    exp = np.floor(enc * 255 + 0.5).astype(np.int64)
+    bad = got != exp
+    # the two forms can only disagree within rounding of a threshold (0.0031308 is itself a rounded constant)
+    frac = np.abs(enc * 255 + 0.5 - np.round(enc * 255 + 0.5))
+    assert bad.mean() < 1e-3 and np.all(np.abs(got - exp)[bad] == 1) and np.all(frac[bad] < 1e-3)
+
+
 def test_string_mod_curves(oracle):
     """string_mod.rs:36-84: ComplexExp, Hypotrochoid and Lissajous point sets against direct formulas."""
     m = 60
