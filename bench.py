@@ -43,17 +43,43 @@ def algorithmic_flops_per_test(objects):
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock + throttle reasons DURING the timed regions (B200_PROFILING.md recipe).  NVML is polled from a thread of
+    this process every 20 ms (the timed calls are ctypes calls that release the GIL), which gives tens of samples for a
+    half-second region; if NVML cannot be loaded the recipe's `nvidia-smi -lms 200` child process is used instead."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    # nvmlClocksEventReason* bits (nvml.h)
+    BITS = {"sw_power_cap": 0x4, "hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
 
-    def __init__(self, index):
-        self.index = index
-        self.proc = None
-        self.lines = []
+    def __init__(self, index, uuid=None):
+        self.index, self.uuid = index, uuid
+        self.proc = self.th = self.nv = self.h = None
+        self.lines, self.sm, self.power, self.reasons = [], [], [], set()
+        self.sm_max = None
+        self.stop_flag = threading.Event()
 
     def start(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = None
+            if self.uuid:
+                try:
+                    h = nv.nvmlDeviceGetHandleByUUID(("GPU-" + self.uuid).encode())
+                except Exception:
+                    h = None
+            if h is None:
+                vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+                ids = [v for v in vis.split(",") if v.strip().isdigit()]
+                h = nv.nvmlDeviceGetHandleByIndex(int(ids[self.index]) if self.index < len(ids) else self.index)
+            self.sm_max = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            self.nv, self.h = nv, h
+            self.th = threading.Thread(target=self._poll, daemon=True)
+            self.th.start()
+            return
+        except Exception:
+            self.nv = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-lms", "200", "-i", str(self.index)], stdout=subprocess.PIPE,
@@ -63,11 +89,32 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        nv, h = self.nv, self.h
+        while not self.stop_flag.is_set():
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                self.power.append(nv.nvmlDeviceGetPowerUsage(h) / 1000.0)
+                bits = int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))
+                for name, b in self.BITS.items():
+                    if bits & b:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self.stop_flag.wait(0.02)
+
     def _pump(self):
         for ln in self.proc.stdout:
             self.lines.append(ln.strip())
 
     def stop(self):
+        if self.nv is not None:
+            self.stop_flag.set()
+            self.th.join(timeout=2)
+            sm = sorted(self.sm)
+            return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.sm_max,
+                    "sm_min_mhz": sm[0] if sm else None, "power_w_max": max(self.power) if self.power else None,
+                    "reasons": sorted(self.reasons), "samples": len(sm), "source": "nvml, 20 ms period"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -90,7 +137,7 @@ class ClockSampler:
                     reasons.add(name)
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi -lms 200"}
 
 
 def dist_env():
@@ -288,12 +335,17 @@ def main():
     step(True)   # first use of the end-to-end-only pieces (Rgba16Float buffer, finalize kernel, pinned read-back)
     for _ in range(max(3, args.warmup)):
         step(False)
-    sampler = ClockSampler(local) if rank == 0 else None
-    if sampler:
+    sampler = None
+    if rank == 0:
+        try:
+            uuid = str(torch.cuda.get_device_properties(local).uuid)
+        except Exception:
+            uuid = None
+        sampler = ClockSampler(local, uuid)
         sampler.start()
-    ms, agg = timed(args.steps, False)
-    clocks = sampler.stop() if sampler else None
+    ms, agg = timed(args.steps, False)          # the two headline regions (value, e2e) are sampled together
     ms_e2e, agg_e2e = timed(args.steps, True)
+    clocks = sampler.stop() if sampler else None
 
     # the same workload with Tracer::enable_tile_map (device grid): identical segments, fewer
     # exact tests.  Reported next to the headline, which stays the all-objects loop the north star names.
