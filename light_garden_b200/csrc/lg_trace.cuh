@@ -261,6 +261,42 @@ template <> struct Broad<float> {
 };
 
 
+// Table access.  With the table in shared memory the loads are issued in the shared state space from a 32-bit
+// address computed once per kernel: through the generic pointer the compiler rebuilt the shared window base
+// (S2UR SR_CgaCtaId + ULEA) in every 32-object chunk and in every candidate-filter iteration (ncu: ~3 % of the
+// kernel's samples).  In global memory (tables larger than shared memory) the generic path is kept.
+template <class T, bool kSmem> struct TabLoad {
+  typedef typename Vec4<T>::type T4;
+  static __device__ __forceinline__ T4 v4(const T *gen, unsigned, int idx) { return *reinterpret_cast<const T4 *>(gen + idx); }
+  static __device__ __forceinline__ T s(const T *gen, unsigned, int idx) { return gen[idx]; }
+};
+template <> struct TabLoad<float, true> {
+  static __device__ __forceinline__ float4 v4(const float *, unsigned sh, int idx) {
+    float4 v;
+    asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(sh + 4u * (unsigned)idx));
+    return v;
+  }
+  static __device__ __forceinline__ float s(const float *, unsigned sh, int idx) {
+    float v;
+    asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(sh + 4u * (unsigned)idx));
+    return v;
+  }
+};
+template <> struct TabLoad<double, true> {
+  static __device__ __forceinline__ double4 v4(const double *, unsigned sh, int idx) {
+    double4 v;
+    const unsigned a = sh + 8u * (unsigned)idx;
+    asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(a));
+    asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.z), "=d"(v.w) : "r"(a + 16u));
+    return v;
+  }
+  static __device__ __forceinline__ double s(const double *, unsigned sh, int idx) {
+    double v;
+    asm("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(sh + 8u * (unsigned)idx));
+    return v;
+  }
+};
+
 template <class T> __device__ __forceinline__ bool contains_object(const TraceArgs<T> &A, int obj, V2<T> p) {
   return contains_range(A.toks + A.obj_first[obj], 0, A.obj_count[obj] - 1, p);
 }
@@ -312,6 +348,14 @@ __global__ void __launch_bounds__(kTraceBlock, (R >= 4 || sizeof(T) == 8) ? 2 : 
   const T *br2 = by + A.n_pad;
   const T *brb = br2 + A.n_pad;
   typedef typename Vec4<T>::type T4;
+  typedef TabLoad<T, kSmem> TL;
+  // the same four arrays as 32-bit shared-state-space addresses (used when kSmem)
+  unsigned sx = 0u;
+  if (kSmem) // opaque move: keeps the compiler from rematerialising the window base inside the loops
+    asm volatile("mov.u32 %0, %1;" : "=r"(sx) : "r"((unsigned)__cvta_generic_to_shared(smem_raw)));
+  const unsigned sy = sx + (unsigned)(A.n_pad * sizeof(T));
+  const unsigned sr2 = sy + (unsigned)(A.n_pad * sizeof(T));
+  const unsigned srb = sr2 + (unsigned)(A.n_pad * sizeof(T));
 
   const unsigned lane = threadIdx.x & 31u;
   const unsigned lt_mask = (1u << lane) - 1u;
@@ -428,9 +472,9 @@ __global__ void __launch_bounds__(kTraceBlock, (R >= 4 || sizeof(T) == 8) ? 2 : 
       for (int r = 0; r < R; ++r) m[r] = 0u;
 #pragma unroll 4
       for (int q = 0; q < 32; q += 4) {
-        const T4 x4 = *reinterpret_cast<const T4 *>(bx + c0 + q);
-        const T4 y4 = *reinterpret_cast<const T4 *>(by + c0 + q);
-        const T4 r4 = *reinterpret_cast<const T4 *>(br2 + c0 + q);
+        const T4 x4 = TL::v4(bx, sx, c0 + q);
+        const T4 y4 = TL::v4(by, sy, c0 + q);
+        const T4 r4 = TL::v4(br2, sr2, c0 + q);
 #pragma unroll
         for (int r = 0; r < R; ++r) m[r] = Broad<T>::test4(x4, y4, r4, sdx[r], sdy[r], nk[r], m[r]);
       }
@@ -453,8 +497,8 @@ __global__ void __launch_bounds__(kTraceBlock, (R >= 4 || sizeof(T) == 8) ? 2 : 
             const int jj = c0 + 31 - bit;
             // all hits of object jj have t in [tca - rb, tca + rb]: skip it when that lies
             // behind the origin or beyond the nearest hit found so far
-            const T tca = Real<T>::fma(bx[jj], sdx[r], Real<T>::fma(by[jj], sdy[r], nkd[r]));
-            const T rb = brb[jj];
+            const T tca = Real<T>::fma(TL::s(bx, sx, jj), sdx[r], Real<T>::fma(TL::s(by, sy, jj), sdy[r], nkd[r]));
+            const T rb = TL::s(brb, srb, jj);
             if (tca < -rb || tca - rb > tb[r]) continue;
             s = r, j = jj;
           }
@@ -486,8 +530,8 @@ __global__ void __launch_bounds__(kTraceBlock, (R >= 4 || sizeof(T) == 8) ? 2 : 
           const int j = c0 + 31 - bit;
           // all hits of object j have t in [tca - rb, tca + rb]: skip it when that lies
           // behind the origin or beyond the nearest hit found so far
-          const T tca = Real<T>::fma(bx[j], sdx[r], Real<T>::fma(by[j], sdy[r], nkd[r]));
-          const T rb = brb[j];
+          const T tca = Real<T>::fma(TL::s(bx, sx, j), sdx[r], Real<T>::fma(TL::s(by, sy, j), sdy[r], nkd[r]));
+          const T rb = TL::s(brb, srb, j);
           if (tca < -rb || tca - rb > tb[r]) continue;
           const T before = best[r].d2;
           best[r] = narrow_phase(A, best[r], j, o[r], d[r]);
