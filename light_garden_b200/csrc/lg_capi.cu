@@ -395,6 +395,7 @@ template <class T> int launch_trace(lg_ctx *c, TraceArgs<T> &A) {
   // large scenes: per-slot narrow phase (see trace_kernel); LG_TRACE_MERGED=0/1 forces one or the other
   const bool per_slot = c->trace_merged < 0 ? c->n_obj >= 512 : c->trace_merged == 0;
   if (!grid_mode && sizeof(T) == 4 && R == 2 && per_slot) kern = trace_kernel_f32_per_slot(use_smem);
+  if (!grid_mode && sizeof(T) == 8 && per_slot) kern = trace_kernel_f64_large(R, use_smem);
   const size_t smem = use_smem ? A.bounds_bytes : 0;
   if (smem > 48 * 1024) LG_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;

@@ -58,20 +58,20 @@ struct TileArgs {
 };
 
 template <class Seg> struct SegIO;
-// One 4-byte read-only load.  The raster's gather prefetch uses eight of them per segment instead of two 16-byte
+// One 8-byte read-only load.  The raster's gather prefetch uses four of them per segment instead of two 16-byte
 // ones: a vector load needs an aligned register quad, and the compiler copied one component out of that quad right
 // behind the load (ncu r01f: 13 % of the raster kernel's samples on that one move, the prefetch waited out in full).
-__device__ __forceinline__ float ldg_nc_f32(const float *p) {
-  float v;
-  asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(p));
-  return v;
+// Register pairs are placed without such a move; 4-byte loads also avoid it but double the sector requests of the
+// gather again (C2: 555 -> 573 ms).
+__device__ __forceinline__ void ldg_nc_v2(const float *p, float &a, float &b) {
+  asm volatile("ld.global.nc.v2.f32 {%0, %1}, [%2];" : "=f"(a), "=f"(b) : "l"(p));
 }
 template <> struct SegIO<LgSegment> {
   static constexpr bool kLerp = false;
   static __device__ __forceinline__ void load(const LgSegment *s, unsigned long long i, float4 &ab, float4 &ca, float4 &dc) {
     const float *p = reinterpret_cast<const float *>(s + i);
-    ab.x = ldg_nc_f32(p), ab.y = ldg_nc_f32(p + 1), ab.z = ldg_nc_f32(p + 2), ab.w = ldg_nc_f32(p + 3);
-    ca.x = ldg_nc_f32(p + 4), ca.y = ldg_nc_f32(p + 5), ca.z = ldg_nc_f32(p + 6), ca.w = ldg_nc_f32(p + 7);
+    ldg_nc_v2(p, ab.x, ab.y), ldg_nc_v2(p + 2, ab.z, ab.w);
+    ldg_nc_v2(p + 4, ca.x, ca.y), ldg_nc_v2(p + 6, ca.z, ca.w);
     dc = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   static __device__ __forceinline__ float4 load_ab(const LgSegment *s, unsigned long long i) {

@@ -310,7 +310,11 @@ __device__ __forceinline__ bool culled(float r, float g, float b, float a, const
 // kMerged: one narrow-phase instance shared by the R slots (small scenes: the exact tests dominate, lanes busy with
 // different slots run them together, C2 43 vs 78 ms) or one instance per slot (large scenes: the broad phase and the
 // candidate filter dominate and the simpler per-slot loops win, C5 114 vs 123 ms).  Same results either way.
-template <class T, int R, bool kSmem, bool kGrid = false, bool kMerged = true>
+// kLarge: the form for scenes of hundreds of objects and more, where the 32-object sweep is nearly all of the work --
+// table loads in the shared state space from addresses held in registers and the sweep fully unrolled (C5: -3 %,
+// f64 -9 %).  Small scenes (C2, C3) run 3-9 % slower with it (four more live registers in kernels that already spill)
+// and keep the generic loads.
+template <class T, int R, bool kSmem, bool kGrid = false, bool kMerged = true, bool kLarge = !kMerged>
 __global__ void __launch_bounds__(kTraceBlock, (R >= 4 || sizeof(T) == 8) ? 2 : ((kMerged && !kGrid && R == 2) ? LG_MERGED_CTAS : 3))
     trace_kernel(const __grid_constant__ TraceArgs<T> A) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -348,10 +352,10 @@ __global__ void __launch_bounds__(kTraceBlock, (R >= 4 || sizeof(T) == 8) ? 2 : 
   const T *br2 = by + A.n_pad;
   const T *brb = br2 + A.n_pad;
   typedef typename Vec4<T>::type T4;
-  typedef TabLoad<T, kSmem> TL;
+  typedef TabLoad<T, kSmem && kLarge> TL;
   // the same four arrays as 32-bit shared-state-space addresses (used when kSmem)
   unsigned sx = 0u;
-  if (kSmem) // opaque move: keeps the compiler from rematerialising the window base inside the loops
+  if (kSmem && kLarge) // opaque move: keeps the compiler from rematerialising the window base inside the loops
     asm volatile("mov.u32 %0, %1;" : "=r"(sx) : "r"((unsigned)__cvta_generic_to_shared(smem_raw)));
   const unsigned sy = sx + (unsigned)(A.n_pad * sizeof(T));
   const unsigned sr2 = sy + (unsigned)(A.n_pad * sizeof(T));
@@ -470,13 +474,24 @@ __global__ void __launch_bounds__(kTraceBlock, (R >= 4 || sizeof(T) == 8) ? 2 : 
       unsigned m[R];
 #pragma unroll
       for (int r = 0; r < R; ++r) m[r] = 0u;
+      if (kLarge) {
 #pragma unroll
-      for (int q = 0; q < 32; q += 4) {
-        const T4 x4 = TL::v4(bx, sx, c0 + q);
-        const T4 y4 = TL::v4(by, sy, c0 + q);
-        const T4 r4 = TL::v4(br2, sr2, c0 + q);
+        for (int q = 0; q < 32; q += 4) {
+          const T4 x4 = TL::v4(bx, sx, c0 + q);
+          const T4 y4 = TL::v4(by, sy, c0 + q);
+          const T4 r4 = TL::v4(br2, sr2, c0 + q);
 #pragma unroll
-        for (int r = 0; r < R; ++r) m[r] = Broad<T>::test4(x4, y4, r4, sdx[r], sdy[r], nk[r], m[r]);
+          for (int r = 0; r < R; ++r) m[r] = Broad<T>::test4(x4, y4, r4, sdx[r], sdy[r], nk[r], m[r]);
+        }
+      } else {
+#pragma unroll 4
+        for (int q = 0; q < 32; q += 4) {
+          const T4 x4 = *reinterpret_cast<const T4 *>(bx + c0 + q);
+          const T4 y4 = *reinterpret_cast<const T4 *>(by + c0 + q);
+          const T4 r4 = *reinterpret_cast<const T4 *>(br2 + c0 + q);
+#pragma unroll
+          for (int r = 0; r < R; ++r) m[r] = Broad<T>::test4(x4, y4, r4, sdx[r], sdy[r], nk[r], m[r]);
+        }
       }
       if (kMerged) {
       // narrow phase, ONE instance for all slots: a lane walks the survivors of its slots one after the other
@@ -683,6 +698,7 @@ __global__ void __launch_bounds__(kTraceBlock, (R >= 4 || sizeof(T) == 8) ? 2 : 
 const void *trace_kernel_f32(int slots, bool smem);
 const void *trace_kernel_f64(int slots, bool smem);
 const void *trace_kernel_f32_per_slot(bool smem);
+const void *trace_kernel_f64_large(int slots, bool smem);
 const void *trace_kernel_grid_f32(int slots);
 const void *trace_kernel_grid_f64(int slots);
 

@@ -6,7 +6,7 @@ name=$1; shift
 cd "$(dirname "$0")/.."
 out=light_garden_b200/_lib/variants; mkdir -p $out/obj_$name
 F="-ccbin /usr/bin/g++ -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -fmad=false -Xcompiler -fPIC,-ffp-contract=off,-Wall"
-for s in lg_trace_f32 lg_trace_f32_dup lg_trace_f64 lg_trace_grid lg_capi; do
+for s in lg_trace_f32 lg_trace_f32_dup lg_trace_f64 lg_trace_f64_large lg_trace_grid lg_capi; do
   /usr/local/cuda/bin/nvcc $F "$@" -c light_garden_b200/csrc/$s.cu -o $out/obj_$name/$s.o &
 done
 wait
