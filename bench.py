@@ -410,9 +410,9 @@ def main():
             "roofline": {"bound": "fp32", "kernel": "lg::trace_kernel", "achieved": achieved_tflops,
                          "peak": fma.value, "unit": "TFLOP/s", "frac": achieved_tflops / fma.value if fma.value else None,
                          # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this kernel
-                         # (profiles/r01d_trace_full.txt: 5.5 MB + 378.9 MB for 2 M rays = 192 B per ray, the 32-byte
+                         # (profiles/r01f_trace_full.txt: 4.8 MB + 395.3 MB for 2 M rays = 200 B per ray, the 32-byte
                          # segments: 5.9 per ray = 189 B algorithmic), scaled to the rays of one launch
-                         "traffic": 192.2 * rays_per_gpu if args.precision == "f32" else None,
+                         "traffic": 200.0 * rays_per_gpu if args.precision == "f32" else None,
                          "traffic_unit": "bytes per launch (ncu capture at 2 M rays, scaled by rays per launch)",
                          "executed": {"flop_per_test_broad_phase": 6.0,
                                       "tflops": tests * 6.0 / tr_launches / (tr_ms_per_launch * 1e-3) / 1e12,
@@ -423,20 +423,24 @@ def main():
                                  f"({'FP64' if args.precision == 'f64' else 'FP32'} pipe; MEASURED_PEAKS.json has none). "
                                  "frac can exceed 1: the kernel decides most tests with a conservative 3-FMA bounding-"
                                  "circle line test (6 executed flop) and runs the full ORACLE.md test only on survivors; "
-                                 "`executed` counts that broad phase alone. ncu (profiles/r01d_trace_full.txt): FMA pipe "
-                                 "cycles 54 %, issue slots 71 % busy. The contract's hbm/tensor bounds do not apply: the table lives in shared "
+                                 "`executed` counts that broad phase alone. ncu (profiles/r01f_trace_full.txt): FMA pipe "
+                                 "cycles 55 %, issue slots 66 % busy; the sweep runs at 8.7 of the 8.76 cycles per object pair its instruction mix allows (profiles/r01f_ubench.txt). The contract's hbm/tensor bounds do not apply: the table lives in shared "
                                  "memory and the kernel writes 32 B per segment"},
             "roofline_accumulate": {"bound": "hbm",
                                     "kernel": "lg::tile_count/fill/raster_kernel (tile-binned resolve)"
                                     if agg["accumulate_launches"] > 2 * args.steps * world
                                     else "lg::accumulate_segments_kernel (direct resolve)", "achieved": acc_gbs,
-                                    "peak": hbm_peak, "unit": "GB/s", "frac": acc_gbs / hbm_peak, "traffic": None,
+                                    "peak": hbm_peak, "unit": "GB/s", "frac": acc_gbs / hbm_peak,
+                                    # ncu --set full of tile_raster_kernel (profiles/r01f_tile_raster_full.txt): 704.6 MB
+                                    # read + 24.8 MB written for 2 M rays (11.8 M segments) = 61.8 B per segment
+                                    "traffic": 61.8 * agg["segments"] / acc_launches if args.precision == "f32" else None,
+                                    "traffic_unit": "DRAM bytes of the raster kernel per accumulate launch (ncu capture at 2 M rays, scaled by segments; fragments never reach DRAM: they are summed in shared memory and leave as one red.v4 per touched pixel into L2)",
                                     "peak_source": hbm_src,
                                     "red_v4_peak_gred_per_s": {"coalesced": red_coal.value, "random": red_rand.value},
                                     "note": "algorithmic bytes = 32 B per segment read + 16 B per blended fragment, over the "
                                             "whole accumulate phase of a step; the tile-binned resolve is bound by "
-                                            "shared-memory bandwidth (74 % of the wavefront peak, "
-                                            "profiles/r01d_tile_raster_full.txt), the direct one by L2 reductions"},
+                                            "shared-memory latency and bandwidth (72 % of the wavefront peak, "
+                                            "profiles/r01f_tile_raster_full.txt), the direct one by L2 reductions"},
         }
     # CPU baseline: rank 0, N = 1 only, bounded sample
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
