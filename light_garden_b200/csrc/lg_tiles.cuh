@@ -80,12 +80,13 @@ template <> struct SegIO<LgSegment> {
 };
 template <> struct SegIO<Seg2> {
   static constexpr bool kLerp = true;
-  static __device__ __forceinline__ void load(const Seg2 *s, unsigned long long i, float4 &ab, float4 &ca, float4 &dc) {
-    const float4 *p = reinterpret_cast<const float4 *>(s + i);
-    ab = __ldg(p);
-    ca = __ldg(p + 1);
-    const float4 cb = __ldg(p + 2);
-    dc = make_float4(cb.x - ca.x, cb.y - ca.y, cb.z - ca.z, cb.w - ca.w);
+  // `cb` comes back raw: the colour difference is taken when the record is parked, a batch later -- taken here it
+  // made the prefetch wait for its own loads
+  static __device__ __forceinline__ void load(const Seg2 *s, unsigned long long i, float4 &ab, float4 &ca, float4 &cb) {
+    const float *p = reinterpret_cast<const float *>(s + i);
+    ldg_nc_v2(p, ab.x, ab.y), ldg_nc_v2(p + 2, ab.z, ab.w);
+    ldg_nc_v2(p + 4, ca.x, ca.y), ldg_nc_v2(p + 6, ca.z, ca.w);
+    ldg_nc_v2(p + 8, cb.x, cb.y), ldg_nc_v2(p + 10, cb.z, cb.w);
   }
   static __device__ __forceinline__ float4 load_ab(const Seg2 *s, unsigned long long i) {
     return __ldg(reinterpret_cast<const float4 *>(s + i));
@@ -338,7 +339,7 @@ template <class Seg> __global__ void __launch_bounds__(kRasterWarps * 32) tile_r
         const int l0 = max(S.i0 - bmaj, 0), l1 = min(S.i1 - bmaj, kTile);
         P.geo[lane] = make_float4(S.m0, S.inv, S.dn, S.n0);
         P.col[lane] = make_float4(g_ca.x, g_ca.y, g_ca.z, kLerp ? g_ca.w : g_ca.w * g_ca.w);
-        if (kLerp) P.dc[lane] = g_dc;
+        if (kLerp) P.dc[lane] = make_float4(g_dc.x - g_ca.x, g_dc.y - g_ca.y, g_dc.z - g_ca.z, g_dc.w - g_ca.w);
         P.rng[lane] = (unsigned)l0 | ((unsigned)max(l1 - l0, 0) << 8);
       } else if ((int)lane == m) { // the empty partner of an odd last entry
         P.geo[lane] = make_float4(0.f, 0.f, 0.f, 0.f);
