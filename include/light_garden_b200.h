@@ -335,6 +335,23 @@ int32_t lg_render(lg_ctx *ctx, LgTraceStats *stats);
  * bytes, 0 = tight (wgpu's readback pads rows to 256 bytes,
  * renderer.rs:250-255: pass that pitch to get the same layout). */
 int32_t lg_image_read(lg_ctx *ctx, int32_t format, void *dst, size_t pitch);
+/* Display hand-off without the host bounce (replaces the
+ * queue.write_texture of the frame, src/renderer.rs:356-417 keeps its blit):
+ * the frame in `format` lives in device memory that another API can import.
+ * lg_image_export_fd returns a POSIX file descriptor for it (an OPAQUE_FD
+ * handle: Vulkan VkImportMemoryFdInfoKHR, which wgpu-hal exposes, or
+ * cuMemImportFromShareableHandle) and the size of the allocation (the tight
+ * W x H frame at offset 0, rounded up to the allocation granularity); every
+ * call returns a new descriptor of the same memory and the caller closes it.
+ * lg_image_export_refresh converts the current image into that memory and
+ * returns when the stream has drained, so the importer may read right after.
+ * The memory stays valid until lg_image_configure changes the size or the
+ * context is destroyed.  LG_ERR_UNSUPPORTED when the driver cannot export. */
+int32_t lg_image_export_fd(lg_ctx *ctx, int32_t format, int32_t *fd, uint64_t *bytes);
+int32_t lg_image_export_refresh(lg_ctx *ctx, int32_t format);
+/* What a consumer does, for tests and for CUDA-side consumers: imports `fd`
+ * (allocation size `bytes`) on `device` and copies its first dst_bytes out. */
+int32_t lg_import_fd_read(int32_t device, int32_t fd, uint64_t bytes, void *dst, uint64_t dst_bytes);
 
 /* ---- multi-GPU: one context per device ------------------------------------ */
 /* 128-byte ncclUniqueId produced on one rank and handed to all of them. */

@@ -131,6 +131,9 @@ PROTOTYPES = {
     "lg_string_mod_nested_read": [_ctx, _p, C.c_uint64, _p, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)],
     "lg_render": [_ctx, C.POINTER(LgTraceStats)],
     "lg_image_read": [_ctx, C.c_int32, _p, C.c_size_t],
+    "lg_image_export_fd": [_ctx, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_uint64)],
+    "lg_image_export_refresh": [_ctx, C.c_int32],
+    "lg_import_fd_read": [C.c_int32, C.c_int32, C.c_uint64, _p, C.c_uint64],
     "lg_comm_unique_id": [_p],
     "lg_comm_init_rank": [_ctx, _p, C.c_int32, C.c_int32],
     "lg_comm_init_all": [C.POINTER(_ctx), C.c_int32],

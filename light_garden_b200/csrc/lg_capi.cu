@@ -4,6 +4,7 @@
 // See the header for the reference call sites each entry point replaces.
 // There is no CPU fallback anywhere in this file: every compute entry point
 // launches a kernel from lg_trace.cuh / lg_accum.cuh or fails.
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 
@@ -107,6 +108,69 @@ constexpr int kNcclUint8 = 1;   // ncclUint8
 constexpr int kMaxPeers = 16;
 } // namespace
 
+// ---- exportable frames (lg_image_export_fd): the driver's virtual-memory API, looked up through the runtime
+// (cudaGetDriverEntryPoint), so the library keeps no link-time dependency on libcuda
+namespace {
+struct VmmApi {
+  CUresult (*GetGranularity)(size_t *, const CUmemAllocationProp *, CUmemAllocationGranularity_flags) = nullptr;
+  CUresult (*Create)(CUmemGenericAllocationHandle *, size_t, const CUmemAllocationProp *, unsigned long long) = nullptr;
+  CUresult (*Release)(CUmemGenericAllocationHandle) = nullptr;
+  CUresult (*AddressReserve)(CUdeviceptr *, size_t, size_t, CUdeviceptr, unsigned long long) = nullptr;
+  CUresult (*AddressFree)(CUdeviceptr, size_t) = nullptr;
+  CUresult (*Map)(CUdeviceptr, size_t, size_t, CUmemGenericAllocationHandle, unsigned long long) = nullptr;
+  CUresult (*Unmap)(CUdeviceptr, size_t) = nullptr;
+  CUresult (*SetAccess)(CUdeviceptr, size_t, const CUmemAccessDesc *, size_t) = nullptr;
+  CUresult (*Export)(void *, CUmemGenericAllocationHandle, CUmemAllocationHandleType, unsigned long long) = nullptr;
+  CUresult (*Import)(CUmemGenericAllocationHandle *, void *, CUmemAllocationHandleType) = nullptr;
+  bool tried = false, ok = false;
+  std::string why;
+};
+VmmApi g_vmm;
+bool vmm_load() {
+  if (g_vmm.tried) return g_vmm.ok;
+  g_vmm.tried = true;
+  bool ok = true;
+  auto sym = [&](const char *name) -> void * {
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint(name, &fn, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess || !fn) {
+      cudaGetLastError();
+      ok = false;
+      g_vmm.why = std::string("driver entry point ") + name + " not available";
+      return nullptr;
+    }
+    return fn;
+  };
+  g_vmm.GetGranularity = (decltype(g_vmm.GetGranularity))sym("cuMemGetAllocationGranularity");
+  g_vmm.Create = (decltype(g_vmm.Create))sym("cuMemCreate");
+  g_vmm.Release = (decltype(g_vmm.Release))sym("cuMemRelease");
+  g_vmm.AddressReserve = (decltype(g_vmm.AddressReserve))sym("cuMemAddressReserve");
+  g_vmm.AddressFree = (decltype(g_vmm.AddressFree))sym("cuMemAddressFree");
+  g_vmm.Map = (decltype(g_vmm.Map))sym("cuMemMap");
+  g_vmm.Unmap = (decltype(g_vmm.Unmap))sym("cuMemUnmap");
+  g_vmm.SetAccess = (decltype(g_vmm.SetAccess))sym("cuMemSetAccess");
+  g_vmm.Export = (decltype(g_vmm.Export))sym("cuMemExportToShareableHandle");
+  g_vmm.Import = (decltype(g_vmm.Import))sym("cuMemImportFromShareableHandle");
+  g_vmm.ok = ok;
+  return ok;
+}
+// one frame in memory another API can import (POSIX file descriptor handle)
+struct ExportBuf {
+  CUmemGenericAllocationHandle handle = 0;
+  CUdeviceptr va = 0;
+  size_t size = 0; // allocation size (the frame rounded up to the allocation granularity)
+};
+void export_release(ExportBuf &e) {
+  if (e.va && g_vmm.ok) {
+    g_vmm.Unmap(e.va, e.size);
+    g_vmm.AddressFree(e.va, e.size);
+  }
+  if (e.handle && g_vmm.ok) g_vmm.Release(e.handle);
+  e = ExportBuf{};
+}
+constexpr int kExportFormats = 4;
+} // namespace
+
 // ---- context -----------------------------------------------------------------------------
 struct DevBuf {
   void *p = nullptr;
@@ -155,6 +219,7 @@ struct lg_ctx {
   // image
   int W = 0, H = 0;
   DevBuf img, img16, img8, pixctr;
+  ExportBuf exported[kExportFormats]; // lg_image_export_fd, indexed by format
   // tile-binned accumulation (lg_tiles.cuh)
   int accum_mode = 0; // 0 = auto, 1 = direct (one L2 reduction per fragment), 2 = tile-binned
   // auto mode: measured cost of each resolve on this context's recent work (ns per fragment, 0 = no sample yet)
@@ -734,6 +799,7 @@ int32_t lg_destroy(lg_ctx *c) {
                     &c->sync_buf,  &c->peer_xchg,  &c->img8,       &c->grid_start,  &c->grid_obj,
                     &c->nest_lines, &c->nest_counts, &c->nest_points, &c->nest_pairs};
   for (DevBuf *b : bufs) release(*b);
+  for (ExportBuf &e : c->exported) export_release(e);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
   if (c->stream) cudaStreamDestroy(c->stream);
@@ -960,6 +1026,8 @@ int32_t lg_image_configure(lg_ctx *c, uint32_t width, uint32_t height) {
   if (!c) return LG_ERR_INVALID;
   if (width == 0 || height == 0 || width > 32768 || height > 32768) return fail(c, LG_ERR_INVALID, "image size");
   LG_CUDA(c, cudaSetDevice(c->device));
+  if (c->W != (int)width || c->H != (int)height)
+    for (ExportBuf &e : c->exported) export_release(e); // a frame of another size: importers must fetch a new handle
   c->W = (int)width, c->H = (int)height;
   c->peers_ready = false; // the buffers may move: the next lg_image_reduce re-exchanges the peer mappings
   c->img16_valid = false;
@@ -1282,6 +1350,131 @@ int32_t lg_image_read(lg_ctx *c, int32_t format, void *dst, size_t pitch) {
   }
   LG_CUDA(c, cudaStreamSynchronize(c->stream));
   return LG_OK;
+}
+
+// ---- display hand-off without the host bounce ----------------------------------------------
+namespace {
+size_t format_bytes_per_pixel(int32_t format) {
+  return format == LG_RGBA32F ? 16 : format == LG_RGBA16F ? 8 : (format == LG_BGRA8_GAMMA || format == LG_BGRA8_SRGB) ? 4 : 0;
+}
+int vmm_fail(lg_ctx *c, const char *what, CUresult r) {
+  return fail(c, LG_ERR_UNSUPPORTED, std::string(what) + " failed (CUresult " + std::to_string((int)r) + ")");
+}
+} // namespace
+
+int32_t lg_image_export_fd(lg_ctx *c, int32_t format, int32_t *fd, uint64_t *bytes) {
+  int rc = need_image(c);
+  if (rc) return rc;
+  const size_t bpp = format_bytes_per_pixel(format);
+  if (!fd || !bytes || bpp == 0) return fail(c, LG_ERR_INVALID, "format / null output");
+  if (!vmm_load()) return fail(c, LG_ERR_UNSUPPORTED, g_vmm.why);
+  LG_CUDA(c, cudaSetDevice(c->device));
+  LG_CUDA(c, cudaFree(0)); // make sure the primary context is current for the driver calls
+  ExportBuf &e = c->exported[format];
+  const size_t frame = (size_t)c->W * c->H * bpp;
+  if (!e.handle) {
+    CUmemAllocationProp prop{};
+    prop.type = CU_MEM_ALLOCATION_TYPE_PINNED;
+    prop.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+    prop.location.id = c->device;
+    prop.requestedHandleTypes = CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR;
+    size_t gran = 0;
+    CUresult r = g_vmm.GetGranularity(&gran, &prop, CU_MEM_ALLOC_GRANULARITY_MINIMUM);
+    if (r != CUDA_SUCCESS || gran == 0) return vmm_fail(c, "cuMemGetAllocationGranularity", r);
+    ExportBuf n;
+    n.size = (frame + gran - 1) / gran * gran;
+    if ((r = g_vmm.Create(&n.handle, n.size, &prop, 0)) != CUDA_SUCCESS) return vmm_fail(c, "cuMemCreate (exportable)", r);
+    if ((r = g_vmm.AddressReserve(&n.va, n.size, 0, 0, 0)) != CUDA_SUCCESS) {
+      g_vmm.Release(n.handle);
+      return vmm_fail(c, "cuMemAddressReserve", r);
+    }
+    if ((r = g_vmm.Map(n.va, n.size, 0, n.handle, 0)) != CUDA_SUCCESS) {
+      g_vmm.AddressFree(n.va, n.size);
+      g_vmm.Release(n.handle);
+      return vmm_fail(c, "cuMemMap", r);
+    }
+    CUmemAccessDesc acc{};
+    acc.location = prop.location;
+    acc.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+    if ((r = g_vmm.SetAccess(n.va, n.size, &acc, 1)) != CUDA_SUCCESS) {
+      export_release(n);
+      return vmm_fail(c, "cuMemSetAccess", r);
+    }
+    e = n;
+    LG_CUDA(c, cudaMemsetAsync((void *)e.va, 0, e.size, c->stream));
+    LG_CUDA(c, cudaStreamSynchronize(c->stream));
+  }
+  int out = -1;
+  CUresult r = g_vmm.Export(&out, e.handle, CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR, 0);
+  if (r != CUDA_SUCCESS || out < 0) return vmm_fail(c, "cuMemExportToShareableHandle", r);
+  *fd = out;
+  *bytes = e.size;
+  return LG_OK;
+}
+
+int32_t lg_image_export_refresh(lg_ctx *c, int32_t format) {
+  int rc = need_image(c);
+  if (rc) return rc;
+  if (format_bytes_per_pixel(format) == 0) return fail(c, LG_ERR_INVALID, "format");
+  ExportBuf &e = c->exported[format];
+  if (!e.handle) return fail(c, LG_ERR_STATE, "lg_image_export_fd has not been called for this format");
+  LG_CUDA(c, cudaSetDevice(c->device));
+  const size_t npx = (size_t)c->W * c->H;
+  const float4 *src = (const float4 *)c->img.p;
+  if (format == LG_RGBA32F) {
+    LG_CUDA(c, cudaMemcpyAsync((void *)e.va, src, npx * 16, cudaMemcpyDeviceToDevice, c->stream));
+  } else if (format == LG_RGBA16F) {
+    if (c->img16_valid) { // the peer-fused reduce already left the finalized frame in img16
+      LG_CUDA(c, cudaMemcpyAsync((void *)e.va, c->img16.p, npx * 8, cudaMemcpyDeviceToDevice, c->stream));
+    } else {
+      finalize_f16_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(src, (uint2 *)e.va, npx);
+      c->launches++;
+    }
+  } else if (format == LG_BGRA8_GAMMA) {
+    screenshot_bgra8_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(src, (uchar4 *)e.va, npx);
+    c->launches++;
+  } else {
+    static const SrgbThresholds thresholds = srgb_thresholds();
+    surface_bgra8_srgb_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(src, (uchar4 *)e.va, npx, thresholds);
+    c->launches++;
+  }
+  LG_CUDA(c, cudaGetLastError());
+  LG_CUDA(c, cudaStreamSynchronize(c->stream)); // the importer may read as soon as this returns
+  return LG_OK;
+}
+
+int32_t lg_import_fd_read(int32_t device, int32_t fd, uint64_t bytes, void *dst, uint64_t dst_bytes) {
+  if (fd < 0 || !dst || dst_bytes > bytes || bytes == 0) return LG_ERR_INVALID;
+  if (!vmm_load()) return LG_ERR_UNSUPPORTED;
+  if (cudaSetDevice(device) != cudaSuccess || cudaFree(0) != cudaSuccess) {
+    cudaGetLastError();
+    return LG_ERR_CUDA;
+  }
+  CUmemGenericAllocationHandle h = 0;
+  if (g_vmm.Import(&h, (void *)(uintptr_t)fd, CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR) != CUDA_SUCCESS) return LG_ERR_UNSUPPORTED;
+  CUdeviceptr va = 0;
+  int32_t rc = LG_OK;
+  if (g_vmm.AddressReserve(&va, bytes, 0, 0, 0) != CUDA_SUCCESS) {
+    g_vmm.Release(h);
+    return LG_ERR_NOMEM;
+  }
+  if (g_vmm.Map(va, bytes, 0, h, 0) != CUDA_SUCCESS) {
+    rc = LG_ERR_CUDA;
+  } else {
+    CUmemAccessDesc acc{};
+    acc.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+    acc.location.id = device;
+    acc.flags = CU_MEM_ACCESS_FLAGS_PROT_READ;
+    if (g_vmm.SetAccess(va, bytes, &acc, 1) != CUDA_SUCCESS ||
+        cudaMemcpy(dst, (const void *)va, dst_bytes, cudaMemcpyDeviceToHost) != cudaSuccess) {
+      cudaGetLastError();
+      rc = LG_ERR_CUDA;
+    }
+    g_vmm.Unmap(va, bytes);
+  }
+  g_vmm.AddressFree(va, bytes);
+  g_vmm.Release(h);
+  return rc;
 }
 
 // ---- multi-GPU ---------------------------------------------------------------------------

@@ -328,6 +328,17 @@ class Renderer:
         self.ctx.call("lg_image_read", abi.LG_BGRA8_SRGB, abi.array_ptr(out), row)
         return out[:, : self.width * 4].reshape(self.height, self.width, 4)
 
+    def export_fd(self, fmt=abi.LG_RGBA16F):
+        """(fd, allocation bytes) of the frame in `fmt` as device memory another API can import (Vulkan OPAQUE_FD /
+        cuMemImportFromShareableHandle): the display hand-off without renderer.rs's host copy.  The caller closes fd."""
+        fd, n = C.c_int32(-1), C.c_uint64(0)
+        self.ctx.call("lg_image_export_fd", fmt, C.byref(fd), C.byref(n))
+        return fd.value, n.value
+
+    def export_refresh(self, fmt=abi.LG_RGBA16F):
+        """Converts the current image into the exported frame; importers may read when this returns."""
+        self.ctx.call("lg_image_export_refresh", fmt)
+
     def read_rgba16f(self, out=None):
         if out is None:
             out = np.zeros((self.height, self.width, 4), dtype=np.float16)

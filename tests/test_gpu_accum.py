@@ -349,6 +349,48 @@ def test_surface_bgra8_srgb(oracle, ctx):
     assert not r.read_surface_bgra8().any()
 
 
+def test_exported_frame_is_importable_device_memory(oracle, ctx):
+    """SURVEY.md §8f rank 3 (display hand-off without the host bounce, renderer.rs:356-417): the frame as device memory
+    behind a POSIX file descriptor.  A consumer that imports the descriptor (here cuMemImportFromShareableHandle through
+    lg_import_fd_read; Vulkan's OPAQUE_FD import takes the same handle) sees exactly what lg_image_read returns."""
+    import os
+    from light_garden_b200 import abi
+    from light_garden_b200._lib import LightGardenError, check, load
+    from light_garden_b200.tracer import Renderer
+    W, H = 200, 120
+    r = Renderer(ctx, W, H)
+    r.render_lines(random_pairs(3000, seed=23, pow2=False))
+    try:
+        fd, nbytes = r.export_fd(abi.LG_RGBA16F)
+    except LightGardenError as e:                      # a driver that cannot export says so instead of faking it
+        assert e.code == abi.LG_ERR_UNSUPPORTED
+        pytest.skip("driver cannot export device memory: " + e.message)
+    try:
+        assert fd >= 0 and nbytes >= W * H * 8
+        r.export_refresh(abi.LG_RGBA16F)
+        got = np.zeros((H, W, 4), dtype=np.float16)
+        check(None, load().lg_import_fd_read(0, fd, nbytes, abi.array_ptr(got), got.nbytes))
+        assert np.array_equal(got.view(np.uint16), r.read_rgba16f().view(np.uint16))
+        # the same memory after more lines and another refresh: importers keep their mapping
+        r.render_lines(random_pairs(500, seed=24, pow2=False))
+        r.export_refresh(abi.LG_RGBA16F)
+        check(None, load().lg_import_fd_read(0, fd, nbytes, abi.array_ptr(got), got.nbytes))
+        assert np.array_equal(got.view(np.uint16), r.read_rgba16f().view(np.uint16))
+    finally:
+        os.close(fd)
+    # the 8-bit surface frame through a second descriptor
+    fd8, n8 = r.export_fd(abi.LG_BGRA8_SRGB)
+    try:
+        r.export_refresh(abi.LG_BGRA8_SRGB)
+        got8 = np.zeros((H, W, 4), dtype=np.uint8)
+        check(None, load().lg_import_fd_read(0, fd8, n8, abi.array_ptr(got8), got8.nbytes))
+        assert np.array_equal(got8, r.read_surface_bgra8())
+    finally:
+        os.close(fd8)
+    with pytest.raises(LightGardenError):
+        r.export_refresh(abi.LG_RGBA32F)               # never exported in this format: a state error, not a silent no-op
+
+
 def test_clear_value_and_partial_alpha(ctx):
     from light_garden_b200.tracer import Renderer
     r = Renderer(ctx, 40, 30)
