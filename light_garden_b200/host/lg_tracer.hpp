@@ -7,6 +7,7 @@
 //   PointLight::new / SpotLight::new / DirectionalLight::new                      src/light_garden/light.rs:91,153,205
 //   Tracer{max_bounce = 5, cutoff_color = [0.001;4], chunk_size = 100, canvas_bounds}, push_object, push_light,
 //   clear, replace_object, remove_object, remove_light, resize, trace_all()       src/light_garden/tracer.rs:4-358
+//   Renderer{render, make_screenshot, resize} + SubRenderPass::update_vertex_buffer  src/renderer.rs:164-431, src/sub_render_pass.rs:188-212
 // Where the reference panics (tracer.rs:192, framework.rs:44) this throws lg::Error carrying lg_last_error().
 // All computation happens in the CUDA library; this file only holds and flattens data.
 #pragma once
@@ -324,6 +325,82 @@ private:
   bool tile_map_enabled_ = false;
   std::vector<Object> objects_;
   std::vector<Light> lights_;
+};
+
+// The line pass (boundary B2): Renderer::render's LineList draw of the traced lines into the Rgba16Float target
+// (src/renderer.rs:164-188,431; SubRenderPass::update_vertex_buffer + render, src/sub_render_pass.rs:188-212), the
+// screenshot conversion (renderer.rs:190-328) and the frame hand-off.  Shares the tracer's context.
+class Renderer {
+public:
+  uint32_t width, height;
+  LgTraceStats last_stats{};
+
+  Renderer(Tracer &tracer, uint32_t w, uint32_t h) : width(w), height(h), t_(tracer) {
+    t_.check(lg_image_configure(t_.context(), w, h));
+  }
+  // SurfaceConfiguration change (renderer.rs:resize): a new target of the new size, cleared
+  void resize(uint32_t w, uint32_t h) {
+    width = w, height = h;
+    t_.check(lg_image_configure(t_.context(), w, h));
+  }
+  // LoadOp::Clear(BLACK), renderer.rs:174-177
+  void clear(float clear_alpha = 1.0f) { t_.check(lg_image_clear(t_.context(), clear_alpha)); }
+  // Renderer::render: trace_all + update_vertex_buffer + the line pass, fused on the device
+  const LgTraceStats &render() {
+    t_.upload();
+    t_.check(lg_tags_enable(t_.context(), 0));
+    t_.check(lg_render(t_.context(), &last_stats));
+    return last_stats;
+  }
+  // sub_rpass_lines.render for the segments of the last Tracer::trace_all
+  const LgTraceStats &render_traced() {
+    t_.check(lg_accumulate_traced(t_.context(), &last_stats));
+    return last_stats;
+  }
+  // SubRenderPass::update_vertex_buffer(&lines) + render for a host LineList (vertex pairs): control lines, grid,
+  // drawer overlays (tracer.rs:342-349, mod.rs:692)
+  const LgTraceStats &render_lines(const std::vector<std::pair<P2, Color>> &lines) {
+    std::vector<LgVertexPair> vp(lines.size() / 2);
+    for (size_t k = 0; k < vp.size(); ++k) {
+      const auto &a = lines[2 * k], &b = lines[2 * k + 1];
+      vp[k].a[0] = a.first.x, vp[k].a[1] = a.first.y, vp[k].b[0] = b.first.x, vp[k].b[1] = b.first.y;
+      std::copy(a.second.begin(), a.second.end(), vp[k].color_a);
+      std::copy(b.second.begin(), b.second.end(), vp[k].color_b);
+    }
+    t_.check(lg_accumulate_segments(t_.context(), vp.data(), vp.size(), &last_stats));
+    return last_stats;
+  }
+  std::vector<float> read_rgba32f() {
+    std::vector<float> img((size_t)width * height * 4);
+    t_.check(lg_image_read(t_.context(), LG_RGBA32F, img.data(), 0));
+    return img;
+  }
+  // the Rgba16Float texture's bits (texture_renderer.rs:5)
+  std::vector<uint16_t> read_rgba16f() {
+    std::vector<uint16_t> img((size_t)width * height * 4);
+    t_.check(lg_image_read(t_.context(), LG_RGBA16F, img.data(), 0));
+    return img;
+  }
+  // Renderer::make_screenshot's pixels: [b, g, r, a] bytes, rows padded to `padded_bytes_per_row` (0 = tight;
+  // renderer.rs:250-255 pads to 256); render_to_texture selects the fp16 gamma conversion (renderer.rs:313-328) or
+  // the 8-bit sRGB surface (renderer.rs:207-209)
+  std::vector<uint8_t> make_screenshot(bool render_to_texture = true, size_t padded_bytes_per_row = 0) {
+    const size_t row = padded_bytes_per_row ? padded_bytes_per_row : (size_t)width * 4;
+    std::vector<uint8_t> px(row * height);
+    t_.check(lg_image_read(t_.context(), render_to_texture ? LG_BGRA8_GAMMA : LG_BGRA8_SRGB, px.data(), row));
+    return px;
+  }
+  // the frame as importable device memory instead of a host copy (include/light_garden_b200.h: lg_image_export_fd)
+  std::pair<int, uint64_t> export_fd(int32_t format = LG_RGBA16F) {
+    int32_t fd = -1;
+    uint64_t bytes = 0;
+    t_.check(lg_image_export_fd(t_.context(), format, &fd, &bytes));
+    return {fd, bytes};
+  }
+  void export_refresh(int32_t format = LG_RGBA16F) { t_.check(lg_image_export_refresh(t_.context(), format)); }
+
+private:
+  Tracer &t_;
 };
 
 } // namespace lg

@@ -1,6 +1,8 @@
 // tests/host_cpp_smoke.cpp — the C++ host mirror (light_garden_b200/host/lg_tracer.hpp) driving the C ABI:
 // builds default.ron's scene through the reference's constructor names, traces it, renders it, prints a digest
 // that tests/test_host_cpp.py compares with the Python host layer.  Needs a GPU.
+#include <algorithm>
+#include <cmath>
 #include <cstdio>
 
 #include "../light_garden_b200/host/lg_tracer.hpp"
@@ -28,6 +30,26 @@ int main() {
     std::printf("vertices %zu segments %llu ray_steps %llu\n", lines.size(), (unsigned long long)t.last_stats.segments,
                 (unsigned long long)t.last_stats.ray_steps);
     std::printf("checksum %.9e %.9e %.9e\n", sx, sy, sc);
+    // boundary B2 through the same mirror: the traced lines as a host LineList vs the fused device frame
+    lg::Renderer rend(t, 480, 270);
+    rend.render_lines(lines);
+    const unsigned long long frag_lines = rend.last_stats.pixel_updates;
+    const std::vector<float> img_lines = rend.read_rgba32f();
+    rend.clear();
+    rend.render();                      // trace + accumulate on the device; the control lines are host lines
+    rend.render_lines(std::vector<std::pair<lg::P2, lg::Color>>(lines.end() - 6, lines.end()));
+    const std::vector<float> img_dev = rend.read_rgba32f();
+    double si = 0, worst = 0;
+    for (size_t k = 0; k < img_dev.size(); ++k) {
+      si += img_dev[k];
+      const double tol = 1e-5 * std::max(1.0, (double)std::fabs(img_lines[k]));
+      worst = std::max(worst, std::fabs((double)img_dev[k] - img_lines[k]) / tol);
+    }
+    const std::vector<uint8_t> shot = rend.make_screenshot(true, 2048), surf = rend.make_screenshot(false);
+    unsigned long long sb = 0, ss = 0;
+    for (uint8_t v : shot) sb += v;
+    for (uint8_t v : surf) ss += v;
+    std::printf("image fragments %llu sum %.9e worst_tol_ratio %.3f screenshot %llu surface %llu\n", frag_lines, si, worst, sb, ss);
     // the remaining Object constructors (object.rs:34-45): a prism and an ellipse in front of a point light
     lg::Tracer extra(lg::Rect::from_tlbr(1., -aspect, -1., aspect));
     extra.push_object(lg::Object::new_convex_polygon({{-0.5, -0.3}, {0.5, -0.3}, {0.0, 0.5}, {0.0, 0.0}}));

@@ -14,6 +14,14 @@ LIBDIR = os.path.join(ROOT, "light_garden_b200", "_lib")
 CXX = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
 
 
+def seg_pairs(seg):
+    """LgSegment records (one colour) as host vertex pairs."""
+    from light_garden_b200 import abi
+    p = np.zeros(len(seg), dtype=abi.VERTEX_PAIR_DTYPE)
+    p["a"], p["b"], p["color_a"], p["color_b"] = seg["a"], seg["b"], seg["color"], seg["color"]
+    return p
+
+
 def build(tmp_path, product_lib):
     exe = str(tmp_path / "host_cpp_smoke")
     cmd = [CXX, "-std=c++17", "-O1", "-Wall", "-o", exe, os.path.join(ROOT, "tests", "host_cpp_smoke.cpp"),
@@ -49,3 +57,15 @@ def test_cpp_host_mirror_matches_python_host(tmp_path, product_lib):
     sy = float(seg["a"][:, 1].astype(np.float64).sum() + seg["b"][:, 1].astype(np.float64).sum())
     sc = 2 * float(seg["color"][:, :3].astype(np.float64).sum())
     np.testing.assert_allclose(cs, [sx, sy, sc], rtol=1e-7)   # the digest is printed with 10 significant digits
+    # boundary B2 through the C++ Renderer: host LineList == fused device frame (worst deviation within the stated
+    # 1e-5 tolerance), and the same fragments / image / 8-bit frames as the Python host layer
+    from light_garden_b200.tracer import Renderer
+    im = re.search(r"image fragments (\d+) sum (\S+) worst_tol_ratio (\S+) screenshot (\d+) surface (\d+)", r.stdout)
+    assert im and float(im.group(3)) <= 1.0
+    rend = Renderer(t.ctx, 480, 270)
+    st = rend.render_lines(seg_pairs(seg))
+    assert int(im.group(1)) == st.pixel_updates
+    img = rend.read_rgba32f()
+    np.testing.assert_allclose(float(im.group(2)), float(img.astype(np.float64).sum()), rtol=1e-5)
+    assert abs(int(im.group(4)) - int(rend.make_screenshot().astype(np.int64).sum())) <= 1e-4 * int(im.group(4))
+    assert abs(int(im.group(5)) - int(rend.read_surface_bgra8().astype(np.int64).sum())) <= 1e-4 * int(im.group(5))
