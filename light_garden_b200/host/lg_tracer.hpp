@@ -8,6 +8,7 @@
 //   Tracer{max_bounce = 5, cutoff_color = [0.001;4], chunk_size = 100, canvas_bounds}, push_object, push_light,
 //   clear, replace_object, remove_object, remove_light, resize, trace_all()       src/light_garden/tracer.rs:4-358
 //   Renderer{render, make_screenshot, resize} + SubRenderPass::update_vertex_buffer  src/renderer.rs:164-431, src/sub_render_pass.rs:188-212
+//   StringMod{modulo = 5, num = 1, color = [1;4], turns = 1, Circle, Mul}, ModRemColor, Curve    src/light_garden/string_mod.rs:4-31,160-188
 // Where the reference panics (tracer.rs:192, framework.rs:44) this throws lg::Error carrying lg_last_error().
 // All computation happens in the CUDA library; this file only holds and flattens data.
 #pragma once
@@ -327,6 +328,50 @@ private:
   std::vector<Light> lights_;
 };
 
+// StringMod (src/light_garden/string_mod.rs:4-31,160-188): same fields and defaults as StringMod::new()
+struct ModRemColor {
+  uint64_t modulo = 1, rem = 0;
+  Color color{1.f, 1.f, 1.f, 1.f};
+};
+enum class StringModMode { Add = LG_SM_ADD, Mul = LG_SM_MUL, Pow = LG_SM_POW, Base = LG_SM_BASE };
+struct Curve {
+  int kind = LG_CURVE_CIRCLE;
+  std::array<double, 4> params{};
+  static Curve Circle() { return {}; }
+  static Curve ComplexExp(double re, double im) { return {LG_CURVE_COMPLEX_EXP, {re, im, 0, 0}}; }
+  static Curve Hypotrochoid(uint64_t r, uint64_t s, uint64_t d) {
+    return {LG_CURVE_HYPOTROCHOID, {(double)r, (double)s, (double)d, 0}};
+  }
+  static Curve Lissajous(uint64_t a, uint64_t b, double delta) { return {LG_CURVE_LISSAJOUS, {(double)a, (double)b, delta, 0}}; }
+};
+struct StringMod {
+  uint64_t modulo = 5, num = 1;
+  uint32_t pow = 0;
+  Color color{1.f, 1.f, 1.f, 1.f};
+  uint64_t turns = 1;
+  Curve init_curve = Curve::Circle();
+  StringModMode mode = StringModMode::Mul;
+  std::vector<ModRemColor> modulo_colors;
+  std::shared_ptr<StringMod> nested; // Option<Box<StringMod>>
+
+  LgStringMod pod() const {
+    LgStringMod s{};
+    s.modulo = modulo, s.num = num, s.turns = turns;
+    s.mode = (int32_t)mode, s.curve = init_curve.kind;
+    std::copy(color.begin(), color.end(), s.color);
+    std::copy(init_curve.params.begin(), init_curve.params.end(), s.curve_p);
+    return s;
+  }
+  std::vector<LgModRemColor> rules() const {
+    std::vector<LgModRemColor> r(modulo_colors.size());
+    for (size_t k = 0; k < r.size(); ++k) {
+      r[k].modulo = modulo_colors[k].modulo, r[k].rem = modulo_colors[k].rem;
+      std::copy(modulo_colors[k].color.begin(), modulo_colors[k].color.end(), r[k].color);
+    }
+    return r;
+  }
+};
+
 // The line pass (boundary B2): Renderer::render's LineList draw of the traced lines into the Rgba16Float target
 // (src/renderer.rs:164-188,431; SubRenderPass::update_vertex_buffer + render, src/sub_render_pass.rs:188-212), the
 // screenshot conversion (renderer.rs:190-328) and the frame hand-off.  Shares the tracer's context.
@@ -368,6 +413,19 @@ public:
       std::copy(b.second.begin(), b.second.end(), vp[k].color_b);
     }
     t_.check(lg_accumulate_segments(t_.context(), vp.data(), vp.size(), &last_stats));
+    return last_stats;
+  }
+  // LightGarden::draw in Mode::StringMod (mod.rs:681-689: StringMod::draw, string_mod.rs:152-158) + the line pass
+  const LgTraceStats &render_string_mod(const StringMod &sm) {
+    const LgStringMod pod = sm.pod();
+    if (sm.nested) {
+      const LgStringMod inner = sm.nested->pod();
+      const std::vector<LgModRemColor> irules = sm.nested->rules();
+      t_.check(lg_string_mod_nested(t_.context(), &pod, &inner, irules.data(), (uint32_t)irules.size(), &last_stats));
+    } else {
+      const std::vector<LgModRemColor> r = sm.rules();
+      t_.check(lg_string_mod(t_.context(), &pod, r.data(), (uint32_t)r.size(), 0, 0, &last_stats));
+    }
     return last_stats;
   }
   std::vector<float> read_rgba32f() {

@@ -50,6 +50,16 @@ int main() {
     for (uint8_t v : shot) sb += v;
     for (uint8_t v : surf) ss += v;
     std::printf("image fragments %llu sum %.9e worst_tol_ratio %.3f screenshot %llu surface %llu\n", frag_lines, si, worst, sb, ss);
+    // Mode::StringMod through the mirror: 3000 chords i -> 2 i mod 3000 with the three colour rules of BASELINE's C4
+    lg::StringMod sm;
+    sm.modulo = 3000, sm.num = 2;
+    sm.color = {1e-2f, 1e-2f, 1e-2f, 1e-2f};
+    sm.modulo_colors = {{3, 0, {1e-2f, 0.f, 0.f, 1e-2f}}, {3, 1, {0.f, 1e-2f, 0.f, 1e-2f}}, {3, 2, {0.f, 0.f, 1e-2f, 1e-2f}}};
+    lg::Renderer srend(t, 256, 256);
+    srend.render_string_mod(sm);
+    double ssum = 0;
+    for (float v : srend.read_rgba32f()) ssum += v;
+    std::printf("string_mod fragments %llu sum %.9e\n", (unsigned long long)srend.last_stats.pixel_updates, ssum);
     // the remaining Object constructors (object.rs:34-45): a prism and an ellipse in front of a point light
     lg::Tracer extra(lg::Rect::from_tlbr(1., -aspect, -1., aspect));
     extra.push_object(lg::Object::new_convex_polygon({{-0.5, -0.3}, {0.5, -0.3}, {0.0, 0.5}, {0.0, 0.0}}));

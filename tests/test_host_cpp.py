@@ -69,3 +69,13 @@ def test_cpp_host_mirror_matches_python_host(tmp_path, product_lib):
     np.testing.assert_allclose(float(im.group(2)), float(img.astype(np.float64).sum()), rtol=1e-5)
     assert abs(int(im.group(4)) - int(rend.make_screenshot().astype(np.int64).sum())) <= 1e-4 * int(im.group(4))
     assert abs(int(im.group(5)) - int(rend.read_surface_bgra8().astype(np.int64).sum())) <= 1e-4 * int(im.group(5))
+    # Mode::StringMod through the C++ StringMod / Renderer::render_string_mod
+    from light_garden_b200.scene import ModRemColor, StringMod, StringModMode
+    smm = re.search(r"string_mod fragments (\d+) sum (\S+)", r.stdout)
+    srend = Renderer(t.ctx, 256, 256)
+    c = 1e-2
+    st = srend.render_string_mod(StringMod(modulo=3000, num=2, mode=StringModMode.Mul, turns=1, color=[c] * 4,
+                                           modulo_colors=[ModRemColor(3, 0, [c, 0, 0, c]), ModRemColor(3, 1, [0, c, 0, c]),
+                                                          ModRemColor(3, 2, [0, 0, c, c])]))
+    assert smm and int(smm.group(1)) == st.pixel_updates
+    np.testing.assert_allclose(float(smm.group(2)), float(srend.read_rgba32f().astype(np.float64).sum()), rtol=1e-5)
