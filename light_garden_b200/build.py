@@ -15,7 +15,7 @@ OUT_DIR = os.path.join(HERE, "_lib")
 OBJ_DIR = os.path.join(OUT_DIR, "obj")
 LIB = os.path.join(OUT_DIR, "liblight_garden_b200.so")
 SOURCES = ["lg_capi.cu", "lg_trace_f32.cu", "lg_trace_f64.cu", "lg_trace_grid.cu", "lg_trace_f32_dup.cu", "lg_trace_f64_large.cu"]
-HEADERS = ["lg_geom.cuh", "lg_nearest.cuh", "lg_trace.cuh", "lg_accum.cuh", "lg_tiles.cuh", "lg_nested.cuh", "lg_reduce.cuh", "lg_bench.cuh", "lg_scene.h", "lg_tables.h", "../../include/light_garden_b200.h"]
+HEADERS = ["lg_geom.cuh", "lg_nearest.cuh", "lg_trace.cuh", "lg_accum.cuh", "lg_tiles.cuh", "lg_nested.cuh", "lg_reduce.cuh", "lg_bench.cuh", "lg_srgb.h", "lg_scene.h", "lg_tables.h", "../../include/light_garden_b200.h"]
 
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 CCBIN = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"

@@ -21,6 +21,7 @@
 #include <stdint.h>
 
 #include "../../include/light_garden_b200.h"
+#include "lg_srgb.h"
 
 namespace lg {
 
@@ -420,31 +421,6 @@ __global__ void screenshot_bgra8_kernel(const float4 *img, uchar4 *dst, size_t n
 // additive fragments the order-free limit of that blend is min(sum, 1).  Colour is stored sRGB-encoded and rounded
 // to nearest: byte = #{k in 1..255 : T[k] <= c}, T[k] = the linear value whose encoding is (k - 0.5) / 255
 // (f64 on the host, rounded to f32) -- a table look-up, so the bytes do not depend on any device pow().
-struct SrgbThresholds {
-  float t[256]; // t[0] = -inf (unused), t[1..255] ascending
-};
-inline SrgbThresholds srgb_thresholds() {
-  SrgbThresholds T;
-  T.t[0] = -INFINITY;
-  for (int k = 1; k < 256; ++k) {
-    const double v = ((double)k - 0.5) / 255.0;
-    const double lin = v <= 0.04045 ? v / 12.92 : pow((v + 0.055) / 1.055, 2.4);
-    T.t[k] = (float)lin;
-  }
-  return T;
-}
-__host__ __device__ __forceinline__ unsigned char srgb_byte(const float *t, float c) {
-  // largest k with t[k] <= c (t[0] = -inf; NaN compares false everywhere -> 0)
-  int k = 0;
-#pragma unroll
-  for (int step = 128; step > 0; step >>= 1)
-    if (t[k + step] <= c) k += step;
-  return (unsigned char)k;
-}
-__host__ __device__ __forceinline__ unsigned char unorm_byte(float a) {
-  if (!(a > 0.f)) return 0; // NaN -> 0, like the ROP's clamp
-  return (unsigned char)(fminf(a, 1.f) * 255.f + 0.5f);
-}
 __global__ void surface_bgra8_srgb_kernel(const float4 *img, uchar4 *dst, size_t n_px,
                                           const __grid_constant__ SrgbThresholds T) {
   __shared__ float t[256];

@@ -1072,4 +1072,21 @@ inline uint64_t raster_segment(const Proj &pr, const float a[2], const float b[2
   return n;
 }
 
+// ---- ORACLE.md 8.7: the 8-bit surface target (sub_render_pass.rs:59-63; Bgra8UnormSrgb, renderer.rs:207-209) ---------
+// colour byte = number of k in 1..255 whose threshold T[k] = f32(linear value encoding to (k - 0.5) / 255) is <= c;
+// alpha byte = floor(min(a, 1) * 255 + 0.5) in f32; anything not > 0 (NaN included) is 0.
+inline void surface_thresholds(float thr[256]) {
+  thr[0] = -INFINITY;
+  for (int k = 1; k < 256; ++k) {
+    const double enc = ((double)k - 0.5) / 255.0;
+    thr[k] = (float)(enc <= 0.04045 ? enc / 12.92 : std::pow((enc + 0.055) / 1.055, 2.4));
+  }
+}
+inline uint8_t surface_colour_byte(const float thr[256], float v) {
+  int n = 0;
+  for (int k = 1; k < 256; ++k) n += thr[k] <= v ? 1 : 0;
+  return (uint8_t)n;
+}
+inline uint8_t surface_alpha_byte(float a) { return !(a > 0.f) ? 0 : (uint8_t)((a < 1.f ? a : 1.f) * 255.f + 0.5f); }
+
 } // namespace lgo

@@ -421,21 +421,11 @@ void lgo_image_to_bgra8(const float *img, uint64_t n_px, uint8_t *dst) {
 // alpha byte = floor(min(a, 1) * 255 + 0.5) in f32; anything not > 0 (NaN included) is 0.  Stored [b, g, r, a].
 void lgo_image_to_bgra8_srgb(const float *img, uint64_t n_px, uint8_t *dst) {
   float thr[256];
-  for (int k = 1; k < 256; ++k) {
-    const double enc = ((double)k - 0.5) / 255.0;
-    thr[k] = (float)(enc <= 0.04045 ? enc / 12.92 : std::pow((enc + 0.055) / 1.055, 2.4));
-  }
+  lgo::surface_thresholds(thr);
   for (uint64_t i = 0; i < n_px; ++i) {
-    uint8_t c[4];
-    for (int ch = 0; ch < 3; ++ch) {
-      const float v = img[4 * i + ch];
-      int n = 0;
-      for (int k = 1; k < 256; ++k) n += thr[k] <= v ? 1 : 0;
-      c[ch] = (uint8_t)n;
-    }
-    const float a = img[4 * i + 3];
-    c[3] = !(a > 0.f) ? 0 : (uint8_t)((a < 1.f ? a : 1.f) * 255.f + 0.5f);
-    dst[4 * i] = c[2], dst[4 * i + 1] = c[1], dst[4 * i + 2] = c[0], dst[4 * i + 3] = c[3];
+    const float *p = img + 4 * i;
+    dst[4 * i] = lgo::surface_colour_byte(thr, p[2]), dst[4 * i + 1] = lgo::surface_colour_byte(thr, p[1]);
+    dst[4 * i + 2] = lgo::surface_colour_byte(thr, p[0]), dst[4 * i + 3] = lgo::surface_alpha_byte(p[3]);
   }
 }
 void lgo_image_to_f16(const float *img, uint64_t n_floats, uint16_t *dst) {

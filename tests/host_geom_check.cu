@@ -15,6 +15,7 @@
 #include "../light_garden_b200/csrc/lg_scene.h"
 #include "../light_garden_b200/csrc/lg_nearest.cuh"
 #include "../light_garden_b200/csrc/lg_tables.h"
+#include "../light_garden_b200/csrc/lg_srgb.h"
 #include "../oracle/lg_oracle.hpp"
 
 static uint64_t s_state = 0x4C47BEEFull;
@@ -443,11 +444,38 @@ static long check_grid(int n_scenes) {
   return n;
 }
 
+// ORACLE.md 8.7: the product's 8-bit surface encoding (binary search over its threshold table) against the oracle's
+// (its own table, linear count): random values, every threshold and its two neighbours, the special values.
+static long check_surface(int iters) {
+  const lg::SrgbThresholds T = lg::srgb_thresholds();
+  float thr[256];
+  lgo::surface_thresholds(thr);
+  long n = 0;
+  auto one = [&](float v) {
+    if (lg::srgb_byte(T.t, v) != lgo::surface_colour_byte(thr, v) || lg::unorm_byte(v) != lgo::surface_alpha_byte(v)) {
+      if (g_bad < 20) std::printf("MISMATCH surface byte of %.9g\n", (double)v);
+      ++g_bad;
+    }
+    ++n;
+  };
+  for (int k = 1; k < 256; ++k) {
+    one(thr[k]), one(std::nextafterf(thr[k], 0.f)), one(std::nextafterf(thr[k], 2.f));
+    one((float)k / 255.f), one(((float)k - 0.5f) / 255.f), one(std::nextafterf(((float)k - 0.5f) / 255.f, 0.f));
+  }
+  const float special[] = {0.f, -0.f, 1.f, 2.f, -1.f, INFINITY, -INFINITY, NAN, 1e-30f, 1e-45f, 0.0031308f, 0.04045f, 0.5f};
+  for (float v : special) one(v);
+  for (int i = 0; i < iters; ++i) {
+    one((float)uni(0.0, 1.2)), one((float)uni(0.0, 0.01)), one((float)uni(-0.5, 300.0));
+  }
+  return n;
+}
+
 int main(int argc, char **argv) {
   int iters = argc > 1 ? std::atoi(argv[1]) : 200000;
   long n = run<float>(iters) + run<double>(iters);
   n += check_lowering(iters / 500 + 10);
   n += check_grid(iters / 2500 + 4);
+  n += check_surface(iters);
   if (g_bad) {
     std::printf("FAILED %ld mismatches\n", g_bad);
     return 1;
