@@ -14,7 +14,9 @@ every segment, sum the partial images onto rank 0.
   roofline : the trace kernel against the FP32 FMA peak measured in this run (16.5 algorithmic
           flops per ray-object test for this mix); roofline_accumulate: the accumulate kernel's algorithmic bytes
           against the measured HBM copy bandwidth
-  cpu_baseline : the oracle (restated reference, f64, chunks of 100 rays over all host cores) on a bounded sample
+  cpu_baseline : the oracle (restated reference, f64, chunks of 100 rays over all host cores) on a bounded sample, in
+          the reference's default configuration (its TileMap culling enabled, tile_map.rs:61); the all-objects loop's
+          rate -- the loop the GPU headline runs -- is reported beside it
 
 `--impl reference` times that CPU restatement alone (the real rayon binary cannot be built offline: no Rust
 toolchain, collision2d not vendored).
@@ -147,6 +149,32 @@ def dist_env():
     return rank, world, local
 
 
+def cpu_reference_sample(oracle, osc, spec, abi, seconds, tile_map=True, with_image=True, repeats=1):
+    """Times the restated reference on a bounded sample of the workload: every stride-th primary ray, chunks of 100
+    rays over all host cores, f64 -- with its TileMap on (the app's default, tile_map.rs:61) or off (the all-objects
+    loop the GPU headline runs).  Returns (rays/s, segments/s, stride, rays per repeat, seconds per repeat)."""
+    osc.enable_tile_map(tile_map)
+    stride = max(1, spec.total_rays() // 4000)
+    t0 = time.perf_counter()
+    probe = osc.trace_all(spec.lights, abi.LG_PRECISION_F64, stride=stride, store=False)
+    rps = probe.primary_rays / max(time.perf_counter() - t0, 1e-6)
+    sample = int(min(spec.total_rays(), max(20_000, rps * seconds)))
+    stride = max(1, spec.total_rays() // sample)
+    img = oracle.new_image(WIDTH, HEIGHT) if with_image else None
+    total, rays, segs = 0.0, 0, 0
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        res = osc.trace_all(spec.lights, abi.LG_PRECISION_F64, stride=stride, store=with_image)
+        if with_image:
+            img[...] = 0
+            img[..., 3] = 1
+            oracle.accumulate_segments(img, res.seg)
+        total += time.perf_counter() - t0
+        rays += res.primary_rays
+        segs += res.segments_emitted
+    return rays / total, segs / total, stride, rays // repeats, total / repeats
+
+
 def run_reference(args):
     """The reference arm: the CPU restatement of Tracer::trace_all + the line pass on the host cores."""
     rank, world, _ = dist_env()
@@ -160,38 +188,29 @@ def run_reference(args):
     spec = scenes.c5_large(n_lights=n, rays_per_light=RAYS_PER_GPU)
     osc = oracle.OracleScene.from_spec(spec)
     cores = oracle.num_threads()
-    # probe to size a bounded sample (~8 s of trace per step)
-    stride = max(1, spec.total_rays() // 4000)
     t0 = time.perf_counter()
-    probe = osc.trace_all(spec.lights, abi.LG_PRECISION_F64, stride=stride, store=False)
-    dt = time.perf_counter() - t0
-    rps = probe.primary_rays / max(dt, 1e-6)
-    sample = int(min(spec.total_rays(), max(20_000, rps * args.ref_seconds)))
-    stride = max(1, spec.total_rays() // sample)
-    img = oracle.new_image(WIDTH, HEIGHT)
-    times, rays_done, segs = [], 0, 0
-    for it in range(args.warmup + args.steps):
-        t0 = time.perf_counter()
-        res = osc.trace_all(spec.lights, abi.LG_PRECISION_F64, stride=stride, store=True)
-        img[...] = 0
-        img[..., 3] = 1
-        oracle.accumulate_segments(img, res.seg)
-        dt = time.perf_counter() - t0
-        if it >= args.warmup:
-            times.append(dt)
-            rays_done += res.primary_rays
-            segs += res.segments_emitted
-    total = sum(times)
-    value = rays_done / total
+    entries = osc.enable_tile_map(True)      # TileMap::new(w, h, 100, 100, 8), tracer.rs:27; built once per scene
+    build_s = time.perf_counter() - t0
+    for _ in range(args.warmup):
+        cpu_reference_sample(oracle, osc, spec, abi, args.ref_seconds, tile_map=True)
+    value, segs_per_s, stride, rays_step, sec_step = cpu_reference_sample(oracle, osc, spec, abi, args.ref_seconds,
+                                                                          tile_map=True, repeats=args.steps)
+    brute, _, bstride, brays, bsec = cpu_reference_sample(oracle, osc, spec, abi, min(4.0, args.ref_seconds),
+                                                          tile_map=False, with_image=False)
     out = {
         "impl": "reference", "metric": "rays_per_sec_traced_and_accumulated", "value": value, "unit": "rays/s",
-        "n_gpus": n, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
+        "n_gpus": n, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sec_step,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": workload_config(n),
-        "segments_per_s": segs / total,
+        "segments_per_s": segs_per_s,
         "cpu_baseline": {"value": value, "unit": "rays/s", "cores": cores, "kind": "port",
-                         "sample": f"every {stride}-th primary ray of the workload per step "
-                                   f"({rays_done // len(times)} rays/step), f64 restated oracle, rayon-style chunks of 100"},
+                         "sample": f"every {stride}-th primary ray of the workload per step ({rays_step} rays/step), f64 "
+                                   "restated oracle, rayon-style chunks of 100, TileMap 100x100x8 enabled (the "
+                                   f"reference's default, tile_map.rs:61; {entries} list entries built in {build_s:.1f} s, "
+                                   "not timed) + host accumulate",
+                         "all_objects_loop": {"value": brute, "unit": "rays/s",
+                                              "sample": f"every {bstride}-th ray ({brays} rays, {bsec:.1f} s), TileMap off, "
+                                                        "trace only"}},
         "e2e": {"value": value, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "restated reference (oracle/): the real rayon binary cannot be built offline (no Rust, collision2d unvendored)",
     }
@@ -444,25 +463,25 @@ def main():
         }
     # CPU baseline: rank 0, N = 1 only, bounded sample
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        sys.path.insert(0, os.path.join(ROOT, "oracle"))
-        import lg_oracle as oracle
-        oracle.build()
-        osc = oracle.OracleScene.from_spec(spec)
-        stride = max(1, spec.total_rays() // 4000)
-        t0 = time.perf_counter()
-        probe = osc.trace_all(spec.lights, abi.LG_PRECISION_F64, stride=stride, store=False)
-        rps = probe.primary_rays / max(time.perf_counter() - t0, 1e-6)
-        sample = int(min(spec.total_rays(), max(20_000, rps * args.cpu_seconds)))
-        stride = max(1, spec.total_rays() // sample)
-        t0 = time.perf_counter()
-        res = osc.trace_all(spec.lights, abi.LG_PRECISION_F64, stride=stride, store=True)
-        img = oracle.new_image(WIDTH, HEIGHT)
-        oracle.accumulate_segments(img, res.seg)
-        dt = time.perf_counter() - t0
-        out["cpu_baseline"] = {"value": res.primary_rays / dt, "unit": "rays/s", "cores": oracle.num_threads(),
-                               "kind": "port",
-                               "sample": f"every {stride}-th primary ray ({res.primary_rays} rays, {dt:.1f} s): f64 "
-                                         "restated oracle trace (chunks of 100 rays over all cores) + host accumulate"}
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "oracle"))
+            import lg_oracle as oracle
+            oracle.build()
+            osc = oracle.OracleScene.from_spec(spec)
+            osc.enable_tile_map(True)            # the reference's default (tile_map.rs:61); the build is scene set-up
+            v, _, stride, nrays, dt = cpu_reference_sample(oracle, osc, spec, abi, args.cpu_seconds, tile_map=True)
+            b, _, bstride, brays, bdt = cpu_reference_sample(oracle, osc, spec, abi, min(4.0, args.cpu_seconds),
+                                                             tile_map=False, with_image=False)
+            del osc
+            out["cpu_baseline"] = {"value": v, "unit": "rays/s", "cores": oracle.num_threads(), "kind": "port",
+                                   "sample": f"every {stride}-th primary ray ({nrays} rays, {dt:.1f} s): f64 restated oracle "
+                                             "trace (chunks of 100 rays over all cores, TileMap 100x100x8 enabled as in the "
+                                             "reference's default) + host accumulate",
+                                   "all_objects_loop": {"value": b, "unit": "rays/s",
+                                                        "sample": f"every {bstride}-th ray ({brays} rays, {bdt:.1f} s), TileMap "
+                                                                  "off (the loop the GPU headline runs), trace only"}}
+        except Exception as e:   # the GPU line must not be lost to a failure of the CPU leg; the error is reported
+            out["cpu_baseline"] = {"error": f"{type(e).__name__}: {e}"}
     elif rank == 0:
         out["cpu_baseline"] = None
     if rank == 0:

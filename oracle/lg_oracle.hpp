@@ -677,7 +677,163 @@ struct SegOut {
 
 struct TraceCounters {
   uint64_t ray_steps = 0, segments = 0;
+  uint64_t object_tests = 0; // Ray::intersect(&obj.get_geometry()) calls of the nearest-hit search
 };
+
+// ---------------------------------------------------------------------------
+// TileMap (src/light_garden/tile_map.rs), ORACLE.md §5.6.  The reference's CPU-side culling, ENABLED by default
+// (tile_map.rs:61): the window is cut into num_tilesx x num_tilesy tiles (Tracer::new: 100 x 100, tracer.rs:27),
+// every tile has num_slabs (8) angular sectors; a sector lists the objects whose bounding box can be seen from the
+// tile in that range of directions, and the tile lists the objects whose box overlaps it.  A ray tests the sector of
+// its direction in the tile of its origin plus the tile's overlaps (tracer.rs:385-411) instead of every object.
+// The box-to-box angular range (collision2d Aabb::get_crossover) and the boxes themselves (HasAabb) are not in the
+// repository: here a box is the hull of the object's leaves and the range is the hull of the 16 corner-to-corner
+// directions, widened by 1e-9 rad -- conservative, so the nearest hit is the one of the all-objects loop.
+// ---------------------------------------------------------------------------
+struct TileMap {
+  double w = 0, h = 0;
+  int nx = 0, ny = 0, ns = 0;
+  std::vector<uint64_t> start; // (tile * ns + slab) -> range of `cand`
+  std::vector<int32_t> cand;   // ascending object indices: the sector's objects and the tile's overlaps, merged
+  bool enabled = false;
+
+  static long to_usize(double v) { return !(v > 0.0) ? 0 : (v >= 4e18 ? (long)4e18 : (long)v); } // Rust `as usize`
+  // TileMap::get_tile, tile_map.rs:134-146 (the window is centred on the origin)
+  int tile_of(double x, double y) const {
+    const long ix = to_usize((x + w * 0.5) / (w / nx)), iy = to_usize((y + h * 0.5) / (h / ny));
+    return (ix < nx && iy < ny) ? (int)(ix + iy * nx) : -1;
+  }
+  // clockwise angle from +y, Tile::get_index tile_map.rs:229-235
+  static double angle_of(double dx, double dy) {
+    const double TAU = 6.283185307179586;
+    double a = std::acos(dy > 1.0 ? 1.0 : (dy < -1.0 ? -1.0 : dy));
+    if (dx < 0.0) a = TAU - a;
+    return a;
+  }
+  int slab_of_angle(double a) const {
+    const double TAU = 6.283185307179586;
+    const long k = to_usize((double)ns * a / TAU - 2.220446049250313e-16);
+    return (int)(k >= ns ? ns - 1 : k);
+  }
+  int slab_of(double dx, double dy) const { return slab_of_angle(angle_of(dx, dy)); }
+};
+
+struct Box {
+  double x0 = 1e300, y0 = 1e300, x1 = -1e300, y1 = -1e300;
+  void add(double x, double y) { x0 = std::min(x0, x), y0 = std::min(y0, y), x1 = std::max(x1, x), y1 = std::max(y1, y); }
+};
+// hull of the object's leaves (a superset of the object for every LogicOp)
+inline Box object_box(const Scene &s, int ob) {
+  Box b;
+  const Object &o = s.objects[ob];
+  for (int k = o.first; k < o.first + o.count; ++k) {
+    const Token &t = s.tokens[k];
+    switch (t.kind) {
+    case TOK_CIRCLE:
+      b.add(t.p[0] - t.p[2], t.p[1] - t.p[2]), b.add(t.p[0] + t.p[2], t.p[1] + t.p[2]);
+      break;
+    case TOK_RECT:
+      for (int su = -1; su <= 1; su += 2)
+        for (int sv = -1; sv <= 1; sv += 2) b.add(t.p[0] + su * t.p[2] + sv * t.p[4], t.p[1] + su * t.p[3] + sv * t.p[5]);
+      break;
+    case TOK_SEGMENT:
+      b.add(t.p[0], t.p[1]), b.add(t.p[2], t.p[3]);
+      break;
+    case TOK_BEZIER: // the curve lies in the hull of its control points
+      for (int q = 0; q < 4; ++q) b.add(t.p[2 * q], t.p[2 * q + 1]);
+      break;
+    case TOK_ELLIPSE: {
+      const double r = std::max(std::fabs(t.p[4]), std::fabs(t.p[5]));
+      b.add(t.p[0] - r, t.p[1] - r), b.add(t.p[0] + r, t.p[1] + r);
+      break;
+    }
+    case TOK_VERTS:
+      for (int q = 0; q < t.op; ++q) b.add(t.p[2 * q], t.p[2 * q + 1]);
+      break;
+    default:
+      break;
+    }
+  }
+  return b;
+}
+
+inline TileMap build_tile_map(const Scene &s, int nx, int ny, int ns) {
+  const double TAU = 6.283185307179586, PI = 3.141592653589793;
+  TileMap tm;
+  tm.nx = nx, tm.ny = ny, tm.ns = ns;
+  tm.w = s.canvas_tlbr[3] - s.canvas_tlbr[1]; // canvas_bounds.width, tracer.rs:27
+  tm.h = s.canvas_tlbr[0] - s.canvas_tlbr[2];
+  const int nobj = (int)s.objects.size(), ntiles = nx * ny;
+  std::vector<Box> boxes(nobj);
+  for (int i = 0; i < nobj; ++i) boxes[i] = object_box(s, i);
+  std::vector<std::vector<int32_t>> per_tile(ntiles);       // candidates of the tile's sectors, concatenated
+  std::vector<std::vector<uint32_t>> per_tile_start(ntiles); // ns + 1 offsets into per_tile[t]
+  const double stepx = tm.w / nx, stepy = tm.h / ny;
+#pragma omp parallel for schedule(dynamic, 16)
+  for (int t = 0; t < ntiles; ++t) {
+    // TileMap::get_aabb, tile_map.rs:65-78
+    const double left = (t % nx) * stepx - tm.w * 0.5, bottom = (t / nx) * stepy - tm.h * 0.5;
+    const double tx[2] = {left, left + stepx}, ty[2] = {bottom, bottom + stepy};
+    const double tcx = left + 0.5 * stepx, tcy = bottom + 0.5 * stepy;
+    std::vector<std::vector<int32_t>> slab(ns);
+    std::vector<int32_t> ovl;
+    for (int i = 0; i < nobj; ++i) {
+      const Box &b = boxes[i];
+      // Tile::update_overlap, tile_map.rs:237-251: the boxes touch -> the object is tested from every sector
+      if (!(b.x0 > tx[1] || b.x1 < tx[0] || b.y0 > ty[1] || b.y1 < ty[0])) {
+        ovl.push_back(i);
+        continue;
+      }
+      // Tile::get_range, tile_map.rs:296-331: the sectors between the two extreme directions
+      const double ocx = 0.5 * (b.x0 + b.x1), ocy = 0.5 * (b.y0 + b.y1);
+      const double rl = std::hypot(ocx - tcx, ocy - tcy);
+      const double ar = TileMap::angle_of((ocx - tcx) / rl, (ocy - tcy) / rl);
+      const double ox[2] = {b.x0, b.x1}, oy[2] = {b.y0, b.y1};
+      double lo = 0, hi = 0;
+      for (int q = 0; q < 16; ++q) {
+        const double dx = ox[q & 1] - tx[(q >> 2) & 1], dy = oy[(q >> 1) & 1] - ty[(q >> 3) & 1];
+        const double l = std::hypot(dx, dy);
+        if (!(l > 0)) continue;
+        double da = TileMap::angle_of(dx / l, dy / l) - ar;
+        if (da > PI) da -= TAU;
+        if (da < -PI) da += TAU;
+        lo = std::min(lo, da), hi = std::max(hi, da);
+      }
+      lo -= 1e-9, hi += 1e-9;
+      auto wrap = [&](double a) { return a < 0 ? a + TAU : (a >= TAU ? a - TAU : a); };
+      const int k0 = tm.slab_of_angle(wrap(ar + lo)), k1 = tm.slab_of_angle(wrap(ar + hi));
+      for (int k = k0;; k = (k + 1) % ns) {
+        slab[k].push_back(i);
+        if (k == k1) break;
+      }
+    }
+    std::vector<int32_t> &out = per_tile[t];
+    std::vector<uint32_t> &st = per_tile_start[t];
+    st.assign(ns + 1, 0);
+    for (int k = 0; k < ns; ++k) {
+      st[k] = (uint32_t)out.size();
+      out.resize(out.size() + slab[k].size() + ovl.size());
+      std::merge(slab[k].begin(), slab[k].end(), ovl.begin(), ovl.end(), out.begin() + st[k]); // both ascending, disjoint
+    }
+    st[ns] = (uint32_t)out.size();
+  }
+  tm.start.assign((size_t)ntiles * ns + 1, 0);
+  uint64_t total = 0;
+  for (int t = 0; t < ntiles; ++t) {
+    for (int k = 0; k < ns; ++k) tm.start[(size_t)t * ns + k] = total + per_tile_start[t][k];
+    total += per_tile[t].size();
+  }
+  tm.start[(size_t)ntiles * ns] = total;
+  tm.cand.resize(total);
+  total = 0;
+  for (int t = 0; t < ntiles; ++t) {
+    std::copy(per_tile[t].begin(), per_tile[t].end(), tm.cand.begin() + total);
+    total += per_tile[t].size();
+    std::vector<int32_t>().swap(per_tile[t]);
+  }
+  tm.enabled = true;
+  return tm;
+}
 
 template <class T> struct Item {
   V2<T> o, d;
@@ -704,7 +860,7 @@ inline void emit(std::vector<SegOut> *out, TraceCounters &cnt, V2<T> a, V2<T> b,
 
 template <class T>
 inline void trace_ray(const SceneT<T> &s, const LgRay &ray, uint64_t ray_id, std::vector<SegOut> *out,
-                      TraceCounters &cnt) {
+                      TraceCounters &cnt, const TileMap *tm = nullptr) {
   std::vector<Item<T>> cur, next; // trace_rays / back_buffer, tracer.rs:368-369
   Item<T> it0;
   it0.o = {(T)ray.origin[0], (T)ray.origin[1]};
@@ -725,7 +881,22 @@ inline void trace_ray(const SceneT<T> &s, const LgRay &ray, uint64_t ray_id, std
       T nearest = std::numeric_limits<T>::max();
       int best = -1;
       Hit<T> bh{};
-      for (int ix = 0; ix < nobj; ++ix) {
+      // tracer.rs:385-411: with the TileMap, the sector of the ray's direction in the tile of its origin plus the
+      // tile's overlaps (ascending object index here, so ties resolve as in the all-objects loop); a ray that starts
+      // outside the window tests every object (the reference would test none: its origins are always inside)
+      const int32_t *cl = nullptr;
+      int ncl = nobj;
+      if (tm && tm->enabled) {
+        const int tile = tm->tile_of((double)it.o.x, (double)it.o.y);
+        if (tile >= 0) {
+          const size_t q = (size_t)tile * tm->ns + tm->slab_of((double)it.d.x, (double)it.d.y);
+          cl = tm->cand.data() + tm->start[q];
+          ncl = (int)(tm->start[q + 1] - tm->start[q]);
+        }
+      }
+      cnt.object_tests += (uint64_t)ncl;
+      for (int q = 0; q < ncl; ++q) {
+        const int ix = cl ? cl[q] : q;
         intersect_object(s, ix, it.o, it.d, oh);
         for (int j = 0; j < oh.n; ++j) {
           T dx = oh.h[j].p.x - it.o.x, dy = oh.h[j].p.y - it.o.y;

@@ -55,7 +55,16 @@ def lib():
         L.lgo_trace_all.restype = vp
         L.lgo_trace_all.argtypes = [vp, C.c_int32, vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64, C.c_int32,
                                     C.c_int32, C.c_int32]
-        for f in ("lgo_result_count", "lgo_result_stored", "lgo_result_ray_steps", "lgo_result_primary_rays"):
+        L.lgo_tile_map_enable.restype = C.c_uint64
+        L.lgo_tile_map_enable.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32]
+        L.lgo_tile_map_tile.restype = C.c_int32
+        L.lgo_tile_map_tile.argtypes = [vp, C.c_double, C.c_double]
+        L.lgo_tile_map_slab.restype = C.c_int32
+        L.lgo_tile_map_slab.argtypes = [vp, C.c_double, C.c_double]
+        L.lgo_tile_map_candidates.restype = C.c_uint32
+        L.lgo_tile_map_candidates.argtypes = [vp, C.c_int32, C.c_int32, vp, C.c_uint32]
+        for f in ("lgo_result_count", "lgo_result_stored", "lgo_result_ray_steps", "lgo_result_primary_rays",
+                  "lgo_result_object_tests"):
             getattr(L, f).restype = C.c_uint64
             getattr(L, f).argtypes = [vp]
         L.lgo_result_seconds.restype = C.c_double
@@ -92,6 +101,7 @@ class TraceResult:
         L = lib()
         self.segments_emitted = L.lgo_result_count(h)
         self.ray_steps = L.lgo_result_ray_steps(h)
+        self.object_tests = L.lgo_result_object_tests(h)   # Ray::intersect calls of the nearest-hit search
         self.primary_rays = L.lgo_result_primary_rays(h)
         self.seconds = L.lgo_result_seconds(h)
         n = L.lgo_result_stored(h)
@@ -124,6 +134,27 @@ class OracleScene:
         if getattr(self, "h", None):
             self.L.lgo_scene_destroy(self.h)
             self.h = None
+
+    def enable_tile_map(self, enable=True, tiles_x=100, tiles_y=100, slabs=8):
+        """Tracer::enable_tile_map (tracer.rs:137-146); the defaults are TileMap::new's in Tracer::new (tracer.rs:27).
+        The reference starts with it enabled (tile_map.rs:61).  Returns the number of candidate entries."""
+        return self.L.lgo_tile_map_enable(self.h, 1 if enable else 0, tiles_x, tiles_y, slabs)
+
+    def tile_of(self, x, y):
+        """TileMap::get_tile (tile_map.rs:134-146): tile index ixx + ixy * tiles_x, or -1 outside the window."""
+        return self.L.lgo_tile_map_tile(self.h, float(x), float(y))
+
+    def slab_of(self, dx, dy):
+        """Tile::get_index (tile_map.rs:229-235) for a unit direction."""
+        return self.L.lgo_tile_map_slab(self.h, float(dx), float(dy))
+
+    def tile_candidates(self, tile, slab):
+        """Object indices a ray starting in `tile` with a direction in `slab` is tested against (tracer.rs:395-411)."""
+        n = self.L.lgo_tile_map_candidates(self.h, tile, slab, None, 0)
+        out = np.zeros(n, dtype=np.int32)
+        if n:
+            self.L.lgo_tile_map_candidates(self.h, tile, slab, abi.array_ptr(out), n)
+        return out
 
     def tokens(self):
         buf = np.zeros((4096 * 8, 12), dtype=np.float64)

@@ -22,6 +22,7 @@ struct OracleScene {
   Scene base;
   SceneT<double> d;
   SceneT<float> f;
+  TileMap tm; // Tracer::tile_map; built by lgo_tile_map_enable
 };
 
 struct OracleResult {
@@ -49,9 +50,11 @@ static void trace_block(const OracleScene &sc, const LgRay *rays, uint64_t n, ui
 #pragma omp parallel for schedule(dynamic, 1)
   for (int64_t c = 0; c < nchunks; ++c) {
     uint64_t lo = (uint64_t)c * chunk, hi = std::min<uint64_t>(n, lo + chunk);
-    for (uint64_t i = lo; i < hi; ++i) trace_ray<T>(s, rays[i], id0 + i, store ? &parts[c] : nullptr, cnts[c]);
+    for (uint64_t i = lo; i < hi; ++i)
+      trace_ray<T>(s, rays[i], id0 + i, store ? &parts[c] : nullptr, cnts[c], sc.tm.enabled ? &sc.tm : nullptr);
   }
   for (int64_t c = 0; c < nchunks; ++c) {
+    res.cnt.object_tests += cnts[c].object_tests;
     res.cnt.ray_steps += cnts[c].ray_steps;
     res.cnt.segments += cnts[c].segments;
     if (store) res.segs.insert(res.segs.end(), parts[c].begin(), parts[c].end());
@@ -79,6 +82,21 @@ void *lgo_scene_create(const LgObject *objs, uint32_t n_obj, const LgGeoNode *no
   return s.release();
 }
 void lgo_scene_destroy(void *h) { delete (OracleScene *)h; }
+
+// Tracer::enable_tile_map (tracer.rs:137-146) with TileMap::new(width, height, tiles_x, tiles_y, slabs)
+// (tracer.rs:27: 100, 100, 8).  Returns the number of candidate entries (0 when disabled).
+uint64_t lgo_tile_map_enable(void *h, int32_t enable, int32_t tiles_x, int32_t tiles_y, int32_t slabs) {
+  OracleScene *s = (OracleScene *)h;
+  if (!enable) {
+    s->tm.enabled = false;
+    return 0;
+  }
+  if (tiles_x < 1 || tiles_y < 1 || slabs < 1) return 0;
+  if (s->tm.nx != tiles_x || s->tm.ny != tiles_y || s->tm.ns != slabs || s->tm.cand.empty())
+    s->tm = build_tile_map(s->base, tiles_x, tiles_y, slabs);
+  s->tm.enabled = true;
+  return s->tm.cand.size();
+}
 
 // number of lowered tokens and a copy of them (for lowering parity tests):
 // each token is written as 12 doubles: kind, op, a_start, b_start, p[0..7]
@@ -210,9 +228,22 @@ void *lgo_trace_all(void *h, int32_t precision, const LgLight *lights, uint32_t 
   return r.release();
 }
 
+// TileMap::get_tile (tile_map.rs:134-146), Tile::get_index (229-235) and the candidate list of (tile, slab)
+int32_t lgo_tile_map_tile(void *h, double x, double y) { return ((OracleScene *)h)->tm.tile_of(x, y); }
+int32_t lgo_tile_map_slab(void *h, double dx, double dy) { return ((OracleScene *)h)->tm.slab_of(dx, dy); }
+uint32_t lgo_tile_map_candidates(void *h, int32_t tile, int32_t slab, int32_t *dst, uint32_t cap) {
+  const TileMap &tm = ((OracleScene *)h)->tm;
+  if (tile < 0 || slab < 0 || slab >= tm.ns || (size_t)tile * tm.ns + slab + 1 >= tm.start.size()) return 0;
+  const size_t q = (size_t)tile * tm.ns + slab;
+  const uint32_t n = (uint32_t)(tm.start[q + 1] - tm.start[q]);
+  for (uint32_t i = 0; i < n && i < cap; ++i) dst[i] = tm.cand[tm.start[q] + i];
+  return n;
+}
+
 uint64_t lgo_result_count(void *r) { return ((OracleResult *)r)->cnt.segments; }
 uint64_t lgo_result_stored(void *r) { return ((OracleResult *)r)->segs.size(); }
 uint64_t lgo_result_ray_steps(void *r) { return ((OracleResult *)r)->cnt.ray_steps; }
+uint64_t lgo_result_object_tests(void *r) { return ((OracleResult *)r)->cnt.object_tests; }
 uint64_t lgo_result_primary_rays(void *r) { return ((OracleResult *)r)->primary_rays; }
 double lgo_result_seconds(void *r) { return ((OracleResult *)r)->seconds; }
 void lgo_result_copy(void *r, LgSegment *seg, LgSegmentTag *tag, LgSegmentF64 *f64) {
