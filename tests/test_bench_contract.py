@@ -32,6 +32,8 @@ def test_reference_arm_prints_the_contract_line():
     assert d["config"]["objects"] == 4096 and "workload" in d["config"]
     cb = d["cpu_baseline"]
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "sample" in cb
+    # the timed configuration is the reference's default (TileMap on); the all-objects loop is reported beside it
+    assert "TileMap" in cb["sample"] and cb["all_objects_loop"]["value"] > 0 and cb["all_objects_loop"]["unit"] == "rays/s"
     assert d["e2e"] == {"value": d["value"], "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
 
 
