@@ -6,7 +6,7 @@ edges in it depend only on the light, the mirror's end point and end tangent, th
 the shadow edge of the mirror's end on the top border, and the last reflected ray on the left border.  This script
 measures both in the JPEG and computes them with the oracle.  Not a test (the picture cannot travel and the rest of that
 scene is not reproducible from the repository); the numbers are quoted in DESIGN.md section 2.
-    python tools/screenshot_landmarks.py [/root/reference/screenshot.jpg]
+    python tests/screenshot_landmarks.py [/root/reference/screenshot.jpg]
 """
 import os
 import sys

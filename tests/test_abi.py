@@ -45,9 +45,10 @@ def test_create_fails_loudly_without_device(product_lib):
 
 
 def test_product_never_references_the_oracle():
-    """The oracle is test infrastructure: nothing under light_garden_b200/ may import, include or load it."""
-    pkg = os.path.join(ROOT, "light_garden_b200")
-    for dirpath, _, files in os.walk(pkg):
+    """The oracle is test infrastructure: nothing under light_garden_b200/ (nor the tools/ around it) may import,
+    include or load it."""
+    walk = list(os.walk(os.path.join(ROOT, "light_garden_b200"))) + list(os.walk(os.path.join(ROOT, "tools")))
+    for dirpath, _, files in walk:
         if "_lib" in dirpath or "__pycache__" in dirpath:
             continue
         for f in files:
