@@ -238,6 +238,7 @@ def main():
     ap.add_argument("--ref-seconds", type=float, default=8.0)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="headline regions only (profiling runs)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -368,12 +369,15 @@ def main():
 
     # the same workload with Tracer::enable_tile_map (device grid): identical segments, fewer
     # exact tests.  Reported next to the headline, which stays the all-objects loop the north star names.
-    ctx.call("lg_tile_map_enable", 1)
-    for _ in range(5):       # auto-mode samples of this workload + warm-up
-        step(False)
-    ms_grid, agg_grid = timed(args.steps, False)
-    ms_grid_e2e, _ = timed(args.steps, True)
-    ctx.call("lg_tile_map_enable", 0)
+    if args.no_extras:
+        ms_grid, agg_grid, ms_grid_e2e = ms, agg, ms_e2e
+    else:
+        ctx.call("lg_tile_map_enable", 1)
+        for _ in range(5):       # auto-mode samples of this workload + warm-up
+            step(False)
+        ms_grid, agg_grid = timed(args.steps, False)
+        ms_grid_e2e, _ = timed(args.steps, True)
+        ctx.call("lg_tile_map_enable", 0)
 
     total_rays = rays_per_gpu * world * args.steps
     value = total_rays / (ms * 1e-3)

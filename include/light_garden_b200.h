@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define LG_ABI_VERSION 1
+#define LG_ABI_VERSION 2
 
 /* ---- status codes ------------------------------------------------------- */
 enum {
@@ -115,21 +115,37 @@ typedef struct LgTraceParams {
 
 /* ---- lights (src/light_garden/light.rs:10-14) --------------------------- */
 enum { LG_LIGHT_POINT = 0, LG_LIGHT_DIRECTIONAL = 1, LG_LIGHT_SPOT = 2 };
+/* LgLight.flags */
+enum {
+  /* DirectionalLight::set_num_rays calls start.eval_at_r(-(i as f64) / n) (light.rs:111); what collision2d's
+   * LineSegment::eval_at_r does with a negative parameter is not in the reference (the crate is not vendored).
+   * Default: the origins walk the drawn segment, a + (i/n)(b - a) (ORACLE.md 6.3).  With this flag the call is
+   * taken literally on the natural parametrisation eval_at_r(r) = a + r (b - a): origins a - (i/n)(b - a).
+   * One named switch, read by the device code and by the oracle; directional-light parity is UNVERIFIED either way. */
+  LG_LIGHT_DIRECTIONAL_NEG_R = 1,
+  /* start_medium holds the refractive index of the medium the light's rays start in and replaces the scan over
+   * the scene's objects (tracer.rs:279-287).  That scan chains `self.drawing_object` -- the object the user is
+   * dragging out, which is not in the scene yet -- behind the objects, so it wins when it contains the light: the
+   * host evaluates that one `contains` itself and passes the index here. */
+  LG_LIGHT_START_MEDIUM = 2
+};
 typedef struct LgLight {
   int32_t kind;
-  int32_t _pad;
+  int32_t flags;            /* LG_LIGHT_* flags above                        */
   uint64_t num_rays;
   float color[4];
   double position[2];       /* Point/Spot position; Directional: start.a     */
   double b[2];              /* Directional: start.b                          */
   double spot_angle;        /* Spot only                                     */
   double spot_direction[2]; /* Spot only                                     */
-} LgLight; /* 88 bytes */
+  double start_medium;      /* read when flags & LG_LIGHT_START_MEDIUM       */
+} LgLight; /* 96 bytes */
 
 /* One primary ray as Tracer::trace receives it (tracer.rs:360-367). */
 typedef struct LgRay {
   double origin[2];
-  double direction[2]; /* unit                                                */
+  double direction[2]; /* unit: | |d|^2 - 1 | <= 16 eps of the context's precision, else LG_ERR_INVALID
+                        * (Ray::from_origin normalises, light.rs:172; the broad phase relies on it) */
   float color[4];
   double refractive_index; /* medium the ray starts in                        */
 } LgRay; /* 56 bytes */
@@ -250,6 +266,13 @@ int32_t lg_scene_set(lg_ctx *ctx, const LgObject *objects, uint32_t n_objects,
 /* Replaces Tracer.lights; the per-light start medium of tracer.rs:280-287 is
  * evaluated here. */
 int32_t lg_lights_set(lg_ctx *ctx, const LgLight *lights, uint32_t n_lights);
+/* Tracer::add_drawing_object / finish_drawing_object (tracer.rs:61-72): the object the user is dragging out.  It
+ * is not traced against (tracer.rs:412-424 walks self.objects only) but the start-medium scan chains it behind the
+ * scene's objects (tracer.rs:281), so a light inside it starts in its material.  object = NULL clears it
+ * (finish_drawing_object: the host then pushes the object into the scene it sends with lg_scene_set, or drops it).
+ * `object->root` indexes `nodes`.  The reference's drawing_light needs no entry point: it is chained behind
+ * self.lights (tracer.rs:279), i.e. the host appends it to the array it passes to lg_lights_set. */
+int32_t lg_drawing_object_set(lg_ctx *ctx, const LgObject *object, const LgGeoNode *nodes, uint32_t n_nodes);
 /* Data-parallel shard of the primary rays: rank r of `world` takes the rays
  * r, r + world, r + 2*world, ... of every light (interleaved, so that every rank
  * sees every direction of every light and the ranks' work is balanced;
@@ -327,8 +350,18 @@ int32_t lg_string_mod_nested_read(lg_ctx *ctx, LgVertexPair *outer_chords, uint6
                                   double *crossings_xy, uint64_t crossing_cap,
                                   uint64_t *n_chords, uint64_t *n_crossings);
 /* trace_all + render fused: rays are traced in waves through the bounded
- * segment buffer and each wave is accumulated before the next is traced. */
+ * segment buffer.  With the tile-binned resolve the waves form a two-stage
+ * pipeline: the line pass of wave k runs on a second stream while wave k + 1
+ * is being traced into the other half of the buffer (no host round trip in
+ * between); otherwise each wave is accumulated before the next is traced.
+ * Same fragments either way.  trace_ms / accumulate_ms are the sums of the
+ * waves' kernel times: in the pipeline they overlap and add up to more than
+ * the frame. */
 int32_t lg_render(lg_ctx *ctx, LgTraceStats *stats);
+/* The wave pipeline of lg_render: mode 0 = off, 1 = automatic (default: frames
+ * of >= 2^20 rays whose resolve is the tile bins), 2 = always (tests); waves =
+ * how many waves a frame is cut into (0 keeps the current value, default 8). */
+int32_t lg_render_overlap_set(lg_ctx *ctx, int32_t mode, uint32_t waves);
 /* Image out: LG_RGBA32F (16 B/px), LG_RGBA16F (8 B/px, round to nearest even,
  * what the ROP would have stored), LG_BGRA8_GAMMA (4 B/px, the screenshot
  * path) or LG_BGRA8_SRGB (4 B/px, the 8-bit surface target). pitch in
@@ -390,6 +423,10 @@ int32_t lg_measure_fma_peak(lg_ctx *ctx, int32_t precision, int32_t reps, double
 /* red.global.add.v4.f32 throughput in 1e9 reductions/s over an image of
  * `span_px` RGBA fp32 pixels; pattern 0 = coalesced sweep, 1 = random pixels. */
 int32_t lg_measure_red_peak(lg_ctx *ctx, uint64_t span_px, int32_t pattern, int32_t reps, double *gred_per_s);
+/* Ceiling of the tile-binned resolve: 16-byte shared-memory read-modify-writes (LDS.128, 4 FADD, STS.128 on a
+ * private 32x32 RGBA tile per warp, every lane active, conflict-free, the raster kernel's launch shape) in 1e9
+ * fragments/s. */
+int32_t lg_measure_tile_rmw_peak(lg_ctx *ctx, int32_t reps, double *gfrag_per_s);
 
 #ifdef __cplusplus
 }

@@ -8,7 +8,7 @@ import ctypes as C
 
 import numpy as np
 
-LG_ABI_VERSION = 1
+LG_ABI_VERSION = 2
 
 LG_OK, LG_ERR_INVALID, LG_ERR_CUDA, LG_ERR_NOMEM = 0, -1, -2, -3
 LG_ERR_UNSUPPORTED, LG_ERR_OVERFLOW, LG_ERR_NCCL, LG_ERR_STATE = -4, -5, -6, -7
@@ -27,6 +27,7 @@ LG_GEO_POLYGON, LG_GEO_POINTS, LG_POLYGON_MAX_VERTICES = 6, 7, 32
 LG_BO_ADD, LG_BO_SUBTRACT, LG_BO_REVERSE_SUBTRACT, LG_BO_MIN, LG_BO_MAX = range(5)
 LG_OP_AND, LG_OP_OR, LG_OP_ANDNOT = 0, 1, 2
 LG_LIGHT_POINT, LG_LIGHT_DIRECTIONAL, LG_LIGHT_SPOT = 0, 1, 2
+LG_LIGHT_DIRECTIONAL_NEG_R, LG_LIGHT_START_MEDIUM = 1, 2   # LgLight.flags
 LG_SM_ADD, LG_SM_MUL, LG_SM_POW, LG_SM_BASE = 0, 1, 2, 3
 LG_CURVE_CIRCLE, LG_CURVE_COMPLEX_EXP, LG_CURVE_HYPOTROCHOID, LG_CURVE_LISSAJOUS = 0, 1, 2, 3
 LG_RGBA32F, LG_RGBA16F, LG_BGRA8_GAMMA, LG_BGRA8_SRGB = 0, 1, 2, 3
@@ -47,9 +48,9 @@ class LgTraceParams(C.Structure):
 
 
 class LgLight(C.Structure):
-    _fields_ = [("kind", C.c_int32), ("_pad", C.c_int32), ("num_rays", C.c_uint64), ("color", C.c_float * 4),
+    _fields_ = [("kind", C.c_int32), ("flags", C.c_int32), ("num_rays", C.c_uint64), ("color", C.c_float * 4),
                 ("position", C.c_double * 2), ("b", C.c_double * 2), ("spot_angle", C.c_double),
-                ("spot_direction", C.c_double * 2)]
+                ("spot_direction", C.c_double * 2), ("start_medium", C.c_double)]
 
 
 class LgTraceStats(C.Structure):
@@ -90,7 +91,7 @@ SEGMENT_F64_DTYPE = np.dtype([("a", "<f8", 2), ("b", "<f8", 2)], align=True)
 
 SIZES = {
     "LgGeoNode": (C.sizeof(LgGeoNode), 112), "LgObject": (C.sizeof(LgObject), 16),
-    "LgTraceParams": (C.sizeof(LgTraceParams), 56), "LgLight": (C.sizeof(LgLight), 88),
+    "LgTraceParams": (C.sizeof(LgTraceParams), 56), "LgLight": (C.sizeof(LgLight), 96),
     "LgRay": (RAY_DTYPE.itemsize, 56), "LgSegment": (SEGMENT_DTYPE.itemsize, 32),
     "LgVertexPair": (VERTEX_PAIR_DTYPE.itemsize, 64), "LgSegmentTag": (SEGMENT_TAG_DTYPE.itemsize, 24),
     "LgSegmentF64": (SEGMENT_F64_DTYPE.itemsize, 32), "LgModRemColor": (C.sizeof(LgModRemColor), 32),
@@ -108,6 +109,7 @@ PROTOTYPES = {
     "lg_destroy": [_ctx],
     "lg_last_error": [_ctx],
     "lg_scene_set": [_ctx, _p, C.c_uint32, _p, C.c_uint32, C.POINTER(LgTraceParams)],
+    "lg_drawing_object_set": [_ctx, _p, _p, C.c_uint32],
     "lg_lights_set": [_ctx, _p, C.c_uint32],
     "lg_shard_set": [_ctx, C.c_uint32, C.c_uint32],
     "lg_segment_capacity_set": [_ctx, C.c_uint64],
@@ -130,6 +132,7 @@ PROTOTYPES = {
                              C.POINTER(LgTraceStats)],
     "lg_string_mod_nested_read": [_ctx, _p, C.c_uint64, _p, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)],
     "lg_render": [_ctx, C.POINTER(LgTraceStats)],
+    "lg_render_overlap_set": [_ctx, C.c_int32, C.c_uint32],
     "lg_image_read": [_ctx, C.c_int32, _p, C.c_size_t],
     "lg_image_export_fd": [_ctx, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_uint64)],
     "lg_image_export_refresh": [_ctx, C.c_int32],
@@ -147,6 +150,7 @@ PROTOTYPES = {
     "lg_host_free": [C.c_void_p],
     "lg_measure_fma_peak": [_ctx, C.c_int32, C.c_int32, C.POINTER(C.c_double)],
     "lg_measure_red_peak": [_ctx, C.c_uint64, C.c_int32, C.c_int32, C.POINTER(C.c_double)],
+    "lg_measure_tile_rmw_peak": [_ctx, C.c_int32, C.POINTER(C.c_double)],
 }
 
 

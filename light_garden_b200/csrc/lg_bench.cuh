@@ -58,4 +58,33 @@ __global__ void __launch_bounds__(256) red_peak_kernel(float *img, unsigned long
   }
 }
 
+// Ceiling of the tile-binned resolve (lg_tiles.cuh): every warp owns a 32x32 RGBA fp32 tile in shared memory (the
+// raster kernel's launch shape: 4 warps and 72 KB per CTA) and does nothing but the blend's memory work -- four
+// independent 16-byte read-modify-writes per iteration, lane = column (conflict-free), the row taken from a value the
+// compiler cannot see through.  Fragments/s of this loop is what LDS.128 + 4 FADD + STS.128 allow when every lane
+// has a fragment and no instruction is spent on finding it.
+__global__ void __launch_bounds__(128) tile_rmw_peak_kernel(float *sink, int iters) {
+  extern __shared__ __align__(16) unsigned char rmw_smem[];
+  float4 *tile = reinterpret_cast<float4 *>(rmw_smem) + (size_t)(threadIdx.x >> 5) * 1024;
+  const unsigned lane = threadIdx.x & 31u;
+  for (int k = lane; k < 1024; k += 32) tile[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+  __syncwarp();
+  unsigned r = (blockIdx.x * 7u + (threadIdx.x >> 5)) & 31u;
+  const float4 c = make_float4(1.f, 2.f, 3.f, 4.f);
+  for (int i = 0; i < iters; ++i) {
+    float4 *p0 = tile + ((r + 0u) & 31u) * 32u + lane, *p1 = tile + ((r + 7u) & 31u) * 32u + lane;
+    float4 *p2 = tile + ((r + 13u) & 31u) * 32u + lane, *p3 = tile + ((r + 22u) & 31u) * 32u + lane;
+    float4 a = *p0, b = *p1, d = *p2, e = *p3;
+    a.x += c.x, a.y += c.y, a.z += c.z, a.w += c.w;
+    b.x += c.x, b.y += c.y, b.z += c.z, b.w += c.w;
+    d.x += c.x, d.y += c.y, d.z += c.z, d.w += c.w;
+    e.x += c.x, e.y += c.y, e.z += c.z, e.w += c.w;
+    *p0 = a, *p1 = b, *p2 = d, *p3 = e;
+    r = (r * 5u + 1u) & 31u;
+  }
+  __syncwarp();
+  const float4 v = tile[lane];
+  if (v.x + v.y + v.z + v.w == -1.f) sink[0] = v.x; // never true: keeps the loop alive
+}
+
 } // namespace lg

@@ -32,7 +32,7 @@
 static_assert(sizeof(LgGeoNode) == 112, "LgGeoNode ABI");
 static_assert(sizeof(LgObject) == 16, "LgObject ABI");
 static_assert(sizeof(LgTraceParams) == 56, "LgTraceParams ABI");
-static_assert(sizeof(LgLight) == 88, "LgLight ABI");
+static_assert(sizeof(LgLight) == 96, "LgLight ABI");
 static_assert(sizeof(LgRay) == 56, "LgRay ABI");
 static_assert(sizeof(LgSegment) == 32, "LgSegment ABI");
 static_assert(sizeof(LgVertexPair) == 64, "LgVertexPair ABI");
@@ -182,6 +182,18 @@ struct lg_ctx {
   int precision = LG_PRECISION_F32;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  // lg_render's wave pipeline: the accumulate passes of wave k run on stream2 while wave k + 1 is traced on `stream`
+  cudaStream_t stream2 = nullptr;
+  cudaEvent_t ev_pipe = nullptr, ev_t0[2] = {nullptr, nullptr}, ev_t1[2] = {nullptr, nullptr}, ev_a0[2] = {nullptr, nullptr},
+              ev_a1[2] = {nullptr, nullptr};
+  int render_overlap = 1;   // lg_render_overlap_set: 0 = one wave after the other, 1 = automatic, 2 = always (tests)
+  unsigned pipe_waves = 8;  // waves a frame is cut into when the pipeline runs
+  int pipe_trace_ctas = -1; // resident trace CTAs per SM while it runs: < 0 = that many fewer than would fit (LG_PIPE_TRACE_CTAS)
+  int pipe_raster_ctas = -1; // raster CTAs per SM next to a running trace kernel: < 0 = what its shared memory leaves (LG_PIPE_RASTER_CTAS)
+  int raster_cap_now = 0;    // > 0: accumulate_tiled launches at most that many raster CTAs per SM
+  size_t smem_per_sm = 0;
+  size_t last_trace_smem = 0; // dynamic shared memory and resident CTAs per SM of the last trace launch
+  int last_trace_ctas = 0;
   std::string err;
   int sm_count = 0;
   int slots = 2; // ray slots per thread (R)
@@ -190,6 +202,8 @@ struct lg_ctx {
   // scene
   bool have_scene = false;
   HostScene hs;
+  bool have_drawing = false; // lg_drawing_object_set: chained behind the objects in the start-medium scan only
+  HostScene drawing_hs;
   int n_obj = 0, n_pad = 0;
   unsigned bounds_bytes = 0;
   DevBuf bounds, toks, obj_first, obj_count, obj_n, ovl_start, ovl_list;
@@ -248,6 +262,11 @@ struct lg_ctx {
   std::unordered_map<unsigned long long, AutoStat> auto_stats;
   unsigned long long scene_hash = 0, lights_hash = 0;
   DevBuf tile_count, tile_cursor, tile_offset, item_prefix, tile_totals, item_counter, tile_list, seg2, tile_hist;
+  double pairs_per_seg_est = 0;              // (segment, tile) pairs per segment of the last tiled resolve: sizes the next pair list
+  TileArgs tiled_last{};                     // arguments of the last accumulate_tiled (tiled_finish runs fill + raster again from them)
+  int tiled_raster_grid = 0;
+  size_t tiled_hist_smem = 0, tiled_raster_smem = 0;
+  unsigned long long *h_totals = nullptr;    // page-locked: [0..3] totals of the last tiled resolve, [4..] wave status (lg_render)
 
   // comm
   NcclComm comm = nullptr;
@@ -393,6 +412,12 @@ void rebuild_dev_lights(lg_ctx *c) {
     d.id_base = id_base;
     d.n_rays = (double)n;
     d.n0 = c->have_scene ? host_start_medium(c->hs, l.position[0], l.position[1]) : 1.0;
+    // `.chain(&self.drawing_object)` (tracer.rs:281): last in the chain, so it wins when it contains the light
+    if (c->have_drawing && c->drawing_hs.objs.size() == 1 && c->drawing_hs.objs[0].has_material &&
+        host_contains(c->drawing_hs, 0, l.position[0], l.position[1]))
+      d.n0 = c->drawing_hs.objs[0].n;
+    if (l.flags & LG_LIGHT_START_MEDIUM) d.n0 = l.start_medium;
+    d.rsign = (l.flags & LG_LIGHT_DIRECTIONAL_NEG_R) ? -1.0 : 1.0;
     std::memcpy(d.color, l.color, 16);
     d.px = l.position[0], d.py = l.position[1];
     d.ex = l.b[0] - l.position[0], d.ey = l.b[1] - l.position[1];
@@ -451,7 +476,9 @@ template <> struct KernelOf<double> {
   static int clamp(int slots) { return slots == 2 ? 2 : 1; }
 };
 
-template <class T> int launch_trace(lg_ctx *c, TraceArgs<T> &A) {
+// st: the stream to launch on; cta_cap > 0 limits the resident CTAs per SM (lg_render's wave pipeline leaves room
+// on every SM for the accumulate kernels of the previous wave)
+template <class T> int launch_trace(lg_ctx *c, TraceArgs<T> &A, cudaStream_t st, int cta_cap) {
   const bool grid_mode = c->grid_on && c->n_obj > 0;
   int R = KernelOf<T>::clamp(c->slots);
   if (grid_mode) R = (sizeof(T) == 4 && c->grid_slots == 2) ? 2 : 1; // divergent cell walks: one ray per thread by default
@@ -466,6 +493,9 @@ template <class T> int launch_trace(lg_ctx *c, TraceArgs<T> &A) {
   int per_sm = 0;
   LG_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kTraceBlock, smem));
   if (per_sm < 1) return fail(c, LG_ERR_CUDA, "trace kernel does not fit on an SM");
+  if (cta_cap < 0) per_sm = std::max(1, per_sm + cta_cap); // -1: one CTA per SM less than would fit
+  else if (cta_cap > 0) per_sm = std::min(per_sm, cta_cap);
+  c->last_trace_smem = smem, c->last_trace_ctas = per_sm;
   const int grid = c->sm_count * per_sm;
   const size_t nthreads = (size_t)grid * kTraceBlock;
   // split stack: one private stack per slot, depth <= max_bounce - 1 live branches
@@ -476,9 +506,26 @@ template <class T> int launch_trace(lg_ctx *c, TraceArgs<T> &A) {
   if (rc) return rc;
   A.stack = (uint4 *)c->stack.p;
   void *args[] = {(void *)&A};
-  LG_CUDA(c, cudaLaunchKernel(kern, dim3(grid), dim3(kTraceBlock), args, smem, c->stream));
+  LG_CUDA(c, cudaLaunchKernel(kern, dim3(grid), dim3(kTraceBlock), args, smem, st));
   c->launches++;
   return LG_OK;
+}
+
+// queues one trace launch over [first, end) of the ray index space on `st`: segments into seg[0, seg_cap), counters
+// (cleared first) at `ctr`.  ensure_bounds() must have run.
+int trace_async(lg_ctx *c, cudaStream_t st, const LgRay *d_rays, unsigned long long first, unsigned long long end,
+                LgSegment *seg, unsigned long long seg_cap, TraceCounters *ctr, int cta_cap) {
+  LG_CUDA(c, cudaMemsetAsync(ctr, 0, sizeof(TraceCounters), st));
+  if (c->precision == LG_PRECISION_F64) {
+    TraceArgs<double> A{};
+    fill_args(c, A);
+    A.rays = d_rays, A.ray_first = first, A.ray_end = end, A.seg = seg, A.seg_cap = seg_cap, A.ctr = ctr;
+    return launch_trace(c, A, st, cta_cap);
+  }
+  TraceArgs<float> A{};
+  fill_args(c, A);
+  A.rays = d_rays, A.ray_first = first, A.ray_end = end, A.seg = seg, A.seg_cap = seg_cap, A.ctr = ctr;
+  return launch_trace(c, A, st, cta_cap);
 }
 
 int prepare_trace_buffers(lg_ctx *c) {
@@ -488,7 +535,7 @@ int prepare_trace_buffers(lg_ctx *c) {
     if ((rc = ensure(c, c->tags, c->seg_cap * sizeof(LgSegmentTag)))) return rc;
     if (c->precision == LG_PRECISION_F64 && (rc = ensure(c, c->seg64, c->seg_cap * sizeof(LgSegmentF64)))) return rc;
   }
-  if ((rc = ensure(c, c->ctr, sizeof(TraceCounters)))) return rc;
+  if ((rc = ensure(c, c->ctr, 2 * sizeof(TraceCounters)))) return rc; // two: the wave pipeline's buffers
   return LG_OK;
 }
 
@@ -498,20 +545,8 @@ int trace_range(lg_ctx *c, const LgRay *d_rays, unsigned long long first, unsign
                 float *ms, double ray_bound = 0.0) {
   int rb = ensure_bounds(c, ray_bound);
   if (rb) return rb;
-  LG_CUDA(c, cudaMemsetAsync(c->ctr.p, 0, sizeof(TraceCounters), c->stream));
   LG_CUDA(c, cudaEventRecord(c->ev0, c->stream));
-  int rc;
-  if (c->precision == LG_PRECISION_F64) {
-    TraceArgs<double> A{};
-    fill_args(c, A);
-    A.rays = d_rays, A.ray_first = first, A.ray_end = end;
-    rc = launch_trace(c, A);
-  } else {
-    TraceArgs<float> A{};
-    fill_args(c, A);
-    A.rays = d_rays, A.ray_first = first, A.ray_end = end;
-    rc = launch_trace(c, A);
-  }
+  int rc = trace_async(c, c->stream, d_rays, first, end, (LgSegment *)c->seg.p, c->seg_cap, (TraceCounters *)c->ctr.p, 0);
   if (rc) return rc;
   LG_CUDA(c, cudaEventRecord(c->ev1, c->stream));
   LG_CUDA(c, cudaMemcpyAsync(&out, c->ctr.p, sizeof(TraceCounters), cudaMemcpyDeviceToHost, c->stream));
@@ -597,8 +632,17 @@ void note_accum_cost(lg_ctx *c, bool tiled, float ms, unsigned long long frags, 
   if (a.samples[m] < 2) ++a.samples[m];
 }
 
-// count -> scan -> fill -> raster over device segments of type Seg (LgSegment or Seg2)
-template <class Seg> int accumulate_tiled(lg_ctx *c, const Seg *d_seg, unsigned long long n, unsigned *launches) {
+// count -> scan -> fill -> raster over device segments of type Seg (LgSegment or Seg2), queued on `st` without a
+// host round trip: the pair list is sized from what this context has seen so far (pairs per segment of the previous
+// call, with head room); tile_scan_kernel checks the real total against it and, when it does not fit, flags the
+// overflow and leaves fill / raster nothing to do.  tiled_finish() -- after the caller's own synchronisation --
+// reads the totals, grows the list and runs the two passes again in that case (first call of a workload at most).
+// n_dev / skip_dev: the segment count and the "wave overflowed" flag may live on the device (lg_render's waves).
+template <class Seg>
+int accumulate_tiled(lg_ctx *c, cudaStream_t st, const Seg *d_seg, unsigned long long n, const unsigned long long *n_dev,
+                     const unsigned int *skip_dev, unsigned long long *h_totals, unsigned *launches,
+                     unsigned long long n_expect = 0) {
+  if (n_expect == 0) n_expect = n; // segments the pair list is sized for (n is only a capacity when n_dev is given)
   TileArgs T;
   T.A = accum_args(c);
   T.tiles_x = (c->W + kTile - 1) / kTile, T.tiles_y = (c->H + kTile - 1) / kTile;
@@ -608,12 +652,20 @@ template <class Seg> int accumulate_tiled(lg_ctx *c, const Seg *d_seg, unsigned 
   if ((rc = ensure(c, c->tile_cursor, (size_t)T.n_tiles * 4))) return rc;
   if ((rc = ensure(c, c->tile_offset, ((size_t)T.n_tiles + 1) * 8))) return rc;
   if ((rc = ensure(c, c->item_prefix, ((size_t)T.n_tiles + 1) * 4))) return rc;
-  if ((rc = ensure(c, c->tile_totals, 16))) return rc;
+  if ((rc = ensure(c, c->tile_totals, 64))) return rc;
   if ((rc = ensure(c, c->item_counter, 4))) return rc;
+  // pair list: pairs per segment seen so far x 1.25 (4 before the first sample), never shrinks
+  const double pps = c->pairs_per_seg_est > 0 ? c->pairs_per_seg_est * 1.25 : 4.0;
+  unsigned long long want = (unsigned long long)(pps * (double)n_expect) + 4096ull;
+  if (want < c->tile_list.bytes / 4) want = c->tile_list.bytes / 4;
+  if ((rc = ensure(c, c->tile_list, (size_t)want * 4))) return rc;
   T.tile_count = (unsigned *)c->tile_count.p, T.tile_cursor = (unsigned *)c->tile_cursor.p;
   T.tile_offset = (unsigned long long *)c->tile_offset.p, T.item_prefix = (unsigned *)c->item_prefix.p;
   T.totals = (unsigned long long *)c->tile_totals.p, T.item_counter = (unsigned *)c->item_counter.p;
-  T.list = nullptr;
+  T.list = (unsigned *)c->tile_list.p;
+  T.list_cap = c->tile_list.bytes / 4;
+  T.n_dev = n_dev, T.skip_dev = skip_dev;
+  T.raster_warps = 0; // set below
   const size_t hist_smem = (size_t)T.n_tiles * 4;
   auto count_k = tile_count_kernel<Seg>;
   auto fill_k = tile_fill_kernel<Seg>;
@@ -631,30 +683,53 @@ template <class Seg> int accumulate_tiled(lg_ctx *c, const Seg *d_seg, unsigned 
   T.n_ctas = grid;
   if ((rc = ensure(c, c->tile_hist, (size_t)grid * T.n_tiles * 4))) return rc;
   T.hist = (unsigned *)c->tile_hist.p;
-  count_k<<<grid, c->bin_threads, hist_smem, c->stream>>>(T, d_seg, n);
-  LG_CUDA(c, cudaGetLastError());
-  tile_rowscan_kernel<<<(T.n_tiles + 255) / 256, 256, 0, c->stream>>>(T);
-  LG_CUDA(c, cudaGetLastError());
-  tile_scan_kernel<<<1, 1024, 0, c->stream>>>(T);
-  LG_CUDA(c, cudaGetLastError());
-  unsigned long long totals[2] = {0, 0};
-  LG_CUDA(c, cudaMemcpyAsync(totals, T.totals, 16, cudaMemcpyDeviceToHost, c->stream));
-  LG_CUDA(c, cudaStreamSynchronize(c->stream));
-  c->launches += 3;
-  if (launches) *launches += 3;
-  if (totals[0] == 0) return LG_OK; // nothing on the canvas
-  if ((rc = ensure(c, c->tile_list, (size_t)totals[0] * 4))) return rc;
-  T.list = (unsigned *)c->tile_list.p;
-  fill_k<<<grid, c->bin_threads, hist_smem, c->stream>>>(T, d_seg, n);
-  LG_CUDA(c, cudaGetLastError());
   const size_t smem = (size_t)kRasterWarps * ((size_t)kTileFloat4 * sizeof(float4) + sizeof(RasterScratch));
   auto kern = tile_raster_kernel<Seg>;
   LG_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0;
   LG_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kRasterWarps * 32, smem));
   if (per_sm < 1) return fail(c, LG_ERR_CUDA, "tile raster kernel does not fit on an SM");
-  kern<<<c->sm_count * per_sm, kRasterWarps * 32, smem, c->stream>>>(T, d_seg);
+  if (c->raster_cap_now > 0) per_sm = std::min(per_sm, c->raster_cap_now);
+  T.raster_warps = c->sm_count * per_sm * kRasterWarps;
+  c->tiled_last = T;
+  c->tiled_raster_grid = c->sm_count * per_sm;
+  c->tiled_hist_smem = hist_smem, c->tiled_raster_smem = smem;
+  count_k<<<grid, c->bin_threads, hist_smem, st>>>(T, d_seg, n);
   LG_CUDA(c, cudaGetLastError());
+  tile_rowscan_kernel<<<(T.n_tiles + 31) / 32, 32 * kRowscanWarps, 0, st>>>(T);
+  LG_CUDA(c, cudaGetLastError());
+  tile_scan_kernel<<<1, 1024, 0, st>>>(T);
+  LG_CUDA(c, cudaGetLastError());
+  fill_k<<<grid, c->bin_threads, hist_smem, st>>>(T, d_seg, n);
+  LG_CUDA(c, cudaGetLastError());
+  kern<<<c->tiled_raster_grid, kRasterWarps * 32, smem, st>>>(T, d_seg);
+  LG_CUDA(c, cudaGetLastError());
+  LG_CUDA(c, cudaMemcpyAsync(h_totals, T.totals, 32, cudaMemcpyDeviceToHost, st));
+  c->launches += 5;
+  if (launches) *launches += 5;
+  return LG_OK;
+}
+
+// After the stream that ran accumulate_tiled() has been synchronised: the pair list was too small -> grow it and run
+// fill + raster again (the counts and offsets of the first three passes are still valid).  Blocking.
+template <class Seg>
+int tiled_finish(lg_ctx *c, cudaStream_t st, const Seg *d_seg, unsigned long long n, const unsigned long long *h_totals,
+                 unsigned *launches) {
+  if (n > 0 && h_totals[0] > 0) c->pairs_per_seg_est = std::max(1.0, (double)h_totals[0] / (double)n);
+  if (!h_totals[2]) return LG_OK;
+  TileArgs T = c->tiled_last;
+  int rc;
+  if ((rc = ensure(c, c->tile_list, (size_t)(h_totals[0] + h_totals[0] / 8 + 4096ull) * 4))) return rc;
+  T.list = (unsigned *)c->tile_list.p;
+  T.list_cap = c->tile_list.bytes / 4;
+  const unsigned long long fixed[4] = {h_totals[0], h_totals[3], 0ull, h_totals[3]};
+  LG_CUDA(c, cudaMemcpyAsync(T.totals, fixed, 32, cudaMemcpyHostToDevice, st));
+  LG_CUDA(c, cudaMemsetAsync(T.item_counter, 0, 4, st)); // the raster's first (empty) launch moved it
+  tile_fill_kernel<Seg><<<T.n_ctas, c->bin_threads, c->tiled_hist_smem, st>>>(T, d_seg, n);
+  LG_CUDA(c, cudaGetLastError());
+  tile_raster_kernel<Seg><<<c->tiled_raster_grid, kRasterWarps * 32, c->tiled_raster_smem, st>>>(T, d_seg);
+  LG_CUDA(c, cudaGetLastError());
+  LG_CUDA(c, cudaStreamSynchronize(st));
   c->launches += 2;
   if (launches) *launches += 2;
   return LG_OK;
@@ -672,7 +747,7 @@ int accumulate_device_segments(lg_ctx *c, unsigned long long n, float *ms, unsig
   if (c->accum_mode == 0 && n >= kTiledMinSegments && (rc = read_pixel_counter(c, &before))) return rc;
   LG_CUDA(c, cudaEventRecord(c->ev0, c->stream));
   if (tiled) {
-    if ((rc = accumulate_tiled<LgSegment>(c, (const LgSegment *)c->seg.p, n, launches))) return rc;
+    if ((rc = accumulate_tiled<LgSegment>(c, c->stream, (const LgSegment *)c->seg.p, n, nullptr, nullptr, c->h_totals, launches))) return rc;
   } else {
     if (c->blend_generic)
       accumulate_segments_kernel<true><<<accum_grid(c), kAccumBlock, 0, c->stream>>>(accum_args(c), (const LgSegment *)c->seg.p, n);
@@ -684,6 +759,7 @@ int accumulate_device_segments(lg_ctx *c, unsigned long long n, float *ms, unsig
   }
   LG_CUDA(c, cudaEventRecord(c->ev1, c->stream));
   LG_CUDA(c, cudaStreamSynchronize(c->stream));
+  if (tiled && (rc = tiled_finish<LgSegment>(c, c->stream, (const LgSegment *)c->seg.p, n, c->h_totals, launches))) return rc;
   float t = 0.f;
   LG_CUDA(c, cudaEventElapsedTime(&t, c->ev0, c->ev1));
   if (ms) *ms += t;
@@ -754,8 +830,25 @@ int32_t lg_create(int32_t device, int32_t precision, lg_ctx **out) {
     delete c;
     return LG_ERR_CUDA;
   }
+  bool ev_ok = cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking) == cudaSuccess &&
+               cudaEventCreate(&c->ev_pipe) == cudaSuccess;
+  for (int b = 0; b < 2 && ev_ok; ++b)
+    ev_ok = cudaEventCreate(&c->ev_t0[b]) == cudaSuccess && cudaEventCreate(&c->ev_t1[b]) == cudaSuccess &&
+            cudaEventCreate(&c->ev_a0[b]) == cudaSuccess && cudaEventCreate(&c->ev_a1[b]) == cudaSuccess;
+  if (!ev_ok) {
+    cudaGetLastError();
+    delete c;
+    return LG_ERR_CUDA;
+  }
+  if (cudaHostAlloc((void **)&c->h_totals, 4096, cudaHostAllocDefault) != cudaSuccess) {
+    cudaGetLastError();
+    delete c;
+    return LG_ERR_NOMEM;
+  }
+  std::memset(c->h_totals, 0, 4096);
   c->sm_count = prop.multiProcessorCount;
   c->smem_optin = prop.sharedMemPerBlockOptin;
+  c->smem_per_sm = prop.sharedMemPerMultiprocessor;
   c->slots = precision == LG_PRECISION_F64 ? 1 : 2;
   if (const char *e = getenv("LG_ACCUM_MODE")) {
     int v = atoi(e);
@@ -777,6 +870,22 @@ int32_t lg_create(int32_t device, int32_t precision, lg_ctx **out) {
   if (const char *e = getenv("LG_GRID_SLOTS")) {
     int v = atoi(e);
     if (v == 1 || v == 2) c->grid_slots = v;
+  }
+  if (const char *e = getenv("LG_RENDER_OVERLAP")) {
+    int v = atoi(e);
+    if (v >= 0 && v <= 2) c->render_overlap = v;
+  }
+  if (const char *e = getenv("LG_PIPE_WAVES")) {
+    int v = atoi(e);
+    if (v >= 2 && v <= 256) c->pipe_waves = (unsigned)v;
+  }
+  if (const char *e = getenv("LG_PIPE_TRACE_CTAS")) {
+    int v = atoi(e);
+    if (v >= -4 && v <= 8) c->pipe_trace_ctas = v;
+  }
+  if (const char *e = getenv("LG_PIPE_RASTER_CTAS")) {
+    int v = atoi(e);
+    if (v >= -1 && v <= 8) c->pipe_raster_ctas = v;
   }
   if (const char *e = getenv("LG_TRACE_SLOTS")) {
     int v = atoi(e);
@@ -800,6 +909,12 @@ int32_t lg_destroy(lg_ctx *c) {
                     &c->nest_lines, &c->nest_counts, &c->nest_points, &c->nest_pairs};
   for (DevBuf *b : bufs) release(*b);
   for (ExportBuf &e : c->exported) export_release(e);
+  if (c->h_totals) cudaFreeHost(c->h_totals);
+  for (int b = 0; b < 2; ++b)
+    for (cudaEvent_t e : {c->ev_t0[b], c->ev_t1[b], c->ev_a0[b], c->ev_a1[b]})
+      if (e) cudaEventDestroy(e);
+  if (c->ev_pipe) cudaEventDestroy(c->ev_pipe);
+  if (c->stream2) cudaStreamDestroy(c->stream2);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
   if (c->stream) cudaStreamDestroy(c->stream);
@@ -836,8 +951,12 @@ int32_t lg_scene_set(lg_ctx *c, const LgObject *objects, uint32_t n_objects, con
 int32_t lg_lights_set(lg_ctx *c, const LgLight *lights, uint32_t n) {
   if (!c) return LG_ERR_INVALID;
   if (n && !lights) return fail(c, LG_ERR_INVALID, "null lights");
-  for (uint32_t i = 0; i < n; ++i)
+  for (uint32_t i = 0; i < n; ++i) {
     if (lights[i].kind < LG_LIGHT_POINT || lights[i].kind > LG_LIGHT_SPOT) return fail(c, LG_ERR_INVALID, "light kind");
+    if (lights[i].flags & ~(LG_LIGHT_DIRECTIONAL_NEG_R | LG_LIGHT_START_MEDIUM)) return fail(c, LG_ERR_INVALID, "light flags");
+    if ((lights[i].flags & LG_LIGHT_START_MEDIUM) && !(lights[i].start_medium > 0.0 && lights[i].start_medium < 1e30))
+      return fail(c, LG_ERR_INVALID, "start_medium must be a positive refractive index");
+  }
   LG_CUDA(c, cudaSetDevice(c->device));
   c->lights.assign(lights, lights + n);
   c->have_lights = true;
@@ -846,6 +965,33 @@ int32_t lg_lights_set(lg_ctx *c, const LgLight *lights, uint32_t n) {
   int rc = upload(c, c->d_lights, c->dev_lights);
   if (rc) return rc;
   LG_CUDA(c, cudaStreamSynchronize(c->stream));
+  return LG_OK;
+}
+
+int32_t lg_drawing_object_set(lg_ctx *c, const LgObject *object, const LgGeoNode *nodes, uint32_t n_nodes) {
+  if (!c) return LG_ERR_INVALID;
+  LG_CUDA(c, cudaSetDevice(c->device));
+  if (!object) {
+    c->have_drawing = false;
+  } else {
+    if (!nodes || n_nodes == 0) return fail(c, LG_ERR_INVALID, "null geometry nodes");
+    LgTraceParams prm{};
+    prm.max_bounce = 1;
+    prm.canvas_tlbr[0] = 1.0, prm.canvas_tlbr[1] = -1.0, prm.canvas_tlbr[2] = -1.0, prm.canvas_tlbr[3] = 1.0;
+    std::string err;
+    HostScene tmp;
+    int rc = lower_scene(object, 1, nodes, n_nodes, prm, tmp, err);
+    if (rc) return fail(c, rc, err);
+    c->drawing_hs = tmp;
+    c->have_drawing = true;
+  }
+  if (c->have_lights) { // start media may have changed
+    rebuild_dev_lights(c);
+    int rc = upload(c, c->d_lights, c->dev_lights);
+    if (rc) return rc;
+    c->lights_hash = mix_sig(hash_bytes(c->lights.data(), c->lights.size() * sizeof(LgLight)), c->have_drawing ? 1 : 0);
+    LG_CUDA(c, cudaStreamSynchronize(c->stream));
+  }
   return LG_OK;
 }
 
@@ -986,8 +1132,17 @@ int32_t lg_trace_rays(lg_ctx *c, const LgRay *rays, uint64_t n, LgTraceStats *st
   float ms = 0.f;
   c->seg_count = 0;
   double ray_bound = 0;
-  for (uint64_t i = 0; i < n; ++i)
+  // directions must be unit vectors (Ray::from_origin normalises, light.rs:172): the broad phase and the range
+  // filter of the trace kernel rely on it, a longer or shorter one would silently lose hits
+  const double tol = 16.0 * (c->precision == LG_PRECISION_F64 ? std::numeric_limits<double>::epsilon()
+                                                              : (double)std::numeric_limits<float>::epsilon());
+  for (uint64_t i = 0; i < n; ++i) {
     ray_bound = std::fmax(ray_bound, std::fmax(std::fabs(rays[i].origin[0]), std::fabs(rays[i].origin[1])));
+    const double dx = rays[i].direction[0], dy = rays[i].direction[1];
+    if (!(std::fabs(dx * dx + dy * dy - 1.0) <= tol))
+      return fail(c, LG_ERR_INVALID, "ray " + std::to_string(i) + ": direction is not a unit vector (|d|^2 - 1 = " +
+                                         std::to_string(dx * dx + dy * dy - 1.0) + ")");
+  }
   if (!(ray_bound < 1e30)) return fail(c, LG_ERR_INVALID, "ray origin is not finite");
   if ((rc = trace_range(c, (const LgRay *)c->rays.p, 0, n, k, &ms, ray_bound))) return rc;
   fill_stats(c, stats, n, k.ray_steps, k.seg_count, ms, 1);
@@ -1080,7 +1235,7 @@ int accumulate_device_pairs(lg_ctx *c, const LgVertexPair *d_pairs, uint64_t n, 
     pairs_to_seg2_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(d_pairs, (Seg2 *)c->seg2.p, n);
     LG_CUDA(c, cudaGetLastError());
     c->launches++, nl++;
-    if ((rc = accumulate_tiled<Seg2>(c, (const Seg2 *)c->seg2.p, n, &nl))) return rc;
+    if ((rc = accumulate_tiled<Seg2>(c, c->stream, (const Seg2 *)c->seg2.p, n, nullptr, nullptr, c->h_totals, &nl))) return rc;
   } else {
     if (c->blend_generic)
       accumulate_pairs_kernel<true><<<accum_grid(c), kAccumBlock, 0, c->stream>>>(accum_args(c), d_pairs, n);
@@ -1091,6 +1246,7 @@ int accumulate_device_pairs(lg_ctx *c, const LgVertexPair *d_pairs, uint64_t n, 
   }
   LG_CUDA(c, cudaEventRecord(c->ev1, c->stream));
   LG_CUDA(c, cudaStreamSynchronize(c->stream));
+  if (tiled && (rc = tiled_finish<Seg2>(c, c->stream, (const Seg2 *)c->seg2.p, n, c->h_totals, &nl))) return rc;
   float t = 0.f;
   LG_CUDA(c, cudaEventElapsedTime(&t, c->ev0, c->ev1));
   uint64_t frag1 = 0;
@@ -1235,7 +1391,7 @@ int32_t lg_string_mod(lg_ctx *c, const LgStringMod *sm, const LgModRemColor *rul
     string_mod_seg2_kernel<<<(unsigned)((count + 255) / 256), 256, 0, c->stream>>>(S, (Seg2 *)c->seg2.p);
     LG_CUDA(c, cudaGetLastError());
     c->launches++, nl++;
-    if ((rc = accumulate_tiled<Seg2>(c, (const Seg2 *)c->seg2.p, count, &nl))) return rc;
+    if ((rc = accumulate_tiled<Seg2>(c, c->stream, (const Seg2 *)c->seg2.p, count, nullptr, nullptr, c->h_totals, &nl))) return rc;
   } else if (count) {
     if (c->blend_generic)
       string_mod_kernel<true><<<accum_grid(c), kAccumBlock, 0, c->stream>>>(accum_args(c), S);
@@ -1246,6 +1402,7 @@ int32_t lg_string_mod(lg_ctx *c, const LgStringMod *sm, const LgModRemColor *rul
   }
   LG_CUDA(c, cudaEventRecord(c->ev1, c->stream));
   LG_CUDA(c, cudaStreamSynchronize(c->stream));
+  if (tiled && (rc = tiled_finish<Seg2>(c, c->stream, (const Seg2 *)c->seg2.p, count, c->h_totals, &nl))) return rc;
   float t = 0.f;
   LG_CUDA(c, cudaEventElapsedTime(&t, c->ev0, c->ev1));
   uint64_t frag1 = 0;
@@ -1260,27 +1417,21 @@ int32_t lg_string_mod(lg_ctx *c, const LgStringMod *sm, const LgModRemColor *rul
   return LG_OK;
 }
 
-int32_t lg_render(lg_ctx *c, LgTraceStats *stats) {
-  int rc = need_scene_lights(c, true);
-  if (rc) return rc;
-  if ((rc = need_image(c))) return rc;
-  LG_CUDA(c, cudaSetDevice(c->device));
-  LgTraceStats local;
-  if (!stats) stats = &local;
-  std::memset(stats, 0, sizeof *stats);
-  if ((rc = prepare_trace_buffers(c))) return rc;
-  // waves through the bounded segment buffer: a wave that overflows is traced
-  // again with half the rays (nothing of it has been accumulated yet)
-  const unsigned mb = c->hs.params.max_bounce;
-  double est = c->segs_per_ray_est > 0 ? c->segs_per_ray_est : std::min<double>(2.0 * (mb ? mb : 1), 64.0);
-  unsigned long long done = 0;
-  const unsigned long long total = c->shard_rays;
+} // extern "C"
+namespace {
+
+// Rays [first, end) of this context's shard, one wave after the other through the whole segment buffer: trace,
+// wait, accumulate, wait.  A wave that overflows is traced again with half the rays (nothing of it has been
+// accumulated yet).
+int render_range_sync(lg_ctx *c, LgTraceStats *stats, unsigned long long first, unsigned long long end, double &est) {
+  int rc;
+  unsigned long long done = first;
   unsigned long long limit = ~0ull; // shrinks when a wave overflowed
-  while (done < total) {
+  while (done < end) {
     unsigned long long wave = (unsigned long long)((double)c->seg_cap / (est * 1.25 + 1.0));
     if (wave < 1) wave = 1;
     if (wave > limit) wave = limit;
-    if (wave > total - done) wave = total - done;
+    if (wave > end - done) wave = end - done;
     TraceCounters k{};
     float ms = 0.f;
     if ((rc = trace_range(c, nullptr, done, done + wave, k, &ms))) return rc;
@@ -1299,7 +1450,169 @@ int32_t lg_render(lg_ctx *c, LgTraceStats *stats) {
     if ((rc = accumulate_device_segments(c, k.seg_count, &stats->accumulate_ms, &stats->accumulate_launches))) return rc;
     done += wave;
   }
+  return LG_OK;
+}
+
+// Has the automatic accumulate mode settled on the tile bins for this workload (and is this not one of its probe calls)?
+bool auto_settled_on_tiles(lg_ctx *c, unsigned long long sig) {
+  auto it = c->auto_stats.find(sig);
+  if (it == c->auto_stats.end()) return false;
+  const lg_ctx::AutoStat &a = it->second;
+  if (a.samples[1] < 2 || a.samples[2] < 2) return false;
+  if ((a.calls + 1) % 64 == 0) return false; // the next call re-probes the other resolve: let the sequential path take it
+  return a.ns_per_frag[2] <= a.ns_per_frag[1];
+}
+
+// The frame as a two-stage pipeline over waves of rays (tile-binned resolve only).  The segment buffer is used as
+// two halves; wave k is traced into half k & 1 on `stream` with one CTA per SM less than would fit, and its
+// count / scan / fill / raster passes are queued on `stream2` behind an event -- they read the segment count from the
+// trace kernel's counters on the device, so the host never waits in between: while the passes of wave k run, wave
+// k + 1 is being traced on the SMs' remaining issue slots, registers and shared memory.  The host looks at a wave
+// again only when its half of the buffer is needed for wave k + 2 (by then it has long finished): statistics, and the
+// two rare repairs -- a wave that overflowed its half (skipped by the passes on the device: its rays are traced
+// again at the end, in smaller waves) and a pair list that turned out too small (that wave's passes run again).
+int render_pipelined(lg_ctx *c, LgTraceStats *stats, double &est) {
+  const unsigned long long total = c->shard_rays;
+  const unsigned long long half = c->seg_cap / 2;
+  LgSegment *seg[2] = {(LgSegment *)c->seg.p, (LgSegment *)c->seg.p + half};
+  TraceCounters *ctr = (TraceCounters *)c->ctr.p;
+  unsigned long long *hst[2] = {c->h_totals + 8, c->h_totals + 24}; // [0..3] tile totals, [4..7] TraceCounters
+  struct Wave {
+    unsigned long long first, end;
+    bool busy;
+  } w[2] = {{0, 0, false}, {0, 0, false}};
+  std::vector<std::pair<unsigned long long, unsigned long long>> redo; // ray ranges whose wave overflowed its half
+  int rc;
+  // everything queued on `stream` so far (the clear) comes first on stream2 as well
+  LG_CUDA(c, cudaEventRecord(c->ev_pipe, c->stream));
+  LG_CUDA(c, cudaStreamWaitEvent(c->stream2, c->ev_pipe, 0));
+
+  auto queue_passes = [&](int b, unsigned long long expect) -> int {
+    LG_CUDA(c, cudaEventRecord(c->ev_a0[b], c->stream2));
+    int r = accumulate_tiled<LgSegment>(c, c->stream2, seg[b], half, &ctr[b].seg_count, &ctr[b].seg_overflow, hst[b],
+                                        &stats->accumulate_launches, expect);
+    if (r) return r;
+    LG_CUDA(c, cudaMemcpyAsync(hst[b] + 4, &ctr[b], sizeof(TraceCounters), cudaMemcpyDeviceToHost, c->stream2));
+    LG_CUDA(c, cudaEventRecord(c->ev_a1[b], c->stream2));
+    return LG_OK;
+  };
+  auto reclaim = [&](int b) -> int { // the wave in half b has been drawn (or skipped): statistics and repairs
+    if (!w[b].busy) return LG_OK;
+    w[b].busy = false;
+    LG_CUDA(c, cudaEventSynchronize(c->ev_a1[b]));
+    TraceCounters k;
+    std::memcpy(&k, hst[b] + 4, sizeof k);
+    float tms = 0.f, ams = 0.f;
+    LG_CUDA(c, cudaEventElapsedTime(&tms, c->ev_t0[b], c->ev_t1[b]));
+    LG_CUDA(c, cudaEventElapsedTime(&ams, c->ev_a0[b], c->ev_a1[b]));
+    stats->trace_ms += tms, stats->accumulate_ms += ams;
+    if (k.stack_overflow) return fail(c, LG_ERR_OVERFLOW, "split stack overflow (max_bounce with refraction > 65)");
+    const unsigned long long rays = w[b].end - w[b].first;
+    if (k.seg_overflow) { // nothing of this wave was drawn
+      est = std::max(est, (double)k.seg_count / (double)rays);
+      redo.emplace_back(w[b].first, w[b].end);
+      return LG_OK;
+    }
+    est = std::max(1.0, (double)k.seg_count / (double)rays);
+    fill_stats(c, stats, rays, k.ray_steps, k.seg_count, 0.f, 0);
+    if (k.seg_count > 0) c->pairs_per_seg_est = std::max(1.0, (double)hst[b][0] / (double)k.seg_count);
+    if (hst[b][2]) { // the pair list was too small: the later wave's passes (queued already) share the bin buffers, so
+      // let them finish, then run this wave's passes again with the list sized from its own count
+      LG_CUDA(c, cudaStreamSynchronize(c->stream2));
+      const int o = b ^ 1;
+      const bool other_drawn = w[o].busy; // its passes ran just now; its own status is looked at when it is reclaimed
+      (void)other_drawn;
+      if ((rc = accumulate_tiled<LgSegment>(c, c->stream2, seg[b], k.seg_count, nullptr, nullptr, c->h_totals,
+                                            &stats->accumulate_launches, k.seg_count)))
+        return rc;
+      LG_CUDA(c, cudaStreamSynchronize(c->stream2));
+      if (c->h_totals[2]) return fail(c, LG_ERR_NOMEM, "pair list still too small after it was sized from the wave's own count");
+    }
+    return LG_OK;
+  };
+
+  unsigned long long wave_rays = std::max<unsigned long long>((total + c->pipe_waves - 1) / c->pipe_waves, 1ull);
+  unsigned long long done = 0;
+  for (unsigned k = 0; done < total; ++k) {
+    const int b = (int)(k & 1u);
+    if ((rc = reclaim(b))) return rc;
+    unsigned long long fit = (unsigned long long)((double)half / (est * 1.25 + 1.0));
+    if (fit < 1) fit = 1;
+    const unsigned long long wave = std::min(std::min(wave_rays, fit), total - done);
+    LG_CUDA(c, cudaEventRecord(c->ev_t0[b], c->stream));
+    if ((rc = trace_async(c, c->stream, nullptr, done, done + wave, seg[b], half, &ctr[b], c->pipe_trace_ctas))) return rc;
+    LG_CUDA(c, cudaEventRecord(c->ev_t1[b], c->stream));
+    stats->trace_launches += 1;
+    LG_CUDA(c, cudaStreamWaitEvent(c->stream2, c->ev_t1[b], 0));
+    // this wave's passes run next to the NEXT wave's trace kernel: leave its CTAs their shared memory (the last
+    // wave's passes have the device to themselves)
+    c->raster_cap_now = 0;
+    if (done + wave < total) {
+      if (c->pipe_raster_ctas >= 0) {
+        c->raster_cap_now = c->pipe_raster_ctas;
+      } else if (c->last_trace_smem > 0) {
+        const size_t raster_smem = (size_t)kRasterWarps * ((size_t)kTileFloat4 * sizeof(float4) + sizeof(RasterScratch)) + 1024;
+        const size_t taken = (size_t)c->last_trace_ctas * (c->last_trace_smem + 1024 + 64);
+        c->raster_cap_now = (int)std::max<size_t>(1, c->smem_per_sm > taken ? (c->smem_per_sm - taken) / raster_smem : 0);
+      }
+    }
+    rc = queue_passes(b, (unsigned long long)((double)wave * est * 1.1) + 1024ull);
+    c->raster_cap_now = 0;
+    if (rc) return rc;
+    w[b] = {done, done + wave, true};
+    done += wave;
+  }
+  // drain, older wave first
+  const int last = w[0].busy && w[1].busy ? (w[0].first < w[1].first ? 0 : 1) : (w[0].busy ? 0 : 1);
+  if ((rc = reclaim(last))) return rc;
+  if ((rc = reclaim(last ^ 1))) return rc;
+  LG_CUDA(c, cudaStreamSynchronize(c->stream2));
+  LG_CUDA(c, cudaStreamSynchronize(c->stream));
+  for (const auto &r : redo)
+    if ((rc = render_range_sync(c, stats, r.first, r.second, est))) return rc;
+  return LG_OK;
+}
+
+} // namespace
+extern "C" {
+
+int32_t lg_render(lg_ctx *c, LgTraceStats *stats) {
+  int rc = need_scene_lights(c, true);
+  if (rc) return rc;
+  if ((rc = need_image(c))) return rc;
+  LG_CUDA(c, cudaSetDevice(c->device));
+  LgTraceStats local;
+  if (!stats) stats = &local;
+  std::memset(stats, 0, sizeof *stats);
+  if ((rc = prepare_trace_buffers(c))) return rc;
+  if ((rc = ensure_bounds(c, 0.0))) return rc;
+  const unsigned mb = c->hs.params.max_bounce;
+  double est = c->segs_per_ray_est > 0 ? c->segs_per_ray_est : std::min<double>(2.0 * (mb ? mb : 1), 64.0);
+  // the wave pipeline: tile-binned resolve (forced, or what the automatic mode has settled on for this workload),
+  // enough rays to cut into waves that still fill the device
+  const unsigned long long total = c->shard_rays;
+  const unsigned long long expect_segments = (unsigned long long)((double)total * est);
+  bool pipe = c->render_overlap != 0 && !c->tags_on && !c->blend_generic && c->accum_mode != 1 && total >= 2 &&
+              tiled_possible(c, std::max<unsigned long long>(1ull, std::min<unsigned long long>(expect_segments, (1ull << 32) - 1)));
+  if (pipe && c->render_overlap == 1) {
+    pipe = total >= (1ull << 20) && expect_segments / c->pipe_waves >= kTiledMinSegments &&
+           (c->accum_mode == 2 || auto_settled_on_tiles(c, traced_signature(c)));
+  }
+  if (pipe && c->seg_cap / 2 >= (1ull << 32)) pipe = false; // 32-bit segment indices in the pair lists
+  c->img16_valid = false;
+  if (pipe) {
+    if (c->accum_mode == 0) ++c->auto_stats[traced_signature(c)].calls;
+    rc = render_pipelined(c, stats, est);
+  } else {
+    rc = render_range_sync(c, stats, 0, total, est);
+  }
+  if (rc) {
+    cudaStreamSynchronize(c->stream2);
+    cudaStreamSynchronize(c->stream);
+    return rc;
+  }
   c->segs_per_ray_est = est;
+  if (pipe) c->seg_count = 0; // the halves hold the last two waves: nothing lg_segments_read could hand out as one list
   return read_pixel_counter(c, &stats->pixel_updates);
 }
 
@@ -1741,6 +2054,45 @@ int32_t lg_measure_red_peak(lg_ctx *c, uint64_t span_px, int32_t pattern, int32_
   }
   release(tmp);
   *gred = best;
+  return LG_OK;
+}
+
+int32_t lg_measure_tile_rmw_peak(lg_ctx *c, int32_t reps, double *gfrag) {
+  if (!c || !gfrag) return LG_ERR_INVALID;
+  LG_CUDA(c, cudaSetDevice(c->device));
+  DevBuf tmp;
+  int rc = ensure(c, tmp, 64);
+  if (rc) return rc;
+  const size_t smem = (size_t)kRasterWarps * ((size_t)kTileFloat4 * sizeof(float4) + sizeof(RasterScratch));
+  LG_CUDA(c, cudaFuncSetAttribute(tile_rmw_peak_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 0;
+  LG_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tile_rmw_peak_kernel, kRasterWarps * 32, smem));
+  if (per_sm < 1) return fail(c, LG_ERR_CUDA, "tile microbenchmark does not fit on an SM");
+  const int grid = c->sm_count * per_sm, iters = 1 << 15;
+  double best = 0;
+  for (int r = 0; r < std::max(1, reps) + 1; ++r) {
+    LG_CUDA(c, cudaEventRecord(c->ev0, c->stream));
+    tile_rmw_peak_kernel<<<grid, kRasterWarps * 32, smem, c->stream>>>((float *)tmp.p, iters);
+    LG_CUDA(c, cudaGetLastError());
+    c->launches++;
+    LG_CUDA(c, cudaEventRecord(c->ev1, c->stream));
+    LG_CUDA(c, cudaStreamSynchronize(c->stream));
+    float ms = 0.f;
+    LG_CUDA(c, cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    const double n = 4.0 * (double)iters * (double)grid * (double)(kRasterWarps * 32);
+    if (r > 0 && ms > 0) best = std::max(best, n / (ms * 1e-3) / 1e9);
+  }
+  release(tmp);
+  *gfrag = best;
+  return LG_OK;
+}
+
+int32_t lg_render_overlap_set(lg_ctx *c, int32_t mode, uint32_t waves) {
+  if (!c) return LG_ERR_INVALID;
+  if (mode < 0 || mode > 2) return fail(c, LG_ERR_INVALID, "overlap mode");
+  if (waves == 1 || waves > 4096) return fail(c, LG_ERR_INVALID, "waves");
+  c->render_overlap = mode;
+  if (waves) c->pipe_waves = waves;
   return LG_OK;
 }
 

@@ -32,7 +32,8 @@ namespace lg {
 constexpr int kTile = 32;          // tile edge in pixels
 constexpr int kTileShift = 5;
 constexpr int kTilePitch = 32;     // float4 per major-axis line of the tile in shared memory
-constexpr int kChunk = 2048;       // list entries per work item
+constexpr int kChunk = 2048;       // list entries per work item, at least ...
+constexpr int kChunkMax = 16384;   // ... and at most: tile_scan_kernel doubles it while every raster warp still gets >= 16 items
 constexpr int kRasterWarps = 4;    // warps per CTA of tile_raster_kernel
 constexpr int kTileFloat4 = kTile * kTilePitch;
 
@@ -50,12 +51,26 @@ struct TileArgs {
   unsigned int *tile_cursor;  // [n_tiles]
   unsigned long long *tile_offset; // [n_tiles + 1]
   unsigned int *item_prefix;  // [n_tiles + 1]
-  unsigned long long *totals; // [0] = pairs, [1] = items
+  unsigned long long *totals; // [0] = pairs, [1] = items (0 when the list is too small), [2] = 1: list too small,
+                              // [3] = items, [4] = list entries per work item
   unsigned int *list;         // segment index per pair
+  unsigned long long list_cap; // entries `list` can hold: sized from the previous call, checked by tile_scan_kernel
   unsigned int *item_counter;
   unsigned int *hist;         // [n_ctas][n_tiles] per-CTA counts, then per-CTA exclusive offsets within a tile
   int n_ctas;
+  int raster_warps;           // warps of the raster launch (work-item size: totals[4])
+  // segment count and "do nothing" flag that live on the device (the trace kernel's counters): the passes of a wave
+  // are queued behind the trace kernel without the host learning the count first.  NULL: use the kernel argument.
+  const unsigned long long *n_dev;
+  const unsigned int *skip_dev;
 };
+
+// number of segments the count / fill passes walk
+__device__ __forceinline__ unsigned long long pass_segments(const TileArgs &T, unsigned long long n) {
+  if (T.n_dev) n = *T.n_dev < n ? *T.n_dev : n; // n = capacity of the segment buffer in that case
+  if (T.skip_dev && *T.skip_dev) n = 0ull;      // the wave overflowed its buffer: nothing of it is drawn
+  return n;
+}
 
 template <class Seg> struct SegIO;
 // One 8-byte read-only load.  The raster's gather prefetch uses four of them per segment instead of two 16-byte
@@ -127,6 +142,7 @@ template <class Seg> __global__ void __launch_bounds__(1024) tile_count_kernel(T
   extern __shared__ unsigned int s_hist[];
   for (int t = threadIdx.x; t < T.n_tiles; t += blockDim.x) s_hist[t] = 0u;
   __syncthreads();
+  n = pass_segments(T, n);
   unsigned long long lo, hi;
   cta_range(n, blockIdx.x, gridDim.x, lo, hi);
   for (unsigned long long i = lo + threadIdx.x; i < hi; i += blockDim.x) {
@@ -140,25 +156,45 @@ template <class Seg> __global__ void __launch_bounds__(1024) tile_count_kernel(T
   for (int t = threadIdx.x; t < T.n_tiles; t += blockDim.x) out[t] = s_hist[t];
 }
 
-// thread = tile: exclusive scan down the CTA dimension; hist[c][t] becomes CTA c's offset inside tile t's list
-__global__ void __launch_bounds__(256) tile_rowscan_kernel(TileArgs T) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+// Exclusive scan down the CTA dimension: hist[c][t] becomes CTA c's offset inside list t.  A block owns 32 lists
+// (lane = list: every row access is one coalesced 128-byte line) and its 8 warps split the CTA rows between them:
+// slice sums first, then the scan of each slice from its carry-in (the table is read twice, from L2).  One thread
+// per list walking all rows took 2.1 ms of the 35 ms accumulate of C5 (r01f launch list): 64 blocks for 148 SMs.
+constexpr int kRowscanWarps = 8;
+__global__ void __launch_bounds__(32 * kRowscanWarps) tile_rowscan_kernel(TileArgs T) {
+  __shared__ unsigned int part[kRowscanWarps][32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int t = blockIdx.x * 32 + lane;
+  const int c0 = (int)((long long)T.n_ctas * w / kRowscanWarps), c1 = (int)((long long)T.n_ctas * (w + 1) / kRowscanWarps);
+  unsigned int sum = 0u;
+  if (t < T.n_tiles) {
+    const unsigned int *p = T.hist + (size_t)c0 * T.n_tiles + t;
+    int c = c0;
+    for (; c + 4 <= c1; c += 4, p += 4 * (size_t)T.n_tiles)
+      sum += p[0] + p[T.n_tiles] + p[2 * (size_t)T.n_tiles] + p[3 * (size_t)T.n_tiles];
+    for (; c < c1; ++c, p += T.n_tiles) sum += *p;
+  }
+  part[w][lane] = sum;
+  __syncthreads();
   if (t >= T.n_tiles) return;
-  unsigned int run = 0;
-  for (int c = 0; c < T.n_ctas; ++c) {
-    unsigned int *p = T.hist + (size_t)c * T.n_tiles + t; // coalesced across the warp's tiles
+  unsigned int run = 0u;
+  for (int k = 0; k < w; ++k) run += part[k][lane];
+  unsigned int *p = T.hist + (size_t)c0 * T.n_tiles + t;
+  for (int c = c0; c < c1; ++c, p += T.n_tiles) {
     const unsigned int v = *p;
     *p = run;
     run += v;
   }
-  T.tile_count[t] = run;
+  if (w == kRowscanWarps - 1) T.tile_count[t] = run;
 }
 
 template <class Seg> __global__ void __launch_bounds__(1024) tile_fill_kernel(TileArgs T, const Seg *seg, unsigned long long n) {
   extern __shared__ unsigned int s_cur[]; // this CTA's next slot in every tile's list, relative to the tile's offset
   const unsigned int *mine = T.hist + (size_t)blockIdx.x * T.n_tiles;
+  if (T.totals[2]) return; // the list is too small (tile_scan_kernel): the host grows it and runs this pass again
   for (int t = threadIdx.x; t < T.n_tiles; t += blockDim.x) s_cur[t] = mine[t];
   __syncthreads();
+  n = pass_segments(T, n);
   unsigned long long lo, hi;
   cta_range(n, blockIdx.x, gridDim.x, lo, hi);
   for (unsigned long long i = lo + threadIdx.x; i < hi; i += blockDim.x) {
@@ -178,12 +214,30 @@ __global__ void __launch_bounds__(1024) tile_scan_kernel(TileArgs T) {
   __shared__ unsigned int s_items[1024];
   __shared__ unsigned long long carry_pairs;
   __shared__ unsigned int carry_items;
-  if (threadIdx.x == 0) carry_pairs = 0, carry_items = 0;
+  __shared__ unsigned long long s_total;
+  __shared__ unsigned int s_chunk;
+  if (threadIdx.x == 0) carry_pairs = 0, carry_items = 0, s_total = 0ull;
   __syncthreads();
+  // work-item size: every item pays for clearing and flushing a tile (1024 pixels; a transposed tile is read
+  // against the banks), so items grow with the job as long as every raster warp still gets >= 16 of them
+  {
+    unsigned long long mine = 0ull;
+    for (int t = threadIdx.x; t < T.n_tiles; t += 1024) mine += T.tile_count[t];
+    for (int off = 16; off > 0; off >>= 1) mine += __shfl_down_sync(0xffffffffu, mine, off);
+    if ((threadIdx.x & 31) == 0 && mine) atomicAdd(&s_total, mine);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned int ch = kChunk;
+      while (ch < kChunkMax && s_total / (2ull * ch) >= 16ull * (unsigned long long)max(T.raster_warps, 1)) ch *= 2u;
+      s_chunk = ch;
+    }
+    __syncthreads();
+  }
+  const unsigned int chunk_sz = s_chunk;
   for (int base = 0; base < T.n_tiles; base += 1024) {
     const int t = base + threadIdx.x;
     const unsigned int c = t < T.n_tiles ? T.tile_count[t] : 0u;
-    const unsigned int it = (c + kChunk - 1) / kChunk;
+    const unsigned int it = (c + chunk_sz - 1) / chunk_sz;
     s_pairs[threadIdx.x] = c;
     s_items[threadIdx.x] = it;
     __syncthreads();
@@ -207,8 +261,12 @@ __global__ void __launch_bounds__(1024) tile_scan_kernel(TileArgs T) {
   if (threadIdx.x == 0) {
     T.tile_offset[T.n_tiles] = carry_pairs;
     T.item_prefix[T.n_tiles] = carry_items;
+    const bool fits = carry_pairs <= T.list_cap;
     T.totals[0] = carry_pairs;
-    T.totals[1] = carry_items;
+    T.totals[1] = fits ? carry_items : 0u; // nothing for the raster to do until the list has been grown and filled
+    T.totals[2] = fits ? 0ull : 1ull;
+    T.totals[3] = carry_items;
+    T.totals[4] = chunk_sz;
     *T.item_counter = 0u;
   }
 }
@@ -218,34 +276,74 @@ struct RasterScratch {
   float4 geo[32];        // m0, 1/(m1 - m0), minor delta, minor start (RasterSetup)
   float4 col[32];        // colour at a (single-colour segments: alpha already squared)
   float4 dc[32];         // colour delta (two-colour segments only)
-  unsigned int rng[32];  // lanes of this tile the segment covers along its major axis: first | count << 8
+  unsigned int mask[32]; // lanes (major-axis steps of this tile) whose fragment lies inside the tile
 };
 
-// Blends parked entries into the warp's private tile.  lane = major-axis step; the tile is stored
-// major-axis-fastest, so a fragment at minor offset j sits at j * kTilePitch + lane; [nlo, nhi) is the minor pixel
-// range of the tile on the canvas, mc the lane's major pixel centre.
-// The arithmetic per fragment is raster_walk's (ORACLE.md 8.2-8.4).  Two entries are in flight: both pixels are
-// read before either is written; a lane that hits the same pixel in both carries the first sum into the second.
+// Exact set of lanes of a tile whose fragment of one segment lies inside the tile, computed once per (segment, tile)
+// pair when the entry is parked.  The fragment's minor coordinate f(l) = floor(fma((mc(l) - m0) * inv, dn, n0)) is
+// weakly monotone in the lane l (every step -- subtraction, product, fma, floor -- is a correctly rounded monotone
+// function of its varying argument), so the lanes inside [nlo, nhi) form ONE interval [la, lb) of the major-axis
+// range [l0, l1): two binary searches over at most 32 lanes with the exact arithmetic of raster_walk().  The blend
+// loop then needs no range test at all, and the number of fragments of the pair is popc(mask).
+__device__ __forceinline__ unsigned lane_mask_in_tile(const RasterSetup &S, int bmaj, int l0, int l1, float nlo, float nhi) {
+  if (l1 <= l0) return 0u;
+  const bool inc = (S.inv < 0.f) == (S.dn < 0.f); // f non-decreasing in l
+  // left_bad(l): the fragment is still before the tile's minor range (true on a prefix of the lanes);
+  // right_bad(l): it is already past it (true on a suffix)
+  auto left_bad = [&](int l) {
+    const float f = frag_minor(S, bmaj + l);
+    return inc ? f < nlo : f >= nhi;
+  };
+  auto right_bad = [&](int l) {
+    const float f = frag_minor(S, bmaj + l);
+    return inc ? f >= nhi : f < nlo;
+  };
+  int la = l0, lb = l1;
+  if (left_bad(l0)) { // first lane that is not left_bad, in (l0, l1]
+    int lo = l0 + 1, hi = l1;
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (left_bad(mid)) lo = mid + 1; else hi = mid;
+    }
+    la = lo;
+  }
+  if (la >= l1) return 0u;
+  if (right_bad(l1 - 1)) { // first right_bad lane, in [la, l1 - 1]
+    int lo = la, hi = l1 - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (right_bad(mid)) hi = mid; else lo = mid + 1;
+    }
+    lb = lo;
+  }
+  const int n = lb - la;
+  if (n <= 0) return 0u;
+  return (n >= 32 ? 0xffffffffu : ((1u << n) - 1u)) << la;
+}
+
 // the records of two parked entries, as the blend loop holds them in registers
 struct PairRecs {
   float4 ga, gb, ca, cb, da, db;
-  uint2 r;
+  uint2 m;
 };
 template <bool kLerp> __device__ __forceinline__ void load_recs(const RasterScratch &P, int k, PairRecs &q) {
   q.ga = P.geo[k], q.gb = P.geo[k + 1], q.ca = P.col[k], q.cb = P.col[k + 1];
   if (kLerp) q.da = P.dc[k], q.db = P.dc[k + 1];
-  q.r = *reinterpret_cast<const uint2 *>(&P.rng[k]);
+  q.m = *reinterpret_cast<const uint2 *>(&P.mask[k]);
 }
-// two entries against the tile; lane_base = this lane's byte address of minor offset 0, row_bytes = bytes per minor step
+// Blends two parked entries into the warp's private tile.  lane = major-axis step; the tile is stored
+// major-axis-fastest, so a fragment at minor coordinate j sits at lane_base + j * row_bytes (lane_base is this lane's
+// byte address of canvas minor coordinate 0).  The arithmetic per fragment is raster_walk's (ORACLE.md 8.2-8.4); which
+// lanes have a fragment in this tile was settled when the entry was parked (lane_mask_in_tile).  Both pixels are
+// read before either is written; a lane that hits the same pixel in both carries the first sum into the second.
+// Straight-line predicated code: no branch, no range test, no counting.
 template <bool kLerp>
-__device__ __forceinline__ unsigned blend_two(unsigned char *lane_base, int row_bytes, const PairRecs &q, float mc, float nlo,
-                                              float nhi, unsigned lane) {
+__device__ __forceinline__ void blend_two(unsigned char *lane_base, int row_bytes, const PairRecs &q, float mc, unsigned lane_bit) {
   const float sa = (mc - q.ga.x) * q.ga.y, sb = (mc - q.gb.x) * q.gb.y;
-  const float fa = floorf(__fmaf_rn(sa, q.ga.z, q.ga.w)), fb = floorf(__fmaf_rn(sb, q.gb.z, q.gb.w));
-  const bool act_a = (lane - (q.r.x & 255u)) < (q.r.x >> 8) && fa >= nlo && fa < nhi;
-  const bool act_b = (lane - (q.r.y & 255u)) < (q.r.y >> 8) && fb >= nlo && fb < nhi;
-  float4 *pa = reinterpret_cast<float4 *>(lane_base + (int)fa * row_bytes);
-  float4 *pb = reinterpret_cast<float4 *>(lane_base + (int)fb * row_bytes);
+  const int ja = __float2int_rd(__fmaf_rn(sa, q.ga.z, q.ga.w)), jb = __float2int_rd(__fmaf_rn(sb, q.gb.z, q.gb.w));
+  const bool act_a = (q.m.x & lane_bit) != 0u, act_b = (q.m.y & lane_bit) != 0u;
+  float4 *pa = reinterpret_cast<float4 *>(lane_base + ja * row_bytes);
+  float4 *pb = reinterpret_cast<float4 *>(lane_base + jb * row_bytes);
   float a0 = q.ca.x, a1 = q.ca.y, a2 = q.ca.z, a3 = q.ca.w, b0 = q.cb.x, b1 = q.cb.y, b2 = q.cb.z, b3 = q.cb.w;
   if (kLerp) {
     a0 = __fmaf_rn(sa, q.da.x, q.ca.x), a1 = __fmaf_rn(sa, q.da.y, q.ca.y), a2 = __fmaf_rn(sa, q.da.z, q.ca.z);
@@ -253,39 +351,33 @@ __device__ __forceinline__ unsigned blend_two(unsigned char *lane_base, int row_
     b0 = __fmaf_rn(sb, q.db.x, q.cb.x), b1 = __fmaf_rn(sb, q.db.y, q.cb.y), b2 = __fmaf_rn(sb, q.db.z, q.cb.z);
     b3 = __fmaf_rn(sb, q.db.w, q.cb.w), b3 *= b3;
   }
-  float4 va, vb;
+  float4 va, vb; // an inactive lane adds into registers nobody reads: no need to clear them
   if (act_a) va = *pa;
   if (act_b) vb = *pb;
-  if (act_a) {
-    va.x += a0, va.y += a1, va.z += a2, va.w += a3; // mod.rs:57-73
-    if (act_b && pa == pb) vb = va;
-    *pa = va;
-  }
-  if (act_b) {
-    vb.x += b0, vb.y += b1, vb.z += b2, vb.w += b3;
-    *pb = vb;
-  }
-  return (act_a ? 1u : 0u) + (act_b ? 1u : 0u);
+  va.x += a0, va.y += a1, va.z += a2, va.w += a3; // mod.rs:57-73
+  const bool same = act_a && ja == jb;            // (only read when act_b)
+  vb.x = same ? va.x : vb.x, vb.y = same ? va.y : vb.y, vb.z = same ? va.z : vb.z, vb.w = same ? va.w : vb.w;
+  vb.x += b0, vb.y += b1, vb.z += b2, vb.w += b3;
+  if (act_a) *pa = va;
+  if (act_b) *pb = vb;
 }
 template <bool kLerp>
-__device__ __forceinline__ unsigned blend_run(unsigned char *lane_base, int row_bytes, const RasterScratch &P, int m, float mc,
-                                              float nlo, float nhi, unsigned lane) {
-  // entries [0, m) two at a time; when m is odd the caller has parked an empty entry (lane range 0) at index m.
+__device__ __forceinline__ void blend_run(unsigned char *lane_base, int row_bytes, const RasterScratch &P, int m, float mc,
+                                          unsigned lane_bit) {
+  // entries [0, m) two at a time; when m is odd the caller has parked an empty entry (mask 0) at index m.
   // The records of the NEXT two entries are fetched before the current two touch the tile (the compiler cannot
   // move those loads across the tile's stores by itself: same shared-memory array); the two register sets swap
   // roles every half iteration, so nothing is copied.
-  unsigned n = 0;
   PairRecs A, B;
   A.da = A.db = B.da = B.db = make_float4(0.f, 0.f, 0.f, 0.f);
   load_recs<kLerp>(P, 0, A);
   for (int k = 0; k < m; k += 4) {
     load_recs<kLerp>(P, k + 2 < m ? k + 2 : k, B);
-    n += blend_two<kLerp>(lane_base, row_bytes, A, mc, nlo, nhi, lane);
+    blend_two<kLerp>(lane_base, row_bytes, A, mc, lane_bit);
     if (k + 2 >= m) break;
     load_recs<kLerp>(P, k + 4 < m ? k + 4 : k, A);
-    n += blend_two<kLerp>(lane_base, row_bytes, B, mc, nlo, nhi, lane);
+    blend_two<kLerp>(lane_base, row_bytes, B, mc, lane_bit);
   }
-  return n;
 }
 
 template <class Seg> __global__ void __launch_bounds__(kRasterWarps * 32) tile_raster_kernel(TileArgs T, const Seg *seg) {
@@ -297,6 +389,7 @@ template <class Seg> __global__ void __launch_bounds__(kRasterWarps * 32) tile_r
                                                        (size_t)kRasterWarps * kTileFloat4)[warp_in_block];
   constexpr bool kLerp = SegIO<Seg>::kLerp;
   const unsigned int n_items = (unsigned int)T.totals[1];
+  const unsigned int chunk_sz = (unsigned int)T.totals[4];
   unsigned long long cnt = 0;
   while (true) {
     unsigned int item = 0;
@@ -313,7 +406,7 @@ template <class Seg> __global__ void __launch_bounds__(kRasterWarps * 32) tile_r
     const bool xmajor = (list & 1) == 0;
     const unsigned int chunk = item - T.item_prefix[list];
     const unsigned int count = T.tile_count[list];
-    const unsigned int first = chunk * kChunk, last = min(count, first + kChunk);
+    const unsigned int first = chunk * chunk_sz, last = min(count, first + chunk_sz);
     const unsigned int *lst = T.list + T.tile_offset[list];
     const int tx = t % T.tiles_x, ty = t / T.tiles_x;
     const int bx = tx << kTileShift, by = ty << kTileShift;
@@ -337,20 +430,22 @@ template <class Seg> __global__ void __launch_bounds__(kRasterWarps * 32) tile_r
       if ((int)lane < m) {
         const RasterSetup S = raster_setup(T.A, g_ab.x, g_ab.y, g_ab.z, g_ab.w);
         const int l0 = max(S.i0 - bmaj, 0), l1 = min(S.i1 - bmaj, kTile);
+        const unsigned msk = lane_mask_in_tile(S, bmaj, l0, l1, nlo, nhi);
+        cnt += (unsigned)__popc(msk);
         P.geo[lane] = make_float4(S.m0, S.inv, S.dn, S.n0);
         P.col[lane] = make_float4(g_ca.x, g_ca.y, g_ca.z, kLerp ? g_ca.w : g_ca.w * g_ca.w);
         if (kLerp) P.dc[lane] = make_float4(g_dc.x - g_ca.x, g_dc.y - g_ca.y, g_dc.z - g_ca.z, g_dc.w - g_ca.w);
-        P.rng[lane] = (unsigned)l0 | ((unsigned)max(l1 - l0, 0) << 8);
+        P.mask[lane] = msk;
       } else if ((int)lane == m) { // the empty partner of an odd last entry
         P.geo[lane] = make_float4(0.f, 0.f, 0.f, 0.f);
         P.col[lane] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (kLerp) P.dc[lane] = make_float4(0.f, 0.f, 0.f, 0.f);
-        P.rng[lane] = 0u;
+        P.mask[lane] = 0u;
       }
       if (base + 32 + lane < last) SegIO<Seg>::load(seg, idx_next, g_ab, g_ca, g_dc);
       idx_next = base + 64 + lane < last ? lst[base + 64 + lane] : 0u;
       __syncwarp();
-      cnt += blend_run<kLerp>(lane_base, kTilePitch * (int)sizeof(float4), P, m, mc, nlo, nhi, lane);
+      blend_run<kLerp>(lane_base, kTilePitch * (int)sizeof(float4), P, m, mc, 1u << lane);
       __syncwarp();
     }
     // flush: one vector reduction per touched pixel, lanes sweep an image row (coalesced 512 B).  A transposed

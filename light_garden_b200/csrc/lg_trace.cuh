@@ -55,6 +55,7 @@ struct DevLight {
   double px, py;               // position / segment a
   double ex, ey;               // directional: b - a
   double min_angle, spot_angle, sign; // spot: light.rs:230-243
+  double rsign;                // directional: +1 origins a + (i/n)(b - a); -1 (LG_LIGHT_DIRECTIONAL_NEG_R) a - (i/n)(b - a)
 };
 
 struct TraceCounters {
@@ -174,7 +175,7 @@ __device__ __forceinline__ void emit_ray(const DevLight &l, unsigned long long i
     oy = l.py;
     unit_from(__dmul_rn(l.sign, c), __dmul_rn(l.sign, s), dx, dy);
   } else { // directional, light.rs:103-115 (ORACLE.md §6.3)
-    double rr = __ddiv_rn((double)i, l.n_rays);
+    double rr = __dmul_rn(l.rsign, __ddiv_rn((double)i, l.n_rays)); // eval_at_r(-(i / n)) under the chosen convention
     ox = __dadd_rn(l.px, __dmul_rn(rr, l.ex));
     oy = __dadd_rn(l.py, __dmul_rn(rr, l.ey));
     unit_from(-l.ey, l.ex, dx, dy);

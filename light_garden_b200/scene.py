@@ -224,9 +224,14 @@ class SpotLight:
 
 @dataclass
 class DirectionalLight:
+    """light.rs:77-115.  `neg_r`: how `start.eval_at_r(-(i as f64) / n)` (light.rs:111) is read -- collision2d's
+    LineSegment::eval_at_r is not in the reference.  False (default): ray origins walk the drawn segment,
+    a + (i/n)(b - a) (ORACLE.md 6.3).  True: the call taken literally on eval_at_r(r) = a + r (b - a), origins
+    a - (i/n)(b - a).  Directional-light parity is UNVERIFIED either way."""
     color: Color
     num_rays: int
     start: LineSegment
+    neg_r: bool = False
 
     @staticmethod
     def new(color, num_rays, start):  # light.rs:91
@@ -249,8 +254,16 @@ def light_to_pod(l) -> abi.LgLight:
         o.kind = abi.LG_LIGHT_DIRECTIONAL
         o.position[:] = l.start.a
         o.b[:] = l.start.b
+        if l.neg_r:
+            o.flags |= abi.LG_LIGHT_DIRECTIONAL_NEG_R
     else:
         raise TypeError(f"not a light: {l!r}")
+    # tracer.rs:279-287 chains `drawing_object` behind the scene's objects: when the object being dragged out contains
+    # the light and has a material it wins the start-medium scan (Tracer.add_drawing_object sets this attribute)
+    sm = getattr(l, "start_medium", None)
+    if sm is not None:
+        o.flags |= abi.LG_LIGHT_START_MEDIUM
+        o.start_medium = float(sm)
     return o
 
 

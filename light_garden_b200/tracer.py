@@ -5,6 +5,7 @@ that tests read like tests of the reference would; every computation happens in
 liblight_garden_b200.so on the GPU.
 """
 import ctypes as C
+import weakref
 from typing import List, Optional
 
 import numpy as np
@@ -48,30 +49,17 @@ class Context:
 
 
 def pinned_array(shape, dtype):
-    """numpy array over page-locked host memory (lg_host_alloc); keeps the allocation alive with the array."""
+    """numpy array over page-locked host memory (lg_host_alloc).  The allocation lives exactly as long as the array
+    (and its views, which keep it alive through .base): a finalizer on the owning array calls lg_host_free."""
     lib = load()
     dt = np.dtype(dtype)
     n = int(np.prod(shape)) * dt.itemsize
     p = C.c_void_p()
     check(None, lib.lg_host_alloc(n, C.byref(p)))
     buf = (C.c_ubyte * n).from_address(p.value)
-    arr = np.frombuffer(buf, dtype=dt).reshape(shape)
-
-    class _Owner:
-        def __init__(self, ptr):
-            self.ptr = ptr
-
-        def __del__(self):
-            try:
-                lib.lg_host_free(self.ptr)
-            except Exception:
-                pass
-
-    _PINNED[id(buf)] = (buf, _Owner(p))
-    return arr
-
-
-_PINNED = {}
+    owner = np.frombuffer(buf, dtype=dt)        # every view derived from it has .base == owner
+    weakref.finalize(owner, lib.lg_host_free, C.c_void_p(p.value))
+    return owner.reshape(shape)
 
 
 def sort_segments(seg, tags, f64=None):
@@ -93,19 +81,48 @@ class Tracer:
         self.chunk_size = 100                            # tracer.rs:39 (rayon chunking; unused on the device)
         self.canvas_bounds = canvas_bounds
         self.last_stats = abi.LgTraceStats()
+        self.drawing_object: Optional[Object] = None     # tracer.rs:8-9
+        self.drawing_light = None
         self._scene_dirty = True
         self._lights_dirty = True
+        self._sent_params = None
         self._rank, self._world = 0, 1
 
     # -- scene editing: tracer.rs:48-181 ------------------------------------------------------
     def clear(self):
+        self.drawing_object = self.drawing_light = None
         self.objects.clear()
         self.lights.clear()
         self._scene_dirty = self._lights_dirty = True
 
     def clear_objects(self):
+        self.drawing_object = None
         self.objects.clear()
-        self._scene_dirty = True
+        self._scene_dirty = self._lights_dirty = True
+
+    def add_drawing_object(self, obj: Object):
+        """tracer.rs:61-63: the object being dragged out takes part in the start-medium scan only (tracer.rs:281)."""
+        self.drawing_object = obj
+        self._lights_dirty = True
+
+    def finish_drawing_object(self, abort: bool):
+        """tracer.rs:65-72"""
+        obj, self.drawing_object = self.drawing_object, None
+        self._lights_dirty = True
+        if not abort and obj is not None:
+            self.push_object(obj)
+
+    def add_drawing_light(self, light):
+        """tracer.rs:74-76: traced like any other light, after them (tracer.rs:279)."""
+        self.drawing_light = light
+        self._lights_dirty = True
+
+    def finish_drawing_light(self, abort: bool):
+        """tracer.rs:78-84"""
+        light, self.drawing_light = self.drawing_light, None
+        self._lights_dirty = True
+        if not abort and light is not None:
+            self.push_light(light)
 
     def push_object(self, obj: Object):
         self.objects.append(obj)
@@ -152,6 +169,11 @@ class Tracer:
         self.clear()
         self.objects, self.lights = objects, lights
 
+    def serialize(self) -> str:
+        """Tracer::serialize (tracer.rs:183-188): RON text of (Vec<Object>, Vec<Light>) that load() reads back."""
+        from .ron import serialize_scene
+        return serialize_scene(self.objects, self.lights)
+
     def enable_tile_map(self, enable: bool):
         """Tracer::enable_tile_map (tracer.rs:137-146): nearest-hit search through the device grid (same segments)."""
         self._tile_map_enabled = bool(enable)
@@ -166,16 +188,35 @@ class Tracer:
         self._rank, self._world = rank, world
         self.ctx.call("lg_shard_set", rank, world)
 
-    def sync_scene(self):
-        """lg_scene_set / lg_lights_set when the host copy changed (the reference's `moved` dirty bit, object.rs:54)."""
-        # scalar knobs (max_bounce, cutoff_color) are public fields in the reference: always re-sent
-        objs, n_obj, nodes, n_nodes = flatten_objects(self.objects)
-        prm = trace_params(self.max_bounce, self.cutoff_color, self.canvas_bounds)
-        self.ctx.call("lg_scene_set", C.cast(objs, C.c_void_p), n_obj, C.cast(nodes, C.c_void_p), n_nodes,
-                      C.byref(prm))
-        arr = lights_to_array(self.lights)
-        self.ctx.call("lg_lights_set", C.cast(arr, C.c_void_p), len(self.lights))
-        self._scene_dirty = self._lights_dirty = False
+    def sync_scene(self, force: bool = False):
+        """lg_scene_set / lg_lights_set only when the host copy changed (the reference's `moved` dirty bit,
+        object.rs:54): every edit method sets a flag; the scalar knobs (max_bounce, cutoff_color, canvas_bounds) are
+        public fields in the reference, so their values are compared with what was last sent.  Code that mutates an
+        Object or Light it kept a reference to must go through index_object / index_light again (or pass force)."""
+        owner = getattr(self.ctx, "_scene_owner", None)
+        if owner is None or owner() is not self:      # another Tracer drove this context in between
+            force = True
+            self.ctx._scene_owner = weakref.ref(self)
+        cb = self.canvas_bounds
+        params = (int(self.max_bounce), tuple(float(v) for v in self.cutoff_color),
+                  (tuple(cb.origin), tuple(cb.rotation), float(cb.width), float(cb.height)), id(self.ctx))
+        if force or self._scene_dirty or params != self._sent_params:
+            objs, n_obj, nodes, n_nodes = flatten_objects(self.objects)
+            prm = trace_params(self.max_bounce, self.cutoff_color, self.canvas_bounds)
+            self.ctx.call("lg_scene_set", C.cast(objs, C.c_void_p), n_obj, C.cast(nodes, C.c_void_p), n_nodes,
+                          C.byref(prm))
+            self._sent_params = params
+            self._scene_dirty = False
+        if force or self._lights_dirty:
+            if self.drawing_object is not None:   # before the lights: their start media depend on it
+                o, _, nd, nn = flatten_objects([self.drawing_object])
+                self.ctx.call("lg_drawing_object_set", C.cast(o, C.c_void_p), C.cast(nd, C.c_void_p), nn)
+            else:
+                self.ctx.call("lg_drawing_object_set", None, None, 0)
+            lights = list(self.lights) + ([self.drawing_light] if self.drawing_light is not None else [])
+            arr = lights_to_array(lights)
+            self.ctx.call("lg_lights_set", C.cast(arr, C.c_void_p), len(lights))
+            self._lights_dirty = False
 
     # -- tracing -----------------------------------------------------------------------------------
     def emit_rays(self, light_index: int, first: int = 0, count: Optional[int] = None):

@@ -1021,7 +1021,9 @@ inline void emit_ray(const LgLight &l, uint64_t i, LgRay &r) {
   }
   default: { // Directional, light.rs:103-115 + ORACLE.md §6.3
     double ex = l.b[0] - l.position[0], ey = l.b[1] - l.position[1];
-    double rr = (double)i / n;
+    // start.eval_at_r(-(i as f64) / n), light.rs:111: origins walk the segment by default; LG_LIGHT_DIRECTIONAL_NEG_R
+    // takes the call literally on eval_at_r(r) = a + r (b - a)
+    double rr = ((l.flags & LG_LIGHT_DIRECTIONAL_NEG_R) ? -1.0 : 1.0) * ((double)i / n);
     r.origin[0] = l.position[0] + rr * ex;
     r.origin[1] = l.position[1] + rr * ey;
     unit_from(-ey, ex, r.direction);
@@ -1038,6 +1040,8 @@ inline double start_medium(const SceneT<double> &s, const LgLight &l) {
   V2<double> p{l.position[0], l.position[1]};
   for (size_t i = 0; i < s.objects.size(); ++i)
     if (contains_object(s, (int)i, p) && s.objects[i].has_material) n = s.objects[i].n;
+  // `.chain(&self.drawing_object)` (tracer.rs:281): the host evaluated that last link of the chain itself
+  if (l.flags & LG_LIGHT_START_MEDIUM) n = l.start_medium;
   return n;
 }
 

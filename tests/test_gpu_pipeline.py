@@ -1,0 +1,124 @@
+"""lg_render's wave pipeline (trace of wave k + 1 on one stream while the line pass of wave k runs on another, no host
+round trip in between) against the one-wave-after-the-other path and against the oracle: same fragments, same counters,
+and the two repairs it has -- a wave that overflows its half of the segment buffer, a pair list that turns out too
+small -- produce the same frame."""
+import numpy as np
+import pytest
+
+from light_garden_b200 import abi, scenes
+from util import have_cuda, small_specs
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not have_cuda(), reason="no CUDA device")]
+
+TILED = 2
+
+
+def _frame(ctx, spec, overlap, waves=0, clear_alpha=1.0):
+    from light_garden_b200.tracer import Renderer, Tracer
+    ctx.call("lg_render_overlap_set", overlap, waves)
+    t = spec.apply(Tracer(spec.canvas_bounds, ctx=ctx))
+    r = Renderer(ctx, spec.width, spec.height)
+    r.clear(clear_alpha)
+    st = r.render(t)
+    return st, r.read_rgba32f(), r, t
+
+
+@pytest.mark.parametrize("precision", [abi.LG_PRECISION_F32, abi.LG_PRECISION_F64])
+@pytest.mark.parametrize("name", ["C1", "C3", "C5-16"])
+def test_pipelined_frame_equals_sequential_frame(oracle, name, precision):
+    from light_garden_b200.tracer import Context
+    spec = small_specs()[name]
+    ctx = Context(0, precision)
+    try:
+        ctx.call("lg_accumulate_mode_set", TILED)
+        st0, img0, _, _ = _frame(ctx, spec, 0)
+        for waves in (2, 3, 7):
+            st1, img1, r, t = _frame(ctx, spec, 2, waves)
+            assert st1.trace_launches == waves
+            for k in ("primary_rays", "ray_steps", "object_tests", "segments", "pixel_updates"):
+                assert getattr(st1, k) == getattr(st0, k), k
+            assert np.array_equal(img1[..., 3] > 1, img0[..., 3] > 1)
+            # the same fragments, summed per tile in a different grouping (waves): fp32 association only
+            assert (np.abs(img1 - img0) <= 2e-5 * np.maximum(1.0, np.abs(img0))).all()
+        # and against the oracle's f64 sums of the device's own segments
+        seg = t.trace_all(ordered=False, control_lines=False)
+        exact = np.zeros((spec.height, spec.width, 4), dtype=np.float64)
+        exact[..., 3] = 1.0
+        assert oracle.accumulate_segments_f64(exact, seg) == st1.pixel_updates
+        assert (np.abs(img1 - exact) <= 2e-5 * np.maximum(1.0, np.abs(exact))).all()
+    finally:
+        ctx.close()
+
+
+def test_pipeline_repairs_overflowing_waves_and_short_pair_lists(oracle):
+    """A fresh context learns 1 segment per ray and ~1 pair per segment from an empty scene on a tiny image; the cavity
+    frame that follows (64 bounces, 480x270) overflows the halves of a small segment buffer and the pair list.  The
+    frame must still be the sequential one."""
+    from light_garden_b200.scene import PointLight, Rect
+    from light_garden_b200.tracer import Context
+    cav = small_specs()["C2"]
+    empty = scenes.SceneSpec("empty", [], [PointLight((0.0, 0.0), 3000, (0.01, 0.01, 0.01, 0.02))], 5, 64, 64)
+    ref_ctx = Context(0, abi.LG_PRECISION_F32)
+    ctx = Context(0, abi.LG_PRECISION_F32)
+    try:
+        for c in (ref_ctx, ctx):
+            c.call("lg_accumulate_mode_set", TILED)
+        st0, img0, _, _ = _frame(ref_ctx, cav, 0)
+        ctx.call("lg_segment_capacity_set", 16384)
+        st_e, _, _, _ = _frame(ctx, empty, 2, 2)
+        assert st_e.segments == 3000                       # one segment per ray: the estimate the next frame starts from
+        st1, img1, _, _ = _frame(ctx, cav, 2, 2)
+        assert st1.segments == st0.segments > 8 * 16384 // 2   # many times what one half holds
+        for k in ("primary_rays", "ray_steps", "segments", "pixel_updates"):
+            assert getattr(st1, k) == getattr(st0, k), k
+        assert st1.trace_launches > 2                       # the overflowed waves were traced again in smaller ones
+        assert (np.abs(img1 - img0) <= 2e-5 * np.maximum(1.0, np.abs(img0))).all()
+        # once more: the estimates have adapted, nothing overflows, same frame
+        st2, img2, _, _ = _frame(ctx, cav, 2, 2)
+        assert st2.pixel_updates == st0.pixel_updates
+        assert (np.abs(img2 - img0) <= 2e-5 * np.maximum(1.0, np.abs(img0))).all()
+    finally:
+        ctx.close()
+        ref_ctx.close()
+
+
+def test_pipeline_repairs_a_short_pair_list(oracle):
+    """Default segment capacity (no wave overflows), but the pair list is sized from what the context has seen: an
+    empty scene on a 64x64 image.  The cavity's waves need many times that; the passes of those waves run again."""
+    from light_garden_b200.scene import PointLight
+    from light_garden_b200.tracer import Context
+    cav = small_specs()["C2"]
+    empty = scenes.SceneSpec("empty", [], [PointLight((0.0, 0.0), 500, (0.01, 0.01, 0.01, 0.02))], 2, 64, 64)
+    ref_ctx = Context(0, abi.LG_PRECISION_F32)
+    ctx = Context(0, abi.LG_PRECISION_F32)
+    try:
+        for c in (ref_ctx, ctx):
+            c.call("lg_accumulate_mode_set", TILED)
+        st0, img0, _, _ = _frame(ref_ctx, cav, 0)
+        _frame(ctx, empty, 2, 2)
+        st1, img1, _, _ = _frame(ctx, cav, 2, 2)
+        assert st1.trace_launches == 2 and st1.accumulate_launches > 2 * 5      # passes of a wave ran twice
+        for k in ("primary_rays", "ray_steps", "segments", "pixel_updates"):
+            assert getattr(st1, k) == getattr(st0, k), k
+        assert (np.abs(img1 - img0) <= 2e-5 * np.maximum(1.0, np.abs(img0))).all()
+        st2, img2, _, _ = _frame(ctx, cav, 2, 2)
+        assert st2.accumulate_launches == 2 * 5 and st2.pixel_updates == st0.pixel_updates
+    finally:
+        ctx.close()
+        ref_ctx.close()
+
+
+def test_pipeline_is_skipped_where_it_cannot_run(oracle):
+    """Direct resolve, tags, non-default blend states: lg_render falls back to the sequential waves, silently and with
+    the same result."""
+    from light_garden_b200.tracer import Context
+    spec = small_specs()["C1"]
+    ctx = Context(0, abi.LG_PRECISION_F32)
+    try:
+        ctx.call("lg_accumulate_mode_set", 1)
+        st0, img0, _, _ = _frame(ctx, spec, 0)
+        st1, img1, _, _ = _frame(ctx, spec, 2, 4)
+        assert st1.trace_launches == st0.trace_launches == 1 and st1.pixel_updates == st0.pixel_updates
+        assert (np.abs(img1 - img0) <= 1e-5 * np.maximum(1.0, np.abs(img0))).all()
+    finally:
+        ctx.close()

@@ -12,7 +12,7 @@ import pytest
 
 from light_garden_b200 import abi, scenes
 from light_garden_b200.scene import (AND_NOT, Circle, CubicBezier, Logic, Material, Object, PointLight, Rect,
-                                     SpotLight)
+                                     SpotLight, lights_to_array)
 from util import assert_same_segments, have_cuda, primary_rays, small_specs, ulp_diff64
 
 pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not have_cuda(), reason="no CUDA device")]
@@ -335,3 +335,81 @@ def test_errors_are_reported_not_hidden(ctx32):
     with pytest.raises(LightGardenError) as e:
         t2.sync_scene()
     assert e.value.code == abi.LG_ERR_UNSUPPORTED
+
+
+def test_directional_light_conventions(oracle, ctx64):
+    """light.rs:111 calls start.eval_at_r(-(i as f64) / n); collision2d's eval_at_r is not in the reference.  Both
+    readings exist behind ONE named switch (LG_LIGHT_DIRECTIONAL_NEG_R), read by the device and by the oracle."""
+    from light_garden_b200.scene import DirectionalLight, LineSegment
+    from light_garden_b200.tracer import Tracer
+    spec = SPECS["C1"]
+    for neg in (False, True):
+        light = DirectionalLight((0.5, 0.25, 0.125, 1.0), 257, LineSegment((-0.7, -0.9), (0.6, -0.8)), neg_r=neg)
+        t = spec.apply(Tracer(spec.canvas_bounds, ctx=ctx64))
+        t.lights[:] = [light]
+        t._lights_dirty = True
+        got, exp = t.emit_rays(0), oracle.emit_rays(light)
+        assert np.array_equal(got["origin"], exp["origin"]) and np.array_equal(got["direction"], exp["direction"])
+        step = np.array([0.6 - -0.7, -0.8 - -0.9]) / 257
+        np.testing.assert_allclose(got["origin"][5] - got["origin"][4], -step if neg else step, atol=1e-15)
+        assert np.array_equal(got["origin"][0], [-0.7, -0.9])          # ray 0 starts at `a` either way
+
+
+def test_drawing_object_joins_the_start_medium_scan(oracle, ctx64):
+    """tracer.rs:279-287: `self.objects.iter().chain(&self.drawing_object)` -- the object being dragged out decides the
+    start medium of a light inside it (last match wins) without being traced against (tracer.rs:412-424)."""
+    from light_garden_b200.tracer import Tracer
+    spec = SPECS["C1"]                      # the point light sits inside the n = 1.73 rect
+    t = spec.apply(Tracer(spec.canvas_bounds, ctx=ctx64))
+    pos = spec.lights[0].position
+    assert np.all(t.emit_rays(0)["refractive_index"] == 1.73)
+    t.add_drawing_object(Object.new_circle(pos, 0.05).with_index(2.4))
+    assert np.all(t.emit_rays(0)["refractive_index"] == 2.4)           # last in the chain wins
+    assert np.all(t.emit_rays(1)["refractive_index"] == 1.0)           # the spot light is outside of it
+    # not an obstacle: the traced segments are those of the scene without it, starting in its medium
+    rays = t.emit_rays(0, 0, 300)
+    osc = oracle.OracleScene.from_spec(spec)
+    assert_same_segments(t.trace(rays), osc.trace_rays(rays, abi.LG_PRECISION_F64), f64=True)
+    t.add_drawing_object(Object.new_mirror((pos[0] - 1, pos[1]), (pos[0] + 1, pos[1])))   # no material: no medium
+    assert np.all(t.emit_rays(0)["refractive_index"] == 1.73)
+    t.finish_drawing_object(abort=True)
+    assert np.all(t.emit_rays(0)["refractive_index"] == 1.73)
+    # the same through the plain override field a host can fill in itself
+    larr = lights_to_array(spec.lights)
+    larr[0].flags |= abi.LG_LIGHT_START_MEDIUM
+    larr[0].start_medium = 1.31
+    ctx64.call("lg_lights_set", C.cast(larr, C.c_void_p), len(spec.lights))
+    out = np.zeros(4, dtype=abi.RAY_DTYPE)
+    ctx64.call("lg_emit_rays", 0, 0, 4, abi.array_ptr(out))
+    assert np.all(out["refractive_index"] == 1.31)
+    larr[0].start_medium = -1.0
+    with pytest.raises(Exception):
+        ctx64.call("lg_lights_set", C.cast(larr, C.c_void_p), len(spec.lights))
+    t.sync_scene(force=True)
+    # a drawing light is traced like the others, after them (tracer.rs:279)
+    t.add_drawing_light(PointLight((0.3, 0.3), 64, (0.01, 0.01, 0.01, 0.02)))
+    seg = t.trace_all(ordered=False, control_lines=False)
+    assert t.last_stats.primary_rays == spec.total_rays() + 64 and len(seg) > 0
+    t.finish_drawing_light(abort=False)
+    assert len(t.lights) == 3 and t.drawing_light is None
+
+
+def test_trace_rays_rejects_directions_that_are_not_unit(oracle, ctx64, ctx32):
+    """Ray::from_origin normalises (light.rs:172); LgRay.direction must already be unit: the broad phase and the range
+    filter rely on it, so anything else is refused instead of silently losing hits."""
+    spec = SPECS["C1"]
+    for ctx in (ctx64, ctx32):
+        t = make_tracer(spec, ctx)
+        rays = t.emit_rays(0, 0, 8)
+        t.trace(rays)                                     # what the library itself emits passes
+        for bad in (1.0 + 1e-3, 0.0, float("nan")):
+            r = rays.copy()
+            r["direction"][3] *= bad
+            with pytest.raises(Exception) as e:
+                t.trace(r)
+            assert "unit" in str(e.value)
+    r = rays.copy()                                       # f32-rounded directions: fine for the f32 context only
+    r["direction"] = r["direction"].astype(np.float32).astype(np.float64)
+    make_tracer(spec, ctx32).trace(r)
+    with pytest.raises(Exception):
+        make_tracer(spec, ctx64).trace(r)

@@ -757,3 +757,16 @@ def test_blend_states(oracle):
     # ReverseSubtract: the lines darken the image; OneMinusSrc as the factor
     img = run((abi.LG_BF_ONE_MINUS_SRC, ONE, abi.LG_BO_REVERSE_SUBTRACT), (abi.LG_BF_ZERO, ONE, ADD))
     np.testing.assert_array_equal(img[8, 3], (-(0.5 * 0.5), -(0.25 * 0.75), -(0.125 * 0.875), 1.0))
+
+
+def test_directional_light_negative_parameter_switch(oracle):
+    """light.rs:111 passes -(i as f64)/n to LineSegment::eval_at_r, whose definition is in collision2d (not vendored).
+    neg_r = False (default): origins a + (i/n)(b - a), on the drawn segment; neg_r = True (LG_LIGHT_DIRECTIONAL_NEG_R):
+    the call taken literally on eval_at_r(r) = a + r (b - a).  Same direction (the left normal of b - a) either way."""
+    seg = LineSegment((1.0, -1.0), (3.0, -1.0))
+    fwd = oracle.emit_rays(DirectionalLight((1, 1, 1, 1), 4, seg))
+    neg = oracle.emit_rays(DirectionalLight((1, 1, 1, 1), 4, seg, neg_r=True))
+    np.testing.assert_array_equal(fwd["origin"][:, 0], [1.0, 1.5, 2.0, 2.5])
+    np.testing.assert_array_equal(neg["origin"][:, 0], [1.0, 0.5, 0.0, -0.5])
+    np.testing.assert_array_equal(fwd["origin"][:, 1], neg["origin"][:, 1])
+    np.testing.assert_array_equal(fwd["direction"], neg["direction"])

@@ -32,3 +32,50 @@ def test_load_minimal_scene():
     assert objects[0].geo.radius == 0.1 and objects[0].material_opt.refractive_index == 1.5
     assert objects[1].geo.op == scenes.AND_NOT and objects[1].material_opt is None
     assert lights[0].num_rays == 7
+
+
+def test_serialize_round_trips_every_variant():
+    """Tracer::serialize -> Tracer::load (tracer.rs:183-204) over every ObjectE and Light variant, incl. ConvexPolygon
+    (object.rs:12, 34-36) both as an object and inside a Geo tree."""
+    from light_garden_b200.ron import serialize_scene
+    from light_garden_b200.scene import (AND, AND_NOT, OR, Circle, ConvexPolygon, CubicBezier, DirectionalLight, Ellipse,
+                                         LineSegment, Logic, Material, Object, PointLight, Rect, SpotLight, rot2)
+    tri = ConvexPolygon(((0.0, -0.25), (0.25, 0.2), (-0.25, 0.2)), (0.3, -0.1), rot2(0.4))
+    objects = [
+        Object.new_mirror((-1.0, 0.5), (1.0, 0.25)),
+        Object.new_curved_mirror(CubicBezier(((-0.6, 0.4), (-0.3, 0.8), (0.27, 0.8), (0.57, 0.4)))),
+        Object.new_circle((0.1, 0.2), 0.3),
+        Object.new_rect((0.5, -0.5), 0.4, 0.2).with_index(1.73),
+        Object.new_lens((0.7, 0.0), 2.0, 3.8),
+        Object.new_convex_polygon([(0.2, 0.2), (0.8, 0.25), (0.95, 0.6), (0.5, 0.85), (0.15, 0.6)]).with_index(1.33),
+        Object(tri, None, "ConvexPolygon", False),
+        Object.new_ellipse((-0.9, 0.2), 0.5, 0.2),
+        Object(Logic(AND_NOT, tri, Circle((0.1, 0.0), 0.15), (-0.4, 0.55), rot2(-0.3)), Material(1.2), "Geo", False),
+        Object(Logic(OR, Ellipse((0.0, 0.0), 0.3, 0.12, rot2(0.2)), Logic(AND, Rect((0.0, 0.0), rot2(0.9), 0.15, 0.5),
+                                                                         Circle((0.0, 0.0), 0.2), (0.1, 0.1), rot2(0.0)),
+                     (-0.2, -0.55), rot2(1.1)), Material(2.4), "Geo", True),
+        Object(LineSegment((0.0, 0.0), (0.0, 1e-17)), None, "Geo", False),
+    ]
+    lights = [PointLight((0.05, 0.1), 1234, (0.012, 0.01, 0.008, 0.02)),
+              SpotLight((-1.5, 0.8), 1.2, (1.0, -0.5), 77, (0.006, 0.01, 0.014, 0.02)),
+              DirectionalLight((0.5, 0.25, 0.125, 1.0), 9, LineSegment((-1.0, -1.0), (1.0, -0.5)))]
+    text = serialize_scene(objects, lights)
+    o2, l2 = load_scene(text)
+    assert o2 == objects
+    # colours are f32 in the reference (light.rs:7): the text holds the f32 values
+    import numpy as np
+    for a, b in zip(l2, lights):
+        assert type(a) is type(b) and a.num_rays == b.num_rays
+        assert np.array_equal(np.float32(a.color), np.float32(b.color))
+    assert serialize_scene(o2, l2) == text                       # a fixed point
+    o3, l3 = load_scene(serialize_scene(*load_scene(open(REF).read()))) if os.path.exists(REF) else (None, None)
+    if o3 is not None:
+        assert o3 == scenes.default_objects() and l3 == scenes.default_lights()
+
+
+def test_polygon_object_in_reference_style_text():
+    text = """([ ( object_enum: ConvexPolygon(( points: [[0, 0], [1, 0], [0.5, 1]], )), material_opt: Some(( refractive_index: 1.5, )), moved: false, ),
+                ( object_enum: Geo(GeoConvexPolygon(( points: [[0, 0], [1, 0], [0.5, 1]], origin: [0.25, 0.5], rot: [0, 1, -1, 0], ))), material_opt: None, moved: false, ), ], [])"""
+    objects, lights = load_scene(text)
+    assert objects[0].kind == "ConvexPolygon" and objects[0].geo.points == ((0, 0), (1, 0), (0.5, 1))
+    assert objects[1].geo.origin == (0.25, 0.5) and objects[1].geo.rotation == (0, 1, -1, 0) and lights == []
