@@ -350,17 +350,20 @@ int32_t lg_string_mod_nested_read(lg_ctx *ctx, LgVertexPair *outer_chords, uint6
                                   double *crossings_xy, uint64_t crossing_cap,
                                   uint64_t *n_chords, uint64_t *n_crossings);
 /* trace_all + render fused: rays are traced in waves through the bounded
- * segment buffer.  With the tile-binned resolve the waves form a two-stage
- * pipeline: the line pass of wave k runs on a second stream while wave k + 1
- * is being traced into the other half of the buffer (no host round trip in
- * between); otherwise each wave is accumulated before the next is traced.
- * Same fragments either way.  trace_ms / accumulate_ms are the sums of the
+ * segment buffer and each wave is accumulated before the next is traced.
+ * lg_render_overlap_set can turn the waves into a two-stage pipeline instead
+ * (tile-binned resolve only): the line pass of wave k runs on a second stream
+ * while wave k + 1 is being traced into the other half of the buffer, with no
+ * host round trip in between.  Same fragments either way.  trace_ms / accumulate_ms are the sums of the
  * waves' kernel times: in the pipeline they overlap and add up to more than
  * the frame. */
 int32_t lg_render(lg_ctx *ctx, LgTraceStats *stats);
-/* The wave pipeline of lg_render: mode 0 = off, 1 = automatic (default: frames
- * of >= 2^20 rays whose resolve is the tile bins), 2 = always (tests); waves =
- * how many waves a frame is cut into (0 keeps the current value, default 8). */
+/* The wave pipeline of lg_render: mode 0 = off (default: on B200 the two kernels
+ * compete for the same issue slots and shared memory, and the trace kernel needs
+ * its full occupancy -- measured 73 ms sequential against 83-95 ms pipelined per
+ * 16 M rays of C5), 1 = automatic (frames of >= 2^20 rays whose
+ * resolve is the tile bins), 2 = always; waves = how many waves a frame is cut
+ * into (0 keeps the current value, default 8). */
 int32_t lg_render_overlap_set(lg_ctx *ctx, int32_t mode, uint32_t waves);
 /* Image out: LG_RGBA32F (16 B/px), LG_RGBA16F (8 B/px, round to nearest even,
  * what the ROP would have stored), LG_BGRA8_GAMMA (4 B/px, the screenshot

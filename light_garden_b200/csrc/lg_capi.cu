@@ -186,7 +186,7 @@ struct lg_ctx {
   cudaStream_t stream2 = nullptr;
   cudaEvent_t ev_pipe = nullptr, ev_t0[2] = {nullptr, nullptr}, ev_t1[2] = {nullptr, nullptr}, ev_a0[2] = {nullptr, nullptr},
               ev_a1[2] = {nullptr, nullptr};
-  int render_overlap = 1;   // lg_render_overlap_set: 0 = one wave after the other, 1 = automatic, 2 = always (tests)
+  int render_overlap = 0;   // lg_render_overlap_set: 0 = one wave after the other (default: measured faster), 1 = automatic, 2 = always
   unsigned pipe_waves = 8;  // waves a frame is cut into when the pipeline runs
   int pipe_trace_ctas = -1; // resident trace CTAs per SM while it runs: < 0 = that many fewer than would fit (LG_PIPE_TRACE_CTAS)
   int pipe_raster_ctas = -1; // raster CTAs per SM next to a running trace kernel: < 0 = what its shared memory leaves (LG_PIPE_RASTER_CTAS)
@@ -665,7 +665,6 @@ int accumulate_tiled(lg_ctx *c, cudaStream_t st, const Seg *d_seg, unsigned long
   T.list = (unsigned *)c->tile_list.p;
   T.list_cap = c->tile_list.bytes / 4;
   T.n_dev = n_dev, T.skip_dev = skip_dev;
-  T.raster_warps = 0; // set below
   const size_t hist_smem = (size_t)T.n_tiles * 4;
   auto count_k = tile_count_kernel<Seg>;
   auto fill_k = tile_fill_kernel<Seg>;
@@ -690,7 +689,6 @@ int accumulate_tiled(lg_ctx *c, cudaStream_t st, const Seg *d_seg, unsigned long
   LG_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kRasterWarps * 32, smem));
   if (per_sm < 1) return fail(c, LG_ERR_CUDA, "tile raster kernel does not fit on an SM");
   if (c->raster_cap_now > 0) per_sm = std::min(per_sm, c->raster_cap_now);
-  T.raster_warps = c->sm_count * per_sm * kRasterWarps;
   c->tiled_last = T;
   c->tiled_raster_grid = c->sm_count * per_sm;
   c->tiled_hist_smem = hist_smem, c->tiled_raster_smem = smem;
@@ -719,7 +717,8 @@ int tiled_finish(lg_ctx *c, cudaStream_t st, const Seg *d_seg, unsigned long lon
   if (!h_totals[2]) return LG_OK;
   TileArgs T = c->tiled_last;
   int rc;
-  if ((rc = ensure(c, c->tile_list, (size_t)(h_totals[0] + h_totals[0] / 8 + 4096ull) * 4))) return rc;
+  // sized the way the next call will ask for it (pairs per segment x 1.25), so that call does not allocate again
+  if ((rc = ensure(c, c->tile_list, (size_t)((double)h_totals[0] * 1.25 + (double)n + 8192.0) * 4))) return rc;
   T.list = (unsigned *)c->tile_list.p;
   T.list_cap = c->tile_list.bytes / 4;
   const unsigned long long fixed[4] = {h_totals[0], h_totals[3], 0ull, h_totals[3]};

@@ -32,8 +32,9 @@ namespace lg {
 constexpr int kTile = 32;          // tile edge in pixels
 constexpr int kTileShift = 5;
 constexpr int kTilePitch = 32;     // float4 per major-axis line of the tile in shared memory
-constexpr int kChunk = 2048;       // list entries per work item, at least ...
-constexpr int kChunkMax = 16384;   // ... and at most: tile_scan_kernel doubles it while every raster warp still gets >= 16 items
+constexpr int kChunk = 2048;       // list entries per work item (larger items were measured: 8192 saves 0.5 % of the
+                                   // C5 step -- fewer tile clears and flushes -- and costs accuracy in the hot pixels,
+                                   // whose partial sums then grow four times as large before they reach the image)
 constexpr int kRasterWarps = 4;    // warps per CTA of tile_raster_kernel
 constexpr int kTileFloat4 = kTile * kTilePitch;
 
@@ -52,13 +53,12 @@ struct TileArgs {
   unsigned long long *tile_offset; // [n_tiles + 1]
   unsigned int *item_prefix;  // [n_tiles + 1]
   unsigned long long *totals; // [0] = pairs, [1] = items (0 when the list is too small), [2] = 1: list too small,
-                              // [3] = items, [4] = list entries per work item
+                              // [3] = items
   unsigned int *list;         // segment index per pair
   unsigned long long list_cap; // entries `list` can hold: sized from the previous call, checked by tile_scan_kernel
   unsigned int *item_counter;
   unsigned int *hist;         // [n_ctas][n_tiles] per-CTA counts, then per-CTA exclusive offsets within a tile
   int n_ctas;
-  int raster_warps;           // warps of the raster launch (work-item size: totals[4])
   // segment count and "do nothing" flag that live on the device (the trace kernel's counters): the passes of a wave
   // are queued behind the trace kernel without the host learning the count first.  NULL: use the kernel argument.
   const unsigned long long *n_dev;
@@ -214,26 +214,9 @@ __global__ void __launch_bounds__(1024) tile_scan_kernel(TileArgs T) {
   __shared__ unsigned int s_items[1024];
   __shared__ unsigned long long carry_pairs;
   __shared__ unsigned int carry_items;
-  __shared__ unsigned long long s_total;
-  __shared__ unsigned int s_chunk;
-  if (threadIdx.x == 0) carry_pairs = 0, carry_items = 0, s_total = 0ull;
+  if (threadIdx.x == 0) carry_pairs = 0, carry_items = 0;
   __syncthreads();
-  // work-item size: every item pays for clearing and flushing a tile (1024 pixels; a transposed tile is read
-  // against the banks), so items grow with the job as long as every raster warp still gets >= 16 of them
-  {
-    unsigned long long mine = 0ull;
-    for (int t = threadIdx.x; t < T.n_tiles; t += 1024) mine += T.tile_count[t];
-    for (int off = 16; off > 0; off >>= 1) mine += __shfl_down_sync(0xffffffffu, mine, off);
-    if ((threadIdx.x & 31) == 0 && mine) atomicAdd(&s_total, mine);
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      unsigned int ch = kChunk;
-      while (ch < kChunkMax && s_total / (2ull * ch) >= 16ull * (unsigned long long)max(T.raster_warps, 1)) ch *= 2u;
-      s_chunk = ch;
-    }
-    __syncthreads();
-  }
-  const unsigned int chunk_sz = s_chunk;
+  constexpr unsigned int chunk_sz = kChunk;
   for (int base = 0; base < T.n_tiles; base += 1024) {
     const int t = base + threadIdx.x;
     const unsigned int c = t < T.n_tiles ? T.tile_count[t] : 0u;
@@ -266,7 +249,6 @@ __global__ void __launch_bounds__(1024) tile_scan_kernel(TileArgs T) {
     T.totals[1] = fits ? carry_items : 0u; // nothing for the raster to do until the list has been grown and filled
     T.totals[2] = fits ? 0ull : 1ull;
     T.totals[3] = carry_items;
-    T.totals[4] = chunk_sz;
     *T.item_counter = 0u;
   }
 }
@@ -276,50 +258,8 @@ struct RasterScratch {
   float4 geo[32];        // m0, 1/(m1 - m0), minor delta, minor start (RasterSetup)
   float4 col[32];        // colour at a (single-colour segments: alpha already squared)
   float4 dc[32];         // colour delta (two-colour segments only)
-  unsigned int mask[32]; // lanes (major-axis steps of this tile) whose fragment lies inside the tile
+  unsigned int mask[32]; // lanes of this tile inside the segment's major-axis range [i0, i1)
 };
-
-// Exact set of lanes of a tile whose fragment of one segment lies inside the tile, computed once per (segment, tile)
-// pair when the entry is parked.  The fragment's minor coordinate f(l) = floor(fma((mc(l) - m0) * inv, dn, n0)) is
-// weakly monotone in the lane l (every step -- subtraction, product, fma, floor -- is a correctly rounded monotone
-// function of its varying argument), so the lanes inside [nlo, nhi) form ONE interval [la, lb) of the major-axis
-// range [l0, l1): two binary searches over at most 32 lanes with the exact arithmetic of raster_walk().  The blend
-// loop then needs no range test at all, and the number of fragments of the pair is popc(mask).
-__device__ __forceinline__ unsigned lane_mask_in_tile(const RasterSetup &S, int bmaj, int l0, int l1, float nlo, float nhi) {
-  if (l1 <= l0) return 0u;
-  const bool inc = (S.inv < 0.f) == (S.dn < 0.f); // f non-decreasing in l
-  // left_bad(l): the fragment is still before the tile's minor range (true on a prefix of the lanes);
-  // right_bad(l): it is already past it (true on a suffix)
-  auto left_bad = [&](int l) {
-    const float f = frag_minor(S, bmaj + l);
-    return inc ? f < nlo : f >= nhi;
-  };
-  auto right_bad = [&](int l) {
-    const float f = frag_minor(S, bmaj + l);
-    return inc ? f >= nhi : f < nlo;
-  };
-  int la = l0, lb = l1;
-  if (left_bad(l0)) { // first lane that is not left_bad, in (l0, l1]
-    int lo = l0 + 1, hi = l1;
-    while (lo < hi) {
-      const int mid = (lo + hi) >> 1;
-      if (left_bad(mid)) lo = mid + 1; else hi = mid;
-    }
-    la = lo;
-  }
-  if (la >= l1) return 0u;
-  if (right_bad(l1 - 1)) { // first right_bad lane, in [la, l1 - 1]
-    int lo = la, hi = l1 - 1;
-    while (lo < hi) {
-      const int mid = (lo + hi) >> 1;
-      if (right_bad(mid)) hi = mid; else lo = mid + 1;
-    }
-    lb = lo;
-  }
-  const int n = lb - la;
-  if (n <= 0) return 0u;
-  return (n >= 32 ? 0xffffffffu : ((1u << n) - 1u)) << la;
-}
 
 // the records of two parked entries, as the blend loop holds them in registers
 struct PairRecs {
@@ -333,15 +273,19 @@ template <bool kLerp> __device__ __forceinline__ void load_recs(const RasterScra
 }
 // Blends two parked entries into the warp's private tile.  lane = major-axis step; the tile is stored
 // major-axis-fastest, so a fragment at minor coordinate j sits at lane_base + j * row_bytes (lane_base is this lane's
-// byte address of canvas minor coordinate 0).  The arithmetic per fragment is raster_walk's (ORACLE.md 8.2-8.4); which
-// lanes have a fragment in this tile was settled when the entry was parked (lane_mask_in_tile).  Both pixels are
-// read before either is written; a lane that hits the same pixel in both carries the first sum into the second.
-// Straight-line predicated code: no branch, no range test, no counting.
+// byte address of canvas minor coordinate 0).  The arithmetic per fragment is raster_walk's (ORACLE.md 8.2-8.4): the
+// minor coordinate is floor(fma(s, dn, n0)), taken here with one float -> int conversion rounding down (the same
+// integer for every value a tile can own), and "inside this tile" is ONE unsigned compare of j - bmin against the
+// tile's extent; which lanes lie inside the segment's major-axis range is a bit mask made when the entry is parked.
+// Both pixels are read before either is written; a lane that hits the same pixel in both carries the first sum into
+// the second.  Straight-line predicated code: no branch.
 template <bool kLerp>
-__device__ __forceinline__ void blend_two(unsigned char *lane_base, int row_bytes, const PairRecs &q, float mc, unsigned lane_bit) {
+__device__ __forceinline__ void blend_two(unsigned char *lane_base, int row_bytes, const PairRecs &q, float mc, unsigned lane_bit,
+                                          int bmin, unsigned extent, unsigned &cnt) {
   const float sa = (mc - q.ga.x) * q.ga.y, sb = (mc - q.gb.x) * q.gb.y;
   const int ja = __float2int_rd(__fmaf_rn(sa, q.ga.z, q.ga.w)), jb = __float2int_rd(__fmaf_rn(sb, q.gb.z, q.gb.w));
-  const bool act_a = (q.m.x & lane_bit) != 0u, act_b = (q.m.y & lane_bit) != 0u;
+  const bool act_a = (q.m.x & lane_bit) != 0u && (unsigned)(ja - bmin) < extent;
+  const bool act_b = (q.m.y & lane_bit) != 0u && (unsigned)(jb - bmin) < extent;
   float4 *pa = reinterpret_cast<float4 *>(lane_base + ja * row_bytes);
   float4 *pb = reinterpret_cast<float4 *>(lane_base + jb * row_bytes);
   float a0 = q.ca.x, a1 = q.ca.y, a2 = q.ca.z, a3 = q.ca.w, b0 = q.cb.x, b1 = q.cb.y, b2 = q.cb.z, b3 = q.cb.w;
@@ -358,26 +302,28 @@ __device__ __forceinline__ void blend_two(unsigned char *lane_base, int row_byte
   const bool same = act_a && ja == jb;            // (only read when act_b)
   vb.x = same ? va.x : vb.x, vb.y = same ? va.y : vb.y, vb.z = same ? va.z : vb.z, vb.w = same ? va.w : vb.w;
   vb.x += b0, vb.y += b1, vb.z += b2, vb.w += b3;
-  if (act_a) *pa = va;
-  if (act_b) *pb = vb;
+  if (act_a) *pa = va, ++cnt;
+  if (act_b) *pb = vb, ++cnt;
 }
 template <bool kLerp>
-__device__ __forceinline__ void blend_run(unsigned char *lane_base, int row_bytes, const RasterScratch &P, int m, float mc,
-                                          unsigned lane_bit) {
+__device__ __forceinline__ unsigned blend_run(unsigned char *lane_base, int row_bytes, const RasterScratch &P, int m, float mc,
+                                              unsigned lane_bit, int bmin, unsigned extent) {
   // entries [0, m) two at a time; when m is odd the caller has parked an empty entry (mask 0) at index m.
   // The records of the NEXT two entries are fetched before the current two touch the tile (the compiler cannot
   // move those loads across the tile's stores by itself: same shared-memory array); the two register sets swap
   // roles every half iteration, so nothing is copied.
+  unsigned cnt = 0u;
   PairRecs A, B;
   A.da = A.db = B.da = B.db = make_float4(0.f, 0.f, 0.f, 0.f);
   load_recs<kLerp>(P, 0, A);
   for (int k = 0; k < m; k += 4) {
     load_recs<kLerp>(P, k + 2 < m ? k + 2 : k, B);
-    blend_two<kLerp>(lane_base, row_bytes, A, mc, lane_bit);
+    blend_two<kLerp>(lane_base, row_bytes, A, mc, lane_bit, bmin, extent, cnt);
     if (k + 2 >= m) break;
     load_recs<kLerp>(P, k + 4 < m ? k + 4 : k, A);
-    blend_two<kLerp>(lane_base, row_bytes, B, mc, lane_bit);
+    blend_two<kLerp>(lane_base, row_bytes, B, mc, lane_bit, bmin, extent, cnt);
   }
+  return cnt;
 }
 
 template <class Seg> __global__ void __launch_bounds__(kRasterWarps * 32) tile_raster_kernel(TileArgs T, const Seg *seg) {
@@ -389,7 +335,7 @@ template <class Seg> __global__ void __launch_bounds__(kRasterWarps * 32) tile_r
                                                        (size_t)kRasterWarps * kTileFloat4)[warp_in_block];
   constexpr bool kLerp = SegIO<Seg>::kLerp;
   const unsigned int n_items = (unsigned int)T.totals[1];
-  const unsigned int chunk_sz = (unsigned int)T.totals[4];
+  constexpr unsigned int chunk_sz = kChunk;
   unsigned long long cnt = 0;
   while (true) {
     unsigned int item = 0;
@@ -414,7 +360,7 @@ template <class Seg> __global__ void __launch_bounds__(kRasterWarps * 32) tile_r
     // y-major one (tile stored transposed)
     const int bmaj = xmajor ? bx : by, bmin = xmajor ? by : bx;
     const float mc = (float)(bmaj + (int)lane) + 0.5f;
-    const float nlo = (float)bmin, nhi = (float)min(xmajor ? T.A.H : T.A.W, bmin + kTile);
+    const unsigned extent = (unsigned)(min(xmajor ? T.A.H : T.A.W, bmin + kTile) - bmin); // minor pixels of the tile on the canvas
     // byte address of this lane's pixel at minor offset 0 of the canvas (the tile starts at minor offset bmin)
     unsigned char *lane_base = reinterpret_cast<unsigned char *>(tile) + ((int)lane - bmin * kTilePitch) * (int)sizeof(float4);
     for (int k = lane; k < kTileFloat4; k += 32) tile[k] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -430,8 +376,8 @@ template <class Seg> __global__ void __launch_bounds__(kRasterWarps * 32) tile_r
       if ((int)lane < m) {
         const RasterSetup S = raster_setup(T.A, g_ab.x, g_ab.y, g_ab.z, g_ab.w);
         const int l0 = max(S.i0 - bmaj, 0), l1 = min(S.i1 - bmaj, kTile);
-        const unsigned msk = lane_mask_in_tile(S, bmaj, l0, l1, nlo, nhi);
-        cnt += (unsigned)__popc(msk);
+        const int nl = l1 - l0;
+        const unsigned msk = nl <= 0 ? 0u : ((nl >= 32 ? 0xffffffffu : ((1u << nl) - 1u)) << l0);
         P.geo[lane] = make_float4(S.m0, S.inv, S.dn, S.n0);
         P.col[lane] = make_float4(g_ca.x, g_ca.y, g_ca.z, kLerp ? g_ca.w : g_ca.w * g_ca.w);
         if (kLerp) P.dc[lane] = make_float4(g_dc.x - g_ca.x, g_dc.y - g_ca.y, g_dc.z - g_ca.z, g_dc.w - g_ca.w);
@@ -445,7 +391,7 @@ template <class Seg> __global__ void __launch_bounds__(kRasterWarps * 32) tile_r
       if (base + 32 + lane < last) SegIO<Seg>::load(seg, idx_next, g_ab, g_ca, g_dc);
       idx_next = base + 64 + lane < last ? lst[base + 64 + lane] : 0u;
       __syncwarp();
-      blend_run<kLerp>(lane_base, kTilePitch * (int)sizeof(float4), P, m, mc, 1u << lane);
+      cnt += blend_run<kLerp>(lane_base, kTilePitch * (int)sizeof(float4), P, m, mc, 1u << lane, bmin, extent);
       __syncwarp();
     }
     // flush: one vector reduction per touched pixel, lanes sweep an image row (coalesced 512 B).  A transposed

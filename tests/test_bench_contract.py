@@ -29,12 +29,20 @@ def test_reference_arm_prints_the_contract_line():
         assert k in d, k
     assert d["impl"] == "reference" and d["n_gpus"] == 1 and d["steps"] == 1 and d["higher_is_better"] is True
     assert d["unit"] == "rays/s" and d["value"] > 0 and d["vs_baseline"] is None and d["dtype"] == "f64"
-    assert d["config"]["objects"] == 4096 and "workload" in d["config"]
+    assert d["config"]["objects"] == 4096 and d["config"]["lights"] == 8 and "workload" in d["config"]
     cb = d["cpu_baseline"]
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "sample" in cb
     # the timed configuration is the reference's default (TileMap on); the all-objects loop is reported beside it
     assert "TileMap" in cb["sample"] and cb["all_objects_loop"]["value"] > 0 and cb["all_objects_loop"]["unit"] == "rays/s"
     assert d["e2e"] == {"value": d["value"], "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_reference_arm_ignores_omp_num_threads():
+    """torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU legs size their thread pool from the cores the process
+    may run on instead (round-1 SCALE record: the N >= 2 reference arm ran on one core)."""
+    d = json.loads(run({"OMP_NUM_THREADS": "1"})[0])
+    assert d["cpu_baseline"]["cores"] == len(os.sched_getaffinity(0))
+    assert d["cpu_baseline"]["omp_num_threads_env"] == "1"
 
 
 def test_reference_arm_under_a_two_rank_launch_only_rank_zero_works():

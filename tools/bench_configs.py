@@ -12,6 +12,7 @@ import sys
 import time
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+WARM = 5
 sys.path.insert(0, ROOT)
 
 
@@ -41,13 +42,13 @@ def main():
         t = spec.apply(Tracer(spec.canvas_bounds, ctx=ctx))
         r = Renderer(ctx, spec.width, spec.height)
         best = None
-        for it in range(args.repeat + 1):
+        for it in range(args.repeat + WARM):
             r.clear()
             t0 = time.perf_counter()
             st = r.render(t)
             dt = time.perf_counter() - t0
-            if it == 0:
-                continue  # warm-up
+            if it < WARM:
+                continue  # warm-up: the accumulate auto mode samples each resolve twice before it settles
             if best is None or dt < best[0]:
                 best = (dt, st.as_dict())
         dt, st = best
@@ -66,12 +67,12 @@ def main():
         sm = scenes.c4_string_mod(modulo=int(10_000_000 * k), num=num)
         r = Renderer(ctx, 4096, 4096)
         best = None
-        for it in range(args.repeat + 1):
+        for it in range(args.repeat + WARM):
             r.clear()
             t0 = time.perf_counter()
             st = r.render_string_mod(sm)
             dt = time.perf_counter() - t0
-            if it and (best is None or dt < best[0]):
+            if it >= WARM and (best is None or dt < best[0]):
                 best = (dt, st.as_dict())
         dt, st = best
         print(json.dumps({

@@ -13,7 +13,7 @@ AB_LIBS="${AB_LIBS:-new light_garden_b200/_lib/variants/lib_r01.so}"
 for w in "$@"; do
   case $w in
     tests)
-      timeout 900 python -m pytest tests -m gpu -q -x --durations=10 --timeout=300 --timeout-method=thread \
+      timeout 900 python -m pytest tests -m gpu -q --durations=10 --timeout=300 --timeout-method=thread \
         > gpurun_out/pytest_gpu.log 2>&1
       echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
       timeout 200 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1
@@ -57,6 +57,16 @@ PY
       ;;
     benchf64)
       timeout 600 python bench.py --precision f64 --rays-per-gpu 8000000 --no-cpu-baseline > gpurun_out/bench_f64.log 2>&1
+      ;;
+    cfglaunches)
+      # per-kernel times of C1 / C2 (quarter size) under ncu, this tree and the round-1 tree (_r01/, if present)
+      for tree in . _r01; do
+        [ -d $tree/tools ] || continue
+        n=$(echo $tree | tr -d './_'); n=${n:-new}
+        (cd $tree && LG_ACCUM_MODE=2 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 120 --csv \
+          --log-file $OLDPWD/gpurun_out/launches_cfg_$n.csv python tools/bench_configs.py --scale 0.25 --repeat 1 --only C1,C2 \
+          > $OLDPWD/gpurun_out/cfg_under_ncu_$n.log 2>&1)
+      done
       ;;
     launches)
       LG_ACCUM_MODE=2 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv \
