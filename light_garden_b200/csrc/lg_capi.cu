@@ -628,8 +628,13 @@ void note_accum_cost(lg_ctx *c, bool tiled, float ms, unsigned long long frags, 
   const double v = (double)ms * 1e6 / (double)frags;
   lg_ctx::AutoStat &a = c->auto_stats[sig];
   const int m = tiled ? 2 : 1;
-  a.ns_per_frag[m] = a.samples[m] < 2 ? v : 0.5 * a.ns_per_frag[m] + 0.5 * v; // the warm second sample replaces the cold first
+  // the best sample so far: a call that paid for an allocation, or one odd slow call, must not flip the choice
+  // (round 2: one driver-style run settled on the direct resolve, 60 ms instead of 33 ms per step, after such a sample)
+  a.ns_per_frag[m] = a.samples[m] < 1 ? v : std::min(a.ns_per_frag[m], v);
   if (a.samples[m] < 2) ++a.samples[m];
+  if (getenv("LG_DEBUG_AUTO"))
+    fprintf(stderr, "[lg auto] %s: %.3f ms, %llu fragments, %llu segments -> %.4f ns/fragment (direct %.4f, tiled %.4f)\n",
+            tiled ? "tiled" : "direct", ms, frags, n, v, a.ns_per_frag[1], a.ns_per_frag[2]);
 }
 
 // count -> scan -> fill -> raster over device segments of type Seg (LgSegment or Seg2), queued on `st` without a
@@ -714,11 +719,16 @@ template <class Seg>
 int tiled_finish(lg_ctx *c, cudaStream_t st, const Seg *d_seg, unsigned long long n, const unsigned long long *h_totals,
                  unsigned *launches) {
   if (n > 0 && h_totals[0] > 0) c->pairs_per_seg_est = std::max(1.0, (double)h_totals[0] / (double)n);
-  if (!h_totals[2]) return LG_OK;
-  TileArgs T = c->tiled_last;
   int rc;
-  // sized the way the next call will ask for it (pairs per segment x 1.25), so that call does not allocate again
-  if ((rc = ensure(c, c->tile_list, (size_t)((double)h_totals[0] * 1.25 + (double)n + 8192.0) * 4))) return rc;
+  // the list is grown HERE, outside the caller's timed region, to what the next call will ask for (pairs per segment
+  // x 1.25 and head room), whether or not this call overflowed it
+  const size_t next = (size_t)((double)h_totals[0] * 1.25 + (double)n + 8192.0) * 4;
+  if (!h_totals[2]) {
+    if (next > c->tile_list.bytes && (rc = ensure(c, c->tile_list, next))) return rc;
+    return LG_OK;
+  }
+  TileArgs T = c->tiled_last;
+  if ((rc = ensure(c, c->tile_list, next))) return rc;
   T.list = (unsigned *)c->tile_list.p;
   T.list_cap = c->tile_list.bytes / 4;
   const unsigned long long fixed[4] = {h_totals[0], h_totals[3], 0ull, h_totals[3]};
