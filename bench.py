@@ -489,6 +489,26 @@ def main():
         ctx.call("lg_tile_map_enable", 0)
         grid_line = (ms_grid, agg_grid, ms_grid_e2e)
 
+    # round 1's workload (ONE light x 32 M rays per GPU: a different light per rank, so not the same work at every N --
+    # why it was replaced) once more, for continuity with BENCH_r01.json: N = 1 only
+    r01_line = None
+    if world == 1 and not args.no_extras:
+        old = scenes.c5_large(n_lights=1, rays_per_light=rays_per_gpu)
+        t_old = old.apply(Tracer(old.canvas_bounds, ctx=ctx))
+        t_old.sync_scene()
+        t_old.set_shard(0, 1)
+        for _ in range(6):       # auto-mode samples of this workload + warm-up
+            step(False)
+        ms_old, agg_old = timed(args.steps, False)
+        r01_line = {"value": rays_per_gpu * args.steps / (ms_old * 1e-3), "unit": "rays/s", "ms_per_step": ms_old / args.steps,
+                    "phase_ms_per_step": phases(agg_old, args.steps), "segments_per_ray": agg_old["segments"] / (rays_per_gpu * args.steps),
+                    "ray_object_tests_per_s_in_kernel": agg_old["ray_steps"] * len(old.objects) / (agg_old["trace_ms"] * 1e-3),
+                    "note": "round 1's bench workload: one C5 light x 32 M rays (BENCH_r01.json: 146.2 ms/step, trace 111.2, "
+                            "accumulate 35.1); the headline now traces all eight C5 lights x 4 M rays: more segments per ray "
+                            "and more ray steps, identical at every N"}
+        tracer.sync_scene(force=True)
+        tracer.set_shard(rank, world)
+
     # multi-GPU correctness, untimed: the reduced frame is the rank-ordered sum of the partial frames, bit for bit,
     # and the ranks' fragment counts add up to a one-rank render's
     reduce_check = None
@@ -625,6 +645,8 @@ def main():
                         "headline because the north star's metric counts the all-objects loop"}
         if reduce_check is not None:
             out["reduce_check"] = reduce_check
+        if r01_line is not None:
+            out["r01_workload"] = r01_line
     # N = 1 only, after the timed regions: the other BASELINE configs and the reference-width mode
     if rank == 0 and world == 1 and not args.no_extras:
         ctx.close()
