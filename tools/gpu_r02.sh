@@ -60,11 +60,11 @@ PY
       ;;
     cfglaunches)
       # per-kernel times of C1 / C2 (quarter size) under ncu, this tree and the round-1 tree (_r01/, if present)
-      for tree in . _r01; do
+      for tree in ${CFG_TREES:-. _r01}; do
         [ -d $tree/tools ] || continue
         n=$(echo $tree | tr -d './_'); n=${n:-new}
-        (cd $tree && LG_ACCUM_MODE=2 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 120 --csv \
-          --log-file $OLDPWD/gpurun_out/launches_cfg_$n.csv python tools/bench_configs.py --scale 0.25 --repeat 1 --only C1,C2 \
+        (cd $tree && LG_ACCUM_MODE=2 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \
+          --log-file $OLDPWD/gpurun_out/launches_cfg_$n.csv python tools/bench_configs.py --scale 0.25 --repeat 1 --only ${CFG_ONLY:-C1,C2} \
           > $OLDPWD/gpurun_out/cfg_under_ncu_$n.log 2>&1)
       done
       ;;

@@ -5,7 +5,7 @@ import collections
 import csv
 import sys
 
-MICRO = ("red_peak_kernel", "fma_peak_kernel", "dfma_peak_kernel")
+MICRO = ("red_peak_kernel", "fma_peak_kernel", "dfma_peak_kernel", "tile_rmw_peak_kernel")
 
 
 def main(path, cmd):
