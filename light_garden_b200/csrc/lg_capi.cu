@@ -205,6 +205,7 @@ struct lg_ctx {
   bool have_drawing = false; // lg_drawing_object_set: chained behind the objects in the start-medium scan only
   HostScene drawing_hs;
   int n_obj = 0, n_pad = 0;
+  bool scene_flat = false; // object i == token i (SceneArgs::flat)
   unsigned bounds_bytes = 0;
   DevBuf bounds, toks, obj_first, obj_count, obj_n, ovl_start, ovl_list;
   double canvas[8] = {0};
@@ -341,6 +342,9 @@ template <class T> int upload_scene(lg_ctx *c) {
     obj_n.push_back(o.has_material ? (T)o.n : std::numeric_limits<T>::quiet_NaN());
   }
   c->n_obj = (int)hs.objs.size();
+  c->scene_flat = true;
+  for (size_t i = 0; i < hs.objs.size(); ++i)
+    if (hs.objs[i].first != (int)i || hs.objs[i].count != 1) c->scene_flat = false;
   int rc;
   if ((rc = upload(c, c->toks, toks))) return rc;
   if ((rc = upload(c, c->obj_first, obj_first))) return rc;
@@ -443,6 +447,7 @@ template <class T> void fill_args(lg_ctx *c, TraceArgs<T> &A) {
   A.delta = (T)c->delta;
   A.toks = (const Tok<T> *)c->toks.p;
   A.obj_first = (const int *)c->obj_first.p, A.obj_count = (const int *)c->obj_count.p;
+  A.flat = c->scene_flat ? 1 : 0;
   A.obj_n = (const T *)c->obj_n.p;
   A.ovl_start = (const int *)c->ovl_start.p, A.ovl_list = (const int *)c->ovl_list.p;
   for (int k = 0; k < 8; ++k) A.canvas[k] = (T)c->canvas[k];

@@ -75,7 +75,7 @@ template <class T> LG_HD V2<T> ray_at(V2<T> o, T t, V2<T> d) {
 }
 
 // One lowered token of an object's postfix program (lg_scene.h builds them).
-template <class T> struct Tok {
+template <class T> struct alignas(16) Tok { // 48 / 80 bytes: header and parameters load as 16-byte vectors
   int32_t kind, op, a_start, b_start;
   T p[8];
   // CIRCLE : cx cy r r2          SEGMENT: ax ay ex ey
@@ -97,7 +97,10 @@ template <class T> struct CandList {
 };
 
 // ---- ORACLE.md §3.1 circle -------------------------------------------------
-template <class T> LG_HD void hit_circle(const T *c, V2<T> o, V2<T> d, CandList<T> &out) {
+// The *_each forms hand every hit to a callable in the library's point order instead of appending it to a CandList:
+// a list indexed by a running count lives in local memory (STL / LDL in the trace kernel's narrow phase, ncu r02), a
+// callable keeps the hit in registers.  Same arithmetic, same order.
+template <class T, class F> LG_HD void hit_circle_each(const T *c, V2<T> o, V2<T> d, F &&emit) {
   V2<T> m{c[0] - o.x, c[1] - o.y};
   T cr = cross(m, d);
   T disc = Real<T>::fma(-cr, cr, c[3]);
@@ -105,8 +108,11 @@ template <class T> LG_HD void hit_circle(const T *c, V2<T> o, V2<T> d, CandList<
   T tca = dot(m, d);
   T thc = Real<T>::sqrt(disc);
   T t0 = tca - thc, t1 = tca + thc;
-  if (t0 > (T)kTMin) out.h[out.n++] = {t0, ray_at(o, t0, d), (T)0};
-  if (t1 > (T)kTMin) out.h[out.n++] = {t1, ray_at(o, t1, d), (T)1};
+  if (t0 > (T)kTMin) emit(Cand<T>{t0, ray_at(o, t0, d), (T)0});
+  if (t1 > (T)kTMin) emit(Cand<T>{t1, ray_at(o, t1, d), (T)1});
+}
+template <class T> LG_HD void hit_circle(const T *c, V2<T> o, V2<T> d, CandList<T> &out) {
+  hit_circle_each(c, o, d, [&](const Cand<T> &h) { out.h[out.n++] = h; });
 }
 
 // ---- ORACLE.md §3.2 segment a + u e ---------------------------------------
@@ -126,9 +132,12 @@ LG_HD bool hit_edge(V2<T> a, V2<T> e, V2<T> o, V2<T> d, T aux, Cand<T> &h) {
   h.aux = aux;
   return true;
 }
-template <class T> LG_HD void hit_segment(const T *s, V2<T> o, V2<T> d, CandList<T> &out) {
+template <class T, class F> LG_HD void hit_segment_each(const T *s, V2<T> o, V2<T> d, F &&emit) {
   Cand<T> h;
-  if (hit_edge(V2<T>{s[0], s[1]}, V2<T>{s[2], s[3]}, o, d, (T)0, h)) out.h[out.n++] = h;
+  if (hit_edge(V2<T>{s[0], s[1]}, V2<T>{s[2], s[3]}, o, d, (T)0, h)) emit(h);
+}
+template <class T> LG_HD void hit_segment(const T *s, V2<T> o, V2<T> d, CandList<T> &out) {
+  hit_segment_each(s, o, d, [&](const Cand<T> &h) { out.h[out.n++] = h; });
 }
 
 // ---- ORACLE.md §3.3 rect (centre, half axes u, v) ---------------------------
@@ -156,15 +165,18 @@ template <class T> LG_HD void rect_edge(const T *r, int k, V2<T> &a, V2<T> &e) {
     e = u2;
   }
 }
-template <class T> LG_HD void hit_rect(const T *r, V2<T> o, V2<T> d, CandList<T> &out) {
+template <class T, class F> LG_HD void hit_rect_each(const T *r, V2<T> o, V2<T> d, F &&emit) {
   if (rect_sat_reject(r, o, d)) return;
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     V2<T> a, e;
     rect_edge(r, k, a, e);
     Cand<T> h;
-    if (hit_edge(a, e, o, d, (T)k, h)) out.h[out.n++] = h;
+    if (hit_edge(a, e, o, d, (T)k, h)) emit(h);
   }
+}
+template <class T> LG_HD void hit_rect(const T *r, V2<T> o, V2<T> d, CandList<T> &out) {
+  hit_rect_each(r, o, d, [&](const Cand<T> &h) { out.h[out.n++] = h; });
 }
 
 // ---- ORACLE.md §3.4 cubic Bézier --------------------------------------------

@@ -16,6 +16,10 @@ namespace lg {
 template <class T> struct SceneArgs {
   const Tok<T> *toks;
   const int *obj_first, *obj_count;
+  // every object is ONE leaf token and token i belongs to object i (scenes of plain circles / rects / mirrors, C5):
+  // the narrow phase then reads toks[obj] directly instead of waiting for obj_first[obj] first -- one dependent
+  // global load less on the path the nearest-hit search stalls on (ncu r02: long_scoreboard, ~10 % of the samples)
+  int flat;
   T delta; // rounding margin of the broad phase (64 eps x coordinate bound)
   // uniform grid over the objects' bounding circles (lg_tile_map_enable; SURVEY.md 8f rank 1, the device-side
   // stand-in for tile_map.rs): cell (ix, iy) covers [x0 + ix cs, x0 + (ix + 1) cs) x [y0 + iy cs, ...) and lists
@@ -98,22 +102,25 @@ LG_HD void sweep_csg_object(const SceneArgs<T> &A, int obj, V2<T> o, V2<T> d, Be
 // per test.
 template <class T>
 LG_HD Best<T> narrow_phase(const SceneArgs<T> &A, Best<T> b, int obj, V2<T> o, V2<T> d) {
-  const int first = A.obj_first[obj];
-  if (A.obj_count[obj] == 1) {
+  const int first = A.flat ? obj : A.obj_first[obj];
+  if (A.flat || A.obj_count[obj] == 1) {
     const Tok<T> &k = A.toks[first];
-    CandList<T> hl;
-    hl.n = 0;
-    if (k.kind == TOK_CIRCLE)
-      hit_circle(k.p, o, d, hl);
-    else if (k.kind == TOK_SEGMENT)
-      hit_segment(k.p, o, d, hl);
-    else if (k.kind == TOK_RECT)
-      hit_rect(k.p, o, d, hl);
-    else if (k.kind == TOK_ELLIPSE)
-      hit_ellipse(k.p, o, d, hl);
-    else
-      hit_bezier(k.p, o, d, hl);
-    for (int q = 0; q < hl.n; ++q) take(b, o, hl.h[q], obj, first);
+    auto emit = [&](const Cand<T> &h) { take(b, o, h, obj, first); }; // hits stay in registers, library order
+    if (k.kind == TOK_CIRCLE) {
+      hit_circle_each(k.p, o, d, emit);
+    } else if (k.kind == TOK_SEGMENT) {
+      hit_segment_each(k.p, o, d, emit);
+    } else if (k.kind == TOK_RECT) {
+      hit_rect_each(k.p, o, d, emit);
+    } else {
+      CandList<T> hl;
+      hl.n = 0;
+      if (k.kind == TOK_ELLIPSE)
+        hit_ellipse(k.p, o, d, hl);
+      else
+        hit_bezier(k.p, o, d, hl);
+      for (int q = 0; q < hl.n; ++q) take(b, o, hl.h[q], obj, first);
+    }
   } else {
     sweep_csg_object(A, obj, o, d, b);
   }
