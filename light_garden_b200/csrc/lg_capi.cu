@@ -282,6 +282,13 @@ struct lg_ctx {
   bool peer_opened16[kMaxPeers] = {false};
   bool peer_fused_ok = true;
   DevBuf sync_buf, peer_xchg;
+  // device-side barriers of the fused reduce (lg_reduce.cuh: peer_barrier_kernel): this rank's flag words, every
+  // peer's mapped here; they outlive lg_image_configure (only the images move)
+  DevBuf flags, flag_status;
+  void *peer_flags[kMaxPeers] = {nullptr};
+  bool peer_flags_opened[kMaxPeers] = {false};
+  bool flags_ready = false;
+  unsigned long long flag_epoch = 0;
   bool img16_valid = false; // the fp16 frame already holds the finalized image
 
   unsigned long long launches = 0;
@@ -290,6 +297,7 @@ struct lg_ctx {
 namespace {
 
 void close_peers(lg_ctx *c);
+void close_peer_flags(lg_ctx *c);
 
 int fail(lg_ctx *c, int code, const std::string &msg) {
   if (c) c->err = msg;
@@ -913,13 +921,14 @@ int32_t lg_destroy(lg_ctx *c) {
   if (!c) return LG_ERR_INVALID;
   cudaSetDevice(c->device);
   close_peers(c);
+  close_peer_flags(c);
   if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
   DevBuf *bufs[] = {&c->bounds,    &c->toks,
                     &c->obj_first, &c->obj_count, &c->obj_n,    &c->ovl_start, &c->ovl_list, &c->d_lights, &c->seg,
                     &c->tags,      &c->seg64,    &c->ctr,      &c->stack,   &c->rays,     &c->img,     &c->img16,
                     &c->pixctr,    &c->tile_count, &c->tile_cursor, &c->tile_offset, &c->item_prefix,
                     &c->tile_totals, &c->item_counter, &c->tile_list, &c->seg2,       &c->tile_hist,
-                    &c->sync_buf,  &c->peer_xchg,  &c->img8,       &c->grid_start,  &c->grid_obj,
+                    &c->sync_buf,  &c->peer_xchg,  &c->img8,       &c->grid_start,  &c->grid_obj, &c->flags, &c->flag_status,
                     &c->nest_lines, &c->nest_counts, &c->nest_points, &c->nest_pairs};
   for (DevBuf *b : bufs) release(*b);
   for (ExportBuf &e : c->exported) export_release(e);
@@ -1847,8 +1856,8 @@ int32_t lg_comm_init_all(lg_ctx **ctxs, int32_t n) {
 namespace {
 
 struct PeerInfo { // what every rank tells the others about its buffers
-  cudaIpcMemHandle_t h_img, h_img16;
-  unsigned long long ptr_img, ptr_img16;
+  cudaIpcMemHandle_t h_img, h_img16, h_flags;
+  unsigned long long ptr_img, ptr_img16, ptr_flags, epoch;
   long long pid;
   int device, has16;
   unsigned long long bytes_img;
@@ -1862,6 +1871,16 @@ void close_peers(lg_ctx *c) {
     c->peer_opened[p] = c->peer_opened16[p] = false;
   }
   c->peers_ready = false;
+  cudaGetLastError();
+}
+
+void close_peer_flags(lg_ctx *c) {
+  for (int p = 0; p < kMaxPeers; ++p) {
+    if (c->peer_flags_opened[p] && c->peer_flags[p]) cudaIpcCloseMemHandle(c->peer_flags[p]);
+    c->peer_flags[p] = nullptr;
+    c->peer_flags_opened[p] = false;
+  }
+  c->flags_ready = false;
   cudaGetLastError();
 }
 
@@ -1880,15 +1899,24 @@ int comm_max(lg_ctx *c, int value, int *out) {
 // all ranks exchange their buffer handles and map each other's images (collective)
 int exchange_peers(lg_ctx *c, int root) {
   close_peers(c);
+  close_peer_flags(c);
   const int n = c->comm_world;
   int rc;
   if (c->comm_rank == root && (rc = ensure(c, c->img16, (size_t)c->W * c->H * 8))) return rc;
+  if (!c->flags.p) { // allocated once per context, never moved: peers keep their mapping of it
+    if ((rc = ensure(c, c->flags, (size_t)kFlagPhases * 16 * 8))) return rc;
+    if ((rc = ensure(c, c->flag_status, 16))) return rc;
+    LG_CUDA(c, cudaMemsetAsync(c->flags.p, 0, c->flags.bytes, c->stream));
+  }
   PeerInfo mine{};
+  mine.ptr_flags = (unsigned long long)(uintptr_t)c->flags.p;
+  mine.epoch = c->flag_epoch;
   mine.pid = (long long)getpid();
   mine.device = c->device;
   mine.ptr_img = (unsigned long long)(uintptr_t)c->img.p;
   mine.bytes_img = (unsigned long long)c->W * c->H * 16;
   bool ok = cudaIpcGetMemHandle(&mine.h_img, c->img.p) == cudaSuccess;
+  ok = ok && cudaIpcGetMemHandle(&mine.h_flags, c->flags.p) == cudaSuccess;
   if (c->comm_rank == root) {
     mine.has16 = 1;
     mine.ptr_img16 = (unsigned long long)(uintptr_t)c->img16.p;
@@ -1905,8 +1933,10 @@ int exchange_peers(lg_ctx *c, int root) {
   LG_CUDA(c, cudaStreamSynchronize(c->stream));
   for (int p = 0; p < n && ok; ++p) {
     if (all[p].bytes_img != mine.bytes_img) ok = false; // ranks disagree on the image size
+    c->flag_epoch = std::max(c->flag_epoch, all[p].epoch); // every rank continues from the same epoch
     if (p == c->comm_rank) {
       c->peer_img[p] = c->img.p;
+      c->peer_flags[p] = c->flags.p;
       if (p == root) c->peer_img16[p] = c->img16.p;
       continue;
     }
@@ -1920,6 +1950,7 @@ int exchange_peers(lg_ctx *c, int root) {
       if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) ok = false;
       cudaGetLastError();
       c->peer_img[p] = (void *)(uintptr_t)all[p].ptr_img;
+      c->peer_flags[p] = (void *)(uintptr_t)all[p].ptr_flags;
       if (p == root) c->peer_img16[p] = (void *)(uintptr_t)all[p].ptr_img16;
     } else { // another process (one rank per GPU under torchrun): CUDA IPC
       if (cudaIpcOpenMemHandle(&c->peer_img[p], all[p].h_img, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
@@ -1927,6 +1958,12 @@ int exchange_peers(lg_ctx *c, int root) {
         ok = false;
       } else {
         c->peer_opened[p] = true;
+      }
+      if (ok && cudaIpcOpenMemHandle(&c->peer_flags[p], all[p].h_flags, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+        c->peer_flags[p] = nullptr;
+        ok = false;
+      } else if (ok) {
+        c->peer_flags_opened[p] = true;
       }
       if (ok && p == root) {
         if (cudaIpcOpenMemHandle(&c->peer_img16[p], all[p].h_img16, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
@@ -1943,7 +1980,8 @@ int exchange_peers(lg_ctx *c, int root) {
   int any_bad = 0;
   if ((rc = comm_max(c, ok ? 0 : 1, &any_bad))) return rc;
   c->peer_fused_ok = any_bad == 0;
-  if (!c->peer_fused_ok) close_peers(c);
+  if (!c->peer_fused_ok) close_peers(c), close_peer_flags(c);
+  c->flags_ready = c->peer_fused_ok;
   c->peers_ready = true; // the exchange happened (even if it ended in the NCCL fallback)
   c->peers_root = root;
   return LG_OK;
@@ -1970,32 +2008,65 @@ int32_t lg_image_reduce(lg_ctx *c, int32_t root, float *reduce_ms) {
   LG_CUDA(c, cudaSetDevice(c->device));
   LG_CUDA(c, cudaEventRecord(c->ev0, c->stream));
   bool fused = c->reduce_mode != 1 && c->comm_world <= kMaxPeers;
-  if (fused) {
-    // barrier (every rank's accumulation is complete) + consensus: does anybody need the handle exchange?
+  const int mine_need = (!c->peers_ready || c->peers_root != root) ? 1 : 0;
+  bool started = false; // a barrier in front of the reduce kernel has run (every rank's accumulation is complete)
+  if (fused && !c->flags_ready) {
+    // first call of this communicator (or after a failed mapping): NCCL is the barrier and carries the consensus on
+    // "does anybody need the handle exchange", then the handles travel through ncclAllGather
     int need = 0;
-    const int mine = (!c->peers_ready || c->peers_root != root) ? 1 : 0;
-    if ((rc = comm_max(c, mine, &need))) return rc;
+    if ((rc = comm_max(c, mine_need, &need))) return rc;
     if (need && (rc = exchange_peers(c, root))) return rc;
     fused = c->peer_fused_ok;
     if (!fused && c->reduce_mode == 2) return fail(c, LG_ERR_UNSUPPORTED, "peer memory is not reachable from every rank");
+    started = true;
   }
   if (fused) {
-    PeerPtrs P{};
-    P.n = c->comm_world;
-    for (int p = 0; p < P.n; ++p) P.img[p] = (const float4 *)c->peer_img[p];
-    P.root_img = (float4 *)c->peer_img[root];
-    P.root_img16 = (uint2 *)c->peer_img16[root];
-    const size_t rows0 = (size_t)c->H * c->comm_rank / c->comm_world, rows1 = (size_t)c->H * (c->comm_rank + 1) / c->comm_world;
-    const size_t px0 = rows0 * c->W, px1 = rows1 * c->W;
-    if (px1 > px0) {
-      reduce_finalize_peer_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(P, px0, px1);
+    // the steady state: two device-side barriers over peer-mapped flag words around the kernel, no NCCL call and no
+    // host synchronisation until the end.  Barrier 0 ("my accumulation is complete", + the need-exchange bit of every
+    // rank), the reduce of this rank's band, barrier 1 ("my band has landed in the root's buffers": nobody touches its
+    // partial image or reads the frame before that).
+    for (int attempt = 0; attempt < 2; ++attempt) {
+      PeerFlags F{};
+      F.n = c->comm_world, F.rank = c->comm_rank, F.mine = (unsigned long long *)c->flags.p;
+      for (int p = 0; p < F.n; ++p) F.peer[p] = (unsigned long long *)c->peer_flags[p];
+      const unsigned long long epoch = ++c->flag_epoch;
+      const long long timeout = 20ll * 1000 * 1000 * 1000; // ~10 s of SM clocks: a peer that is not in this protocol
+      unsigned int *status = (unsigned int *)c->flag_status.p;
+      LG_CUDA(c, cudaMemsetAsync(status, 0, 16, c->stream));
+      const int need_bit = (attempt == 0 && !started) ? mine_need : 0;
+      peer_barrier_kernel<<<1, 32, 0, c->stream>>>(F, 0, epoch, (unsigned)need_bit, status, timeout);
       LG_CUDA(c, cudaGetLastError());
-      c->launches++;
+      PeerPtrs P{};
+      P.n = c->comm_world;
+      for (int p = 0; p < P.n; ++p) P.img[p] = (const float4 *)c->peer_img[p];
+      P.root_img = (float4 *)c->peer_img[root];
+      P.root_img16 = (uint2 *)c->peer_img16[root];
+      const size_t rows0 = (size_t)c->H * c->comm_rank / c->comm_world, rows1 = (size_t)c->H * (c->comm_rank + 1) / c->comm_world;
+      const size_t px0 = rows0 * c->W, px1 = rows1 * c->W;
+      if (px1 > px0 && P.root_img && P.root_img16) {
+        reduce_finalize_peer_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(P, px0, px1, status);
+        LG_CUDA(c, cudaGetLastError());
+        c->launches++;
+      }
+      peer_barrier_kernel<<<1, 32, 0, c->stream>>>(F, 1, epoch, 0u, status + 1, timeout);
+      LG_CUDA(c, cudaGetLastError());
+      c->launches += 2;
+      unsigned int *h_status = (unsigned int *)(c->h_totals + 40);
+      LG_CUDA(c, cudaMemcpyAsync(h_status, status, 8, cudaMemcpyDeviceToHost, c->stream));
+      LG_CUDA(c, cudaEventRecord(c->ev1, c->stream));
+      LG_CUDA(c, cudaStreamSynchronize(c->stream));
+      if ((h_status[0] | h_status[1]) & 2u)
+        return fail(c, LG_ERR_NCCL, "lg_image_reduce: a peer did not arrive at the barrier (is every rank calling it?)");
+      if (!(h_status[0] & 1u)) break; // done
+      // some rank's buffers moved (lg_image_configure): nobody reduced anything; exchange the handles again (collective:
+      // every rank saw the same bit) and run the three kernels once more
+      if (attempt == 1) return fail(c, LG_ERR_STATE, "lg_image_reduce: handle exchange requested twice");
+      if ((rc = exchange_peers(c, root))) return rc;
+      if (!c->peer_fused_ok) return fail(c, LG_ERR_UNSUPPORTED, "peer memory is no longer reachable from every rank");
     }
-    // barrier: every band has landed in the root's buffers, nobody touches its partial image before that
-    int dummy = 0;
-    if ((rc = comm_max(c, 0, &dummy))) return rc;
     if (c->comm_rank == root) c->img16_valid = true;
+    if (reduce_ms) LG_CUDA(c, cudaEventElapsedTime(reduce_ms, c->ev0, c->ev1));
+    return LG_OK;
   } else {
     int r = g_nccl.Reduce(c->img.p, c->img.p, (size_t)c->W * c->H * 4, kNcclFloat32, kNcclSum, root, c->comm, c->stream);
     if (r != 0) return fail(c, LG_ERR_NCCL, std::string("ncclReduce: ") + g_nccl.GetErrorString(r));
@@ -2011,6 +2082,7 @@ int32_t lg_comm_destroy(lg_ctx *c) {
   if (!c) return LG_ERR_INVALID;
   cudaSetDevice(c->device);
   close_peers(c);
+  close_peer_flags(c);
   if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
   c->comm = nullptr;
   c->comm_world = 1, c->comm_rank = 0;
