@@ -1946,9 +1946,13 @@ int exchange_peers(lg_ctx *c, int root) {
         ok = false;
         break;
       }
-      cudaError_t e = cudaDeviceEnablePeerAccess(all[p].device, 0);
-      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) ok = false;
-      cudaGetLastError();
+      static bool enabled[kMaxPeers][kMaxPeers] = {{false}}; // per (this device, peer device): enable once per process
+      if (c->device < kMaxPeers && all[p].device < kMaxPeers && !enabled[c->device][all[p].device]) {
+        cudaError_t e = cudaDeviceEnablePeerAccess(all[p].device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) ok = false;
+        else enabled[c->device][all[p].device] = true;
+        cudaGetLastError();
+      }
       c->peer_img[p] = (void *)(uintptr_t)all[p].ptr_img;
       c->peer_flags[p] = (void *)(uintptr_t)all[p].ptr_flags;
       if (p == root) c->peer_img16[p] = (void *)(uintptr_t)all[p].ptr_img16;

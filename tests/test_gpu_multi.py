@@ -87,3 +87,49 @@ def test_two_device_render_equals_one_device(oracle):
         one.close()
         for c in ctxs:
             c.close()
+
+
+@pytest.mark.skipif(not have_cuda() or device_count() < 2, reason="needs 2 GPUs")
+def test_reduce_survives_a_resized_image_on_the_device_side_barriers(oracle):
+    """The steady state of lg_image_reduce has no NCCL call: two device-side barriers over peer-mapped flag words around
+    the fused kernel.  When a rank's image moves (lg_image_configure with another size) its "exchange the handles again"
+    bit rides on the first barrier, every rank skips the kernel, the handles travel through NCCL once more and the reduce
+    is repeated -- also when only ONE rank noticed."""
+    from light_garden_b200 import _lib
+    from light_garden_b200.tracer import Context, Renderer, Tracer
+    spec = small_specs()["C1"]
+    ctxs = [Context(d, abi.LG_PRECISION_F32) for d in range(2)]
+    try:
+        arr = (C.c_void_p * 2)(*[c.h for c in ctxs])
+        _lib.check(ctxs[0].h, _lib.load().lg_comm_init_all(arr, 2))
+        tracers = []
+        for rk, c in enumerate(ctxs):
+            t = spec.apply(Tracer(spec.canvas_bounds, ctx=c))
+            t.set_shard(rk, 2)
+            tracers.append(t)
+
+        def frame(sizes):
+            rends = [Renderer(c, w, h) for c, (w, h) in zip(ctxs, sizes)]      # lg_image_configure: buffers may move
+            for rk, r in enumerate(rends):
+                r.clear(1.0 if rk == 0 else 0.0)
+                r.render(tracers[rk])
+            parts = [r.read_rgba32f() for r in rends]
+            reduce_all(ctxs, 0)
+            total = rends[0].read_rgba32f()
+            assert np.array_equal(total, parts[0] + parts[1])
+            half = rends[0].read_rgba16f()
+            assert np.array_equal(half.view(np.uint16), total.astype(np.float16).view(np.uint16))
+            return total
+
+        a = frame([(480, 270)] * 2)
+        b = frame([(480, 270)] * 2)                    # steady state: flags only
+        assert np.array_equal(a, b) or (np.abs(a - b) <= 1e-5 * np.maximum(1.0, np.abs(a))).all()
+        c_ = frame([(640, 360)] * 2)                   # every rank's image moved
+        assert c_.shape == (360, 640, 4)
+        for r in (0, 1):                               # one rank re-configures to the SAME size: only it asks
+            ctxs[r].call("lg_image_configure", 640, 360)
+            d = frame([(640, 360)] * 2)
+            assert (np.abs(d - c_) <= 1e-5 * np.maximum(1.0, np.abs(c_))).all()
+    finally:
+        for c in ctxs:
+            c.close()
