@@ -90,7 +90,7 @@ PY
       ;;
     sanitize)
       timeout 1500 compute-sanitizer --tool memcheck --error-exitcode 9 --print-limit 3 python -m pytest tests -m gpu -q -x \
-        -k "not full_size" > gpurun_out/sanitize_memcheck.log 2>&1
+        -k "not full_size and not bench_contract" > gpurun_out/sanitize_memcheck.log 2>&1
       echo "memcheck rc=$?" >> gpurun_out/sanitize_memcheck.log
       timeout 900 compute-sanitizer --tool racecheck --error-exitcode 9 python __graft_entry__.py smoke > gpurun_out/sanitize_racecheck.log 2>&1
       echo "racecheck rc=$?" >> gpurun_out/sanitize_racecheck.log
