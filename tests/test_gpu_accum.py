@@ -62,6 +62,15 @@ def test_pairs_exact_coverage_and_sums(oracle, ctx, size, mode):
     p["a"][2], p["b"][2] = (-1e6, -1e6), (1e6, 1e6)
     p["a"][3], p["b"][3] = (0.0, 0.0), (0.5, 0.0)
     p["a"][4], p["b"][4] = (0.25, -3.0), (0.25, 3.0)
+    # non-finite and out-of-range end points draw nothing (ORACLE.md 8.2), whichever end they are on
+    nan, inf = float("nan"), float("inf")
+    p["a"][5] = (nan, 0.0)
+    p["b"][6] = (0.0, nan)
+    p["a"][7] = (inf, 0.1)
+    p["b"][8] = (0.2, -inf)
+    p["a"][9], p["b"][9] = (-inf, -inf), (inf, inf)
+    p["a"][10], p["b"][10] = (1e300, 0.0), (0.0, 0.0)          # overflows the `as f32` cast
+    p["a"][11], p["b"][11] = (0.1, 0.1), (0.1 + 1e-12, 0.1 - 1e-12)   # shorter than a pixel: between two centres or on one
     st = r.render_lines(p)
     got = r.read_rgba32f()
     exp = oracle.new_image(W, H)
