@@ -159,6 +159,67 @@ def test_random_scene_frame_equals_the_oracle_accumulation(oracle, ctxs, seed, m
         ctx.call("lg_accumulate_mode_set", 0)
 
 
+def degenerate_spec():
+    """Ties and degenerate shapes: coincident objects (equal hit distances: the order of tracer.rs:412-424 decides),
+    surfaces shared by neighbours, zero-size shapes, CSG of a shape with itself, and rays aimed exactly at centres,
+    corners, tangent lines and end points."""
+    objs = [
+        Object.new_circle((0.0, 0.0), 0.25).with_index(1.5),
+        Object.new_circle((0.0, 0.0), 0.25).with_index(1.3),                 # the same circle twice
+        Object.new_rect((0.75, 0.0), 0.5, 0.5).with_index(1.4),
+        Object.new_rect((1.25, 0.0), 0.5, 0.5).with_index(1.6),              # shares the edge x = 1.0 with the one before
+        Object.new_mirror((-1.0, -0.5), (-1.0, 0.5)),
+        Object.new_mirror((-1.0, 0.5), (-0.5, 0.5)),                         # meets the one before in a corner
+        Object.new_mirror((-0.5, -0.75), (-0.5, -0.75)),                     # zero length
+        Object.new_circle((0.5, 0.75), 0.0).with_index(1.5),                 # zero radius
+        Object(Rect((-0.25, 0.75), rot2(0.0), 0.0, 0.25), Material(1.5), "Rect"),          # zero width
+        Object(Logic(AND, Circle((0.0, 0.0), 0.125), Circle((0.0, 0.0), 0.125), (0.0, -0.75), rot2(0.0)), Material(1.5), "Geo"),
+        Object(Logic(AND_NOT, Circle((0.0, 0.0), 0.125), Circle((0.0, 0.0), 0.125), (0.5, -0.75), rot2(0.0)), Material(1.5), "Geo"),
+        Object(Logic(OR, Rect((0.0, 0.0), rot2(0.0), 0.25, 0.25), Rect((0.25, 0.0), rot2(0.0), 0.25, 0.25), (1.0, -0.75), rot2(0.0)),
+               Material(1.5), "Geo"),                                        # two boxes that share an edge
+    ]
+    lights = [PointLight((-0.5, 0.0), 256, (0.5, 0.5, 0.5, 0.5)),          # 256 rays: exact multiples of 2 pi / 256, axis-aligned ones included
+              PointLight((0.0, 0.0), 64, (0.5, 0.4, 0.3, 0.5)),            # at the centre of the doubled circle
+              PointLight((1.0, 0.0), 64, (0.3, 0.4, 0.5, 0.5)),            # on the shared edge
+              SpotLight((-1.0, 0.5), 1.0, (1.0, -1.0), 33, (0.5, 0.5, 0.5, 0.5)),           # in the mirrors' corner
+              DirectionalLight((0.5, 0.5, 0.5, 0.5), 65, LineSegment((-1.5, 0.25), (1.5, 0.25)))]   # grazes the circles' top (y = 0.25)
+    return scenes.SceneSpec("degenerate", objs, lights, 8, 320, 180, (1e-4,) * 4)
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not have_cuda(), reason="no CUDA device")
+def test_ties_and_degenerate_shapes_equal_the_oracle(oracle, ctxs):
+    from light_garden_b200.tracer import Tracer
+    spec = degenerate_spec()
+    osc = oracle.OracleScene.from_spec(spec)
+    rays = primary_rays(oracle, spec, osc)
+    # plus hand-aimed rays: at a corner, along an edge, tangent to the circle, along a mirror, from inside the zero-width box
+    extra = np.zeros(6, dtype=abi.RAY_DTYPE)
+    aims = [((-1.5, 0.9), (0.5, 0.25)), ((0.5, -0.9), (0.5, 0.25)), ((-1.5, 0.25), (1.0, 0.0)), ((-1.0, -0.9), (0.0, 1.0)),
+            ((-0.25, 0.75), (1.0, 0.0)), ((1.0, 0.9), (0.0, -1.0))]
+    for k, (o, d) in enumerate(aims):
+        n = math.hypot(*d)
+        extra[k]["origin"], extra[k]["direction"] = o, (d[0] / n, d[1] / n)
+        extra[k]["color"], extra[k]["refractive_index"] = (0.5, 0.5, 0.5, 0.5), 1.0
+    rays = np.concatenate([rays, extra])
+    # a flat ellipse has no frame to intersect in (ORACLE.md 3.7 divides by the semi axes): refused, not traced
+    from light_garden_b200._lib import LightGardenError
+    flat = Tracer(spec.canvas_bounds, ctx=ctxs[abi.LG_PRECISION_F32])
+    flat.push_object(Object(Ellipse((-1.25, -0.5), 0.25, 0.0, rot2(0.0)), Material(1.5), "Ellipse"))
+    with pytest.raises(LightGardenError, match="LG_ERR_INVALID"):
+        flat.trace(extra)
+    for prec, ctx in ctxs.items():
+        exp = osc.trace_rays(rays, prec)
+        assert exp.segments_emitted > len(rays)
+        t = spec.apply(Tracer(spec.canvas_bounds, ctx=ctx))
+        for grid in (False, True):
+            t.enable_tile_map(grid)
+            try:
+                assert_same_segments(t.trace(rays), exp, f64=prec == abi.LG_PRECISION_F64)
+            finally:
+                t.enable_tile_map(False)
+
+
 def test_the_random_scenes_exercise_what_they_claim(oracle):
     """Guard against a generator that quietly stops producing the hard cases: over the seeds there are lights that start
     inside a medium, rays that cross from one object directly into another (two refractive hits in a row with no
