@@ -220,6 +220,48 @@ def test_ties_and_degenerate_shapes_equal_the_oracle(oracle, ctxs):
                 t.enable_tile_map(False)
 
 
+@pytest.mark.gpu
+@pytest.mark.skipif(not have_cuda(), reason="no CUDA device")
+@pytest.mark.parametrize("mode", [1, 2], ids=["direct", "tiled"])
+def test_random_string_mod_patterns_equal_the_oracle(oracle, ctxs, mode):
+    """string_mod.rs over random parameters: every mode (u64 wrapping powers included), tiny and prime moduli, factors
+    far above the modulo, colour rules that overlap (the LAST matching rule wins, string_mod.rs:141-150)."""
+    from light_garden_b200.scene import ModRemColor, StringMod, StringModMode
+    from light_garden_b200.tracer import Renderer
+    ctx = ctxs[abi.LG_PRECISION_F32]
+    ctx.call("lg_accumulate_mode_set", mode)
+    rng = np.random.default_rng(0x4C475D)
+    k = 2.0 ** -8
+    W = H = 192
+    try:
+        r = Renderer(ctx, W, H)
+        for case in range(24):
+            m = int(rng.choice([1, 2, 3, 64, 997, 1024, 2311, 4096]))
+            num = int(rng.choice([0, 1, 2, 3, 7, 255, 65537, 2 ** 31 + 11, 2 ** 63 + 5]))
+            md = [StringModMode.Mul, StringModMode.Add, StringModMode.Pow, StringModMode.Base][int(rng.integers(0, 4))]
+            rules = [ModRemColor(int(rng.integers(1, 9)), int(rng.integers(0, 4)), tuple(k * float(v) for v in rng.integers(0, 3, 4)))
+                     for _ in range(int(rng.integers(0, 4)))]
+            sm = StringMod(modulo=m, num=num, mode=md, color=(k, k, k, k), modulo_colors=rules)
+            r.clear()
+            st = r.render_string_mod(sm)
+            got = r.read_rgba32f()
+            exp = oracle.new_image(W, H)
+            n = oracle.accumulate_pairs(exp, oracle.string_mod(sm))
+            assert st.segments == m
+            # end points pass through sincos on both sides: a handful of fragments may move (test_gpu_accum.py)
+            assert abs(int(st.pixel_updates) - int(n)) <= 8, (case, m, num, md, st.pixel_updates, n)
+            # the direct resolve adds fragment by fragment like the oracle's fp32 loop; the tiled one adds per-tile partial
+            # sums (closer to the exact sum, test_traced_segments_image): thousands of chords meeting in one point
+            # (num^i = 1 mod m) differ by fp32 association there
+            tol = 1e-6 if mode == 1 else 3e-4
+            diff = np.nonzero((np.abs(got - exp) > tol * np.maximum(1.0, np.abs(exp))).any(axis=2))
+            assert len(diff[0]) <= 16, (case, m, num, md, len(diff[0]))
+            moved = np.nonzero(((got != (0, 0, 0, 1)).any(axis=2)) != ((exp != (0, 0, 0, 1)).any(axis=2)))
+            assert len(moved[0]) <= 16, (case, m, num, md, len(moved[0]))
+    finally:
+        ctx.call("lg_accumulate_mode_set", 0)
+
+
 def test_the_random_scenes_exercise_what_they_claim(oracle):
     """Guard against a generator that quietly stops producing the hard cases: over the seeds there are lights that start
     inside a medium, rays that cross from one object directly into another (two refractive hits in a row with no
