@@ -1541,10 +1541,7 @@ int render_pipelined(lg_ctx *c, LgTraceStats *stats, double &est) {
     if (k.seg_count > 0) c->pairs_per_seg_est = std::max(1.0, (double)hst[b][0] / (double)k.seg_count);
     if (hst[b][2]) { // the pair list was too small: the later wave's passes (queued already) share the bin buffers, so
       // let them finish, then run this wave's passes again with the list sized from its own count
-      LG_CUDA(c, cudaStreamSynchronize(c->stream2));
-      const int o = b ^ 1;
-      const bool other_drawn = w[o].busy; // its passes ran just now; its own status is looked at when it is reclaimed
-      (void)other_drawn;
+      LG_CUDA(c, cudaStreamSynchronize(c->stream2)); // (the other wave's own status is looked at when it is reclaimed)
       if ((rc = accumulate_tiled<LgSegment>(c, c->stream2, seg[b], k.seg_count, nullptr, nullptr, c->h_totals,
                                             &stats->accumulate_launches, k.seg_count)))
         return rc;
