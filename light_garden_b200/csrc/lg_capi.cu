@@ -242,6 +242,8 @@ struct lg_ctx {
   bool blend_generic = false; // lg_blend_set: a non-default (order-independent) blend state
   bool blend_linear = true;   // the image is a sum of fragment terms (Add / ReverseSubtract): partial images can be summed
   BlendCfg blend{};
+  int fill_wide = 0; // LG_FILL_WIDE=1: always the 64-bit form of tile_fill (tests; otherwise only lists of 2^32 entries and more)
+  int bin_grid = 0; // LG_BIN_GRID: CTAs of the count / fill passes, absolute (0 = sm_count x bin_ctas)
   int bin_ctas = 3, bin_threads = 1024; // count / fill passes (measured: 19.1 ms against 20.7 ms with 4 x 256): CTAs per SM and threads per CTA (LG_BIN_CTAS, LG_BIN_THREADS)
   int trace_merged = -1; // -1 = by scene size
   bool grid_on = false;
@@ -266,7 +268,7 @@ struct lg_ctx {
   double pairs_per_seg_est = 0;              // (segment, tile) pairs per segment of the last tiled resolve: sizes the next pair list
   TileArgs tiled_last{};                     // arguments of the last accumulate_tiled (tiled_finish runs fill + raster again from them)
   int tiled_raster_grid = 0;
-  size_t tiled_hist_smem = 0, tiled_raster_smem = 0;
+  size_t tiled_raster_smem = 0;
   unsigned long long *h_totals = nullptr;    // page-locked: [0..3] totals of the last tiled resolve, [4..] wave status (lg_render)
 
   // comm
@@ -685,17 +687,18 @@ int accumulate_tiled(lg_ctx *c, cudaStream_t st, const Seg *d_seg, unsigned long
   T.n_dev = n_dev, T.skip_dev = skip_dev;
   const size_t hist_smem = (size_t)T.n_tiles * 4;
   auto count_k = tile_count_kernel<Seg>;
-  auto fill_k = tile_fill_kernel<Seg>;
-  if (hist_smem > 48 * 1024) {
-    LG_CUDA(c, cudaFuncSetAttribute(count_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_smem));
-    LG_CUDA(c, cudaFuncSetAttribute(fill_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_smem));
-  }
+  // positions in the pair list fit 32 bits unless the list itself is larger than that (C2 at full size: 5.7e9 pairs)
+  const bool pos64 = T.list_cap >= (1ull << 32) || c->fill_wide;
+  const size_t fill_smem = (size_t)T.n_tiles * (pos64 ? 12 : 4);
+  auto fill_k = pos64 ? tile_fill_kernel<Seg, true> : tile_fill_kernel<Seg, false>;
+  if (hist_smem > 48 * 1024) LG_CUDA(c, cudaFuncSetAttribute(count_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_smem));
+  if (fill_smem > 48 * 1024) LG_CUDA(c, cudaFuncSetAttribute(fill_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fill_smem));
   // CTAs of the count and fill passes (the same split of the segments in both): one resident wave -- the histogram
   // in shared memory decides how many fit on an SM -- and no more than the segments can keep busy
   int hist_per_sm = 0;
-  LG_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&hist_per_sm, fill_k, c->bin_threads, hist_smem));
+  LG_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&hist_per_sm, fill_k, c->bin_threads, fill_smem));
   if (hist_per_sm < 1) return fail(c, LG_ERR_CUDA, "tile histogram does not fit in shared memory");
-  int grid = c->sm_count * c->bin_ctas;
+  int grid = c->bin_grid > 0 ? c->bin_grid : c->sm_count * c->bin_ctas;
   grid = (int)std::max<unsigned long long>(1ull, std::min<unsigned long long>((unsigned long long)grid, (n + 1023ull) / 1024ull));
   T.n_ctas = grid;
   if ((rc = ensure(c, c->tile_hist, (size_t)grid * T.n_tiles * 4))) return rc;
@@ -709,14 +712,14 @@ int accumulate_tiled(lg_ctx *c, cudaStream_t st, const Seg *d_seg, unsigned long
   if (c->raster_cap_now > 0) per_sm = std::min(per_sm, c->raster_cap_now);
   c->tiled_last = T;
   c->tiled_raster_grid = c->sm_count * per_sm;
-  c->tiled_hist_smem = hist_smem, c->tiled_raster_smem = smem;
+  c->tiled_raster_smem = smem;
   count_k<<<grid, c->bin_threads, hist_smem, st>>>(T, d_seg, n);
   LG_CUDA(c, cudaGetLastError());
   tile_rowscan_kernel<<<(T.n_tiles + 31) / 32, 32 * kRowscanWarps, 0, st>>>(T);
   LG_CUDA(c, cudaGetLastError());
   tile_scan_kernel<<<1, 1024, 0, st>>>(T);
   LG_CUDA(c, cudaGetLastError());
-  fill_k<<<grid, c->bin_threads, hist_smem, st>>>(T, d_seg, n);
+  fill_k<<<grid, c->bin_threads, fill_smem, st>>>(T, d_seg, n);
   LG_CUDA(c, cudaGetLastError());
   kern<<<c->tiled_raster_grid, kRasterWarps * 32, smem, st>>>(T, d_seg);
   LG_CUDA(c, cudaGetLastError());
@@ -747,7 +750,11 @@ int tiled_finish(lg_ctx *c, cudaStream_t st, const Seg *d_seg, unsigned long lon
   const unsigned long long fixed[4] = {h_totals[0], h_totals[3], 0ull, h_totals[3]};
   LG_CUDA(c, cudaMemcpyAsync(T.totals, fixed, 32, cudaMemcpyHostToDevice, st));
   LG_CUDA(c, cudaMemsetAsync(T.item_counter, 0, 4, st)); // the raster's first (empty) launch moved it
-  tile_fill_kernel<Seg><<<T.n_ctas, c->bin_threads, c->tiled_hist_smem, st>>>(T, d_seg, n);
+  const bool pos64 = T.list_cap >= (1ull << 32) || c->fill_wide; // the grown list may have crossed the line
+  const size_t fill_smem = (size_t)T.n_tiles * (pos64 ? 12 : 4);
+  auto fill_k = pos64 ? tile_fill_kernel<Seg, true> : tile_fill_kernel<Seg, false>;
+  if (fill_smem > 48 * 1024) LG_CUDA(c, cudaFuncSetAttribute(fill_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fill_smem));
+  fill_k<<<T.n_ctas, c->bin_threads, fill_smem, st>>>(T, d_seg, n);
   LG_CUDA(c, cudaGetLastError());
   tile_raster_kernel<Seg><<<c->tiled_raster_grid, kRasterWarps * 32, c->tiled_raster_smem, st>>>(T, d_seg);
   LG_CUDA(c, cudaGetLastError());
@@ -877,6 +884,8 @@ int32_t lg_create(int32_t device, int32_t precision, lg_ctx **out) {
     if (v >= 0 && v <= 2) c->accum_mode = v;
   }
   if (const char *e = getenv("LG_TRACE_MERGED")) c->trace_merged = atoi(e) ? 1 : 0;
+  if (const char *e = getenv("LG_BIN_GRID")) c->bin_grid = std::max(0, atoi(e));
+  if (const char *e = getenv("LG_FILL_WIDE")) c->fill_wide = atoi(e) ? 1 : 0;
   if (const char *e = getenv("LG_BIN_CTAS")) {
     int v = atoi(e);
     if (v >= 1 && v <= 16) c->bin_ctas = v;

@@ -444,3 +444,30 @@ def test_full_size_string_mod_properties(ctx, wh):
         st2 = r.render_string_mod(sm)
         assert int(st2.pixel_updates) == n
         assert np.array_equal(r.read_rgba32f(), img), mode
+
+
+def test_wide_fill_pass_gives_the_same_frame(oracle):
+    """tile_fill has a form for pair lists of 2^32 entries and more (C2 at full size: 5.7e9 pairs; 64-bit list starts
+    staged in shared memory).  Forced here on a small frame: same fragments, same sums as the 32-bit form."""
+    import os
+    from light_garden_b200.tracer import Context, Renderer, Tracer
+    spec = small_specs()["C2"]
+    frames = []
+    for wide in ("0", "1"):
+        os.environ["LG_FILL_WIDE"] = wide
+        try:
+            c = Context(0, abi.LG_PRECISION_F32)
+        finally:
+            del os.environ["LG_FILL_WIDE"]
+        try:
+            c.call("lg_accumulate_mode_set", TILED)
+            t = spec.apply(Tracer(spec.canvas_bounds, ctx=c))
+            r = Renderer(c, spec.width, spec.height)
+            r.clear()
+            st = r.render(t)
+            frames.append((st.pixel_updates, st.segments, r.read_rgba32f()))
+        finally:
+            c.close()
+    assert frames[0][0] == frames[1][0] > 0 and frames[0][1] == frames[1][1]
+    # entries land in a list in a different order (atomics): fp32 association within a tile only
+    assert (np.abs(frames[0][2] - frames[1][2]) <= 2e-5 * np.maximum(1.0, np.abs(frames[0][2]))).all()
