@@ -183,6 +183,29 @@ class Tracer:
         """Tracer::tile_map_enabled (tracer.rs:126-129)."""
         return getattr(self, "_tile_map_enabled", False)
 
+    def new_tile_map(self, num_tiles_x: int, num_tiles_y: int, num_slabs: int):
+        """Tracer::new_tile_map (tracer.rs:148-160).  The device grid sizes itself from the scene (one cell per ~object,
+        LG_GRID_DENSITY) and has no angular slabs; the arguments are accepted for the caller's sake and the state they
+        leave behind is the reference's: a fresh map, enabled as before."""
+        if num_tiles_x <= 0 or num_tiles_y <= 0 or num_slabs <= 0:
+            raise ValueError("new_tile_map: tile and slab counts must be positive")
+        self._scene_dirty = True
+
+    def update_tile_map(self):
+        """Tracer::update_tile_map (tracer.rs:131-135): the device grid is rebuilt with the next trace."""
+        self._scene_dirty = True
+
+    def obj_changed(self, obj_index: int):
+        """Tracer::obj_changed (tracer.rs:126-129): an object was edited in place through index_object."""
+        self.objects[obj_index].moved = True
+        self._scene_dirty = True
+
+    def get_trace_time(self) -> float:
+        """Tracer::get_trace_time (tracer.rs:206-208): mean of the last (up to 20) trace_all times in milliseconds
+        (tracer.rs:350-354); NaN before the first one, like the reference's 0 / 0.  Device time of the trace kernels."""
+        t = getattr(self, "_trace_times", [])
+        return sum(t) / len(t) if t else float("nan")
+
     # -- device state -----------------------------------------------------------------------------
     def set_shard(self, rank: int, world: int):
         self._rank, self._world = rank, world
@@ -247,11 +270,13 @@ class Tracer:
         st = abi.LgTraceStats()
         self.ctx.call("lg_trace", C.byref(st))
         self.last_stats = st
+        self._trace_times = (getattr(self, "_trace_times", []) + [float(st.trace_ms)])[-20:]  # trace_time_vd, tracer.rs:350-354
         seg, tg, f64 = self._read_segments(ordered or return_tags)
         if ordered:
             seg, tg, f64 = sort_segments(seg, tg, f64)
         if control_lines:  # tracer.rs:342-346
-            extra = [cl for ob in self.objects for cl in ob.get_control_lines()]
+            shown = self.objects + ([self.drawing_object] if self.drawing_object is not None else [])
+            extra = [cl for ob in shown for cl in ob.get_control_lines()]
             if extra:
                 add = np.zeros(len(extra), dtype=abi.SEGMENT_DTYPE)
                 for i, (a, b, col) in enumerate(extra):

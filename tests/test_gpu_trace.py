@@ -146,6 +146,43 @@ def test_trace_all_appends_control_lines(ctx32):
     np.testing.assert_allclose(seg["b"][-1], p[3], rtol=1e-7)
 
 
+def test_tracer_bookkeeping_mirrors(ctx32):
+    """The rest of the Tracer surface a caller of the reference uses around trace_all: get_trace_time is the mean of the
+    last 20 trace times in milliseconds (tracer.rs:206-208, 350-354), the control polygon of a curved mirror that is
+    still being drawn is shown as well (tracer.rs:341), obj_changed / update_tile_map / new_tile_map leave the scene to be
+    lowered again (tracer.rs:126-160)."""
+    import math
+    from light_garden_b200.scene import CubicBezier
+    spec = SPECS["C1"]
+    t = make_tracer(spec, ctx32)
+    assert math.isnan(t.get_trace_time())
+    for _ in range(23):
+        t.trace_all(ordered=False, control_lines=False)
+    assert len(t._trace_times) == 20 and 0.0 < t.get_trace_time() < 1e3
+    assert abs(t.get_trace_time() - sum(t._trace_times) / 20) < 1e-12
+    n0 = len(t.trace_all())
+    t.add_drawing_object(Object.new_curved_mirror(CubicBezier(((1.2, 0.6), (1.3, 0.8), (1.5, 0.8), (1.6, 0.6)))))
+    seg = t.trace_all()
+    assert len(seg) == n0 + 3 and np.all(seg["color"][-6:] == np.float32([1, 0, 0, 1]))
+    np.testing.assert_allclose(seg["a"][-3], (1.2, 0.6), rtol=1e-7)
+    t.finish_drawing_object(True)
+    assert len(t.trace_all()) == n0
+    t.enable_tile_map(True)
+    try:
+        before = t.trace_all(control_lines=False)
+        t.index_object(2).geo.width *= 0.5            # edited in place: the caller says so
+        t.obj_changed(2)
+        after = t.trace_all(control_lines=False)
+        assert len(after) != len(before) or not np.array_equal(after["b"], before["b"])
+        t.new_tile_map(50, 50, 4)
+        t.update_tile_map()
+        assert np.array_equal(t.trace_all(control_lines=False)["b"], after["b"])
+        with pytest.raises(ValueError):
+            t.new_tile_map(0, 10, 8)
+    finally:
+        t.enable_tile_map(False)
+
+
 def test_shards_partition_the_rays(oracle, ctx32):
     """rank r of R takes the rays r, r + R, ... of every light; the union is the whole trace."""
     spec = SPECS["C1"]
