@@ -658,6 +658,20 @@ void note_accum_cost(lg_ctx *c, bool tiled, float ms, unsigned long long frags, 
 // overflow and leaves fill / raster nothing to do.  tiled_finish() -- after the caller's own synchronisation --
 // reads the totals, grows the list and runs the two passes again in that case (first call of a workload at most).
 // n_dev / skip_dev: the segment count and the "wave overflowed" flag may live on the device (lg_render's waves).
+// The fill pass of the tile bins (lg_tiles.cuh: which form of the cursors).  T.n_ctas is the count pass's split of the segments.
+template <class Seg> int launch_fill(lg_ctx *c, const TileArgs &T, cudaStream_t st, const Seg *d_seg, unsigned long long n) {
+  // positions in the pair list fit 32 bits unless the list itself is larger than that (C2 at full size: 5.7e9 pairs; the
+  // list keeps its size afterwards, so a later 4096 x 4096 frame sees it too)
+  const bool wide = T.list_cap >= (1ull << 32) || c->fill_wide;
+  const bool staged = wide && (size_t)T.n_tiles * 12 + 1024 <= c->smem_optin;
+  const size_t smem = (size_t)T.n_tiles * (staged ? 12 : 4);
+  auto k = !wide ? tile_fill_kernel<Seg, 0> : (staged ? tile_fill_kernel<Seg, 1> : tile_fill_kernel<Seg, 2>);
+  if (smem > 48 * 1024) LG_CUDA(c, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k<<<T.n_ctas, c->bin_threads, smem, st>>>(T, d_seg, n);
+  LG_CUDA(c, cudaGetLastError());
+  return LG_OK;
+}
+
 template <class Seg>
 int accumulate_tiled(lg_ctx *c, cudaStream_t st, const Seg *d_seg, unsigned long long n, const unsigned long long *n_dev,
                      const unsigned int *skip_dev, unsigned long long *h_totals, unsigned *launches,
@@ -687,16 +701,11 @@ int accumulate_tiled(lg_ctx *c, cudaStream_t st, const Seg *d_seg, unsigned long
   T.n_dev = n_dev, T.skip_dev = skip_dev;
   const size_t hist_smem = (size_t)T.n_tiles * 4;
   auto count_k = tile_count_kernel<Seg>;
-  // positions in the pair list fit 32 bits unless the list itself is larger than that (C2 at full size: 5.7e9 pairs)
-  const bool pos64 = T.list_cap >= (1ull << 32) || c->fill_wide;
-  const size_t fill_smem = (size_t)T.n_tiles * (pos64 ? 12 : 4);
-  auto fill_k = pos64 ? tile_fill_kernel<Seg, true> : tile_fill_kernel<Seg, false>;
   if (hist_smem > 48 * 1024) LG_CUDA(c, cudaFuncSetAttribute(count_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hist_smem));
-  if (fill_smem > 48 * 1024) LG_CUDA(c, cudaFuncSetAttribute(fill_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fill_smem));
   // CTAs of the count and fill passes (the same split of the segments in both): one resident wave -- the histogram
   // in shared memory decides how many fit on an SM -- and no more than the segments can keep busy
   int hist_per_sm = 0;
-  LG_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&hist_per_sm, fill_k, c->bin_threads, fill_smem));
+  LG_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&hist_per_sm, count_k, c->bin_threads, hist_smem));
   if (hist_per_sm < 1) return fail(c, LG_ERR_CUDA, "tile histogram does not fit in shared memory");
   int grid = c->bin_grid > 0 ? c->bin_grid : c->sm_count * c->bin_ctas;
   grid = (int)std::max<unsigned long long>(1ull, std::min<unsigned long long>((unsigned long long)grid, (n + 1023ull) / 1024ull));
@@ -719,8 +728,7 @@ int accumulate_tiled(lg_ctx *c, cudaStream_t st, const Seg *d_seg, unsigned long
   LG_CUDA(c, cudaGetLastError());
   tile_scan_kernel<<<1, 1024, 0, st>>>(T);
   LG_CUDA(c, cudaGetLastError());
-  fill_k<<<grid, c->bin_threads, fill_smem, st>>>(T, d_seg, n);
-  LG_CUDA(c, cudaGetLastError());
+  if ((rc = launch_fill<Seg>(c, T, st, d_seg, n))) return rc;
   kern<<<c->tiled_raster_grid, kRasterWarps * 32, smem, st>>>(T, d_seg);
   LG_CUDA(c, cudaGetLastError());
   LG_CUDA(c, cudaMemcpyAsync(h_totals, T.totals, 32, cudaMemcpyDeviceToHost, st));
@@ -750,12 +758,7 @@ int tiled_finish(lg_ctx *c, cudaStream_t st, const Seg *d_seg, unsigned long lon
   const unsigned long long fixed[4] = {h_totals[0], h_totals[3], 0ull, h_totals[3]};
   LG_CUDA(c, cudaMemcpyAsync(T.totals, fixed, 32, cudaMemcpyHostToDevice, st));
   LG_CUDA(c, cudaMemsetAsync(T.item_counter, 0, 4, st)); // the raster's first (empty) launch moved it
-  const bool pos64 = T.list_cap >= (1ull << 32) || c->fill_wide; // the grown list may have crossed the line
-  const size_t fill_smem = (size_t)T.n_tiles * (pos64 ? 12 : 4);
-  auto fill_k = pos64 ? tile_fill_kernel<Seg, true> : tile_fill_kernel<Seg, false>;
-  if (fill_smem > 48 * 1024) LG_CUDA(c, cudaFuncSetAttribute(fill_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fill_smem));
-  fill_k<<<T.n_ctas, c->bin_threads, fill_smem, st>>>(T, d_seg, n);
-  LG_CUDA(c, cudaGetLastError());
+  if ((rc = launch_fill<Seg>(c, T, st, d_seg, n))) return rc; // (the grown list may have crossed 2^32 entries)
   tile_raster_kernel<Seg><<<c->tiled_raster_grid, kRasterWarps * 32, c->tiled_raster_smem, st>>>(T, d_seg);
   LG_CUDA(c, cudaGetLastError());
   LG_CUDA(c, cudaStreamSynchronize(st));

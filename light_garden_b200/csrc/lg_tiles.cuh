@@ -189,23 +189,25 @@ __global__ void __launch_bounds__(32 * kRowscanWarps) tile_rowscan_kernel(TileAr
 }
 
 // The cursors in shared memory give ABSOLUTE positions in the pair list, so an entry costs one shared-memory atomic and
-// one store (with cursors relative to the list's start the store's address also waited for a global load of
-// tile_offset[list] per entry).
-// kWide = false: the list's capacity is below 2^32 (the host decides), a cursor is the 32-bit absolute position.
-// kWide = true (C2 at full size: 5.7e9 pairs): 32-bit cursors relative to the list's start (64-bit atomics on shared
-// memory are CAS loops) and the 64-bit starts staged beside them.
+// one store (with cursors relative to the list's start the store's address also waits for a global load of
+// tile_offset[list] per entry).  kMode, chosen by the host:
+//   0  the list's capacity is below 2^32: a cursor is the 32-bit absolute position;
+//   1  larger lists (C2 at full size: 5.7e9 pairs): 32-bit cursors relative to the list's start (64-bit atomics on shared
+//      memory are CAS loops) and the 64-bit starts staged beside them, 12 bytes per list;
+//   2  larger lists on frames whose lists do not fit 12 bytes each in shared memory: the starts are read from global memory.
 // What bounds the pass is the scattered 4-byte store (profiles/r02_tile_fill_c2.txt): the same walk
 // with the atomic's return value used but nothing stored takes 8.6 ms where this takes 34.
-template <class Seg, bool kWide>
+template <class Seg, int kMode>
 __global__ void __launch_bounds__(1024) tile_fill_kernel(TileArgs T, const Seg *seg, unsigned long long n) {
   extern __shared__ __align__(8) unsigned char s_fill_raw[];
-  unsigned long long *s_off = reinterpret_cast<unsigned long long *>(s_fill_raw);                   // kWide only
-  unsigned int *s_cur = reinterpret_cast<unsigned int *>(s_fill_raw + (kWide ? (size_t)T.n_tiles * 8 : 0)); // next slot per list
+  unsigned long long *s_off = reinterpret_cast<unsigned long long *>(s_fill_raw);                          // mode 1 only
+  unsigned int *s_cur = reinterpret_cast<unsigned int *>(s_fill_raw + (kMode == 1 ? (size_t)T.n_tiles * 8 : 0)); // next slot per list
   const unsigned int *mine = T.hist + (size_t)blockIdx.x * T.n_tiles;
   if (T.totals[2]) return; // the list is too small (tile_scan_kernel): the host grows it and runs this pass again
   for (int t = threadIdx.x; t < T.n_tiles; t += blockDim.x) {
-    if (kWide) s_off[t] = T.tile_offset[t], s_cur[t] = mine[t];
-    else s_cur[t] = (unsigned int)(T.tile_offset[t] + mine[t]);
+    if (kMode == 0) s_cur[t] = (unsigned int)(T.tile_offset[t] + mine[t]);
+    else s_cur[t] = mine[t];
+    if (kMode == 1) s_off[t] = T.tile_offset[t];
   }
   __syncthreads();
   n = pass_segments(T, n);
@@ -218,8 +220,8 @@ __global__ void __launch_bounds__(1024) tile_fill_kernel(TileArgs T, const Seg *
     for_each_tile(S, T.A.W, T.A.H, T.tiles_x, [&](int tile) {
       const int l = 2 * tile + axis;
       const unsigned int p = atomicAdd(&s_cur[l], 1u);
-      if (kWide) T.list[s_off[l] + p] = (unsigned int)i;
-      else T.list[p] = (unsigned int)i;
+      if (kMode == 0) T.list[p] = (unsigned int)i;
+      else T.list[(kMode == 1 ? s_off[l] : T.tile_offset[l]) + p] = (unsigned int)i;
     });
   }
 }

@@ -471,3 +471,22 @@ def test_wide_fill_pass_gives_the_same_frame(oracle):
     assert frames[0][0] == frames[1][0] > 0 and frames[0][1] == frames[1][1]
     # entries land in a list in a different order (atomics): fp32 association within a tile only
     assert (np.abs(frames[0][2] - frames[1][2]) <= 2e-5 * np.maximum(1.0, np.abs(frames[0][2]))).all()
+    # a 4096 x 4096 frame has 32768 lists: their 64-bit starts no longer fit in shared memory beside the cursors and are
+    # read from global memory instead (a round-2 bench run failed right here: C4 after C2 had grown the list past 2^32)
+    k = 2.0 ** -8
+    sm = StringMod(modulo=20000, num=7, mode=StringModMode.Mul, color=(k, k, k, k))
+    counts = []
+    for wide in ("0", "1"):
+        os.environ["LG_FILL_WIDE"] = wide
+        try:
+            c = Context(0, abi.LG_PRECISION_F32)
+        finally:
+            del os.environ["LG_FILL_WIDE"]
+        try:
+            c.call("lg_accumulate_mode_set", TILED)
+            r = Renderer(c, 4096, 4096)
+            r.clear()
+            counts.append(r.render_string_mod(sm).pixel_updates)
+        finally:
+            c.close()
+    assert counts[0] == counts[1] > 20000 * 1000
