@@ -122,3 +122,47 @@ def test_pipeline_is_skipped_where_it_cannot_run(oracle):
         assert (np.abs(img1 - img0) <= 1e-5 * np.maximum(1.0, np.abs(img0))).all()
     finally:
         ctx.close()
+
+
+def test_one_context_through_many_workloads_equals_fresh_contexts(oracle):
+    """A context carries estimates and buffers from one call to the next (segments per ray, pairs per segment, the pair
+    list, the per-workload choice of resolve, the image).  Very different workloads in a row on ONE context -- a deep
+    cavity, a 4096 x 4096 chord pattern, a many-object scene on a small frame, a large frame with few rays, with and
+    without the wave pipeline, and the first one again -- must each give what a fresh context gives."""
+    from light_garden_b200.scene import StringMod, StringModMode
+    from light_garden_b200.tracer import Context, Renderer, Tracer
+    specs = small_specs()
+    k = 2.0 ** -8
+    chords = StringMod(modulo=30000, num=11, mode=StringModMode.Mul, color=(k, k, k, k))
+    big = scenes.c1_default(total_rays=3000, width=1920, height=1080)
+    plan = [("trace", specs["C2"], 0), ("chords", chords, 0), ("trace", specs["C5-16"], 2), ("trace", big, 0),
+            ("chords", chords, 0), ("trace", specs["C3"], 1), ("trace", specs["C2"], 2)]
+
+    def run(ctx, kind, what, overlap):
+        ctx.call("lg_render_overlap_set", overlap, 3)
+        if kind == "chords":
+            r = Renderer(ctx, 4096, 4096)
+            r.clear()
+            st = r.render_string_mod(what)
+            img = r.read_rgba32f()
+            return (st.segments, st.pixel_updates), img[::8, ::8].copy()
+        t = what.apply(Tracer(what.canvas_bounds, ctx=ctx))
+        r = Renderer(ctx, what.width, what.height)
+        r.clear()
+        st = r.render(t)
+        return (st.primary_rays, st.ray_steps, st.segments, st.pixel_updates), r.read_rgba32f()
+
+    shared = Context(0, abi.LG_PRECISION_F32)
+    try:
+        for step, (kind, what, overlap) in enumerate(plan):
+            got_c, got_i = run(shared, kind, what, overlap)
+            fresh = Context(0, abi.LG_PRECISION_F32)
+            try:
+                exp_c, exp_i = run(fresh, kind, what, 0)
+            finally:
+                fresh.close()
+            assert got_c == exp_c, (step, kind, got_c, exp_c)
+            # either resolve, waves or not: fp32 association only (the direct resolve rounds hot pixels per fragment)
+            assert (np.abs(got_i - exp_i) <= 3e-4 * np.maximum(1.0, np.abs(exp_i))).all(), step
+    finally:
+        shared.close()
