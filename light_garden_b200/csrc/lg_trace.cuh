@@ -515,7 +515,7 @@ __global__ void __launch_bounds__(kTraceBlock, (R >= 4 || sizeof(T) == 8) ? 2 : 
             // behind the origin or beyond the nearest hit found so far
             const T tca = Real<T>::fma(TL::s(bx, sx, jj), sdx[r], Real<T>::fma(TL::s(by, sy, jj), sdy[r], nkd[r]));
             const T rb = TL::s(brb, srb, jj);
-            if (tca < -rb || tca - rb > tb[r]) continue;
+            if (jj >= A.n_obj || tca < -rb || tca - rb > tb[r]) continue; // (jj >= n_obj: see the per-slot loop)
             s = r, j = jj;
           }
         }
@@ -553,7 +553,11 @@ __global__ void __launch_bounds__(kTraceBlock, (R >= 4 || sizeof(T) == 8) ? 2 : 
           // behind the origin or beyond the nearest hit found so far
           const T tca = Real<T>::fma(TL::s(bx, sx, j), sdx[r], Real<T>::fma(TL::s(by, sy, j), sdy[r], nkd[r]));
           const T rb = TL::s(brb, srb, j);
-          if (tca < -rb || tca - rb > tb[r]) continue;
+          // j >= n_obj: a padding entry of the table.  Its squared radius is negative, so a ray never selects it -- except
+          // a ray whose direction is NaN (reflected off a zero-radius circle, say): NaN's sign bit says "not missed" for
+          // every entry, and the range test below lets NaN through.  Found by compute-sanitizer on the scene of
+          // degenerate shapes (a 4-byte read past obj_first[]); such a ray hits nothing, here as in the oracle.
+          if (j >= A.n_obj || tca < -rb || tca - rb > tb[r]) continue;
           const T before = best[r].d2;
           best[r] = narrow_phase(A, best[r], j, o[r], d[r]);
           if (best[r].d2 != before) tb[r] = Real<T>::sqrt(best[r].d2) * (T)1.000001 + A.delta;
