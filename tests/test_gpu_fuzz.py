@@ -223,6 +223,42 @@ def test_ties_and_degenerate_shapes_equal_the_oracle(oracle, ctxs):
 @pytest.mark.gpu
 @pytest.mark.skipif(not have_cuda(), reason="no CUDA device")
 @pytest.mark.parametrize("mode", [1, 2], ids=["direct", "tiled"])
+def test_frame_of_the_degenerate_scene(oracle, ctxs, mode):
+    """The scene of ties and degenerate shapes through lg_render (device emission, waves, both resolves, both widths,
+    with and without the grid): rays whose direction turns NaN on the way, zero-length segments and all.  The frame is the
+    oracle's accumulation of the device's own segments; the run is part of the compute-sanitizer pass."""
+    from light_garden_b200.tracer import Renderer, Tracer
+    spec = degenerate_spec()
+    for prec, ctx in ctxs.items():
+        ctx.call("lg_accumulate_mode_set", mode)
+        try:
+            t = spec.apply(Tracer(spec.canvas_bounds, ctx=ctx))
+            counts = []
+            for grid in (False, True):
+                t.enable_tile_map(grid)
+                try:
+                    r = Renderer(ctx, spec.width, spec.height)
+                    r.clear()
+                    st = r.render(t)
+                    got = r.read_rgba32f()
+                    seg = t.trace_all(ordered=False, control_lines=False)
+                finally:
+                    t.enable_tile_map(False)
+                exact = np.zeros((spec.height, spec.width, 4), dtype=np.float64)
+                exact[..., 3] = 1.0
+                assert oracle.accumulate_segments_f64(exact, seg) == st.pixel_updates
+                assert st.segments == len(seg)
+                rel = np.abs(got - exact) / np.maximum(1.0, np.abs(exact))
+                assert rel.max() < (3e-4 if mode == 1 else 2e-5), rel.max()
+                counts.append((st.segments, st.pixel_updates))
+            assert counts[0] == counts[1]
+        finally:
+            ctx.call("lg_accumulate_mode_set", 0)
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not have_cuda(), reason="no CUDA device")
+@pytest.mark.parametrize("mode", [1, 2], ids=["direct", "tiled"])
 def test_random_string_mod_patterns_equal_the_oracle(oracle, ctxs, mode):
     """string_mod.rs over random parameters: every mode (u64 wrapping powers included), tiny and prime moduli, factors
     far above the modulo, colour rules that overlap (the LAST matching rule wins, string_mod.rs:141-150)."""
