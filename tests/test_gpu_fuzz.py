@@ -220,6 +220,92 @@ def test_ties_and_degenerate_shapes_equal_the_oracle(oracle, ctxs):
                 t.enable_tile_map(False)
 
 
+def _scaled_geo(g, k):
+    import dataclasses
+    sc = lambda p: (p[0] * k, p[1] * k)
+    if isinstance(g, Circle):
+        return Circle(sc(g.origin), g.radius * k)
+    if isinstance(g, Rect):
+        return Rect(sc(g.origin), g.rotation, g.width * k, g.height * k)
+    if isinstance(g, Ellipse):
+        return Ellipse(sc(g.origin), g.a * k, g.b * k, g.rot)
+    if isinstance(g, ConvexPolygon):
+        return ConvexPolygon(tuple(sc(p) for p in g.points), sc(g.origin), g.rotation)
+    if isinstance(g, LineSegment):
+        return LineSegment(sc(g.a), sc(g.b))
+    if isinstance(g, CubicBezier):
+        return CubicBezier(tuple(sc(p) for p in g.points))
+    if isinstance(g, Logic):
+        return Logic(g.op, _scaled_geo(g.a, k), _scaled_geo(g.b, k), sc(g.origin), g.rotation)
+    raise TypeError(type(g))
+
+
+def scaled_spec(spec, k):
+    """The same scene in units k times as large (canvas included)."""
+    objs = [Object(_scaled_geo(o.geo, k), o.material_opt, o.kind, o.moved) for o in spec.objects]
+    lights = []
+    for l in spec.lights:
+        if isinstance(l, PointLight):
+            lights.append(PointLight((l.position[0] * k, l.position[1] * k), l.num_rays, l.color))
+        elif isinstance(l, SpotLight):
+            lights.append(SpotLight((l.position[0] * k, l.position[1] * k), l.spot_angle, l.spot_direction, l.num_rays, l.color))
+        else:
+            lights.append(DirectionalLight(l.color, l.num_rays, _scaled_geo(l.start, k)))
+    out = scenes.SceneSpec(f"{spec.name}x{k}", objs, lights, spec.max_bounce, spec.width, spec.height, tuple(spec.cutoff_color))
+    cb = spec.canvas_bounds
+    out.canvas_bounds = Rect((cb.origin[0] * k, cb.origin[1] * k), cb.rotation, cb.width * k, cb.height * k)
+    return out
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not have_cuda(), reason="no CUDA device")
+@pytest.mark.parametrize("k", [2.0 ** -20, 1000.0, 2.0 ** 20], ids=["micro", "pixel-units", "mega"])
+def test_scenes_in_other_units_equal_the_oracle(oracle, ctxs, k):
+    """The broad phase's rounding margin, the grid's cell size and the table's padding all scale with the coordinate bound
+    of the scene: random scenes in units 2^-20, 1000 (a scene kept in pixels) and 2^20 times the usual ones, both widths,
+    both nearest-hit paths, against the oracle bit for bit."""
+    from light_garden_b200.tracer import Tracer
+    for seed in range(10):
+        spec = scaled_spec(random_spec(seed), k)
+        osc = oracle.OracleScene.from_spec(spec)
+        rays = primary_rays(oracle, spec, osc)
+        for prec, ctx in ctxs.items():
+            exp = osc.trace_rays(rays, prec)
+            t = spec.apply(Tracer(spec.canvas_bounds, ctx=ctx))
+            for grid in (False, True):
+                t.enable_tile_map(grid)
+                try:
+                    assert_same_segments(t.trace(rays), exp, f64=prec == abi.LG_PRECISION_F64)
+                finally:
+                    t.enable_tile_map(False)
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not have_cuda(), reason="no CUDA device")
+@pytest.mark.parametrize("index", [1.0, 0.5, 1.0 + 2.0 ** -20, 100.0, 1e-3], ids=["one", "half", "one-plus-eps", "hundred", "milli"])
+def test_extreme_refractive_indices_equal_the_oracle(oracle, ctxs, index):
+    """Every material of the random scenes replaced by one extreme index: no bending at all (reflectance 0), denser outside
+    than inside (total internal reflection from the outside), a hair above 1, and ratios of 100 and 1000 either way
+    (ORACLE.md 4: Snell, Fresnel, the critical angle)."""
+    from light_garden_b200.tracer import Tracer
+    for seed in range(8):
+        spec = random_spec(seed)
+        for o in spec.objects:
+            if o.material_opt is not None:
+                o.material_opt = Material(index)
+        osc = oracle.OracleScene.from_spec(spec)
+        rays = primary_rays(oracle, spec, osc)
+        for prec, ctx in ctxs.items():
+            exp = osc.trace_rays(rays, prec)
+            t = spec.apply(Tracer(spec.canvas_bounds, ctx=ctx))
+            for grid in (False, True):
+                t.enable_tile_map(grid)
+                try:
+                    assert_same_segments(t.trace(rays), exp, f64=prec == abi.LG_PRECISION_F64)
+                finally:
+                    t.enable_tile_map(False)
+
+
 @pytest.mark.gpu
 @pytest.mark.skipif(not have_cuda(), reason="no CUDA device")
 @pytest.mark.parametrize("mode", [1, 2], ids=["direct", "tiled"])
