@@ -49,7 +49,7 @@ def random_pairs(n, seed, span=2.2, pow2=True):
 
 
 @pytest.mark.parametrize("mode", MODES)
-@pytest.mark.parametrize("size", [(96, 54), (257, 131), (64, 64), (33, 200)])
+@pytest.mark.parametrize("size", [(96, 54), (257, 131), (64, 64), (33, 200), (1, 1), (1, 300), (300, 1), (4097, 3)])
 def test_pairs_exact_coverage_and_sums(oracle, ctx, size, mode):
     from light_garden_b200.tracer import Renderer
     ctx.call("lg_accumulate_mode_set", mode)

@@ -5,6 +5,7 @@ the oracle implement the same ORACLE.md formulas with IEEE-exact operations only
 primary rays EVERYTHING (tags, endpoints, colours) is compared bit for bit, in both precisions.
 """
 import ctypes as C
+import math
 import os
 
 import numpy as np
@@ -450,3 +451,53 @@ def test_trace_rays_rejects_directions_that_are_not_unit(oracle, ctx64, ctx32):
     make_tracer(spec, ctx32).trace(r)
     with pytest.raises(Exception):
         make_tracer(spec, ctx64).trace(r)
+
+
+def test_many_lights_few_rays_and_a_chain_200_generations_deep(oracle, ctx32):
+    """600 lights of one to three rays each (the prefix search over lights, shards that get no ray of a light), and a
+    split chain far deeper than any BASELINE config."""
+    objs = [Object.new_circle((0.0, 0.0), 0.4).with_index(1.5), Object.new_mirror((-1.2, -0.8), (-1.1, 0.8))]
+    lights = [PointLight((-0.9 + 0.003 * k, 0.3 * math.sin(k)), 1 + k % 3, (0.3, 0.2, 0.1, 0.5)) for k in range(600)]
+    spec = scenes.SceneSpec("many lights", objs, lights, 4, 320, 180)
+    osc = oracle.OracleScene.from_spec(spec)
+    t = make_tracer(spec, ctx32)
+    exp = osc.trace_all(spec.lights, abi.LG_PRECISION_F32)
+    seg, tags, _ = t.trace_all(control_lines=False, return_tags=True)
+    assert len(seg) == exp.segments_emitted and np.array_equal(tags["ray"], exp.tags["ray"])
+    assert np.array_equal(seg["b"], exp.seg["b"])
+    seen = 0
+    for r in range(7):                                    # 7 shards over lights of 1..3 rays: most shards skip most lights
+        t.set_shard(r, 7)
+        part = t.trace_all(control_lines=False)
+        assert len(part) == osc.trace_all(spec.lights, abi.LG_PRECISION_F32, rank=r, world=7).segments_emitted
+        seen += len(part)
+    t.set_shard(0, 1)
+    assert seen == len(seg)
+    # a light inside a lens, nothing culled, 200 generations: every hit splits, the transmitted ray leaves and the
+    # reflected one goes round again -- a chain 200 deep whose colours run down to denormals
+    deep = scenes.SceneSpec("deep chain", [Object.new_circle((0.0, 0.0), 0.4).with_index(1.5)],
+                            [PointLight((0.1, 0.05), 64, (0.5, 0.5, 0.5, 0.5))], 200, 320, 180, (0.0,) * 4)
+    exp = oracle.OracleScene.from_spec(deep).trace_all(deep.lights, abi.LG_PRECISION_F32)
+    seg, tags, _ = make_tracer(deep, ctx32).trace_all(control_lines=False, return_tags=True)
+    assert len(seg) == exp.segments_emitted > 64 * 300 and int(tags["generation"].max()) == 199
+    assert np.array_equal(seg["b"], exp.seg["b"]) and np.array_equal(seg["color"], exp.seg["color"])
+
+
+def test_split_stack_overflow_is_an_error_not_a_silent_loss(ctx32):
+    """A ray through 45 glass slabs refracts 90 times in a row and leaves a live reflected sibling behind at every surface:
+    more parked branches than the 64 a slot's stack holds (lg_capi.cu: min(max_bounce - 1, 64)).  The reference's Vec
+    grows without bound; here the call must fail with LG_ERR_OVERFLOW rather than return a frame with rays missing."""
+    from light_garden_b200._lib import LightGardenError
+    from light_garden_b200.tracer import Tracer
+    t = Tracer(scenes.canvas(16 / 9), ctx=ctx32)
+    for k in range(45):
+        t.push_object(Object.new_rect((-0.9 + 0.04 * k, 0.0), 0.02, 1.5).with_index(1.5))
+    t.push_light(SpotLight((-1.5, 0.0), 0.01, (1.0, 0.02), 16, (0.5, 0.5, 0.5, 0.5)))
+    t.max_bounce = 200
+    t.cutoff_color = [1e-5] * 4                              # siblings die after a reflection or two: the work stays bounded
+    with pytest.raises(LightGardenError) as e:
+        t.trace_all()
+    assert e.value.code == abi.LG_ERR_OVERFLOW and "stack" in e.value.message
+    t.max_bounce = 60                                        # within the stack: the same scene traces
+    seg, tags, _ = t.trace_all(control_lines=False, return_tags=True)
+    assert int(tags["generation"].max()) == 59 and len(seg) > 16 * 60
