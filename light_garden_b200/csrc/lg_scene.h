@@ -69,6 +69,10 @@ inline bool lower_geo(const LgGeoNode *nodes, uint32_t n_nodes, int32_t ix, cons
     err = "geometry tree deeper than 32 (cycle?)";
     return false;
   }
+  if (out.size() - base > (size_t)1 << 16) { // nodes shared between branches unfold into a tree: 2^depth tokens
+    err = "geometry tree of more than 65536 tokens (shared nodes?)";
+    return false;
+  }
   const LgGeoNode &g = nodes[ix];
   HostTok t{};
   t.a_start = t.b_start = -1;

@@ -355,6 +355,23 @@ def test_errors_are_reported_not_hidden(ctx32):
         with pytest.raises(LightGardenError) as e:
             c.call("lg_scene_set", C.cast(objs, C.c_void_p), 1, C.cast(nodes, C.c_void_p), 1, C.byref(prm))
         assert e.value.code == abi.LG_ERR_INVALID and "range" in e.value.message
+        # hostile node tables: a node that is its own child, and 30 levels that share their children (2^30 tokens unfolded)
+        nodes = (abi.LgGeoNode * 31)()
+        for k in range(31):
+            nodes[k].kind, nodes[k].op = abi.LG_GEO_LOGIC, abi.LG_OP_OR
+            nodes[k].child_a = nodes[k].child_b = 0
+            nodes[k].rot[0] = nodes[k].rot[3] = 1.0
+        objs[0].root = 0
+        with pytest.raises(LightGardenError) as e:
+            c.call("lg_scene_set", C.cast(objs, C.c_void_p), 1, C.cast(nodes, C.c_void_p), 31, C.byref(prm))
+        assert e.value.code == abi.LG_ERR_INVALID and "cycle" in e.value.message
+        for k in range(30):
+            nodes[k].child_a = nodes[k].child_b = k + 1
+        nodes[30].kind = abi.LG_GEO_CIRCLE
+        nodes[30].p[2] = 0.5
+        with pytest.raises(LightGardenError) as e:
+            c.call("lg_scene_set", C.cast(objs, C.c_void_p), 1, C.cast(nodes, C.c_void_p), 31, C.byref(prm))
+        assert e.value.code == abi.LG_ERR_INVALID and "tokens" in e.value.message
     finally:
         c.close()
     # segment buffer too small for lg_trace: LG_ERR_OVERFLOW, not silent truncation
