@@ -384,6 +384,46 @@ def test_random_string_mod_patterns_equal_the_oracle(oracle, ctxs, mode):
         ctx.call("lg_accumulate_mode_set", 0)
 
 
+HOSTILE_LIGHTS = {
+    "spot with a zero direction": lambda: SpotLight((0.5, 0.5), 1.0, (0.0, 0.0), 50, (0.5,) * 4),
+    "spot of angle 0": lambda: SpotLight((0.5, 0.5), 0.0, (1.0, 0.0), 50, (0.5,) * 4),
+    "NaN position": lambda: PointLight((float("nan"), 0.0), 50, (0.5,) * 4),
+    "infinite position": lambda: PointLight((float("inf"), 0.0), 50, (0.5,) * 4),
+    "directional light of zero length": lambda: DirectionalLight((0.5,) * 4, 50, LineSegment((0.3, 0.3), (0.3, 0.3))),
+    "outside the canvas": lambda: PointLight((10.0, 10.0), 50, (0.5,) * 4),
+    "no rays": lambda: PointLight((0.5, 0.5), 0, (0.5,) * 4),
+    "NaN colour": lambda: PointLight((0.5, 0.5), 50, (float("nan"), 0.5, 0.5, 0.5)),
+}
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not have_cuda(), reason="no CUDA device")
+@pytest.mark.parametrize("name", list(HOSTILE_LIGHTS))
+def test_hostile_light_parameters_equal_the_oracle(oracle, ctxs, name):
+    """Lights the GUI can produce by accident (a spot light dragged out by zero pixels) or a file can contain: whatever the
+    reference's arithmetic makes of them -- NaN directions, rays that start nowhere -- the device makes the same of them,
+    in both widths and both nearest-hit paths, and the line pass swallows the result (part of the compute-sanitizer pass)."""
+    from light_garden_b200.tracer import Renderer, Tracer
+    objs = [Object.new_circle((0.0, 0.0), 0.4).with_index(1.5), Object.new_mirror((-1.2, -0.8), (-1.1, 0.8))]
+    spec = scenes.SceneSpec(name, objs, [HOSTILE_LIGHTS[name]()], 5, 160, 90)
+    osc = oracle.OracleScene.from_spec(spec)
+    for prec, ctx in ctxs.items():
+        exp = osc.trace_all(spec.lights, prec)
+        t = spec.apply(Tracer(spec.canvas_bounds, ctx=ctx))
+        for grid in (False, True):
+            t.enable_tile_map(grid)
+            try:
+                seg, tags, _ = t.trace_all(control_lines=False, return_tags=True)
+                r = Renderer(ctx, spec.width, spec.height)
+                r.clear()
+                st = r.render(t)
+            finally:
+                t.enable_tile_map(False)
+            assert len(seg) == exp.segments_emitted == st.segments
+            assert np.array_equal(seg["a"], exp.seg["a"], equal_nan=True) and np.array_equal(seg["b"], exp.seg["b"], equal_nan=True)
+            assert np.array_equal(seg["color"], exp.seg["color"], equal_nan=True)
+
+
 def test_the_random_scenes_exercise_what_they_claim(oracle):
     """Guard against a generator that quietly stops producing the hard cases: over the seeds there are lights that start
     inside a medium, rays that cross from one object directly into another (two refractive hits in a row with no
