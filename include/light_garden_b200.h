@@ -83,7 +83,12 @@ enum { LG_OP_AND = 0, LG_OP_OR = 1, LG_OP_ANDNOT = 2 };
 /* One node of a geometry tree. `rot` is a nalgebra Rotation2 exactly as serde
  * writes it, column-major [m11, m21, m12, m22] = [cos, sin, -sin, cos]
  * (default.ron:24-29). Children of a LOGIC node live in that node's local
- * frame: world = origin + rot * local (src/light_garden/object.rs:393-410). */
+ * frame: world = origin + rot * local (src/light_garden/object.rs:393-410).
+ * lg_scene_set / lg_drawing_object_set answer LG_ERR_INVALID for a node whose
+ * parameters are not finite or exceed 1e12 in magnitude, whose radius, width or
+ * height is negative, or whose `rot` is not orthonormal within 1e-6: the
+ * bounding circles and the grid are built from these numbers, and a shape they
+ * cannot bound would be traced differently from the reference. */
 typedef struct LgGeoNode {
   int32_t kind;    /* LG_GEO_*                                               */
   int32_t op;      /* LG_OP_* (LOGIC only)                                   */

@@ -59,6 +59,50 @@ inline void xform(const Affine &A, double x, double y, double *o) {
   o[1] = A.m21 * x + A.m22 * y + A.ty;
 }
 
+// What a node may hold.  The exact tests follow the oracle for any IEEE input, but the bounding circles and the grid
+// that decide WHICH objects get an exact test are built from these numbers: with a non-finite or absurdly large one, a
+// negative extent or a "rotation" that scales, they would prune hits the reference finds
+// (tests/test_gpu_fuzz.py::test_hostile_object_parameters...).  Such a node is refused, never traced differently.
+constexpr double kMaxCoordinate = 1e12;
+inline bool node_ok(const LgGeoNode &g, std::string &err) {
+  int np = 0;
+  bool rot = false, extents = false;
+  switch (g.kind) {
+  case LG_GEO_CIRCLE: np = 3; break;
+  case LG_GEO_RECT: np = 4, rot = true, extents = true; break;
+  case LG_GEO_SEGMENT: np = 4; break;
+  case LG_GEO_BEZIER: np = 8; break;
+  case LG_GEO_ELLIPSE: np = 4, rot = true; break;
+  case LG_GEO_LOGIC: np = 2, rot = true; break;
+  case LG_GEO_POLYGON: np = 2, rot = true; break;
+  case LG_GEO_POINTS: np = (g.op >= 1 && g.op <= 4) ? 2 * g.op : 0; break;
+  default: return true; // refused by kind further down
+  }
+  for (int k = 0; k < np; ++k)
+    if (!(std::fabs(g.p[k]) <= kMaxCoordinate)) {
+      err = "geometry parameter is not finite or beyond 1e12";
+      return false;
+    }
+  if (g.kind == LG_GEO_CIRCLE && !(g.p[2] >= 0.0)) {
+    err = "negative radius";
+    return false;
+  }
+  if (extents && (!(g.p[2] >= 0.0) || !(g.p[3] >= 0.0))) {
+    err = "negative width or height";
+    return false;
+  }
+  if (rot) {
+    const double *r = g.rot;
+    const double tol = 1e-6;
+    if (!(std::fabs(r[0] * r[0] + r[1] * r[1] - 1.0) <= tol) || !(std::fabs(r[2] * r[2] + r[3] * r[3] - 1.0) <= tol) ||
+        !(std::fabs(r[0] * r[2] + r[1] * r[3]) <= tol)) {
+      err = "rotation matrix is not orthonormal";
+      return false;
+    }
+  }
+  return true;
+}
+
 inline bool lower_geo(const LgGeoNode *nodes, uint32_t n_nodes, int32_t ix, const Affine &A,
                       std::vector<HostTok> &out, size_t base, int depth, std::string &err) {
   if (ix < 0 || (uint32_t)ix >= n_nodes) {
@@ -74,6 +118,7 @@ inline bool lower_geo(const LgGeoNode *nodes, uint32_t n_nodes, int32_t ix, cons
     return false;
   }
   const LgGeoNode &g = nodes[ix];
+  if (!node_ok(g, err)) return false;
   HostTok t{};
   t.a_start = t.b_start = -1;
   switch (g.kind) {
@@ -168,6 +213,7 @@ inline bool lower_geo(const LgGeoNode *nodes, uint32_t n_nodes, int32_t ix, cons
         err = "convex polygon: bad vertex list";
         return false;
       }
+      if (!node_ok(nodes[pn], err)) return false;
       for (int q = 0; q < nodes[pn].op && got < k; ++q, ++got) {
         xform(W, nodes[pn].p[2 * q], nodes[pn].p[2 * q + 1], dt.p + 2 * (got & 3));
         if ((got & 3) == 3 || got == k - 1) {

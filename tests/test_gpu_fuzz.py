@@ -424,6 +424,61 @@ def test_hostile_light_parameters_equal_the_oracle(oracle, ctxs, name):
             assert np.array_equal(seg["color"], exp.seg["color"], equal_nan=True)
 
 
+NAN, INF = float("nan"), float("inf")
+HOSTILE_OBJECTS = {
+    "circle with a NaN centre": lambda: Object.new_circle((NAN, 0.0), 0.3),
+    "circle of infinite radius": lambda: Object.new_circle((0.0, 0.0), INF),
+    "circle of negative radius": lambda: Object.new_circle((0.0, 0.0), -0.3),
+    "circle of NaN radius": lambda: Object.new_circle((0.0, 0.0), NAN),
+    "rect of negative width": lambda: Object.new_rect((0.2, 0.1), -0.4, 0.3),
+    "rect of NaN height": lambda: Object.new_rect((0.2, 0.1), 0.4, NAN),
+    "rect larger than everything": lambda: Object.new_rect((0.0, 0.0), 1e30, 1e30),
+    "mirror to infinity": lambda: Object.new_mirror((0.0, 0.0), (INF, 1.0)),
+    "mirror with a NaN end": lambda: Object.new_mirror((0.0, NAN), (1.0, 1.0)),
+    "bezier with a NaN control point": lambda: Object.new_curved_mirror(CubicBezier(((0.0, 0.0), (0.3, NAN), (0.6, 0.5), (0.9, 0.0)))),
+    "index 0": lambda: Object.new_circle((0.0, 0.0), 0.3).with_index(0.0),
+    "index NaN": lambda: Object.new_circle((0.0, 0.0), 0.3).with_index(NAN),
+    "index infinite": lambda: Object.new_circle((0.0, 0.0), 0.3).with_index(INF),
+    "rotation that is not a rotation": lambda: Object(Rect((0.1, 0.1), (2.0, 0.5, -3.0, 0.0), 0.4, 0.3), Material(1.5), "Rect"),
+    "polygon with a NaN vertex": lambda: Object(ConvexPolygon(((0.0, 0.0), (0.4, NAN), (0.2, 0.3))), Material(1.5), "ConvexPolygon"),
+}
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not have_cuda(), reason="no CUDA device")
+@pytest.mark.parametrize("name", list(HOSTILE_OBJECTS))
+def test_hostile_object_parameters_are_refused_or_equal_the_oracle(oracle, ctxs, name):
+    """Shapes no constructor of the app would make but a RON file can hold.  Each is either refused when the scene is set
+    (LG_ERR_INVALID / LG_ERR_UNSUPPORTED, with a message) or traced exactly as the oracle traces it -- never a crash, a
+    hang or a read out of bounds (the run is part of the compute-sanitizer pass)."""
+    from light_garden_b200._lib import LightGardenError
+    from light_garden_b200.tracer import Renderer, Tracer
+    objs = [Object.new_mirror((-1.2, -0.8), (-1.1, 0.8)), HOSTILE_OBJECTS[name](), Object.new_circle((0.9, 0.3), 0.2).with_index(1.4)]
+    lights = [PointLight((-0.6, 0.1), 96, (0.5, 0.4, 0.3, 0.5)), SpotLight((0.05, 0.02), 1.0, (1.0, 0.3), 33, (0.3, 0.4, 0.5, 0.5))]
+    spec = scenes.SceneSpec(name, objs, lights, 6, 160, 90)
+    for prec, ctx in ctxs.items():
+        t = spec.apply(Tracer(spec.canvas_bounds, ctx=ctx))
+        try:
+            t.sync_scene(force=True)
+        except LightGardenError as e:
+            assert e.code in (abi.LG_ERR_INVALID, abi.LG_ERR_UNSUPPORTED) and e.message
+            continue
+        osc = oracle.OracleScene.from_spec(spec)
+        exp = osc.trace_all(spec.lights, prec)
+        for grid in (False, True):
+            t.enable_tile_map(grid)
+            try:
+                seg, tags, _ = t.trace_all(control_lines=False, return_tags=True)
+                r = Renderer(ctx, spec.width, spec.height)
+                r.clear()
+                st = r.render(t)
+            finally:
+                t.enable_tile_map(False)
+            assert len(seg) == exp.segments_emitted == st.segments, (name, prec, grid, len(seg), exp.segments_emitted)
+            assert np.array_equal(tags["hit_object"], exp.tags["hit_object"])
+            assert np.array_equal(seg["b"], exp.seg["b"], equal_nan=True) and np.array_equal(seg["color"], exp.seg["color"], equal_nan=True)
+
+
 def test_the_random_scenes_exercise_what_they_claim(oracle):
     """Guard against a generator that quietly stops producing the hard cases: over the seeds there are lights that start
     inside a medium, rays that cross from one object directly into another (two refractive hits in a row with no
