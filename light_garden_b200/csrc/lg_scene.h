@@ -246,7 +246,13 @@ inline int32_t lower_scene(const LgObject *objects, uint32_t n_obj, const LgGeoN
   hs.params = prm;
   const Affine I{1, 0, 0, 1, 0, 0};
   double bound = 0;
-  for (int k = 0; k < 4; ++k) bound = std::fmax(bound, std::fabs(prm.canvas_tlbr[k]));
+  for (int k = 0; k < 4; ++k) {
+    if (!(std::fabs(prm.canvas_tlbr[k]) <= kMaxCoordinate)) { // the grid spans the canvas: see node_ok
+      err = "canvas bounds are not finite or beyond 1e12";
+      return LG_ERR_INVALID;
+    }
+    bound = std::fmax(bound, std::fabs(prm.canvas_tlbr[k]));
+  }
   for (uint32_t i = 0; i < n_obj; ++i) {
     HostObj o{};
     o.first = (int32_t)hs.toks.size();

@@ -479,6 +479,55 @@ def test_hostile_object_parameters_are_refused_or_equal_the_oracle(oracle, ctxs,
             assert np.array_equal(seg["b"], exp.seg["b"], equal_nan=True) and np.array_equal(seg["color"], exp.seg["color"], equal_nan=True)
 
 
+HOSTILE_PARAMS = {
+    "canvas of zero size": dict(canvas=Rect((0.0, 0.0), (1.0, 0.0, 0.0, 1.0), 0.0, 0.0)),
+    "canvas of negative size": dict(canvas=Rect((0.0, 0.0), (1.0, 0.0, 0.0, 1.0), -3.0, -2.0)),
+    "canvas with a NaN": dict(canvas=Rect((NAN, 0.0), (1.0, 0.0, 0.0, 1.0), 3.0, 2.0)),
+    "canvas far from the scene": dict(canvas=Rect((100.0, 100.0), (1.0, 0.0, 0.0, 1.0), 3.0, 2.0)),
+    "infinite canvas": dict(canvas=Rect((0.0, 0.0), (1.0, 0.0, 0.0, 1.0), INF, INF)),
+    "NaN cutoff": dict(cutoff=(NAN, NAN, NAN, NAN)),
+    "negative cutoff": dict(cutoff=(-1.0, -1.0, -1.0, -1.0)),
+    "cutoff above every colour": dict(cutoff=(10.0, 10.0, 10.0, 10.0)),
+    "one generation": dict(max_bounce=1),
+}
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not have_cuda(), reason="no CUDA device")
+@pytest.mark.parametrize("name", list(HOSTILE_PARAMS))
+def test_hostile_trace_parameters_are_refused_or_equal_the_oracle(oracle, ctxs, name):
+    """Canvas bounds, cutoff colours and bounce limits nobody would choose: refused with a message, or the oracle's result."""
+    from light_garden_b200._lib import LightGardenError
+    from light_garden_b200.tracer import Renderer, Tracer
+    hp = HOSTILE_PARAMS[name]
+    spec = random_spec(5)
+    spec.max_bounce = hp.get("max_bounce", 6)
+    spec.cutoff_color = list(hp.get("cutoff", (0.001,) * 4))
+    if "canvas" in hp:
+        spec.canvas_bounds = hp["canvas"]
+    for prec, ctx in ctxs.items():
+        t = spec.apply(Tracer(spec.canvas_bounds, ctx=ctx))
+        try:
+            t.sync_scene(force=True)
+        except LightGardenError as e:
+            assert e.code in (abi.LG_ERR_INVALID, abi.LG_ERR_UNSUPPORTED) and e.message
+            continue
+        osc = oracle.OracleScene.from_spec(spec)
+        exp = osc.trace_all(spec.lights, prec)
+        for grid in (False, True):
+            t.enable_tile_map(grid)
+            try:
+                seg, tags, _ = t.trace_all(control_lines=False, return_tags=True)
+                r = Renderer(ctx, spec.width, spec.height)
+                r.clear()
+                st = r.render(t)
+            finally:
+                t.enable_tile_map(False)
+            assert len(seg) == exp.segments_emitted == st.segments, (name, prec, grid, len(seg), exp.segments_emitted)
+            assert np.array_equal(tags["hit_object"], exp.tags["hit_object"])
+            assert np.array_equal(seg["b"], exp.seg["b"], equal_nan=True) and np.array_equal(seg["color"], exp.seg["color"], equal_nan=True)
+
+
 def test_the_random_scenes_exercise_what_they_claim(oracle):
     """Guard against a generator that quietly stops producing the hard cases: over the seeds there are lights that start
     inside a medium, rays that cross from one object directly into another (two refractive hits in a row with no
