@@ -528,6 +528,62 @@ def test_hostile_trace_parameters_are_refused_or_equal_the_oracle(oracle, ctxs, 
             assert np.array_equal(seg["b"], exp.seg["b"], equal_nan=True) and np.array_equal(seg["color"], exp.seg["color"], equal_nan=True)
 
 
+def _hostile_string_mods():
+    from light_garden_b200.scene import Curve, ModRemColor, StringMod, StringModMode
+    k = 2.0 ** -8
+    col = (k, k, k, k)
+    return {
+        "turns 2^63": StringMod(modulo=997, num=2, turns=2 ** 63, mode=StringModMode.Mul, color=col),
+        "turns 0": StringMod(modulo=997, num=2, turns=0, mode=StringModMode.Mul, color=col),
+        "num 2^64 - 1": StringMod(modulo=997, num=2 ** 64 - 1, mode=StringModMode.Mul, color=col),
+        "power with a huge exponent": StringMod(modulo=1024, num=2 ** 40 + 3, mode=StringModMode.Pow, color=col),
+        "modulo 2 on the Lissajous curve": StringMod(modulo=2, num=1, mode=StringModMode.Add, color=col, init_curve=Curve.Lissajous(3, 2, 0.5)),
+        "NaN Lissajous phase": StringMod(modulo=500, num=3, mode=StringModMode.Mul, color=col, init_curve=Curve.Lissajous(3, 2, NAN)),
+        "complex base outside the unit disc": StringMod(modulo=300, num=3, mode=StringModMode.Mul, color=col,
+                                                        init_curve=Curve.ComplexExp(complex(1.5, 0.7))),
+        "complex base NaN": StringMod(modulo=300, num=3, mode=StringModMode.Mul, color=col, init_curve=Curve.ComplexExp(complex(NAN, 0.1))),
+        "hypotrochoid with r = s": StringMod(modulo=700, num=5, mode=StringModMode.Mul, color=col, init_curve=Curve.Hypotrochoid(4, 4, 2)),
+        "hypotrochoid with zeros": StringMod(modulo=700, num=5, mode=StringModMode.Mul, color=col, init_curve=Curve.Hypotrochoid(0, 0, 0)),
+        "NaN colour": StringMod(modulo=700, num=5, mode=StringModMode.Mul, color=(NAN, k, k, k)),
+        "infinite colour": StringMod(modulo=700, num=5, mode=StringModMode.Mul, color=(INF, k, k, k)),
+        "rule with modulo 0 and a remainder beyond its modulo": StringMod(modulo=700, num=5, mode=StringModMode.Mul, color=col,
+            modulo_colors=[ModRemColor(0, 0, (k, 0, 0, k)), ModRemColor(3, 7, (0, k, 0, k)), ModRemColor(2 ** 63, 1, (0, 0, k, k))]),
+    }
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not have_cuda(), reason="no CUDA device")
+@pytest.mark.parametrize("mode", [1, 2], ids=["direct", "tiled"])
+@pytest.mark.parametrize("name", list(_hostile_string_mods()))
+def test_hostile_string_mod_parameters_are_refused_or_equal_the_oracle(oracle, ctxs, name, mode):
+    """string_mod.rs with numbers no slider reaches: u64 products that wrap, curves that degenerate or turn NaN, colours
+    that are not numbers.  Refused with a message, or the oracle's fragments (a handful may move: sincos, see
+    test_gpu_accum.py) -- no crash, no hang, nothing out of bounds."""
+    from light_garden_b200._lib import LightGardenError
+    from light_garden_b200.tracer import Renderer
+    sm = _hostile_string_mods()[name]
+    ctx = ctxs[abi.LG_PRECISION_F32]
+    ctx.call("lg_accumulate_mode_set", mode)
+    try:
+        r = Renderer(ctx, 160, 160)
+        r.clear()
+        try:
+            st = r.render_string_mod(sm)
+        except LightGardenError as e:
+            assert e.code in (abi.LG_ERR_INVALID, abi.LG_ERR_UNSUPPORTED) and e.message
+            return
+        got = r.read_rgba32f()
+        exp = oracle.new_image(160, 160)
+        n = oracle.accumulate_pairs(exp, oracle.string_mod(sm))
+        assert abs(int(st.pixel_updates) - int(n)) <= 8, (name, st.pixel_updates, n)
+        fin = np.isfinite(exp).all(axis=2) & np.isfinite(got).all(axis=2)
+        assert np.array_equal(np.isfinite(exp).all(axis=2), np.isfinite(got).all(axis=2)) or (~fin).sum() <= 16
+        diff = np.abs(np.where(fin[..., None], got - exp, 0.0)) > (1e-6 if mode == 1 else 3e-4) * np.maximum(1.0, np.abs(np.where(fin[..., None], exp, 0.0)))
+        assert diff.any(axis=2).sum() <= 16, (name, int(diff.any(axis=2).sum()))
+    finally:
+        ctx.call("lg_accumulate_mode_set", 0)
+
+
 def test_the_random_scenes_exercise_what_they_claim(oracle):
     """Guard against a generator that quietly stops producing the hard cases: over the seeds there are lights that start
     inside a medium, rays that cross from one object directly into another (two refractive hits in a row with no
