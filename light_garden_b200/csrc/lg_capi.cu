@@ -283,6 +283,7 @@ struct lg_ctx {
   bool peer_opened[kMaxPeers] = {false};   // mapped through cudaIpcOpenMemHandle (another process)
   bool peer_opened16[kMaxPeers] = {false};
   bool peer_fused_ok = true;
+  bool peer_size_mismatch = false; // the last handle exchange found ranks with images of different sizes
   DevBuf sync_buf, peer_xchg;
   // device-side barriers of the fused reduce (lg_reduce.cuh: peer_barrier_kernel): this rank's flag words, every
   // peer's mapped here; they outlive lg_image_configure (only the images move)
@@ -1940,8 +1941,10 @@ int exchange_peers(lg_ctx *c, int root) {
   std::vector<PeerInfo> all(n);
   LG_CUDA(c, cudaMemcpyAsync(all.data(), d_all, sizeof(PeerInfo) * n, cudaMemcpyDeviceToHost, c->stream));
   LG_CUDA(c, cudaStreamSynchronize(c->stream));
+  bool mismatch = false;
+  for (int p = 0; p < n; ++p)
+    if (all[p].bytes_img != mine.bytes_img) mismatch = true, ok = false; // ranks disagree on the image size
   for (int p = 0; p < n && ok; ++p) {
-    if (all[p].bytes_img != mine.bytes_img) ok = false; // ranks disagree on the image size
     c->flag_epoch = std::max(c->flag_epoch, all[p].epoch); // every rank continues from the same epoch
     if (p == c->comm_rank) {
       c->peer_img[p] = c->img.p;
@@ -1991,8 +1994,9 @@ int exchange_peers(lg_ctx *c, int root) {
   }
   // every rank must take the same path: consensus on "somebody could not map a peer"
   int any_bad = 0;
-  if ((rc = comm_max(c, ok ? 0 : 1, &any_bad))) return rc;
+  if ((rc = comm_max(c, ok ? 0 : (mismatch ? 2 : 1), &any_bad))) return rc;
   c->peer_fused_ok = any_bad == 0;
+  c->peer_size_mismatch = any_bad == 2;
   if (!c->peer_fused_ok) close_peers(c), close_peer_flags(c);
   c->flags_ready = c->peer_fused_ok;
   c->peers_ready = true; // the exchange happened (even if it ended in the NCCL fallback)
@@ -2029,6 +2033,7 @@ int32_t lg_image_reduce(lg_ctx *c, int32_t root, float *reduce_ms) {
     int need = 0;
     if ((rc = comm_max(c, mine_need, &need))) return rc;
     if (need && (rc = exchange_peers(c, root))) return rc;
+    if (c->peer_size_mismatch) return fail(c, LG_ERR_INVALID, "lg_image_reduce: the ranks' images differ in size");
     fused = c->peer_fused_ok;
     if (!fused && c->reduce_mode == 2) return fail(c, LG_ERR_UNSUPPORTED, "peer memory is not reachable from every rank");
     started = true;
@@ -2075,12 +2080,18 @@ int32_t lg_image_reduce(lg_ctx *c, int32_t root, float *reduce_ms) {
       // every rank saw the same bit) and run the three kernels once more
       if (attempt == 1) return fail(c, LG_ERR_STATE, "lg_image_reduce: handle exchange requested twice");
       if ((rc = exchange_peers(c, root))) return rc;
+      if (c->peer_size_mismatch) return fail(c, LG_ERR_INVALID, "lg_image_reduce: the ranks' images differ in size");
       if (!c->peer_fused_ok) return fail(c, LG_ERR_UNSUPPORTED, "peer memory is no longer reachable from every rank");
     }
     if (c->comm_rank == root) c->img16_valid = true;
     if (reduce_ms) LG_CUDA(c, cudaEventElapsedTime(reduce_ms, c->ev0, c->ev1));
     return LG_OK;
   } else {
+    // ncclReduce with different counts per rank does not fail, it hangs or corrupts: agree on the size first
+    const int px = (int)(((size_t)c->W << 16) ^ (size_t)c->H);
+    int hi = 0, lo = 0;
+    if ((rc = comm_max(c, px, &hi)) || (rc = comm_max(c, -px, &lo))) return rc;
+    if (hi != -lo) return fail(c, LG_ERR_INVALID, "lg_image_reduce: the ranks' images differ in size");
     int r = g_nccl.Reduce(c->img.p, c->img.p, (size_t)c->W * c->H * 4, kNcclFloat32, kNcclSum, root, c->comm, c->stream);
     if (r != 0) return fail(c, LG_ERR_NCCL, std::string("ncclReduce: ") + g_nccl.GetErrorString(r));
     c->img16_valid = false;

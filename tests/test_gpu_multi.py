@@ -133,3 +133,56 @@ def test_reduce_survives_a_resized_image_on_the_device_side_barriers(oracle):
     finally:
         for c in ctxs:
             c.close()
+
+
+@pytest.mark.skipif(not have_cuda() or device_count() < 2, reason="needs 2 GPUs")
+@pytest.mark.parametrize("mode", [0, NCCL, PEER], ids=["auto", "nccl", "peer"])
+def test_reduce_of_images_of_different_sizes_is_an_error_on_every_rank(oracle, mode):
+    """A rank whose frame has another size must not reach ncclReduce (different counts per rank hang or corrupt) nor the
+    peer kernel: every rank gets LG_ERR_INVALID, and the next reduce with equal sizes and a root other than 0 works."""
+    from light_garden_b200 import _lib
+    from light_garden_b200._lib import LightGardenError
+    from light_garden_b200.tracer import Context, Renderer, Tracer
+    spec = small_specs()["C1"]
+    ctxs = [Context(d, abi.LG_PRECISION_F32) for d in range(2)]
+    try:
+        arr = (C.c_void_p * 2)(*[c.h for c in ctxs])
+        _lib.check(ctxs[0].h, _lib.load().lg_comm_init_all(arr, 2))
+        tracers = []
+        for rk, c in enumerate(ctxs):
+            c.call("lg_reduce_mode_set", mode)
+            t = spec.apply(Tracer(spec.canvas_bounds, ctx=c))
+            t.set_shard(rk, 2)
+            tracers.append(t)
+
+        def reduce_collect(root):
+            errs = [None, None]
+
+            def run(i):
+                try:
+                    ctxs[i].call("lg_image_reduce", root, C.byref(C.c_float()))
+                except LightGardenError as e:
+                    errs[i] = e
+            th = [threading.Thread(target=run, args=(i,)) for i in range(2)]
+            [x.start() for x in th]
+            [x.join(120) for x in th]
+            assert not any(x.is_alive() for x in th), "lg_image_reduce hangs"
+            return errs
+
+        rends = [Renderer(ctxs[0], 480, 270), Renderer(ctxs[1], 640, 360)]
+        for rk, r in enumerate(rends):
+            r.clear(1.0 if rk == 0 else 0.0)
+            r.render(tracers[rk])
+        errs = reduce_collect(0)
+        assert all(e is not None and e.code == abi.LG_ERR_INVALID and "size" in e.message for e in errs), errs
+        rends = [Renderer(c, 480, 270) for c in ctxs]
+        for rk, r in enumerate(rends):
+            r.clear(1.0 if rk == 1 else 0.0)                 # root 1 owns the clear alpha this time
+            r.render(tracers[rk])
+        parts = [r.read_rgba32f() for r in rends]
+        assert reduce_collect(1) == [None, None]
+        total = rends[1].read_rgba32f()
+        assert (np.abs(total - (parts[0] + parts[1])) <= 1e-6 * np.maximum(1.0, np.abs(total))).all()
+    finally:
+        for c in ctxs:
+            c.close()
