@@ -490,3 +490,33 @@ def test_wide_fill_pass_gives_the_same_frame(oracle):
         finally:
             c.close()
     assert counts[0] == counts[1] > 20000 * 1000
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_colours_that_are_not_numbers_poison_their_own_pixels_only(oracle, ctx, mode):
+    """NaN, infinite, negative and huge colours in the vertex pairs: the pixels those lines cover hold what IEEE addition
+    makes of them (NaN, +-inf, the oracle's sums), every other pixel is untouched, and the 8- and 16-bit read-backs follow
+    ORACLE.md 8.5-8.7 (NaN -> 0)."""
+    from light_garden_b200.tracer import Renderer
+    ctx.call("lg_accumulate_mode_set", mode)
+    W, H = 160, 90
+    r = Renderer(ctx, W, H)
+    p = random_pairs(400, seed=77)
+    nan, inf = float("nan"), float("inf")
+    p["color_a"][0], p["color_b"][0] = (nan, 0.1, 0.1, 0.1), (nan, 0.1, 0.1, 0.1)
+    p["color_a"][1], p["color_b"][1] = (inf, 0.1, 0.1, 0.1), (inf, 0.1, 0.1, 0.1)
+    p["color_a"][2], p["color_b"][2] = (-inf, 0.1, 0.1, 0.1), (inf, 0.1, 0.1, 0.1)          # lerp from -inf to +inf
+    p["color_a"][3], p["color_b"][3] = (-0.5, -0.5, -0.5, -0.5), (-0.5, -0.5, -0.5, -0.5)
+    p["color_a"][4], p["color_b"][4] = (3e38, 3e38, 3e38, 1e19), (3e38, 3e38, 3e38, 1e19)   # sums and alpha^2 overflow
+    st = r.render_lines(p)
+    got = r.read_rgba32f()
+    exp = oracle.new_image(W, H)
+    assert st.pixel_updates == oracle.accumulate_pairs(exp, p)
+    assert np.array_equal(np.isnan(got), np.isnan(exp)) and np.array_equal(np.isinf(got), np.isinf(exp))
+    fin = np.isfinite(exp)
+    assert (np.abs(got[fin] - exp[fin]) <= 2e-6 * np.maximum(1.0, np.abs(exp[fin]))).all()
+    assert np.array_equal(r.read_rgba16f().view(np.uint16) & 0x7fff > 0x7c00, np.isnan(got))   # NaN stays NaN in fp16
+    # the 8-bit conversions of the device's own fp32 frame: NaN and negative channels give 0, +inf saturates
+    d8 = np.abs(r.make_screenshot().astype(np.int32) - oracle.to_bgra8(got).astype(np.int32))
+    assert d8.max() <= 1 and (d8 != 0).mean() < 1e-3          # powf: see test_screenshot_bgra8
+    assert np.array_equal(r.read_surface_bgra8(), oracle.to_bgra8_srgb(got))
