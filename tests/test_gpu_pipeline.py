@@ -166,3 +166,49 @@ def test_one_context_through_many_workloads_equals_fresh_contexts(oracle):
             assert (np.abs(got_i - exp_i) <= 3e-4 * np.maximum(1.0, np.abs(exp_i))).all(), step
     finally:
         shared.close()
+
+
+def test_contexts_come_and_go_without_leaking_device_memory(oracle):
+    """60 contexts created, used (trace, both resolves, string mod, every read-back format, an exported frame) and
+    destroyed: the device's free memory ends where it began (within the allocator's slack), and a context destroyed
+    while its exported frame is still held by the importer does not take the process down."""
+    import ctypes as C
+    import os
+    import torch
+    from light_garden_b200.scene import StringMod, StringModMode
+    from light_garden_b200.tracer import Context, Renderer, Tracer
+    spec = small_specs()["C5-16"]
+    k = 2.0 ** -8
+    sm = StringMod(modulo=2000, num=7, mode=StringModMode.Mul, color=(k, k, k, k))
+
+    def use(ctx, hold_fd):
+        t = spec.apply(Tracer(spec.canvas_bounds, ctx=ctx))
+        r = Renderer(ctx, 640, 360)
+        for mode in (1, 2):
+            ctx.call("lg_accumulate_mode_set", mode)
+            r.clear()
+            r.render(t)
+            r.render_string_mod(sm)
+        r.read_rgba32f(), r.read_rgba16f(), r.make_screenshot(), r.read_surface_bgra8()
+        fd, nbytes = r.export_fd()
+        if not hold_fd:
+            os.close(fd)
+        return fd
+
+    torch.cuda.synchronize()
+    warm = Context(0, abi.LG_PRECISION_F32)
+    os.close(use(warm, True))
+    warm.close()
+    free0 = torch.cuda.mem_get_info(0)[0]
+    held = []
+    for i in range(60):
+        c = Context(0, abi.LG_PRECISION_F64 if i % 5 == 0 else abi.LG_PRECISION_F32)
+        fd = use(c, hold_fd=i % 10 == 0)
+        if i % 10 == 0:
+            held.append(fd)
+        c.close()
+    for fd in held:
+        os.close(fd)
+    torch.cuda.synchronize()
+    free1 = torch.cuda.mem_get_info(0)[0]
+    assert free0 - free1 < 64 << 20, (free0, free1)
