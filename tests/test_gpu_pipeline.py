@@ -212,3 +212,80 @@ def test_contexts_come_and_go_without_leaking_device_memory(oracle):
     torch.cuda.synchronize()
     free1 = torch.cuda.mem_get_info(0)[0]
     assert free0 - free1 < 64 << 20, (free0, free1)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_random_call_sequences_leave_a_usable_context(oracle, seed):
+    """The ABI's calls in random order with random (valid and invalid) arguments on one context: errors may only be the
+    documented ones (state, invalid, overflow, unsupported), nothing crashes, and a canonical frame rendered afterwards
+    equals the frame of a fresh context."""
+    from light_garden_b200._lib import LightGardenError
+    from light_garden_b200.scene import StringMod, StringModMode
+    from light_garden_b200.tracer import Context, Renderer, Tracer
+    rng = np.random.default_rng(0xAB1 + seed)
+    specs = list(small_specs().values())
+    k = 2.0 ** -8
+    ok_codes = (abi.LG_ERR_STATE, abi.LG_ERR_INVALID, abi.LG_ERR_OVERFLOW, abi.LG_ERR_UNSUPPORTED)
+    ctx = Context(0, abi.LG_PRECISION_F32 if seed % 2 == 0 else abi.LG_PRECISION_F64)
+    try:
+        tracer, rend = None, None
+        for step in range(40):
+            op = int(rng.integers(0, 13))
+            try:
+                if op == 0:
+                    spec = specs[int(rng.integers(0, len(specs)))]
+                    tracer = spec.apply(Tracer(spec.canvas_bounds, ctx=ctx))
+                elif op == 1:
+                    rend = Renderer(ctx, int(rng.choice([1, 33, 160, 641])), int(rng.choice([1, 90, 257])))
+                elif op == 2 and rend:
+                    rend.clear(float(rng.choice([0.0, 1.0])))
+                elif op == 3 and rend and tracer:
+                    rend.render(tracer)
+                elif op == 4 and tracer:
+                    tracer.trace_all(ordered=bool(rng.integers(0, 2)), control_lines=False)
+                elif op == 5 and rend:
+                    rend.render_traced()
+                elif op == 6 and rend:
+                    rend.render_string_mod(StringMod(modulo=int(rng.choice([0, 1, 2, 500])), num=int(rng.integers(0, 9)),
+                                                     mode=int(rng.integers(0, 4)), color=(k, k, k, k)))
+                elif op == 7 and rend:
+                    [rend.read_rgba32f, rend.read_rgba16f, rend.make_screenshot, rend.read_surface_bgra8][int(rng.integers(0, 4))]()
+                elif op == 8 and tracer:
+                    tracer.enable_tile_map(bool(rng.integers(0, 2)))
+                elif op == 9:
+                    ctx.call("lg_accumulate_mode_set", int(rng.integers(-1, 4)))
+                elif op == 10 and tracer:
+                    w = int(rng.integers(1, 5))
+                    tracer.set_shard(int(rng.integers(0, w + 1)), w)           # rank == world: invalid
+                elif op == 11:
+                    ctx.call("lg_segment_capacity_set", int(rng.choice([0, 64, 5000, 1 << 20, 64 << 20])))
+                elif op == 12:
+                    ctx.call("lg_render_overlap_set", int(rng.integers(-1, 4)), int(rng.integers(0, 9)))
+            except LightGardenError as e:
+                assert e.code in ok_codes, (step, op, e.code, e.message)
+        # back to a known state, then the canonical frame
+        ctx.call("lg_segment_capacity_set", 64 << 20)
+        ctx.call("lg_accumulate_mode_set", 2)
+        ctx.call("lg_render_overlap_set", 0, 0)
+        spec = small_specs()["C3"]
+        t = spec.apply(Tracer(spec.canvas_bounds, ctx=ctx))
+        t.set_shard(0, 1)
+        t.enable_tile_map(False)
+        r = Renderer(ctx, spec.width, spec.height)
+        r.clear()
+        st = r.render(t)
+        got = r.read_rgba32f()
+        fresh = Context(0, ctx.precision if hasattr(ctx, "precision") else (abi.LG_PRECISION_F32 if seed % 2 == 0 else abi.LG_PRECISION_F64))
+        try:
+            fresh.call("lg_accumulate_mode_set", 2)
+            t2 = spec.apply(Tracer(spec.canvas_bounds, ctx=fresh))
+            r2 = Renderer(fresh, spec.width, spec.height)
+            r2.clear()
+            st2 = r2.render(t2)
+            exp = r2.read_rgba32f()
+        finally:
+            fresh.close()
+        assert (st.primary_rays, st.ray_steps, st.segments, st.pixel_updates) == (st2.primary_rays, st2.ray_steps, st2.segments, st2.pixel_updates)
+        assert (np.abs(got - exp) <= 2e-5 * np.maximum(1.0, np.abs(exp))).all()
+    finally:
+        ctx.close()
