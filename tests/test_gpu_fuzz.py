@@ -602,3 +602,38 @@ def test_the_random_scenes_exercise_what_they_claim(oracle):
         deep += int(exp.tags["generation"].max()) >= 6
     assert started_inside >= 3 and deep >= 5
     assert {"LineSegment", "CubicBezier", "Circle", "Logic", "Rect", "Ellipse", "ConvexPolygon"} <= kinds
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not have_cuda(), reason="no CUDA device")
+def test_grid_corner_cases_equal_the_all_objects_loop(oracle, ctxs):
+    """Scenes the uniform grid has to survive: no object at all, one object larger than the canvas, objects far outside
+    the canvas, two hundred coincident circles in one cell, and 60 000 tiny ones (cell lists, slot counts and indices well
+    past 16 bits) -- each against the oracle, with and without the grid."""
+    from light_garden_b200.tracer import Tracer
+    rng = np.random.default_rng(0x6A1D)
+    tiny = [Object.new_circle((float(rng.uniform(-1.7, 1.7)), float(rng.uniform(-0.95, 0.95))), 0.0015).with_index(1.4) for _ in range(60000)]
+    cases = {
+        "empty": [],
+        "one huge": [Object.new_circle((0.0, 0.0), 50.0).with_index(1.3)],
+        "far outside": [Object.new_circle((500.0, -300.0), 2.0).with_index(1.5), Object.new_mirror((-900.0, 1.0), (-900.0, -1.0)),
+                        Object.new_circle((0.2, 0.1), 0.3).with_index(1.5)],
+        "coincident": [Object.new_circle((0.3, 0.2), 0.25).with_index(1.2 + 0.001 * k) for k in range(200)],
+        "sixty thousand": tiny,
+    }
+    lights = [PointLight((-0.9, 0.05), 120, (0.5, 0.4, 0.3, 0.5)), SpotLight((1.2, -0.6), 0.8, (-1.0, 0.5), 60, (0.3, 0.4, 0.5, 0.5))]
+    for name, objs in cases.items():
+        spec = scenes.SceneSpec(name, objs, lights, 4, 160, 90)
+        osc = oracle.OracleScene.from_spec(spec)
+        rays = primary_rays(oracle, spec, osc)
+        for prec, ctx in ctxs.items():
+            if name == "sixty thousand" and prec == abi.LG_PRECISION_F64:
+                continue                                   # the oracle's all-objects loop over 60 000 objects once is enough
+            exp = osc.trace_rays(rays, prec)
+            t = spec.apply(Tracer(spec.canvas_bounds, ctx=ctx))
+            for grid in (False, True):
+                t.enable_tile_map(grid)
+                try:
+                    assert_same_segments(t.trace(rays), exp, f64=prec == abi.LG_PRECISION_F64)
+                finally:
+                    t.enable_tile_map(False)
